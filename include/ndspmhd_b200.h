@@ -1,0 +1,227 @@
+/*
+ * ndspmhd_b200.h -- C-ABI of the B200-native NDSPMHD hot path.
+ *
+ * The reference (danieljprice/ndspmhd, Fortran 90) has no FFI: its per-step hot
+ * path is three argument-less external subroutines that talk through module
+ * globals, called from `derivs` (src/derivs.f90:74-156):
+ *
+ *     call set_linklist        src/derivs.f90:82    -> src/linkND.f90:45
+ *     call iterate_density     src/derivs.f90:92    -> src/iterate_density.f90:43
+ *     call conservative2primitive  derivs.f90:98    -> src/conservative2primitive.f90:42
+ *     call get_rates           src/derivs.f90:156   -> src/ratesND_mhd.f90:29
+ *
+ * This header declares what an ISO_C_BINDING shim behind those call sites binds
+ * (see INTEGRATION.md and ndspmhd_b200/fortran/ for the shim sources).
+ *
+ * Conventions
+ *  - every real is IEEE double (the reference is built with -fdefault-real-8,
+ *    src/Makefile:27); every integer is 32-bit; logical options are int 0/1.
+ *  - particle arrays are passed in the reference's NATIVE layout: column-major,
+ *    1-based on the Fortran side, i.e. x(ndim,idim) is an array of `idim`
+ *    records of `ndim` doubles; vel/Bfield/Bevol/alpha/force/... are (3,idim).
+ *    `idim` is the allocated length (src/allocateND.f90:313), >= ntotal.
+ *  - rows [0,npart) are real particles, rows [npart,ntotal) are ghosts made by
+ *    set_ghost_particles (src/ghostND_mhd.f90:33); `ireal` holds the 1-based
+ *    parent index exactly as the Fortran array does (src/ghostND_mhd.f90:423).
+ *  - all functions return 0 on success or an ND_ERR_* code; the message is
+ *    available from ndspmhd_b200_last_error().
+ *  - no pointer is retained across calls (Fortran re-allocates its arrays when
+ *    ghosts overflow, src/ghostND_mhd.f90:383-386).
+ */
+#ifndef NDSPMHD_B200_H
+#define NDSPMHD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (reference behaviour: print + `call quit`, ndspmhd.f90:369) ---- */
+enum {
+  ND_OK = 0,
+  ND_ERR_INVALID_ARG = 1,
+  ND_ERR_UNSUPPORTED_OPTION = 2, /* option tuple outside the compiled set: shim falls back to the CPU routine */
+  ND_ERR_H_NONPOSITIVE = 3,      /* iterate_density.f90:99-102, ratesND_mhd.f90:384-387 */
+  ND_ERR_RHO_NONPOSITIVE = 4,    /* iterate_density.f90:168-170 */
+  ND_ERR_DENSITY_NOT_CONVERGED = 5, /* iterate_density.f90:349-351 */
+  ND_ERR_VSIG_DET = 6,           /* ratesND_mhd.f90:1422-1429 */
+  ND_ERR_CUDA = 7,
+  ND_ERR_NO_DEVICE = 8,
+  ND_ERR_LINK = 9,               /* linkND.f90:73-76, :94-99, :122-125 */
+  ND_ERR_NEIGHBOUR_OVERFLOW = 10,
+  ND_ERR_STATE = 11,             /* calls out of order (e.g. get_rates before upload) */
+  ND_NEED_RELINK = 100           /* not an error: host-ghost mode, h grew past hhmax (iterate_density.f90:122-126, :260-262);
+                                    caller must re-run set_ghost_particles, upload again and call iterate_density(resume=1) */
+};
+
+/* particle types, src/variablesND.f90:165-171 */
+enum {
+  ND_ITYPE_GAS = 0, ND_ITYPE_BND = 1, ND_ITYPE_DUST = 2, ND_ITYPE_GAS1 = 3,
+  ND_ITYPE_GAS2 = 4, ND_ITYPE_BND2 = 11, ND_ITYPE_BNDDUST = 12
+};
+
+/*
+ * Run-time options consumed by the path.  Names and meanings are those of the
+ * reference modules `options`, `artvi`, `eos`, `setup_params`, `bound`, `part`
+ * (src/variablesND.f90:33-37, :44-50, :135-155, :245; src/eos.f90:36); defaults
+ * are src/defaults.f90:47-118.  ndspmhd_b200_default_options() fills them.
+ */
+typedef struct nd_options {
+  /* module options */
+  int iener, icty, iav, ikernav, ihvar, iprterm;
+  int imhd, imagforce, idivbzero, iresist;
+  int idust, idrag_nature;
+  int ixsph, igravity, iexternal_force;
+  int ikernel, ikernelalt;
+  int maxdensits;
+  int iavlim[3];
+  int ibound[3];              /* per dimension: 0 none, 1 fixed, 2 reflecting ghosts, 3 periodic ghosts */
+  int usenumdens, ibiascorrection, onef_dust, use_smoothed_rhodust;
+  int islope_limiter, iuse_exact_derivs, iambipolar, ivisc, iquantum, ind_timesteps;
+  int nsubsteps_divB;         /* uninitialised under leapfrog in the reference; treated as 0 (ratesND_mhd.f90:727) */
+  /* library-side switches (no reference counterpart) */
+  int device_ghosts;          /* 1: library makes the ghost rows itself (restating ghostND_mhd.f90) from rows [0,npart) */
+  int want_aux;               /* 1: also produce rhoalt, gradhn, gradsoft, gradgradh (dead for the first-class tuple) */
+  int reserved_i[6];
+  /* reals */
+  double hfact, psep, tolh;   /* setup_params, options */
+  double gamma, polyk;        /* eos */
+  double alphamin, alphaumin, alphaBmin, beta, avdecayconst, avfact; /* artvi */
+  double psidecayfact, etamhd, Kdrag, damp, pext;
+  double xmin[3], xmax[3];    /* bound */
+  double Bconst[3];           /* part */
+  double hhmax;               /* bound:hhmax as set by set_ghost_particles (host-ghost mode); ignored with device_ghosts */
+  double reserved_d[8];
+} nd_options;
+
+/*
+ * Pointers to the host (Fortran module) arrays.  NULL is allowed for arrays the
+ * active option tuple does not touch.  "in" = read by upload, "out" = written
+ * by download.  Shapes use `idim` as the trailing extent.
+ */
+typedef struct nd_arrays {
+  /* --- in --- */
+  const double *x;       /* (ndim,idim)  part:x       */
+  const double *vel;     /* (3,idim)     part:vel     */
+  const double *pmass;   /* (idim)       part:pmass   */
+  const double *hh_in;   /* (idim)       part:hh (guess on entry) */
+  const int    *itype;   /* (idim)       part:itype   */
+  const int    *ireal;   /* (idim)       bound:ireal, 1-based, 0 = unset */
+  const double *en;      /* (idim)       part:en      */
+  const double *Bevol;   /* (3,idim)     part:Bevol   */
+  const double *alpha;   /* (3,idim)     part:alpha   */
+  const double *psi;     /* (idim)       part:psi     */
+  const double *rho_in;  /* (idim)       part:rho on entry (kept on fixed particles with ireal=0) */
+  /* --- out: density phase (iterate_density) --- */
+  double *hh;            /* (idim) */
+  double *rho;           /* (idim) */
+  double *gradh;         /* (idim) hterms:gradh */
+  double *drhodt;        /* (idim) rates:drhodt */
+  double *dhdt;          /* (idim) rates:dhdt   */
+  int    *numneigh;      /* (idim) linklist:numneigh */
+  double *rhoalt;        /* (idim) want_aux */
+  double *gradhn;        /* (idim) want_aux */
+  double *gradsoft;      /* (idim) want_aux */
+  double *gradgradh;     /* (idim) want_aux */
+  /* --- out: conservative2primitive --- */
+  double *dens;          /* (idim) */
+  double *uu;            /* (idim) */
+  double *pr;            /* (idim) */
+  double *spsound;       /* (idim) */
+  double *Bfield;        /* (3,idim) */
+  /* --- out: get_rates --- */
+  double *force;         /* (3,idim) */
+  double *dudt;          /* (idim) */
+  double *dendt;         /* (idim) */
+  double *dBevoldt;      /* (3,idim) */
+  double *daldt;         /* (3,idim) */
+  double *dpsidt;        /* (idim) */
+  double *gradpsi;       /* (3,idim) */
+  double *divB;          /* (idim) */
+  double *curlB;         /* (3,idim) */
+  double *graddivv;      /* (3,idim) */
+  double *del2u;         /* (idim)  local array in the reference (ratesND_mhd.f90:168); exposed for parity tests */
+  /* --- out: ghost rows when device_ghosts=1 (rows [npart,ntotal)) --- */
+  double *x_out;         /* (ndim,idim) */
+  double *vel_out;       /* (3,idim) */
+  int    *ireal_out;     /* (idim) */
+  int    *itype_out;     /* (idim) */
+  void   *reserved_p[8];
+} nd_arrays;
+
+/* download masks */
+enum {
+  ND_DL_DENSITY = 1u,   /* hh rho gradh drhodt dhdt numneigh (+aux) */
+  ND_DL_PRIM    = 2u,   /* dens uu pr spsound Bfield */
+  ND_DL_RATES   = 4u,   /* force dudt dendt dBevoldt daldt dpsidt gradpsi divB curlB graddivv del2u */
+  ND_DL_GHOSTS  = 8u,   /* x_out vel_out ireal_out itype_out rows [npart,ntotal) */
+  ND_DL_ALL     = 15u
+};
+
+/* scalars returned by the path: module timestep (src/variablesND.f90:255-273), hterms:itsdensity, bound:hhmax */
+typedef struct nd_scalars {
+  double dtcourant, dtforce, dtav, dtdrag, dtvisc, vsig2max, vsigmax;
+  double stressmax, ts_min, h_on_csts_max, fhmax;
+  double hhmax, dxcell;
+  double fmean[3];        /* sum m*force, the reference's momentum-conservation diagnostic (ratesND_mhd.f90:678) */
+  int itsdensity, nneigh_min, nneigh_max, nclumped;
+  int ntotal, ncells, ncellsx[3], nrelink;
+  long long ncalctotal;   /* total particle-density evaluations over all rounds (iterate_density.f90:154) */
+  int reserved_i[8];
+} nd_scalars;
+
+typedef struct nd_ctx nd_ctx;
+
+/* fills `o` with src/defaults.f90:47-118 (+ avfact from initialiseND_mhd.f90:168-172 for the default gamma) */
+int ndspmhd_b200_default_options(nd_options *o);
+
+/* library / device probing; no compute */
+int ndspmhd_b200_version(void);
+int ndspmhd_b200_device_count(void);
+
+/* one context per host thread and GPU.  `device` = CUDA ordinal.  Builds the kernel tables
+ * (setkernels + setkerndrag, src/initialiseND_mhd.f90:179-216, src/kernelND.f90:127-4289). */
+int ndspmhd_b200_create(const nd_options *o, int ndim, int device, nd_ctx **out);
+int ndspmhd_b200_set_options(nd_ctx *c, const nd_options *o);
+int ndspmhd_b200_destroy(nd_ctx *c);
+const char *ndspmhd_b200_last_error(const nd_ctx *c);
+
+/* copy of the kernel tables the device uses: w, grw, grgrw, wdrag each (0:4000); returns radkern2, dq2table */
+int ndspmhd_b200_get_kernel_tables(const nd_ctx *c, double *wij, double *grwij, double *grgrwij,
+                                   double *wijdrag, double *radkern2, double *dq2table);
+
+/* host -> device.  With device_ghosts=0 rows [0,ntotal) are taken as given; with device_ghosts=1 only
+ * rows [0,npart) are read and `ntotal` is ignored. */
+int ndspmhd_b200_upload(nd_ctx *c, const nd_arrays *a, int npart, int ntotal, int idim);
+
+/* replaces `call set_linklist` (src/linkND.f90:45): (ghosts if device_ghosts) + cell grid + cell-sorted SoA */
+int ndspmhd_b200_link(nd_ctx *c);
+
+/* replaces `call iterate_density` (src/iterate_density.f90:43).  resume=1 continues after ND_NEED_RELINK. */
+int ndspmhd_b200_iterate_density(nd_ctx *c, int resume, nd_scalars *s);
+
+/* replaces `call conservative2primitive` (element-wise branches, src/conservative2primitive.f90:42) + eos.f90:40 */
+int ndspmhd_b200_cons2prim(nd_ctx *c);
+
+/* replaces `call get_rates` (src/ratesND_mhd.f90:29) */
+int ndspmhd_b200_get_rates(nd_ctx *c, nd_scalars *s);
+
+/* link + iterate_density + cons2prim + get_rates on the resident state = one `derivs` (src/derivs.f90:74-156) */
+int ndspmhd_b200_derivs(nd_ctx *c, nd_scalars *s);
+
+/* device -> host, rows [0,ntotal) of the arrays selected by `mask` (NULL pointers skipped) */
+int ndspmhd_b200_download(nd_ctx *c, nd_arrays *a, unsigned mask, int idim);
+
+/* bench/diagnostic hooks: per-phase device time of the last derivs call (ms): link, density, c2p, rates pair, rates final */
+int ndspmhd_b200_last_timings(const nd_ctx *c, double ms[8]);
+/* number of kernels this library launched since create (bench.py's gpu_launches) */
+long long ndspmhd_b200_launch_count(const nd_ctx *c);
+/* the CUDA stream the context launches on (cudaStream_t as void*), for event timing in bench.py */
+void *ndspmhd_b200_stream(const nd_ctx *c);
+/* neighbour pair list of the rates pass for parity tests: fills up to `cap` (i,j) pairs (1-based, i real) in
+ * unspecified order, returns the total count in *npairs */
+int ndspmhd_b200_rates_pairs(nd_ctx *c, int *pair_i, int *pair_j, long long cap, long long *npairs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDSPMHD_B200_H */
