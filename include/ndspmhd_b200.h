@@ -31,6 +31,8 @@
 #ifndef NDSPMHD_B200_H
 #define NDSPMHD_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -193,6 +195,11 @@ int ndspmhd_b200_get_kernel_tables(const nd_ctx *c, double *wij, double *grwij, 
  * rows [0,npart) are read and `ntotal` is ignored. */
 int ndspmhd_b200_upload(nd_ctx *c, const nd_arrays *a, int npart, int ntotal, int idim);
 
+/* host-ghost mode only, after ND_NEED_RELINK: the caller has downloaded hh, re-run set_ghost_particles
+ * (src/iterate_density.f90:123) and hands over the new ghost rows [npart,ntotal) of x, vel, itype, ireal and the new
+ * bound:hhmax; then calls ndspmhd_b200_iterate_density(c, 1, s). */
+int ndspmhd_b200_update_ghosts(nd_ctx *c, const nd_arrays *a, int ntotal, int idim, double hhmax);
+
 /* replaces `call set_linklist` (src/linkND.f90:45): (ghosts if device_ghosts) + cell grid + cell-sorted SoA */
 int ndspmhd_b200_link(nd_ctx *c);
 
@@ -210,6 +217,10 @@ int ndspmhd_b200_derivs(nd_ctx *c, nd_scalars *s);
 
 /* device -> host, rows [0,ntotal) of the arrays selected by `mask` (NULL pointers skipped) */
 int ndspmhd_b200_download(nd_ctx *c, nd_arrays *a, unsigned mask, int idim);
+
+/* page-locked host memory for the caller's particle arrays (makes upload/download run at PCIe speed) */
+void *ndspmhd_b200_host_alloc(size_t bytes);
+void ndspmhd_b200_host_free(void *p);
 
 /* bench/diagnostic hooks: per-phase device time of the last derivs call (ms): link, density, c2p, rates pair, rates final */
 int ndspmhd_b200_last_timings(const nd_ctx *c, double ms[8]);

@@ -197,7 +197,7 @@ class Particles:
             self.ntotal = self.npart
         for name, (nc, dt) in _ARRAY_SPEC.items():
             ncomp = self.ndim if nc == "ndim" else nc
-            shape = (self.idim,) if ncomp == 1 else (self.idim, ncomp)
+            shape = (self.idim,) if (ncomp == 1 and nc != "ndim") else (self.idim, ncomp)
             self.arrays[name] = np.zeros(shape, dtype=dt)
         self.arrays["sqrtg"][:] = 1.0
 

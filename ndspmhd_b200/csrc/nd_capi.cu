@@ -1,0 +1,1270 @@
+// libndspmhd_b200.so -- C-ABI (include/ndspmhd_b200.h) + host orchestration + O(N) kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include "../../include/ndspmhd_b200.h"
+#include "nd_tables.h"
+#include "nd_device.cuh"
+#include "nd_density.cuh"
+#include "nd_rates.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <cfloat>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace ndk;
+
+// =====================================================================================================
+// context
+// =====================================================================================================
+struct RowBuf { void **p; size_t rowbytes; };   // a per-particle device array that grows with capacity
+
+struct nd_ctx {
+  nd_options o;
+  int ndim = 3, device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  ndt::KernelTables *T = nullptr;
+  TabRec *d_tab = nullptr; TabRec2 *d_tab2 = nullptr; double *d_tabdrag = nullptr;
+  // sizes
+  int npart = 0, ntotal = 0, cap = 0;
+  bool uploaded = false, linked = false, density_done = false, prim_done = false, rates_done = false;
+  // ---- original-order arrays (row r = Fortran index r+1) ----
+  double *x = nullptr, *vel = nullptr, *pmass = nullptr, *hh = nullptr, *en = nullptr, *Bevol = nullptr, *alpha = nullptr, *psi = nullptr;
+  int *itype = nullptr, *ireal = nullptr;
+  double *hhin = nullptr;
+  double *rho = nullptr, *gradh = nullptr, *drhodt = nullptr, *dhdt = nullptr, *rhoalt = nullptr, *gradhn = nullptr, *gradsoft = nullptr, *gradgradh = nullptr;
+  int *numneigh = nullptr;
+  double *dens = nullptr, *uu = nullptr, *pr = nullptr, *spsound = nullptr, *Bfield = nullptr;
+  double *force = nullptr, *dudt = nullptr, *dendt = nullptr, *dBevoldt = nullptr, *daldt = nullptr, *dpsidt = nullptr, *gradpsi = nullptr, *divB = nullptr,
+         *curlB = nullptr, *graddivv = nullptr, *del2u = nullptr;
+  // ---- sorted-order arrays ----
+  double4 *posh = nullptr, *vm = nullptr, *bpsi = nullptr, *thermo = nullptr, *gal = nullptr;
+  double4 *sF = nullptr, *sdB = nullptr, *sC = nullptr, *sP = nullptr, *sV = nullptr;
+  int *typ = nullptr, *perm = nullptr, *permtmp = nullptr, *inv = nullptr, *cellOf = nullptr, *cellOfOrig = nullptr, *redo = nullptr, *list = nullptr,
+      *scanout = nullptr, *ghostcount = nullptr;
+  std::vector<RowBuf> rowbufs;
+  // ---- cell grid ----
+  int *cellStart = nullptr, *cellCount = nullptr; int cellcap = 0;
+  int *blocksums = nullptr; int blocksumcap = 0;
+  int ncellsx[3] = {1, 1, 1}, ncells = 0;
+  double xminpart[3] = {0, 0, 0}, dxcell = 0, hhmax = 0;
+  // ---- small device scratch: reduction keys, flags ----
+  unsigned long long *red = nullptr;   // [16]
+  double *fmean = nullptr;             // [4]
+  int *flags = nullptr;                // [16]
+  unsigned long long *h_red = nullptr; int *h_flags = nullptr; double *h_fmean = nullptr;   // pinned mirrors
+  // ---- iterate_density state (kept across ND_NEED_RELINK) ----
+  int itsdensity = 0, ncalc = 0, nrelink = 0; long long ncalctotal = 0; bool redolink = false;
+  nd_scalars sc;
+  cudaEvent_t ev[8];
+  double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+int set_err(nd_ctx *c, int code, const std::string &m) { if (c) c->err = m; return code; }
+
+#define CU(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) return set_err(c, ND_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+inline int nblocks(long long n, int b) { return (int)((n + b - 1) / b); }
+
+#define LAUNCH(c, kern, grid, block, smem, ...)                      \
+  do {                                                               \
+    if ((grid) > 0) {                                                \
+      auto kfn_ = kern;                                              \
+      kfn_<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);   \
+      (c)->launches++;                                               \
+    }                                                                \
+  } while (0)
+
+// =====================================================================================================
+// primitives: exclusive scan of ints, reductions
+// =====================================================================================================
+constexpr int SCAN_T = 256, SCAN_E = 8, SCAN_TILE = SCAN_T * SCAN_E;
+
+__global__ void k_scan_tile(const int *in, int *out, int n, int *blocksums) {
+  __shared__ int warp_tot[SCAN_T / 32];
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_E;
+  int v[SCAN_E], sum = 0;
+#pragma unroll
+  for (int e = 0; e < SCAN_E; e++) { int i = base + e; v[e] = (i < n) ? in[i] : 0; sum += v[e]; }
+  int incl = sum;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = (lane < SCAN_T / 32) ? warp_tot[lane] : 0, wi = w;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += t; }
+    if (lane < SCAN_T / 32) warp_tot[lane] = wi - w;
+    if (lane == SCAN_T / 32 - 1) blocksums[blockIdx.x] = wi;
+  }
+  __syncthreads();
+  int run = warp_tot[wid] + incl - sum;
+#pragma unroll
+  for (int e = 0; e < SCAN_E; e++) { int i = base + e; if (i < n) out[i] = run; run += v[e]; }
+}
+__global__ void k_scan_sums(int *blocksums, int nb) {   // one block, sequential over chunks of 1024
+  __shared__ int wt[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int b0 = 0; b0 < nb; b0 += 1024) {
+    int i = b0 + threadIdx.x;
+    int v = (i < nb) ? blocksums[i] : 0, incl = v;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wt[wid] = incl;
+    __syncthreads();
+    if (wid == 0) { int w = wt[lane], wi = w; for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += t; } wt[lane] = wi - w; }
+    __syncthreads();
+    int excl = carry_s + wt[wid] + incl - v;
+    if (i < nb) blocksums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) blocksums[nb] = carry_s;   // grand total
+}
+__global__ void k_scan_add(int *out, int n, const int *blocksums, int nb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] += blocksums[i / SCAN_TILE];
+  if (i == 0) out[n] = blocksums[nb];
+}
+
+int ensure_blocksums(nd_ctx *c, int nb) {
+  if (nb + 1 > c->blocksumcap) {
+    if (c->blocksums) cudaFree(c->blocksums);
+    c->blocksumcap = nb + 1 + 1024;
+    CU(cudaMalloc(&c->blocksums, sizeof(int) * c->blocksumcap));
+  }
+  return 0;
+}
+// out[0..n] = exclusive scan of in[0..n-1]; out[n] = total
+int exclusive_scan(nd_ctx *c, const int *in, int *out, int n) {
+  const int nb = nblocks(n, SCAN_TILE);
+  if (int e = ensure_blocksums(c, nb)) return e;
+  LAUNCH(c, k_scan_tile, nb, SCAN_T, 0, in, out, n, c->blocksums);
+  LAUNCH(c, k_scan_sums, 1, 1024, 0, c->blocksums, nb);
+  LAUNCH(c, k_scan_add, nblocks(n, 256), 256, 0, out, n, c->blocksums, nb);
+  return 0;
+}
+
+__global__ void k_max_h(const double *hh, int n, unsigned long long *key) {
+  double m = -DBL_MAX;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmax(m, hh[i]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomic_max_d(key, m);
+}
+template <int NDIM> __global__ void k_minmax_x(const double *x, int n, unsigned long long *keys /* [0..2] min, [3..5] max */) {
+  double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    for (int d = 0; d < NDIM; d++) { double v = x[(size_t)i * NDIM + d]; mn[d] = fmin(mn[d], v); mx[d] = fmax(mx[d], v); }
+  for (int d = 0; d < NDIM; d++) {
+    double a = warp_min(mn[d]), b = warp_max(mx[d]);
+    if ((threadIdx.x & 31) == 0) { atomic_min_d(keys + d, a); atomic_max_d(keys + 3 + d, b); }
+  }
+}
+__global__ void k_check_h(const double *hh, int n, int *flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && hh[i] <= 2.2250738585072014e-308) atomicCAS(&flags[1], 0, ND_ERR_H_NONPOSITIVE);   // iterate_density.f90:99-102
+}
+
+// =====================================================================================================
+// ghosts on the device, restating src/ghostND_mhd.f90:166-346 (periodic ibound=3, reflecting 2/4/6)
+// Two passes (count, scan, write) so ghost rows come out in the reference's order: by parent, then in the
+// order makeghost is called for that parent.
+// =====================================================================================================
+struct GhostArgs {
+  double *x, *vel; const double *hh; int *itype, *ireal; const int *offset; int *count;
+  int npart, cap; int ibound[3]; double xmin[3], xmax[3]; double radkern, hhmax; int *flags;
+};
+template <int NDIM, bool WRITE> __global__ void k_ghosts(GhostArgs A) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= A.npart) return;
+  double xj[3] = {0, 0, 0}, vj[3];
+  for (int d = 0; d < NDIM; d++) xj[d] = A.x[(size_t)j * NDIM + d];
+  for (int d = 0; d < 3; d++) vj[d] = A.vel[(size_t)j * 3 + d];
+  double dxbound[3];
+  for (int d = 0; d < 3; d++) dxbound[d] = A.radkern * A.hhmax;                                   // :80
+  for (int d = 0; d < NDIM; d++) if (A.ibound[d] == 2 || A.ibound[d] == 4 || A.ibound[d] == 6) dxbound[d] = A.radkern * A.hh[j];   // :173
+  int n = 0;
+  const int base = WRITE ? A.npart + A.offset[j] : 0;
+  auto make = [&](const double *xp, const double *vp) {                                            // makeghost, :363-431
+    if (WRITE) {
+      const int r = base + n;
+      if (r < A.cap) {
+        for (int d = 0; d < NDIM; d++) A.x[(size_t)r * NDIM + d] = xp[d];
+        for (int d = 0; d < 3; d++) A.vel[(size_t)r * 3 + d] = vp[d];
+        A.ireal[r] = j + 1;
+        A.itype[r] = A.itype[j];                                                                   // :346
+      }
+    }
+    n++;
+  };
+  bool mk[3][2];
+  double xnew[3][2], xpart[3], vpart[3];
+  for (int idim = 0; idim < NDIM; idim++) {                                                        // :176
+    if (A.ibound[idim] <= 1) { mk[idim][0] = mk[idim][1] = false; continue; }
+    const bool refl = (A.ibound[idim] == 2 || A.ibound[idim] == 4 || A.ibound[idim] == 6);
+    for (int mm = 0; mm < 2; mm++) {                                                               // :184 (0: xmax, 1: xmin)
+      for (int d = 0; d < 3; d++) { xpart[d] = xj[d]; vpart[d] = vj[d]; }
+      double xbound, xperbound, dx;
+      if (mm == 0) { xbound = A.xmax[idim]; xperbound = A.xmin[idim]; dx = A.xmax[idim] - xj[idim]; }
+      else { xbound = A.xmin[idim]; xperbound = A.xmax[idim]; dx = xj[idim] - A.xmin[idim]; }
+      mk[idim][mm] = (dx < dxbound[idim]) && (dx > 0);                                             // :205
+      if (!mk[idim][mm]) continue;
+      const double dxshift = __dsub_rn(xj[idim], xbound);                                          // :212
+      if (!refl) xnew[idim][mm] = __dadd_rn(xperbound, dxshift);                                   // :225
+      else { xnew[idim][mm] = __dsub_rn(xbound, dxshift); vpart[idim] = -vj[idim]; }               // :227-228
+      xpart[idim] = xnew[idim][mm];
+      make(xpart, vpart);                                                                          // :248
+      for (int ip = 0; ip < idim; ip++) {                                                          // :257 edges
+        for (int mp = 0; mp < 2; mp++) {
+          if (!mk[ip][mp]) continue;
+          xpart[ip] = xnew[ip][mp];                                                                // :266
+          const bool reflp = (A.ibound[ip] == 2 || A.ibound[ip] == 4 || A.ibound[ip] == 6);
+          if (reflp) for (int d = 0; d < 3; d++) vpart[d] = vj[d];                                 // :283-284
+          make(xpart, vpart);                                                                      // :287
+          if (ip >= 1) {                                                                           // :293 corners
+            const int ipp = ip - 1;
+            for (int mpp = 0; mpp < 2; mpp++) {
+              if (!mk[ipp][mpp]) continue;
+              xpart[ipp] = xnew[ipp][mpp];                                                         // :300
+              const bool reflpp = (A.ibound[ipp] == 2 || A.ibound[ipp] == 4 || A.ibound[ipp] == 6);
+              if (reflpp) for (int d = 0; d < 3; d++) vpart[d] = -vj[d];                           // :307-309
+              make(xpart, vpart);                                                                  // :316
+              xpart[ipp] = xj[ipp];                                                                // :318
+            }
+          }
+          xpart[ip] = xj[ip];                                                                      // :327
+        }
+      }
+    }
+  }
+  if (!WRITE) A.count[j] = n;
+}
+
+// =====================================================================================================
+// cell grid (src/linkND.f90:119-145) as a counting sort: cell index, histogram, scan, scatter, per-cell ordering
+// =====================================================================================================
+struct CellArgs { const double *x; int ntotal; double xminpart[3], dxcell; int ncellsx[3]; int *cellOfOrig, *cellCount, *flags; };
+template <int NDIM> __global__ void k_cell_index(CellArgs A) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= A.ntotal) return;
+  int ic[3] = {0, 0, 0};
+  bool bad = false;
+  for (int d = 0; d < NDIM; d++) {
+    ic[d] = __double2int_rz((A.x[(size_t)r * NDIM + d] - A.xminpart[d]) / A.dxcell);   // icellx - 1, :121
+    if (ic[d] < 0 || ic[d] >= A.ncellsx[d]) { bad = true; ic[d] = 0; }
+  }
+  if (bad) atomicCAS(&A.flags[1], 0, ND_ERR_LINK);                                      // :122-125
+  const int cell = ic[0] + A.ncellsx[0] * (ic[1] + A.ncellsx[1] * ic[2]);               // :127-135
+  A.cellOfOrig[r] = cell;
+  atomicAdd(&A.cellCount[cell], 1);
+}
+__global__ void k_cell_scatter(const int *cellOfOrig, int ntotal, const int *cellStart, int *cellFill, int *permtmp) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= ntotal) return;
+  const int cell = cellOfOrig[r];
+  permtmp[cellStart[cell] + atomicAdd(&cellFill[cell], 1)] = r;
+}
+// one warp per cell: order the cell's rows by original index (rank sort) so the result is run-to-run deterministic
+__global__ void k_cell_order(const int *cellStart, int ncells, const int *permtmp, int *perm) {
+  const int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (cell >= ncells) return;
+  const int a = cellStart[cell], n = cellStart[cell + 1] - a;
+  for (int e = lane; e < n; e += 32) {
+    const int mine = permtmp[a + e];
+    int rank = 0;
+    for (int f = 0; f < n; f++) rank += (permtmp[a + f] < mine);
+    perm[a + rank] = mine;
+  }
+}
+
+struct GatherArgs {
+  const int *perm, *cellOfOrig, *itype, *ireal; const double *x, *vel, *pmass, *hh;
+  double4 *posh, *vm; int *typ, *cellOf, *inv; int npart, ntotal;
+};
+template <int NDIM> __global__ void k_gather_sorted(GatherArgs A) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= A.ntotal) return;
+  const int r = A.perm[s];
+  const int st = (r < A.npart) ? r : A.ireal[r] - 1;   // ghosts carry their parent's properties (makeghost -> copy_particle)
+  double p[3] = {0, 0, 0};
+  for (int d = 0; d < NDIM; d++) p[d] = A.x[(size_t)r * NDIM + d];
+  A.posh[s] = make_double4(p[0], p[1], p[2], A.hh[st]);
+  A.vm[s] = make_double4(A.vel[(size_t)r * 3], A.vel[(size_t)r * 3 + 1], A.vel[(size_t)r * 3 + 2], A.pmass[st]);
+  A.typ[s] = A.itype[r];
+  A.cellOf[s] = A.cellOfOrig[r];
+  A.inv[r] = s;
+}
+__global__ void k_refresh_h(const int *perm, const int *ireal, const double *hh, double4 *posh, int npart, int ntotal) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ntotal) return;
+  const int r = perm[s];
+  posh[s].w = hh[(r < npart) ? r : ireal[r] - 1];
+}
+__global__ void k_compact(const int *redo, const int *scan, int n, int *list) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n && redo[s]) list[scan[s]] = s;
+}
+__global__ void k_remap_list(int *list, int n, const int *oldperm_rows, const int *inv) {   // after a relink: rows -> new slots
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) list[i] = inv[oldperm_rows[i]];
+}
+__global__ void k_list_rows(const int *list, int n, const int *perm, int *rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rows[i] = perm[list[i]];
+}
+__global__ void k_minmax_neigh(const int *numneigh, int n, int *out /* [0] min [1] max */) {
+  int mn = 1 << 30, mx = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { mn = min(mn, numneigh[i]); mx = max(mx, numneigh[i]); }
+  for (int o = 16; o; o >>= 1) { mn = min(mn, __shfl_xor_sync(FULL, mn, o)); mx = max(mx, __shfl_xor_sync(FULL, mx, o)); }
+  if ((threadIdx.x & 31) == 0) { atomicMin(out, mn); atomicMax(out + 1, mx); }
+}
+
+// copies after the density iteration, src/iterate_density.f90:310-344
+struct CopyArgs { double *rho, *rhoalt, *drhodt, *dhdt, *hh, *gradh, *gradhn, *gradsoft; const int *itype, *ireal; int npart, ntotal; bool aux; };
+__device__ __forceinline__ void copy_density_row(const CopyArgs &A, int i, int j) {
+  A.rho[i] = A.rho[j]; A.drhodt[i] = A.drhodt[j]; A.dhdt[i] = A.dhdt[j]; A.hh[i] = A.hh[j]; A.gradh[i] = A.gradh[j];
+  if (A.aux) { A.rhoalt[i] = A.rhoalt[j]; A.gradhn[i] = A.gradhn[j]; A.gradsoft[i] = A.gradsoft[j]; }
+}
+__global__ void k_copy_fixed_density(CopyArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < A.npart && A.itype[i] == T_BND) { const int j = A.ireal[i] - 1; if (j >= 0) copy_density_row(A, i, j); }
+}
+__global__ void k_copy_ghost_density(CopyArgs A) {
+  const int i = A.npart + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < A.ntotal) { const int j = A.ireal[i] - 1; if (j >= 0) copy_density_row(A, i, j); }
+}
+
+// =====================================================================================================
+// conservative -> primitive + equation of state, element-wise branches of src/conservative2primitive.f90:42-470
+// and src/eos.f90:40-105
+// =====================================================================================================
+struct C2PArgs {
+  const double *rho, *en, *Bevol, *vel; const int *itype, *ireal;
+  double *dens, *uu, *pr, *spsound, *Bfield;
+  // fixed-particle replicas (copy_particle, src/copy_particle.f90:28-115) touch the state arrays too
+  double *pmass, *rho_w, *rhoalt, *hh, *en_w, *Bevol_w, *alpha, *psi, *gradh, *gradhn, *gradsoft, *gradgradh;
+  int npart, ntotal, imhd, iener; double gamma, polyk; bool aux;
+};
+__global__ void k_c2p(C2PArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.npart) return;
+  const double rho = A.rho[i];
+  A.dens[i] = rho;                                                                  // :117
+  double B[3] = {0, 0, 0};
+  if (A.imhd >= 11) for (int k = 0; k < 3; k++) B[k] = A.Bevol[(size_t)i * 3 + k];  // :151-152
+  else if (A.imhd >= 1) for (int k = 0; k < 3; k++) B[k] = A.Bevol[(size_t)i * 3 + k] * rho;   // :190-193
+  if (A.imhd != 0) for (int k = 0; k < 3; k++) A.Bfield[(size_t)i * 3 + k] = B[k];
+  double uu;
+  if (A.iener == 3) {                                                               // :329-346
+    const double *v = A.vel + (size_t)i * 3;
+    const double v2i = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2];
+    const double B2i = ((B[0] * B[0] + B[1] * B[1]) + B[2] * B[2]) / rho;
+    uu = A.en[i] - 0.5 * v2i - 0.5 * B2i;
+    if (uu < 0.) uu = 0.;
+  } else uu = A.en[i];                                                              // :353-368
+  const double gamma1 = A.gamma - 1.;
+  const int t = A.itype[i];
+  if (A.iener == 0) {                                                               // eos.f90:72-89
+    double pr = A.pr[i], cs = A.spsound[i];
+    if (rho > 0. && t == T_GAS) { pr = A.polyk * pow(rho, A.gamma); cs = sqrt(A.gamma * pr / rho); }
+    else if (t == 3 || t == 4) pr = A.polyk * (rho - 1.);
+    else if (t != T_BND) pr = 0.;
+    if (fabs(gamma1) > 1.e-3 && rho > 0.) uu = pr / (gamma1 * rho);
+    A.pr[i] = pr; A.spsound[i] = cs;
+  } else if (rho > 0.) {                                                            // eos.f90:96-101
+    const double pr = gamma1 * uu * rho;
+    A.pr[i] = pr; A.spsound[i] = sqrt(A.gamma * pr / rho);
+  }
+  A.uu[i] = uu;
+}
+__global__ void k_c2p_fixed(C2PArgs A) {                                            // :424-437
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.npart) return;
+  const int t = A.itype[i];
+  if (t != T_BND && t != T_BNDDUST) return;
+  const int j = A.ireal[i] - 1;
+  if (j < 0) return;
+  A.pmass[i] = A.pmass[j]; A.rho_w[i] = A.rho_w[j]; A.hh[i] = A.hh[j]; A.uu[i] = A.uu[j]; A.en_w[i] = A.en_w[j];
+  for (int k = 0; k < 3; k++) { A.alpha[(size_t)i * 3 + k] = A.alpha[(size_t)j * 3 + k]; }
+  if (A.imhd != 0) for (int k = 0; k < 3; k++) { A.Bevol_w[(size_t)i * 3 + k] = A.Bevol_w[(size_t)j * 3 + k]; A.Bfield[(size_t)i * 3 + k] = A.Bfield[(size_t)j * 3 + k]; }
+  A.psi[i] = A.psi[j]; A.gradh[i] = A.gradh[j];
+  if (A.aux) { A.rhoalt[i] = A.rhoalt[j]; A.gradhn[i] = A.gradhn[j]; A.gradsoft[i] = A.gradsoft[j]; A.gradgradh[i] = A.gradgradh[j]; }
+  A.spsound[i] = A.spsound[j]; A.pr[i] = A.pr[j]; A.dens[i] = A.dens[j];
+}
+__global__ void k_c2p_ghost(C2PArgs A) {                                            // :441-467
+  const int i = A.npart + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.ntotal) return;
+  const int j = A.ireal[i] - 1;
+  if (j < 0) return;
+  A.psi[i] = A.psi[j]; A.dens[i] = A.dens[j]; A.uu[i] = A.uu[j]; A.spsound[i] = A.spsound[j]; A.pr[i] = A.pr[j];
+  if (A.imhd != 0) for (int k = 0; k < 3; k++) A.Bfield[(size_t)i * 3 + k] = A.Bfield[(size_t)j * 3 + k];
+}
+
+// =====================================================================================================
+// rates: gather of the sorted inputs, finalisation loop (src/ratesND_mhd.f90:532-965)
+// =====================================================================================================
+struct RGatherArgs {
+  const int *perm, *ireal; const double *hh, *pmass, *rho, *pr, *spsound, *uu, *gradh, *alpha, *psi, *Bfield;
+  double4 *posh, *vm, *bpsi, *thermo, *gal; int npart, ntotal, imhd; unsigned long long *stress_key; int imagforce; double Bconstmax;
+};
+__global__ void k_rates_gather(RGatherArgs A) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  double stress = 0.;
+  if (s < A.ntotal) {
+    const int r = A.perm[s];
+    const int st = (r < A.npart) ? r : A.ireal[r] - 1;
+    A.posh[s].w = A.hh[st];
+    A.vm[s].w = A.pmass[st];
+    A.thermo[s] = make_double4(A.rho[st], A.pr[st], A.spsound[st], A.uu[st]);
+    A.gal[s] = make_double4(A.gradh[st], A.alpha[(size_t)st * 3], A.alpha[(size_t)st * 3 + 1], A.alpha[(size_t)st * 3 + 2]);
+    if (A.imhd != 0) {
+      const double bx = A.Bfield[(size_t)st * 3], by = A.Bfield[(size_t)st * 3 + 1], bz = A.Bfield[(size_t)st * 3 + 2];
+      A.bpsi[s] = make_double4(bx, by, bz, A.psi[st]);
+      const double B2i = (bx * bx + by * by) + bz * bz;
+      stress = fmax(fmax(0.5 * B2i - A.pr[st], 0.), A.Bconstmax);                   // :240-241
+    }
+  }
+  if (A.imhd != 0) {                                                                // stressmax over 1..ntotal, :231-245
+    stress = warp_max(stress);
+    if ((threadIdx.x & 31) == 0 && stress > 0.) atomic_max_d(A.stress_key, stress);
+  }
+}
+
+struct FinalArgs {
+  const int *perm, *typ; const double4 *posh, *vm, *bpsi, *thermo, *gal; RatesSums S; RatesOpts O;
+  const double *drhodt_in, *Bevol, *dens; const unsigned long long *vsigmax_key;
+  double *force, *dudt, *dendt, *dBevoldt, *daldt, *dpsidt, *gradpsi, *divB, *curlB, *graddivv, *del2u, *drhodt, *dhdt;
+  RatesRed R; int npart, ntotal;
+};
+__global__ void k_rates_final(FinalArgs A) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  double fhmax = 0., dtforce = DBL_MAX, fm0 = 0., fm1 = 0., fm2 = 0.;
+  if (s < A.ntotal) {
+    const int i = A.perm[s];
+    if (i < A.npart) {
+      const RatesOpts &O = A.O;
+      const double4 F = A.S.F[s], dB4 = A.S.dB[s], C = A.S.C[s], P = A.S.P[s], V = A.S.V[s];
+      const double4 p = A.posh[s], v = A.vm[s], th = A.thermo[s], g = A.gal[s];
+      const double rhoi = th.x, rho1i = 1. / rhoi, hi = p.w;
+      const double vsigmax = dkey_inv(*A.vsigmax_key);
+      const double vsig2max = (O.imhd != 0 && O.idivbzero >= 2) ? vsigmax * vsigmax : 0.;           // :518-520
+      double fx = F.x, fy = F.y, fz = F.z, dudt = F.w;
+      double divB = dB4.w, cbx = C.x, cby = C.y, cbz = C.z;
+      double bx = 0, by = 0, bz = 0, psii = 0;
+      if (O.imhd != 0) {
+        const double4 b = A.bpsi[s]; bx = b.x; by = b.y; bz = b.z; psii = b.w;
+        if (O.imhd > 0) { cbx *= rho1i; cby *= rho1i; cbz *= rho1i; }                                // :640
+        divB *= rho1i;                                                                               // :643
+      }
+      fm0 = v.w * fx; fm1 = v.w * fy; fm2 = v.w * fz;                                                // :678
+      const double forcemag = sqrt((fx * fx + fy * fy) + fz * fz);
+      const double fonh = forcemag / hi;
+      const int ti = A.typ[s];
+      if (ti != 1) fhmax = fonh;                                                                     // :681
+      double valfven2i = 0.;
+      if (O.imhd != 0) valfven2i = ((bx * bx + by * by) + bz * bz) / A.dens[i];                      // :690
+      const double vsig = sqrt(th.z * th.z + valfven2i);                                             // :695-696
+      const double drhodti = A.drhodt_in[i];
+      double dbx = dB4.x, dby = dB4.y, dbz = dB4.z, gpx = P.x, gpy = P.y, gpz = P.z;
+      if (O.imhd >= 11) {                                                                            // :722-730
+        const double *Be = A.Bevol + (size_t)i * 3;
+        dbx = dbx + Be[0] * rho1i * drhodti; dby = dby + Be[1] * rho1i * drhodti; dbz = dbz + Be[2] * rho1i * drhodti;
+        if (O.idivbzero >= 2) {
+          gpx *= rhoi; gpy *= rhoi; gpz *= rhoi;
+          if (O.nsubsteps_divB <= 0) { dbx += gpx; dby += gpy; dbz += gpz; }
+        }
+      } else if (O.imhd >= 1) {                                                                      // :733-752
+        dbx *= rho1i; dby *= rho1i; dbz *= rho1i;
+        if (O.idivbzero >= 2) { const double r2 = rho1i * rho1i; gpx *= r2; gpy *= r2; gpz *= r2; }
+      } else { dbx = dby = dbz = 0.; }
+      if (O.iresist > 0 && O.iresist != 2 && O.etamhd > DBL_MIN) dtforce = hi * hi / O.etamhd;       // :808-815
+      double dendt;
+      if (O.iener == 3) {                                                                            // :820-826 (+ pair part :1829)
+        dudt = dudt + th.y * (rho1i * rho1i) * drhodti;
+        dendt = ((v.x * fx + v.y * fy) + v.z * fz) + dudt;
+        // NOTE: the reference overwrites the pair-summed dendt here (:824); P.w is therefore discarded
+      } else if (O.iener > 0 && O.iav >= 0) {                                                        // :832-835
+        dudt = dudt + th.y * (rho1i * rho1i) * drhodti;
+        dendt = dudt;
+      } else dendt = dudt;                                                                           // :837
+      if (ti == T_DUST) dendt = 0.;                                                                  // :839
+      double da0 = 0., da1 = 0., da2 = 0.;
+      if (O.iavlim0 != 0 || O.iavlim1 != 0 || O.iavlim2 != 0) {                                      // :845-896
+        const double tdecay1 = (O.avdecayconst * vsig) / hi;
+        if (O.iavlim0 == 1 || O.iavlim0 == 2) {
+          double source = fmax(drhodti * rho1i, 0.0);
+          if (O.iavlim0 == 2) source = source * (2.0 - g.y);
+          da0 = (O.alphamin - g.y) * tdecay1 + O.avfact * source;
+        } else if (O.iavlim0 == 3) {
+          const double graddivvmag = sqrt((V.x * V.x + V.y * V.y) + V.z * V.z);
+          da0 = (O.alphamin - g.y) * tdecay1 + O.avfact * (hi * graddivvmag * (2.0 - g.y));
+        }
+        if (O.iener > 0 && O.iavlim1 > 0) {
+          const double sourceu = (th.w > 2.220446049250313e-16) ? hi * fabs(C.w) / sqrt(th.w) : 0.;
+          da1 = (O.alphaumin - g.z) * tdecay1 + sourceu;
+        }
+        if (O.iavlim2 != 0 && O.imhd != 0) {
+          const double sourceJ = sqrt(((cbx * cbx + cby * cby) + cbz * cbz) * rho1i);
+          const double sourcedivB = 10. * fabs(divB) * sqrt(rho1i);
+          double sourceB = fmax(sourceJ, sourcedivB);
+          if (O.iavlim2 == 2) sourceB = sourceB * (2.0 - g.w);
+          else if (O.iavlim2 == 3) { const double source = fmax(drhodti * rho1i, 0.0) * (2. - g.w); sourceB = sqrt(source * sourceB); }
+          da2 = (O.alphaBmin - g.w) * tdecay1 + sourceB;
+        }
+      }
+      double dpsidt = 0.;
+      if (O.idivbzero >= 2 && O.idivbzero <= 7) dpsidt = -vsig2max * divB - O.psidecayfact * psii * vsigmax / hi;   // :902
+      // zero rates on fixed particles, :949-965
+      const bool fixed = (ti == T_BND || ti == T_BNDDUST);
+      if (fixed) {
+        fx = fy = fz = dudt = dendt = dbx = dby = dbz = da0 = da1 = da2 = dpsidt = divB = cbx = cby = cbz = gpx = gpy = gpz = 0.;
+        A.drhodt[i] = 0.; A.dhdt[i] = 0.;
+      }
+      double *o3;
+      o3 = A.force + (size_t)i * 3; o3[0] = fx; o3[1] = fy; o3[2] = fz;
+      A.dudt[i] = dudt; A.dendt[i] = dendt;
+      if (A.dBevoldt) { o3 = A.dBevoldt + (size_t)i * 3; o3[0] = dbx; o3[1] = dby; o3[2] = dbz; }
+      o3 = A.daldt + (size_t)i * 3; o3[0] = da0; o3[1] = da1; o3[2] = da2;
+      A.dpsidt[i] = dpsidt;
+      o3 = A.gradpsi + (size_t)i * 3; o3[0] = gpx; o3[1] = gpy; o3[2] = gpz;
+      A.divB[i] = divB;
+      o3 = A.curlB + (size_t)i * 3; o3[0] = cbx; o3[1] = cby; o3[2] = cbz;
+      o3 = A.graddivv + (size_t)i * 3; o3[0] = V.x; o3[1] = V.y; o3[2] = V.z;
+      A.del2u[i] = C.w;
+    }
+  }
+  fhmax = warp_max(fhmax); dtforce = warp_min(dtforce);
+  fm0 = warp_sum(fm0); fm1 = warp_sum(fm1); fm2 = warp_sum(fm2);
+  if ((threadIdx.x & 31) == 0) {
+    atomic_max_d(A.R.fhmax_max, fhmax);
+    atomic_min_d(A.R.dtforce_min, dtforce);
+    atomicAdd(A.R.fmean, fm0); atomicAdd(A.R.fmean + 1, fm1); atomicAdd(A.R.fmean + 2, fm2);
+  }
+}
+struct ZeroArgs { double *force, *dudt, *dendt, *dBevoldt, *daldt, *dpsidt, *gradpsi, *divB, *curlB, *graddivv, *del2u, *drhodt, *dhdt; int npart, ntotal; };
+__global__ void k_rates_zero_ghosts(ZeroArgs A) {                                    // :949-965 for rows > npart
+  const int i = A.npart + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.ntotal) return;
+  for (int k = 0; k < 3; k++) {
+    A.force[(size_t)i * 3 + k] = 0.; A.daldt[(size_t)i * 3 + k] = 0.; A.gradpsi[(size_t)i * 3 + k] = 0.; A.curlB[(size_t)i * 3 + k] = 0.;
+    A.graddivv[(size_t)i * 3 + k] = 0.;
+    if (A.dBevoldt) A.dBevoldt[(size_t)i * 3 + k] = 0.;
+  }
+  A.dudt[i] = 0.; A.dendt[i] = 0.; A.dpsidt[i] = 0.; A.divB[i] = 0.; A.del2u[i] = 0.; A.drhodt[i] = 0.; A.dhdt[i] = 0.;
+}
+
+// =====================================================================================================
+// host orchestration
+// =====================================================================================================
+template <class T> int dev_alloc(nd_ctx *c, T **p, size_t n) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (n == 0) n = 1;
+  CU(cudaMalloc((void **)p, n * sizeof(T)));
+  return 0;
+}
+
+void register_rows(nd_ctx *c) {
+  auto &v = c->rowbufs;
+  v.clear();
+  const size_t D = sizeof(double), I = sizeof(int), D4 = sizeof(double4);
+  v.push_back({(void **)&c->x, D * c->ndim});
+#define R3(a) v.push_back({(void **)&c->a, D * 3})
+#define R1(a) v.push_back({(void **)&c->a, D})
+#define RI(a) v.push_back({(void **)&c->a, I})
+#define R4(a) v.push_back({(void **)&c->a, D4})
+  R3(vel); R1(pmass); R1(hh); R1(en); R3(Bevol); R3(alpha); R1(psi); RI(itype); RI(ireal); R1(hhin);
+  R1(rho); R1(gradh); R1(drhodt); R1(dhdt); R1(rhoalt); R1(gradhn); R1(gradsoft); R1(gradgradh); RI(numneigh);
+  R1(dens); R1(uu); R1(pr); R1(spsound); R3(Bfield);
+  R3(force); R1(dudt); R1(dendt); R3(dBevoldt); R3(daldt); R1(dpsidt); R3(gradpsi); R1(divB); R3(curlB); R3(graddivv); R1(del2u);
+  R4(posh); R4(vm); R4(bpsi); R4(thermo); R4(gal); R4(sF); R4(sdB); R4(sC); R4(sP); R4(sV);
+  RI(typ); RI(perm); RI(permtmp); RI(inv); RI(cellOf); RI(cellOfOrig); RI(redo); RI(list); RI(ghostcount);
+#undef R3
+#undef R1
+#undef RI
+#undef R4
+}
+
+// grow every per-particle array to `rows` rows, keeping the first `keep` rows
+int ensure_capacity(nd_ctx *c, int rows, int keep) {
+  if (rows <= c->cap) return 0;
+  const int newcap = (int)std::min<long long>(2000000000LL, (long long)rows + rows / 8 + 1024);
+  for (auto &rb : c->rowbufs) {
+    void *np_ = nullptr;
+    CU(cudaMalloc(&np_, rb.rowbytes * (size_t)newcap));
+    CU(cudaMemsetAsync(np_, 0, rb.rowbytes * (size_t)newcap, c->stream));
+    if (*rb.p && keep > 0) CU(cudaMemcpyAsync(np_, *rb.p, rb.rowbytes * (size_t)keep, cudaMemcpyDeviceToDevice, c->stream));
+    if (*rb.p) { CU(cudaStreamSynchronize(c->stream)); cudaFree(*rb.p); }
+    *rb.p = np_;
+  }
+  // scan output needs rows+1 ints
+  if (c->scanout) cudaFree(c->scanout);
+  CU(cudaMalloc(&c->scanout, sizeof(int) * ((size_t)newcap + 1)));
+  c->cap = newcap;
+  return 0;
+}
+
+int check_options(nd_ctx *c, const nd_options &o, int ndim) {
+  auto bad = [&](const char *m) { return set_err(c, ND_ERR_UNSUPPORTED_OPTION, std::string("unsupported option: ") + m); };
+  if (ndim < 1 || ndim > 3) return set_err(c, ND_ERR_INVALID_ARG, "ndim must be 1, 2 or 3");
+  if (o.ikernav != 3) return bad("ikernav /= 3");
+  if (o.iprterm != 0) return bad("iprterm /= 0");
+  if (!(o.imhd == 0 || o.imhd == 1 || o.imhd == 11)) return bad("imhd not in {0,1,11}");
+  if (o.imhd != 0 && o.imagforce != 2) return bad("imagforce /= 2");
+  if (o.iav < 0 || o.iav > 3) return bad("iav not in 0..3");
+  if (!(o.iener == 0 || o.iener == 2 || o.iener == 3)) return bad("iener not in {0,2,3}");
+  if (!(o.idust == 0 || o.idust == 2)) return bad("idust not in {0,2}");
+  if (!(o.iresist == 0 || o.iresist == 1)) return bad("iresist not in {0,1}");
+  if (o.icty != 0 || o.ixsph != 0 || o.igravity != 0 || o.iexternal_force != 0 || o.damp != 0.) return bad("icty/ixsph/igravity/iexternal_force/damp");
+  if (o.usenumdens || o.ibiascorrection || o.onef_dust || o.iuse_exact_derivs || o.iambipolar || o.ivisc || o.iquantum || o.ind_timesteps || o.islope_limiter >= 0)
+    return bad("usenumdens/ibiascorrection/onef_dust/iuse_exact_derivs/iambipolar/ivisc/iquantum/ind_timesteps/islope_limiter");
+  if (o.ikernelalt != o.ikernel) return bad("ikernelalt /= ikernel");
+  for (int d = 0; d < ndim; d++) {
+    const int b = o.ibound[d];
+    if (!(b == 0 || b == 1 || b == 2 || b == 3)) return bad("ibound not in {0,1,2,3}");
+  }
+  return 0;
+}
+
+Grid make_grid(nd_ctx *c) {
+  Grid G;
+  G.cellStart = c->cellStart; G.cellOf = c->cellOf; G.perm = c->perm; G.posh = c->posh; G.vm = c->vm; G.typ = c->typ;
+  G.nx = c->ncellsx[0]; G.ny = c->ncellsx[1]; G.nz = c->ncellsx[2]; G.ncells = c->ncells;
+  G.npart = c->npart; G.ntotal = c->ntotal;
+  G.radkern2 = c->T->radkern2; G.dq2table = c->T->dq2table; G.ddq2table = c->T->ddq2table;
+  G.tab = c->d_tab; G.tab2 = c->d_tab2; G.tabdrag = c->d_tabdrag;
+  return G;
+}
+
+void fill_link_scalars(nd_ctx *c);
+bool any_ghost_bound(const nd_ctx *c) { for (int d = 0; d < c->ndim; d++) if (c->o.ibound[d] >= 2) return true; return false; }
+bool any_fixed_bound(const nd_ctx *c) { for (int d = 0; d < c->ndim; d++) if (c->o.ibound[d] == 1) return true; return false; }
+
+int sync_flags(nd_ctx *c) {   // D2H of the flag block; returns a pending device-side error code
+  CU(cudaMemcpyAsync(c->h_flags, c->flags, sizeof(int) * 16, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- ghosts (device_ghosts=1) ----
+template <int NDIM> int make_ghosts(nd_ctx *c) {
+  const int np = c->npart;
+  // hhmax = maxval(hh(1:npart)), ghostND_mhd.f90:79
+  CU(cudaMemsetAsync(c->red, 0, sizeof(unsigned long long) * 16, c->stream));
+  LAUNCH(c, k_max_h, std::min(nblocks(np, 256), 1184), 256, 0, c->hh, np, c->red);
+  CU(cudaMemcpyAsync(c->h_red, c->red, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->hhmax = dkey_inv(c->h_red[0]);
+  c->ntotal = np;
+  if (!any_ghost_bound(c)) return 0;
+  GhostArgs A;
+  A.x = c->x; A.vel = c->vel; A.hh = c->hh; A.itype = c->itype; A.ireal = c->ireal; A.offset = c->scanout; A.count = c->ghostcount;
+  A.npart = np; A.cap = c->cap; A.radkern = c->T->radkern; A.hhmax = c->hhmax; A.flags = c->flags;
+  for (int d = 0; d < 3; d++) { A.ibound[d] = d < NDIM ? c->o.ibound[d] : 0; A.xmin[d] = c->o.xmin[d]; A.xmax[d] = c->o.xmax[d]; }
+  LAUNCH(c, (k_ghosts<NDIM, false>), nblocks(np, 256), 256, 0, A);
+  if (int e = exclusive_scan(c, c->ghostcount, c->scanout, np)) return e;
+  int nghost = 0;
+  CU(cudaMemcpyAsync(&nghost, c->scanout + np, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (int e = ensure_capacity(c, np + nghost, np)) return e;
+  A.x = c->x; A.vel = c->vel; A.hh = c->hh; A.itype = c->itype; A.ireal = c->ireal; A.offset = c->scanout; A.count = c->ghostcount; A.cap = c->cap;
+  // ensure_capacity may have reallocated scanout: redo the scan in that case (cheap)
+  if (int e = exclusive_scan(c, c->ghostcount, c->scanout, np)) return e;
+  A.offset = c->scanout;
+  LAUNCH(c, (k_ghosts<NDIM, true>), nblocks(np, 256), 256, 0, A);
+  c->ntotal = np + nghost;
+  return 0;
+}
+
+// ---- set_linklist (src/linkND.f90:45-161): bounds, grid, counting sort, sorted SoA ----
+template <int NDIM> int build_cells(nd_ctx *c) {
+  const int nt = c->ntotal;
+  const nd_options &o = c->o;
+  if (!any_ghost_bound(c) || !o.device_ghosts) {
+    bool allle1 = !any_ghost_bound(c);
+    if (allle1) {                                                                   // :70
+      CU(cudaMemsetAsync(c->red, 0, sizeof(unsigned long long) * 16, c->stream));
+      LAUNCH(c, k_max_h, std::min(nblocks(c->npart, 256), 1184), 256, 0, c->hh, c->npart, c->red);
+      CU(cudaMemcpyAsync(c->h_red, c->red, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      c->hhmax = dkey_inv(c->h_red[0]);
+    } else if (!o.device_ghosts) c->hhmax = o.hhmax;                                // set by the host's set_ghost_particles
+  }
+  c->dxcell = c->T->radkern * c->hhmax;                                             // :72
+  if (!(c->dxcell > 0)) return set_err(c, ND_ERR_LINK, "link: max h <= 0");
+  // :81-89 min/max of the particle distribution including ghosts
+  unsigned long long init[16];
+  for (int k = 0; k < 16; k++) init[k] = 0;
+  for (int k = 0; k < 3; k++) init[k] = ~0ull;
+  CU(cudaMemcpyAsync(c->red, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, (k_minmax_x<NDIM>), std::min(nblocks(nt, 256), 1184), 256, 0, c->x, nt, c->red);
+  CU(cudaMemcpyAsync(c->h_red, c->red, sizeof(unsigned long long) * 6, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  long long nc = 1;
+  c->ncellsx[0] = c->ncellsx[1] = c->ncellsx[2] = 1;
+  for (int d = 0; d < NDIM; d++) {
+    double xminpart = dkey_inv(c->h_red[d]) - 0.00001, xmaxpart = dkey_inv(c->h_red[3 + d]) + 0.00001;
+    xminpart = xminpart - c->dxcell - 0.00001;
+    xmaxpart = xmaxpart + c->dxcell + 0.00001;
+    c->xminpart[d] = xminpart;
+    const double q = (xmaxpart - xminpart) / c->dxcell;
+    if (!(q < 2.0e9)) return set_err(c, ND_ERR_LINK, "link: too many cells");
+    c->ncellsx[d] = (int)q + 1;                                                     // :93
+    nc *= c->ncellsx[d];
+  }
+  if (nc > 1500000000LL) return set_err(c, ND_ERR_LINK, "link: too many cells");
+  c->ncells = (int)nc;
+  if (c->ncells + 2 > c->cellcap) {
+    c->cellcap = c->ncells + c->ncells / 4 + 1024;
+    if (int e = dev_alloc(c, &c->cellStart, (size_t)c->cellcap + 1)) return e;
+    if (int e = dev_alloc(c, &c->cellCount, (size_t)c->cellcap + 1)) return e;
+  }
+  CU(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * ((size_t)c->ncells + 1), c->stream));
+  CellArgs CA;
+  CA.x = c->x; CA.ntotal = nt; CA.dxcell = c->dxcell; CA.cellOfOrig = c->cellOfOrig; CA.cellCount = c->cellCount; CA.flags = c->flags;
+  for (int d = 0; d < 3; d++) { CA.xminpart[d] = c->xminpart[d]; CA.ncellsx[d] = c->ncellsx[d]; }
+  LAUNCH(c, (k_cell_index<NDIM>), nblocks(nt, 256), 256, 0, CA);
+  if (int e = exclusive_scan(c, c->cellCount, c->cellStart, c->ncells)) return e;
+  CU(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * ((size_t)c->ncells + 1), c->stream));
+  LAUNCH(c, k_cell_scatter, nblocks(nt, 256), 256, 0, c->cellOfOrig, nt, c->cellStart, c->cellCount, c->permtmp);
+  LAUNCH(c, k_cell_order, nblocks((long long)c->ncells * 32, 256), 256, 0, c->cellStart, c->ncells, c->permtmp, c->perm);
+  GatherArgs GA;
+  GA.perm = c->perm; GA.cellOfOrig = c->cellOfOrig; GA.itype = c->itype; GA.ireal = c->ireal; GA.x = c->x; GA.vel = c->vel; GA.pmass = c->pmass; GA.hh = c->hh;
+  GA.posh = c->posh; GA.vm = c->vm; GA.typ = c->typ; GA.cellOf = c->cellOf; GA.inv = c->inv; GA.npart = c->npart; GA.ntotal = nt;
+  LAUNCH(c, (k_gather_sorted<NDIM>), nblocks(nt, 256), 256, 0, GA);
+  return 0;
+}
+
+template <int NDIM> int do_link(nd_ctx *c) {
+  if (c->o.device_ghosts) { if (int e = make_ghosts<NDIM>(c)) return e; }
+  if (int e = build_cells<NDIM>(c)) return e;
+  if (int e = sync_flags(c)) return e;
+  if (c->h_flags[1]) { int code = c->h_flags[1]; CU(cudaMemsetAsync(c->flags, 0, sizeof(int) * 16, c->stream)); return set_err(c, code, "link: particle crossed boundary"); }
+  c->linked = true;
+  return 0;
+}
+
+template <int NDIM, bool FIRST> int launch_density_round(nd_ctx *c, const DensityArgs &A, int n) {
+  Grid G = make_grid(c);
+  const size_t smem = sizeof(unsigned) * DENS_CAP * DENS_BLOCK;
+  if (c->o.want_aux) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(density_round_kernel<NDIM, FIRST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    LAUNCH(c, (density_round_kernel<NDIM, FIRST, true>), nblocks(n, DENS_BLOCK), DENS_BLOCK, smem, G, A);
+  } else {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(density_round_kernel<NDIM, FIRST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    LAUNCH(c, (density_round_kernel<NDIM, FIRST, false>), nblocks(n, DENS_BLOCK), DENS_BLOCK, smem, G, A);
+  }
+  return 0;
+}
+
+// ---- iterate_density (src/iterate_density.f90:43-360) ----
+template <int NDIM> int do_iterate_density(nd_ctx *c, int resume) {
+  const nd_options &o = c->o;
+  const int np = c->npart;
+  const int itsdensitymax = (o.ikernav == 3 && o.ihvar != 0) ? o.maxdensits : 0;     // :77-81
+  if (!resume) {
+    c->itsdensity = 0; c->ncalctotal = 0; c->ncalc = np; c->redolink = false; c->nrelink = 0;
+    CU(cudaMemcpyAsync(c->hhin, c->hh, sizeof(double) * np, cudaMemcpyDeviceToDevice, c->stream));   // :98
+    CU(cudaMemsetAsync(c->flags, 0, sizeof(int) * 16, c->stream));
+    LAUNCH(c, k_check_h, nblocks(np, 256), 256, 0, c->hh, np, c->flags);
+    CU(cudaMemsetAsync(c->dhdt, 0, sizeof(double) * c->ntotal, c->stream));          // :90-97
+    CU(cudaMemsetAsync(c->numneigh, 0, sizeof(int) * c->ntotal, c->stream));
+  }
+  while (c->ncalc > 0 && c->itsdensity <= itsdensitymax) {                           // :119
+    if (c->redolink) {                                                               // :122-126
+      // host-made ghosts: the caller re-runs set_ghost_particles, calls update_ghosts() and comes back with resume=1
+      if (any_ghost_bound(c) && !o.device_ghosts && !resume) { fill_link_scalars(c); c->sc.itsdensity = c->itsdensity; return ND_NEED_RELINK; }
+      resume = 0;
+      // remember which ROWS are still to be done (slots change with the re-sort), rebuild ghosts + grid, map back
+      const int n = c->ncalc;
+      const bool partial = (n != np);
+      if (partial) LAUNCH(c, k_list_rows, nblocks(n, 256), 256, 0, c->list, n, c->perm, c->redo);   // redo[] doubles as row scratch
+      if (int e = do_link<NDIM>(c)) return e;
+      if (partial) LAUNCH(c, k_remap_list, nblocks(n, 256), 256, 0, c->list, n, c->redo, c->inv);
+      c->nrelink++;
+      c->redolink = false;
+    }
+    c->itsdensity++;
+    DensityArgs A;
+    A.hh = c->hh; A.hhin = c->hhin; A.rho = c->rho; A.gradh = c->gradh; A.drhodt = c->drhodt; A.dhdt = c->dhdt; A.numneigh = c->numneigh;
+    A.rhoalt = c->rhoalt; A.gradhn = c->gradhn; A.gradsoft = c->gradsoft; A.gradgradh = c->gradgradh;
+    A.list = c->list; A.nlist = c->ncalc; A.redo = c->redo; A.flags = c->flags;
+    A.itsdensity = c->itsdensity; A.itsdensitymax = itsdensitymax; A.hfact = o.hfact; A.psep = o.psep; A.tolh = o.tolh; A.hhmax = c->hhmax;
+    CU(cudaMemsetAsync(c->redo, 0, sizeof(int) * c->ntotal, c->stream));
+    if (c->ncalc == np) {                                                            // :131-132 symmetric `density`
+      if (c->itsdensity > 1) LAUNCH(c, k_refresh_h, nblocks(c->ntotal, 256), 256, 0, c->perm, c->ireal, c->hh, c->posh, np, c->ntotal);
+      if (int e = launch_density_round<NDIM, true>(c, A, c->ntotal)) return e;
+    } else {                                                                         // :133-134 `density_partial`
+      if (int e = launch_density_round<NDIM, false>(c, A, c->ncalc)) return e;
+    }
+    c->ncalctotal += c->ncalc;                                                       // :154
+    if (int e = exclusive_scan(c, c->redo, c->scanout, c->ntotal)) return e;
+    LAUNCH(c, k_compact, nblocks(c->ntotal, 256), 256, 0, c->redo, c->scanout, c->ntotal, c->list);
+    CU(cudaMemcpyAsync(&c->h_flags[16], c->scanout + c->ntotal, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (int e = sync_flags(c)) return e;
+    c->ncalc = c->h_flags[16];
+    if (c->h_flags[1]) { int code = c->h_flags[1]; return set_err(c, code, code == ND_ERR_RHO_NONPOSITIVE ? "error: rho <= 0 in iterate_density" : "error: h <= 0 in density call"); }
+    c->redolink = c->h_flags[0] != 0;
+    CU(cudaMemsetAsync(c->flags, 0, sizeof(int) * 4, c->stream));
+  }
+  if (c->itsdensity > itsdensitymax && itsdensitymax > 0) return set_err(c, ND_ERR_DENSITY_NOT_CONVERGED, "ERROR: DENSITY NOT CONVERGED");   // :349-351
+  // :310-344 copies to fixed particles and ghosts
+  CopyArgs CA;
+  CA.rho = c->rho; CA.rhoalt = c->rhoalt; CA.drhodt = c->drhodt; CA.dhdt = c->dhdt; CA.hh = c->hh; CA.gradh = c->gradh; CA.gradhn = c->gradhn;
+  CA.gradsoft = c->gradsoft; CA.itype = c->itype; CA.ireal = c->ireal; CA.npart = np; CA.ntotal = c->ntotal; CA.aux = o.want_aux != 0;
+  if (any_fixed_bound(c)) LAUNCH(c, k_copy_fixed_density, nblocks(np, 256), 256, 0, CA);
+  if (any_ghost_bound(c)) LAUNCH(c, k_copy_ghost_density, nblocks(c->ntotal - np, 256), 256, 0, CA);
+  c->density_done = true;
+  return 0;
+}
+
+int do_cons2prim(nd_ctx *c) {
+  const nd_options &o = c->o;
+  C2PArgs A;
+  A.rho = c->rho; A.en = c->en; A.Bevol = c->Bevol; A.vel = c->vel; A.itype = c->itype; A.ireal = c->ireal;
+  A.dens = c->dens; A.uu = c->uu; A.pr = c->pr; A.spsound = c->spsound; A.Bfield = c->Bfield;
+  A.pmass = c->pmass; A.rho_w = c->rho; A.rhoalt = c->rhoalt; A.hh = c->hh; A.en_w = c->en; A.Bevol_w = c->Bevol; A.alpha = c->alpha; A.psi = c->psi;
+  A.gradh = c->gradh; A.gradhn = c->gradhn; A.gradsoft = c->gradsoft; A.gradgradh = c->gradgradh;
+  A.npart = c->npart; A.ntotal = c->ntotal; A.imhd = o.imhd; A.iener = o.iener; A.gamma = o.gamma; A.polyk = o.polyk; A.aux = o.want_aux != 0;
+  LAUNCH(c, k_c2p, nblocks(c->npart, 256), 256, 0, A);
+  if (any_fixed_bound(c)) LAUNCH(c, k_c2p_fixed, nblocks(c->npart, 256), 256, 0, A);
+  if (any_ghost_bound(c)) LAUNCH(c, k_c2p_ghost, nblocks(c->ntotal - c->npart, 256), 256, 0, A);
+  c->prim_done = true;
+  return 0;
+}
+
+RatesOpts make_rates_opts(const nd_ctx *c) {
+  const nd_options &o = c->o;
+  RatesOpts O;
+  O.iener = o.iener; O.iav = o.iav; O.imhd = o.imhd; O.idivbzero = o.idivbzero; O.iresist = o.iresist; O.idust = o.idust; O.idrag_nature = o.idrag_nature;
+  O.ikernav = o.ikernav; O.iavlim0 = o.iavlim[0]; O.iavlim1 = o.iavlim[1]; O.iavlim2 = o.iavlim[2]; O.nsubsteps_divB = o.nsubsteps_divB;
+  O.beta = o.beta; O.pext = o.pext; O.etamhd = o.etamhd; O.Kdrag = o.Kdrag; O.stressmax = 0.; O.gamma = o.gamma;
+  O.alphamin = o.alphamin; O.alphaumin = o.alphaumin; O.alphaBmin = o.alphaBmin; O.avdecayconst = o.avdecayconst; O.avfact = o.avfact; O.psidecayfact = o.psidecayfact;
+  for (int d = 0; d < 3; d++) O.Bconst[d] = o.Bconst[d];
+  return O;
+}
+
+enum { RED_DTC = 0, RED_VSIG = 1, RED_DTAV = 2, RED_TS = 3, RED_HCS = 4, RED_FH = 5, RED_DTF = 6, RED_STRESS = 7 };
+
+template <int NDIM, bool MHD, bool DRAG> int launch_rates_pair(nd_ctx *c, const RatesIn &I, const RatesOpts &O, const RatesSums &S, const RatesRed &R, int *pi, int *pj,
+                                                               unsigned long long *pc, long long cap) {
+  Grid G = make_grid(c);
+  const size_t smem = sizeof(unsigned) * RATES_CAP * RATES_BLOCK;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(rates_pair_kernel<NDIM, MHD, DRAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  LAUNCH(c, (rates_pair_kernel<NDIM, MHD, DRAG>), nblocks(c->ntotal, RATES_BLOCK), RATES_BLOCK, smem, G, I, O, S, R, pi, pj, pc, cap);
+  return 0;
+}
+
+// ---- get_rates (src/ratesND_mhd.f90:29-979) ----
+template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long long *pc, long long cap) {
+  const nd_options &o = c->o;
+  const int nt = c->ntotal, np = c->npart;
+  // reduction keys: minima start at +huge (key of DBL_MAX), maxima at 0
+  unsigned long long init[16];
+  for (int k = 0; k < 16; k++) init[k] = 0x8000000000000000ull;                       // key(+0.0)
+  union { double d; unsigned long long u; } cv;
+  auto keyof = [&](double v) { cv.d = v; return cv.u | 0x8000000000000000ull; };     // v >= 0
+  init[RED_DTC] = keyof(1.e6); init[RED_DTAV] = keyof(DBL_MAX); init[RED_TS] = keyof(DBL_MAX); init[RED_DTF] = keyof(DBL_MAX);
+  CU(cudaMemcpyAsync(c->red, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(c->fmean, 0, sizeof(double) * 4, c->stream));
+  CU(cudaMemsetAsync(c->flags, 0, sizeof(int) * 16, c->stream));
+  RGatherArgs GA;
+  GA.perm = c->perm; GA.ireal = c->ireal; GA.hh = c->hh; GA.pmass = c->pmass; GA.rho = c->rho; GA.pr = c->pr; GA.spsound = c->spsound; GA.uu = c->uu;
+  GA.gradh = c->gradh; GA.alpha = c->alpha; GA.psi = c->psi; GA.Bfield = c->Bfield;
+  GA.posh = c->posh; GA.vm = c->vm; GA.bpsi = c->bpsi; GA.thermo = c->thermo; GA.gal = c->gal; GA.npart = np; GA.ntotal = nt; GA.imhd = o.imhd;
+  GA.stress_key = c->red + RED_STRESS; GA.imagforce = o.imagforce;
+  GA.Bconstmax = std::max(o.Bconst[0], std::max(o.Bconst[1], o.Bconst[2]));
+  LAUNCH(c, k_rates_gather, nblocks(nt, 256), 256, 0, GA);
+  RatesOpts O = make_rates_opts(c);
+  if (o.imhd != 0) {   // stressmax feeds the pair kernel by value: one 8-byte D2H
+    CU(cudaMemcpyAsync(c->h_red, c->red + RED_STRESS, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    O.stressmax = dkey_inv(c->h_red[0]);
+  }
+  RatesIn I; I.bpsi = c->bpsi; I.thermo = c->thermo; I.gal = c->gal;
+  RatesSums S; S.F = c->sF; S.dB = c->sdB; S.C = c->sC; S.P = c->sP; S.V = c->sV;
+  RatesRed R;
+  R.dtcourant_min = c->red + RED_DTC; R.vsigmax_max = c->red + RED_VSIG; R.dtav_min = c->red + RED_DTAV; R.ts_min = c->red + RED_TS;
+  R.h_on_csts_max = c->red + RED_HCS; R.fhmax_max = c->red + RED_FH; R.dtforce_min = c->red + RED_DTF; R.fmean = c->fmean;
+  R.nclumped = c->flags + 4; R.err = c->flags + 1;
+  CU(cudaEventRecord(c->ev[3], c->stream));
+  const bool mhd = o.imhd != 0, drag = (o.idust == 2);
+  int e = 0;
+  if (mhd && !drag) e = launch_rates_pair<NDIM, true, false>(c, I, O, S, R, pi, pj, pc, cap);
+  else if (!mhd && !drag) e = launch_rates_pair<NDIM, false, false>(c, I, O, S, R, pi, pj, pc, cap);
+  else if (!mhd && drag) e = launch_rates_pair<NDIM, false, true>(c, I, O, S, R, pi, pj, pc, cap);
+  else e = launch_rates_pair<NDIM, true, true>(c, I, O, S, R, pi, pj, pc, cap);
+  if (e) return e;
+  CU(cudaEventRecord(c->ev[4], c->stream));
+  FinalArgs FA;
+  FA.perm = c->perm; FA.typ = c->typ; FA.posh = c->posh; FA.vm = c->vm; FA.bpsi = c->bpsi; FA.thermo = c->thermo; FA.gal = c->gal; FA.S = S; FA.O = O;
+  FA.drhodt_in = c->drhodt; FA.Bevol = c->Bevol; FA.dens = c->dens; FA.vsigmax_key = c->red + RED_VSIG;
+  FA.force = c->force; FA.dudt = c->dudt; FA.dendt = c->dendt; FA.dBevoldt = c->dBevoldt; FA.daldt = c->daldt; FA.dpsidt = c->dpsidt; FA.gradpsi = c->gradpsi;
+  FA.divB = c->divB; FA.curlB = c->curlB; FA.graddivv = c->graddivv; FA.del2u = c->del2u; FA.drhodt = c->drhodt; FA.dhdt = c->dhdt;
+  FA.R = R; FA.npart = np; FA.ntotal = nt;
+  LAUNCH(c, k_rates_final, nblocks(nt, 256), 256, 0, FA);
+  ZeroArgs ZA;
+  ZA.force = c->force; ZA.dudt = c->dudt; ZA.dendt = c->dendt; ZA.dBevoldt = c->dBevoldt; ZA.daldt = c->daldt; ZA.dpsidt = c->dpsidt; ZA.gradpsi = c->gradpsi;
+  ZA.divB = c->divB; ZA.curlB = c->curlB; ZA.graddivv = c->graddivv; ZA.del2u = c->del2u; ZA.drhodt = c->drhodt; ZA.dhdt = c->dhdt; ZA.npart = np; ZA.ntotal = nt;
+  LAUNCH(c, k_rates_zero_ghosts, nblocks(nt - np, 256), 256, 0, ZA);
+  CU(cudaEventRecord(c->ev[5], c->stream));
+  // scalars back to the host (module timestep)
+  CU(cudaMemcpyAsync(c->h_red, c->red, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_fmean, c->fmean, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (int e2 = sync_flags(c)) return e2;
+  if (c->h_flags[1]) {
+    const int code = c->h_flags[1];
+    return set_err(c, code, code == ND_ERR_VSIG_DET ? "rates: vsig det < 0" : code == ND_ERR_H_NONPOSITIVE ? "rates: h <= 0" : "rates: dx = 0 (coincident particles of the same type)");
+  }
+  nd_scalars &s = c->sc;
+  s.dtcourant = dkey_inv(c->h_red[RED_DTC]);
+  s.vsigmax = dkey_inv(c->h_red[RED_VSIG]);
+  s.dtav = dkey_inv(c->h_red[RED_DTAV]);
+  s.ts_min = dkey_inv(c->h_red[RED_TS]);
+  s.h_on_csts_max = dkey_inv(c->h_red[RED_HCS]);
+  s.fhmax = dkey_inv(c->h_red[RED_FH]);
+  s.stressmax = O.stressmax;
+  s.vsig2max = (o.imhd != 0 && o.idivbzero >= 2) ? s.vsigmax * s.vsigmax : 0.;
+  s.dtvisc = DBL_MAX;
+  s.dtforce = dkey_inv(c->h_red[RED_DTF]);
+  if (s.fhmax > 0.) s.dtforce = std::min(s.dtforce, std::sqrt(1. / s.fhmax));        // :938-943
+  s.dtdrag = DBL_MAX;
+  if (o.idust == 2 && o.idrag_nature != 0 && (o.Kdrag > 0. || o.idrag_nature > 1)) s.dtdrag = std::min(s.dtdrag, s.ts_min);   // :543-547
+  for (int k = 0; k < 3; k++) s.fmean[k] = c->h_fmean[k];
+  s.nclumped = c->h_flags[4];
+  c->rates_done = true;
+  return 0;
+}
+
+void fill_link_scalars(nd_ctx *c) {
+  nd_scalars &s = c->sc;
+  s.hhmax = c->hhmax; s.dxcell = c->dxcell; s.ntotal = c->ntotal; s.ncells = c->ncells;
+  for (int d = 0; d < 3; d++) s.ncellsx[d] = c->ncellsx[d];
+}
+
+int fill_density_scalars(nd_ctx *c) {
+  nd_scalars &s = c->sc;
+  s.itsdensity = c->itsdensity; s.ncalctotal = c->ncalctotal; s.nrelink = c->nrelink;
+  int init[2] = {1 << 30, 0};
+  CU(cudaMemcpyAsync(c->flags + 12, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, k_minmax_neigh, std::min(nblocks(c->npart, 256), 1184), 256, 0, c->numneigh, c->npart, c->flags + 12);
+  if (int e = sync_flags(c)) return e;
+  s.nneigh_min = c->h_flags[12]; s.nneigh_max = c->h_flags[13];
+  fill_link_scalars(c);
+  return 0;
+}
+
+#define DISPATCH_NDIM(c, expr1, expr2, expr3) ((c)->ndim == 1 ? (expr1) : (c)->ndim == 2 ? (expr2) : (expr3))
+
+}  // namespace
+
+// =====================================================================================================
+// C-ABI
+// =====================================================================================================
+extern "C" {
+
+int ndspmhd_b200_version(void) { return 100; }
+
+int ndspmhd_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int ndspmhd_b200_default_options(nd_options *o) {
+  if (!o) return ND_ERR_INVALID_ARG;
+  memset(o, 0, sizeof(*o));
+  o->psep = 0.01; o->gamma = 5. / 3.; o->iener = 2; o->polyk = 1.0; o->icty = 0; o->maxdensits = 250; o->iprterm = 0; o->iav = 2;   // defaults.f90:47-118
+  o->alphamin = 0.1; o->alphaumin = 0.0; o->alphaBmin = 1.0; o->beta = 2.0; o->iavlim[0] = 2; o->iavlim[1] = 1; o->iavlim[2] = 0;
+  o->avdecayconst = 0.1; o->ikernav = 3; o->ihvar = 2; o->hfact = 1.2; o->tolh = 1.e-3; o->imhd = 0; o->imagforce = 2; o->idivbzero = 0;
+  o->psidecayfact = 0.1; o->use_smoothed_rhodust = 1; o->islope_limiter = -1;
+  o->avfact = std::log(4.) / (std::log((o->gamma + 1.) / (o->gamma - 1.)));            // initialiseND_mhd.f90:168-172
+  o->want_aux = 1;
+  return 0;
+}
+
+const char *ndspmhd_b200_last_error(const nd_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int ndspmhd_b200_create(const nd_options *o, int ndim, int device, nd_ctx **out) {
+  if (!o || !out) return ND_ERR_INVALID_ARG;
+  *out = nullptr;
+  nd_ctx *c = new nd_ctx();
+  *out = c;   // returned even on failure so the caller can read the message; destroy() is always safe
+  c->o = *o; c->ndim = ndim; c->device = device;
+  memset(&c->sc, 0, sizeof(c->sc));
+  for (int k = 0; k < 8; k++) c->ev[k] = nullptr;
+  if (int e = check_options(c, *o, ndim)) return e;
+  c->T = new ndt::KernelTables();
+  if (!ndt::build_tables(*c->T, o->ikernel, o->ikernelalt, o->idust, ndim)) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "unsupported kernel (ikernel must be 0, 2 or 3; drag needs 0 or 2)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_err(c, ND_ERR_NO_DEVICE, "no CUDA device: the NDSPMHD hot path has no CPU fallback in this library");
+  if (device < 0 || device >= ndev) return set_err(c, ND_ERR_INVALID_ARG, "bad device ordinal");
+  CU(cudaSetDevice(device));
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 8; k++) CU(cudaEventCreate(&c->ev[k]));
+  // kernel tables -> interpolation records
+  std::vector<TabRec> tab(IKERN + 1);
+  std::vector<TabRec2> tab2(IKERN + 1);
+  std::vector<double> tabd(2 * (IKERN + 1));
+  for (int i = 0; i <= IKERN; i++) {
+    const int i1 = std::min(i + 1, IKERN);
+    tab[i].w = c->T->w[i]; tab[i].dw = (c->T->w[i1] - c->T->w[i]) * c->T->ddq2table;
+    tab[i].g = c->T->grw[i]; tab[i].dg = (c->T->grw[i1] - c->T->grw[i]) * c->T->ddq2table;
+    tab2[i].gg = c->T->grgrw[i]; tab2[i].dgg = (c->T->grgrw[i1] - c->T->grgrw[i]) * c->T->ddq2table;
+    tabd[2 * i] = c->T->wdrag[i]; tabd[2 * i + 1] = (c->T->wdrag[i1] - c->T->wdrag[i]) * c->T->ddq2table;
+  }
+  CU(cudaMalloc(&c->d_tab, sizeof(TabRec) * (IKERN + 1)));
+  CU(cudaMalloc(&c->d_tab2, sizeof(TabRec2) * (IKERN + 1)));
+  CU(cudaMalloc(&c->d_tabdrag, sizeof(double) * 2 * (IKERN + 1)));
+  CU(cudaMemcpy(c->d_tab, tab.data(), sizeof(TabRec) * (IKERN + 1), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->d_tab2, tab2.data(), sizeof(TabRec2) * (IKERN + 1), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->d_tabdrag, tabd.data(), sizeof(double) * 2 * (IKERN + 1), cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&c->red, sizeof(unsigned long long) * 16));
+  CU(cudaMalloc(&c->fmean, sizeof(double) * 4));
+  CU(cudaMalloc(&c->flags, sizeof(int) * 16));
+  CU(cudaMemset(c->flags, 0, sizeof(int) * 16));
+  CU(cudaMallocHost(&c->h_red, sizeof(unsigned long long) * 16));
+  CU(cudaMallocHost(&c->h_flags, sizeof(int) * 32));
+  CU(cudaMallocHost(&c->h_fmean, sizeof(double) * 4));
+  register_rows(c);
+  return 0;
+}
+
+int ndspmhd_b200_set_options(nd_ctx *c, const nd_options *o) {
+  if (!c || !o) return ND_ERR_INVALID_ARG;
+  if (int e = check_options(c, *o, c->ndim)) return e;
+  if (o->ikernel != c->o.ikernel || (o->idust != 0) != (c->o.idust != 0)) return set_err(c, ND_ERR_INVALID_ARG, "kernel choice is fixed at create()");
+  c->o = *o;
+  return 0;
+}
+
+int ndspmhd_b200_destroy(nd_ctx *c) {
+  if (!c) return 0;
+  if (c->stream) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+  for (auto &rb : c->rowbufs) if (*rb.p) { cudaFree(*rb.p); *rb.p = nullptr; }
+  void *singles[] = {c->scanout, c->cellStart, c->cellCount, c->blocksums, c->red, c->fmean, c->flags, c->d_tab, c->d_tab2, c->d_tabdrag};
+  for (void *p : singles) if (p) cudaFree(p);
+  if (c->h_red) cudaFreeHost(c->h_red);
+  if (c->h_flags) cudaFreeHost(c->h_flags);
+  if (c->h_fmean) cudaFreeHost(c->h_fmean);
+  for (int k = 0; k < 8; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c->T;
+  delete c;
+  return 0;
+}
+
+int ndspmhd_b200_get_kernel_tables(const nd_ctx *c, double *wij, double *grwij, double *grgrwij, double *wijdrag, double *radkern2, double *dq2table) {
+  if (!c || !c->T) return ND_ERR_INVALID_ARG;
+  for (int i = 0; i <= IKERN; i++) {
+    if (wij) wij[i] = c->T->w[i];
+    if (grwij) grwij[i] = c->T->grw[i];
+    if (grgrwij) grgrwij[i] = c->T->grgrw[i];
+    if (wijdrag) wijdrag[i] = c->T->wdrag[i];
+  }
+  if (radkern2) *radkern2 = c->T->radkern2;
+  if (dq2table) *dq2table = c->T->dq2table;
+  return 0;
+}
+
+int ndspmhd_b200_upload(nd_ctx *c, const nd_arrays *a, int npart, int ntotal, int idim) {
+  if (!c || !a || !c->stream) return c ? set_err(c, ND_ERR_STATE, "context not initialised") : ND_ERR_INVALID_ARG;
+  const nd_options &o = c->o;
+  if (o.device_ghosts) ntotal = npart;
+  if (npart < 1 || ntotal < npart || idim < ntotal) return set_err(c, ND_ERR_INVALID_ARG, "upload: need 1 <= npart <= ntotal <= idim");
+  if (!a->x || !a->vel || !a->pmass || !a->hh_in || !a->itype) return set_err(c, ND_ERR_INVALID_ARG, "upload: x, vel, pmass, hh_in, itype are required");
+  if (o.imhd != 0 && !a->Bevol) return set_err(c, ND_ERR_INVALID_ARG, "upload: Bevol required with imhd /= 0");
+  if (!a->en || !a->alpha) return set_err(c, ND_ERR_INVALID_ARG, "upload: en and alpha are required");
+  if ((ntotal > npart || any_fixed_bound(c)) && !a->ireal) return set_err(c, ND_ERR_INVALID_ARG, "upload: ireal required with ghosts/fixed particles");
+  CU(cudaSetDevice(c->device));
+  int want = ntotal;
+  if (o.device_ghosts && any_ghost_bound(c)) want = npart + npart / 4 + 1024;   // first guess; make_ghosts grows it if needed
+  if (int e = ensure_capacity(c, want, 0)) return e;
+  const size_t n = (size_t)ntotal;
+  auto up = [&](void *dst, const void *src, size_t bytes) -> cudaError_t { return src ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream) : cudaMemsetAsync(dst, 0, bytes, c->stream); };
+  CU(up(c->x, a->x, sizeof(double) * c->ndim * n));
+  CU(up(c->vel, a->vel, sizeof(double) * 3 * n));
+  CU(up(c->pmass, a->pmass, sizeof(double) * n));
+  CU(up(c->hh, a->hh_in, sizeof(double) * n));
+  CU(up(c->itype, a->itype, sizeof(int) * n));
+  CU(up(c->ireal, a->ireal, sizeof(int) * n));
+  CU(up(c->en, a->en, sizeof(double) * n));
+  CU(up(c->Bevol, a->Bevol, sizeof(double) * 3 * n));
+  CU(up(c->alpha, a->alpha, sizeof(double) * 3 * n));
+  CU(up(c->psi, a->psi, sizeof(double) * n));
+  CU(up(c->rho, a->rho_in, sizeof(double) * n));
+  CU(cudaStreamSynchronize(c->stream));
+  c->npart = npart; c->ntotal = ntotal;
+  c->uploaded = true; c->linked = c->density_done = c->prim_done = c->rates_done = false;
+  return 0;
+}
+
+int ndspmhd_b200_link(nd_ctx *c) {
+  if (!c) return ND_ERR_INVALID_ARG;
+  if (!c->uploaded) return set_err(c, ND_ERR_STATE, "link before upload");
+  CU(cudaSetDevice(c->device));
+  int e = DISPATCH_NDIM(c, do_link<1>(c), do_link<2>(c), do_link<3>(c));
+  if (!e) fill_link_scalars(c);
+  return e;
+}
+
+int ndspmhd_b200_iterate_density(nd_ctx *c, int resume, nd_scalars *s) {
+  if (!c) return ND_ERR_INVALID_ARG;
+  if (!c->linked) return set_err(c, ND_ERR_STATE, "iterate_density before link");
+  CU(cudaSetDevice(c->device));
+  int e = DISPATCH_NDIM(c, do_iterate_density<1>(c, resume), do_iterate_density<2>(c, resume), do_iterate_density<3>(c, resume));
+  if (e) return e;
+  if (int e2 = fill_density_scalars(c)) return e2;
+  if (s) *s = c->sc;
+  return 0;
+}
+
+int ndspmhd_b200_cons2prim(nd_ctx *c) {
+  if (!c) return ND_ERR_INVALID_ARG;
+  if (!c->density_done) return set_err(c, ND_ERR_STATE, "cons2prim before iterate_density");
+  CU(cudaSetDevice(c->device));
+  return do_cons2prim(c);
+}
+
+int ndspmhd_b200_get_rates(nd_ctx *c, nd_scalars *s) {
+  if (!c) return ND_ERR_INVALID_ARG;
+  if (!c->prim_done) return set_err(c, ND_ERR_STATE, "get_rates before cons2prim");
+  CU(cudaSetDevice(c->device));
+  int e = DISPATCH_NDIM(c, do_get_rates<1>(c, nullptr, nullptr, nullptr, 0), do_get_rates<2>(c, nullptr, nullptr, nullptr, 0), do_get_rates<3>(c, nullptr, nullptr, nullptr, 0));
+  if (e) return e;
+  if (s) *s = c->sc;
+  return 0;
+}
+
+int ndspmhd_b200_derivs(nd_ctx *c, nd_scalars *s) {
+  if (!c) return ND_ERR_INVALID_ARG;
+  if (!c->uploaded) return set_err(c, ND_ERR_STATE, "derivs before upload");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  int e = DISPATCH_NDIM(c, do_link<1>(c), do_link<2>(c), do_link<3>(c));
+  if (e) return e;
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  e = DISPATCH_NDIM(c, do_iterate_density<1>(c, 0), do_iterate_density<2>(c, 0), do_iterate_density<3>(c, 0));
+  if (e) return e;
+  CU(cudaEventRecord(c->ev[2], c->stream));
+  e = do_cons2prim(c);
+  if (e) return e;
+  e = DISPATCH_NDIM(c, do_get_rates<1>(c, nullptr, nullptr, nullptr, 0), do_get_rates<2>(c, nullptr, nullptr, nullptr, 0), do_get_rates<3>(c, nullptr, nullptr, nullptr, 0));
+  if (e) return e;
+  if (int e2 = fill_density_scalars(c)) return e2;
+  CU(cudaEventSynchronize(c->ev[5]));
+  float t;
+  for (int k = 0; k < 5; k++) { cudaEventElapsedTime(&t, c->ev[k], c->ev[k + 1]); c->ms[k] = t; }   // link, density, c2p+gather, pair, final
+  if (s) *s = c->sc;
+  return 0;
+}
+
+int ndspmhd_b200_download(nd_ctx *c, nd_arrays *a, unsigned mask, int idim) {
+  if (!c || !a) return ND_ERR_INVALID_ARG;
+  if (!c->uploaded) return set_err(c, ND_ERR_STATE, "download before upload");
+  if (idim < c->ntotal) return set_err(c, ND_ERR_INVALID_ARG, "download: idim < ntotal (re-allocate the host arrays, src/ghostND_mhd.f90:383-386)");
+  CU(cudaSetDevice(c->device));
+  const size_t n = (size_t)c->ntotal;
+  auto dn = [&](void *dst, const void *src, size_t bytes) -> cudaError_t { return (dst && src) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess; };
+  const size_t D = sizeof(double);
+  if (mask & ND_DL_DENSITY) {
+    CU(dn(a->hh, c->hh, D * n)); CU(dn(a->rho, c->rho, D * n)); CU(dn(a->gradh, c->gradh, D * n)); CU(dn(a->drhodt, c->drhodt, D * n));
+    CU(dn(a->dhdt, c->dhdt, D * n)); CU(dn(a->numneigh, c->numneigh, sizeof(int) * n));
+    if (c->o.want_aux) { CU(dn(a->rhoalt, c->rhoalt, D * n)); CU(dn(a->gradhn, c->gradhn, D * n)); CU(dn(a->gradsoft, c->gradsoft, D * n)); CU(dn(a->gradgradh, c->gradgradh, D * n)); }
+  }
+  if (mask & ND_DL_PRIM) {
+    CU(dn(a->dens, c->dens, D * n)); CU(dn(a->uu, c->uu, D * n)); CU(dn(a->pr, c->pr, D * n)); CU(dn(a->spsound, c->spsound, D * n));
+    if (c->o.imhd != 0) CU(dn(a->Bfield, c->Bfield, D * 3 * n));
+  }
+  if (mask & ND_DL_RATES) {
+    CU(dn(a->force, c->force, D * 3 * n)); CU(dn(a->dudt, c->dudt, D * n)); CU(dn(a->dendt, c->dendt, D * n)); CU(dn(a->dBevoldt, c->dBevoldt, D * 3 * n));
+    CU(dn(a->daldt, c->daldt, D * 3 * n)); CU(dn(a->dpsidt, c->dpsidt, D * n)); CU(dn(a->gradpsi, c->gradpsi, D * 3 * n)); CU(dn(a->divB, c->divB, D * n));
+    CU(dn(a->curlB, c->curlB, D * 3 * n)); CU(dn(a->graddivv, c->graddivv, D * 3 * n)); CU(dn(a->del2u, c->del2u, D * n));
+    // drhodt/dhdt are zeroed on ghosts and fixed particles by get_rates (:952-953)
+    CU(dn(a->drhodt, c->drhodt, D * n)); CU(dn(a->dhdt, c->dhdt, D * n));
+  }
+  if (mask & ND_DL_GHOSTS) {
+    const size_t g0 = (size_t)c->npart, ng = n - g0;
+    if (ng > 0) {
+      if (a->x_out) CU(dn(a->x_out + g0 * c->ndim, c->x + g0 * c->ndim, D * c->ndim * ng));
+      if (a->vel_out) CU(dn(a->vel_out + g0 * 3, c->vel + g0 * 3, D * 3 * ng));
+      if (a->ireal_out) CU(dn(a->ireal_out + g0, c->ireal + g0, sizeof(int) * ng));
+      if (a->itype_out) CU(dn(a->itype_out + g0, c->itype + g0, sizeof(int) * ng));
+    }
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int ndspmhd_b200_update_ghosts(nd_ctx *c, const nd_arrays *a, int ntotal, int idim, double hhmax) {
+  if (!c || !a) return ND_ERR_INVALID_ARG;
+  if (!c->uploaded) return set_err(c, ND_ERR_STATE, "update_ghosts before upload");
+  if (c->o.device_ghosts) return set_err(c, ND_ERR_STATE, "update_ghosts with device_ghosts=1");
+  if (ntotal < c->npart || idim < ntotal) return set_err(c, ND_ERR_INVALID_ARG, "update_ghosts: need npart <= ntotal <= idim");
+  if (ntotal > c->npart && (!a->x || !a->vel || !a->itype || !a->ireal)) return set_err(c, ND_ERR_INVALID_ARG, "update_ghosts: x, vel, itype, ireal required");
+  CU(cudaSetDevice(c->device));
+  if (int e = ensure_capacity(c, ntotal, c->npart)) return e;
+  const size_t g0 = (size_t)c->npart, ng = (size_t)ntotal - g0;
+  if (ng > 0) {
+    CU(cudaMemcpyAsync(c->x + g0 * c->ndim, a->x + g0 * c->ndim, sizeof(double) * c->ndim * ng, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->vel + g0 * 3, a->vel + g0 * 3, sizeof(double) * 3 * ng, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->itype + g0, a->itype + g0, sizeof(int) * ng, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->ireal + g0, a->ireal + g0, sizeof(int) * ng, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  c->ntotal = ntotal;
+  c->o.hhmax = hhmax;
+  return 0;
+}
+
+void *ndspmhd_b200_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+void ndspmhd_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int ndspmhd_b200_last_timings(const nd_ctx *c, double ms[8]) {
+  if (!c || !ms) return ND_ERR_INVALID_ARG;
+  for (int k = 0; k < 8; k++) ms[k] = c->ms[k];
+  return 0;
+}
+
+long long ndspmhd_b200_launch_count(const nd_ctx *c) { return c ? c->launches : 0; }
+void *ndspmhd_b200_stream(const nd_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int ndspmhd_b200_rates_pairs(nd_ctx *c, int *pair_i, int *pair_j, long long cap, long long *npairs) {
+  if (!c || !npairs) return ND_ERR_INVALID_ARG;
+  if (!c->prim_done) return set_err(c, ND_ERR_STATE, "rates_pairs before cons2prim");
+  CU(cudaSetDevice(c->device));
+  int *di = nullptr, *dj = nullptr; unsigned long long *dc = nullptr;
+  CU(cudaMalloc(&di, sizeof(int) * std::max<long long>(cap, 1)));
+  CU(cudaMalloc(&dj, sizeof(int) * std::max<long long>(cap, 1)));
+  CU(cudaMalloc(&dc, sizeof(unsigned long long)));
+  CU(cudaMemset(dc, 0, sizeof(unsigned long long)));
+  int e = DISPATCH_NDIM(c, do_get_rates<1>(c, di, dj, dc, cap), do_get_rates<2>(c, di, dj, dc, cap), do_get_rates<3>(c, di, dj, dc, cap));
+  unsigned long long n = 0;
+  cudaMemcpy(&n, dc, sizeof(n), cudaMemcpyDeviceToHost);
+  const long long m = std::min<long long>((long long)n, cap);
+  if (!e && m > 0 && pair_i && pair_j) { cudaMemcpy(pair_i, di, sizeof(int) * m, cudaMemcpyDeviceToHost); cudaMemcpy(pair_j, dj, sizeof(int) * m, cudaMemcpyDeviceToHost); }
+  cudaFree(di); cudaFree(dj); cudaFree(dc);
+  *npairs = (long long)n;
+  return e;
+}
+
+}  // extern "C"
