@@ -224,6 +224,9 @@ void ndspmhd_b200_host_free(void *p);
 
 /* bench/diagnostic hooks: per-phase device time of the last derivs call (ms): link, density, c2p, rates pair, rates final */
 int ndspmhd_b200_last_timings(const nd_ctx *c, double ms[8]);
+/* puts hh back to the guess handed over by the last upload (a D2D copy), so that a repeated derivs() on the resident
+ * state repeats the whole smoothing-length iteration instead of starting from the converged answer */
+int ndspmhd_b200_rewind(nd_ctx *c);
 /* number of kernels this library launched since create (bench.py's gpu_launches) */
 long long ndspmhd_b200_launch_count(const nd_ctx *c);
 /* the CUDA stream the context launches on (cudaStream_t as void*), for event timing in bench.py */

@@ -35,7 +35,7 @@ struct nd_ctx {
   // ---- original-order arrays (row r = Fortran index r+1) ----
   double *x = nullptr, *vel = nullptr, *pmass = nullptr, *hh = nullptr, *en = nullptr, *Bevol = nullptr, *alpha = nullptr, *psi = nullptr;
   int *itype = nullptr, *ireal = nullptr;
-  double *hhin = nullptr;
+  double *hhin = nullptr, *hh0 = nullptr;
   double *rho = nullptr, *gradh = nullptr, *drhodt = nullptr, *dhdt = nullptr, *rhoalt = nullptr, *gradhn = nullptr, *gradsoft = nullptr, *gradgradh = nullptr;
   int *numneigh = nullptr;
   double *dens = nullptr, *uu = nullptr, *pr = nullptr, *spsound = nullptr, *Bfield = nullptr;
@@ -585,7 +585,7 @@ void register_rows(nd_ctx *c) {
 #define R1(a) v.push_back({(void **)&c->a, D})
 #define RI(a) v.push_back({(void **)&c->a, I})
 #define R4(a) v.push_back({(void **)&c->a, D4})
-  R3(vel); R1(pmass); R1(hh); R1(en); R3(Bevol); R3(alpha); R1(psi); RI(itype); RI(ireal); R1(hhin);
+  R3(vel); R1(pmass); R1(hh); R1(en); R3(Bevol); R3(alpha); R1(psi); RI(itype); RI(ireal); R1(hhin); R1(hh0);
   R1(rho); R1(gradh); R1(drhodt); R1(dhdt); R1(rhoalt); R1(gradhn); R1(gradsoft); R1(gradgradh); RI(numneigh);
   R1(dens); R1(uu); R1(pr); R1(spsound); R3(Bfield);
   R3(force); R1(dudt); R1(dendt); R3(dBevoldt); R3(daldt); R1(dpsidt); R3(gradpsi); R1(divB); R3(curlB); R3(graddivv); R1(del2u);
@@ -1101,6 +1101,7 @@ int ndspmhd_b200_upload(nd_ctx *c, const nd_arrays *a, int npart, int ntotal, in
   CU(up(c->vel, a->vel, sizeof(double) * 3 * n));
   CU(up(c->pmass, a->pmass, sizeof(double) * n));
   CU(up(c->hh, a->hh_in, sizeof(double) * n));
+  CU(cudaMemcpyAsync(c->hh0, c->hh, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
   CU(up(c->itype, a->itype, sizeof(int) * n));
   CU(up(c->ireal, a->ireal, sizeof(int) * n));
   CU(up(c->en, a->en, sizeof(double) * n));
@@ -1242,6 +1243,15 @@ void ndspmhd_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
 int ndspmhd_b200_last_timings(const nd_ctx *c, double ms[8]) {
   if (!c || !ms) return ND_ERR_INVALID_ARG;
   for (int k = 0; k < 8; k++) ms[k] = c->ms[k];
+  return 0;
+}
+
+int ndspmhd_b200_rewind(nd_ctx *c) {
+  if (!c) return ND_ERR_INVALID_ARG;
+  if (!c->uploaded) return set_err(c, ND_ERR_STATE, "rewind before upload");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(c->hh, c->hh0, sizeof(double) * c->npart, cudaMemcpyDeviceToDevice, c->stream));
+  c->linked = c->density_done = c->prim_done = c->rates_done = false;
   return 0;
 }
 

@@ -31,7 +31,7 @@ EXPORTS = [
     "ndspmhd_b200_upload", "ndspmhd_b200_update_ghosts", "ndspmhd_b200_link", "ndspmhd_b200_iterate_density",
     "ndspmhd_b200_cons2prim", "ndspmhd_b200_get_rates", "ndspmhd_b200_derivs", "ndspmhd_b200_download",
     "ndspmhd_b200_host_alloc", "ndspmhd_b200_host_free", "ndspmhd_b200_last_timings", "ndspmhd_b200_launch_count",
-    "ndspmhd_b200_stream", "ndspmhd_b200_rates_pairs",
+    "ndspmhd_b200_stream", "ndspmhd_b200_rates_pairs", "ndspmhd_b200_rewind",
 ]
 
 
@@ -74,6 +74,7 @@ def load():
     L.ndspmhd_b200_last_timings.argtypes = [vp, _DP]
     L.ndspmhd_b200_launch_count.argtypes = [vp]
     L.ndspmhd_b200_launch_count.restype = C.c_longlong
+    L.ndspmhd_b200_rewind.argtypes = [vp]
     L.ndspmhd_b200_stream.argtypes = [vp]
     L.ndspmhd_b200_stream.restype = vp
     L.ndspmhd_b200_rates_pairs.argtypes = [vp, _IP, _IP, C.c_longlong, C.POINTER(C.c_longlong)]
@@ -198,6 +199,10 @@ class Hotpath:
         s = NdScalars()
         self._chk(self.L.ndspmhd_b200_derivs(self.ctx, C.byref(s)))
         return s.as_dict()
+
+    def rewind(self) -> None:
+        """Restore the smoothing-length guess of the last upload (bench hook: makes repeated derivs() do identical work)."""
+        self._chk(self.L.ndspmhd_b200_rewind(self.ctx))
 
     # ---- diagnostics ----
     def timings(self):

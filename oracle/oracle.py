@@ -131,9 +131,14 @@ def bruteforce_pairs(p: Particles, radkern2: float = 4.0):
     return pi[:n].copy(), pj[:n].copy()
 
 
-def linklist_pairs(opts: NdOptions, p: Particles):
-    """Pairs visited by the reference's rates loop (src/ratesND_mhd.f90:304-467).  Overwrites rates outputs of `p`."""
+def linklist_pairs(opts: NdOptions, p: Particles, hhmax: float | None = None):
+    """Pairs visited by the reference's rates loop (src/ratesND_mhd.f90:304-467).  Overwrites rates outputs of `p`.
+
+    `hhmax` is bound:hhmax as left by set_ghost_particles (the cell size, src/linkND.f90:72); default max h of the real rows."""
     L = lib()
+    o2 = NdOptions.from_buffer_copy(opts)
+    o2.hhmax = float(np.max(p.hh[: p.npart])) if hhmax is None else hhmax
+    opts = o2
     a = _arrays(p)
     cap = max(1024, 200 * p.ntotal)
     pi = np.zeros(cap, np.int32)

@@ -1,0 +1,282 @@
+"""GPU parity: the CUDA hot path through the C-ABI (upload -> derivs -> download) against the CPU oracle on the
+same seeded inputs, plus size-independent properties at sizes the oracle cannot reach in seconds.
+
+Tolerances (BASELINE.json north_star): neighbour sets, ghost rows, numneigh, iteration counts and cell grids bit-exact;
+rho, h, dv/dt, dB/dt, du/dt and companions within RTOL = 1e-12 relative to the magnitude of the summed pair terms
+(tests/parity.py explains the metric: the sums cancel, only the order of accumulation differs).
+"""
+import numpy as np
+import pytest
+
+import parity
+from ndspmhd_b200 import abi, lib, setups
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    # BASELINE.json configs[2]/[4]: 3D MHD Orszag-Tang box (thin slab and cube), t=0 lattice and an "evolved" glass
+    "ot3d_lattice_t0": (lambda: setups.orszag_tang(ndim=3, nx=16, zfrac=0.5, perturb_amp=0.0, evolved=False), 1),
+    "ot3d_glass": (lambda: setups.orszag_tang(ndim=3, nx=16, zfrac=0.5, perturb_amp=0.2, evolved=True), 1),
+    "ot3d_cube_imhd1": (lambda: setups.orszag_tang(ndim=3, nx=24, cube=True, perturb_amp=0.3, evolved=True, imhd=1, idivbzero=0), 1),
+    "ot3d_isothermal": (lambda: setups.orszag_tang(ndim=3, nx=16, zfrac=0.5, perturb_amp=0.2, evolved=True, iener=0), 1),
+    # configs[1]: 2D Orszag-Tang on the close-packed lattice
+    "ot2d_closepacked": (lambda: setups.orszag_tang(ndim=2, nx=64, lattice="cp", perturb_amp=0.2, evolved=True), 1),
+    "hydro3d": (lambda: setups.hydro_box(ndim=3, nx=16, perturb_amp=0.2), 1),
+    "hydro3d_noaux": (lambda: setups.hydro_box(ndim=3, nx=16, perturb_amp=0.2), 0),
+    "hydro2d": (lambda: setups.hydro_box(ndim=2, nx=48, perturb_amp=0.3), 1),
+    # configs[0]: 1D Brio-Wu / Sod shock tubes with fixed end particles
+    "briowu1d": (lambda: setups.shock1d(nright=60), 1),
+    "briowu1d_totalenergy": (lambda: setups.shock1d(nright=60, iener=3), 1),
+    "sod1d": (lambda: setups.shock1d(nright=60, mhd=False), 1),
+    # configs[3]: two-fluid dust + gas
+    "dustybox3d": (lambda: setups.dustybox(ndim=3, nx=12), 1),
+    "dustybox3d_coincident": (lambda: setups.dustybox(ndim=3, nx=10, coincident=True), 1),
+    "dustybox3d_const_ts": (lambda: setups.dustybox(ndim=3, nx=10, idrag_nature=2, Kdrag=0.3), 1),
+}
+
+
+def run_both(make, aux=1, **optkw):
+    o, p = make()
+    o.device_ghosts = 1
+    o.want_aux = aux
+    for k, v in optkw.items():
+        setattr(o, k, v)
+    po, pg = p.copy(), p.copy()
+    so, _ = oracle.derivs(o, po)
+    sg = lib.derivs_host(o, pg)
+    return o, pg, po, sg, so
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_derivs_parity(name):
+    make, aux = CASES[name]
+    o, pg, po, sg, so = run_both(make, aux)
+    errs = parity.assert_parity(pg, po, sg, so, o, aux=bool(aux))
+    assert max(errs.values()) <= parity.RTOL
+
+
+@pytest.mark.parametrize("optkw", [dict(iav=1), dict(iav=3), dict(iresist=1, etamhd=0.01), dict(iavlim=(1, 0, 1)), dict(iavlim=(3, 1, 2)),
+                                   dict(pext=0.05)])
+def test_option_variants_parity(optkw):
+    def make():
+        o, p = setups.orszag_tang(ndim=3, nx=12, zfrac=0.5, perturb_amp=0.25, evolved=True)
+        return o, p
+    kw = dict(optkw)
+    iavlim = kw.pop("iavlim", None)
+    o, p = make()
+    o.device_ghosts = 1
+    for k, v in kw.items():
+        setattr(o, k, v)
+    if iavlim:
+        for d in range(3):
+            o.iavlim[d] = iavlim[d]
+    po, pg = p.copy(), p.copy()
+    so, _ = oracle.derivs(o, po)
+    sg = lib.derivs_host(o, pg)
+    parity.assert_parity(pg, po, sg, so, o, aux=True)
+
+
+@pytest.mark.parametrize("ikernel", [2, 3])
+def test_quartic_quintic_kernels_parity(ikernel):
+    o, p = setups.hydro_box(ndim=3, nx=12, perturb_amp=0.2)
+    o.device_ghosts = 1
+    o.ikernel = o.ikernelalt = ikernel
+    po, pg = p.copy(), p.copy()
+    so, _ = oracle.derivs(o, po)
+    sg = lib.derivs_host(o, pg)
+    parity.assert_parity(pg, po, sg, so, o, aux=True)
+
+
+def test_kernel_tables_bit_exact():
+    for ndim in (1, 2, 3):
+        for ik, idust in ((0, 2), (2, 2), (3, 0)):
+            o = abi.default_options(ndim)
+            o.ikernel = o.ikernelalt = ik
+            o.idust = idust
+            o.idrag_nature = 1 if idust else 0
+            o.Kdrag = 1.0
+            hot = lib.Hotpath(o, ndim)
+            try:
+                g = hot.kernel_tables()
+            finally:
+                hot.close()
+            r = oracle.kernel_tables(ik, {0: 41, 2: 42}[ik] if idust else 0, ndim)
+            for a, b in zip(g[:3], r[:3]):
+                assert np.array_equal(a, b)
+            if idust:
+                assert np.array_equal(g[3], r[3])
+            assert g[4] == r[4] and g[5] == r[5]
+
+
+@pytest.mark.parametrize("name", ["ot3d_glass", "ot2d_closepacked", "briowu1d", "dustybox3d"])
+def test_neighbour_pair_sets_bit_exact(name):
+    """Pairs accepted by the CUDA rates kernel == pairs visited by the reference's link-list loop == O(N^2) brute force
+    (src/check_neighbourlist.f90:149-173)."""
+    make, aux = CASES[name]
+    o, p = make()
+    o.device_ghosts = 1
+    hot = lib.Hotpath(o, p.ndim)
+    try:
+        hot.upload(p)
+        hot.set_linklist()
+        s = hot.iterate_density()
+        hot.conservative2primitive()
+        p.ntotal = s["ntotal"]
+        gi, gj = hot.rates_pairs(cap=400 * p.ntotal)
+        hot.download(p, abi.DL_ALL)
+    finally:
+        hot.close()
+    # the gather visits every ordered pair with a real target: real-real pairs twice, real-ghost pairs once
+    keys = parity.pair_set(gi, gj)
+    po = p.copy()
+    li, lj = oracle.linklist_pairs(o, po, s["hhmax"])
+    bi, bj = oracle.bruteforce_pairs(p, 4.0)
+    assert np.array_equal(keys, parity.pair_set(li, lj))
+    assert np.array_equal(keys, parity.pair_set(bi, bj))
+    n = p.npart
+    both_real = int(np.sum((li <= n) & (lj <= n)))
+    assert len(gi) == 2 * both_real + (len(li) - both_real)
+
+
+def test_phase_by_phase_calls_equal_fused_derivs():
+    """set_linklist / iterate_density / conservative2primitive / get_rates called one by one (the reference's call
+    sites, src/derivs.f90:82-156) give the same bits as the fused ndspmhd_b200_derivs."""
+    o, p = setups.orszag_tang(ndim=3, nx=16, zfrac=0.5, perturb_amp=0.2, evolved=True)
+    o.device_ghosts = 1
+    p1, p2 = p.copy(), p.copy()
+    s1 = lib.derivs_host(o, p1)
+    hot = lib.Hotpath(o, 3)
+    try:
+        hot.upload(p2)
+        hot.set_linklist()
+        sd = hot.iterate_density()
+        hot.conservative2primitive()
+        s2 = hot.get_rates()
+        p2.ntotal = sd["ntotal"]
+        hot.download(p2)
+    finally:
+        hot.close()
+    for f in parity.DENSITY_FIELDS + parity.PRIM_FIELDS + parity.RATES_FIELDS:
+        assert np.array_equal(getattr(p1, f), getattr(p2, f)), f
+    for k in ("dtcourant", "dtforce", "vsigmax", "itsdensity", "ntotal"):
+        assert s1[k] == s2[k]
+
+
+def test_host_ghost_mode_matches_device_ghost_mode():
+    """device_ghosts=0: the caller (Fortran set_ghost_particles) supplies rows npart+1..ntotal and bound:hhmax."""
+    o, p = setups.orszag_tang(ndim=3, nx=16, zfrac=0.5, perturb_amp=0.0, evolved=True)
+    o.device_ghosts = 1
+    pd = p.copy()
+    sd = lib.derivs_host(o, pd)
+    assert sd["nrelink"] == 0
+    ph = p.copy()
+    so, _ = oracle.derivs(o, ph, phases=oracle.NDO_GHOSTS)       # host-side ghost generation only
+    o2 = abi.NdOptions.from_buffer_copy(o)
+    o2.device_ghosts = 0
+    o2.hhmax = so["hhmax"]
+    sh = lib.derivs_host(o2, ph)
+    assert sh["ntotal"] == sd["ntotal"]
+    for f in parity.DENSITY_FIELDS + parity.RATES_FIELDS:
+        assert np.array_equal(getattr(pd, f)[: p.npart], getattr(ph, f)[: p.npart]), f
+
+
+def test_run_to_run_determinism_and_idempotence():
+    o, p = setups.orszag_tang(ndim=3, nx=20, zfrac=0.5, perturb_amp=0.2, evolved=True)
+    o.device_ghosts = 1
+    hot = lib.Hotpath(o, 3)
+    try:
+        a, b = p.copy(), p.copy()
+        sa = lib.derivs_host(o, a, hot=hot)
+        sb = lib.derivs_host(o, b, hot=hot)
+        for f in parity.DENSITY_FIELDS + parity.PRIM_FIELDS + parity.RATES_FIELDS:
+            assert np.array_equal(getattr(a, f), getattr(b, f)), f
+        # idempotence: feeding the converged h back in converges in one round to the same h within tolh^2
+        c = p.copy()
+        c.hh[: p.npart] = a.hh[: p.npart]
+        sc = lib.derivs_host(o, c, hot=hot)
+        assert sc["itsdensity"] == 1
+        assert np.max(np.abs(c.rho[: p.npart] - a.rho[: p.npart]) / a.rho[: p.npart]) < 1e-12
+    finally:
+        hot.close()
+
+
+def test_relink_when_h_outgrows_the_cell_size():
+    """A badly underestimated h forces hnew > hhmax => ghosts + link list are rebuilt mid-iteration
+    (src/iterate_density.f90:122-126, :260-262)."""
+    o, p = setups.hydro_box(ndim=3, nx=12, perturb_amp=0.2)
+    o.device_ghosts = 1
+    p.hh[: p.npart] *= 0.6
+    po, pg = p.copy(), p.copy()
+    so, _ = oracle.derivs(o, po)
+    sg = lib.derivs_host(o, pg)
+    assert sg["nrelink"] >= 1 and sg["itsdensity"] == so["itsdensity"] > 2
+    parity.assert_parity(pg, po, sg, so, o, aux=True)
+
+
+def test_error_codes():
+    o, p = setups.hydro_box(ndim=3, nx=8, perturb_amp=0.1)
+    o.device_ghosts = 1
+    bad = p.copy()
+    bad.hh[3] = 0.0
+    with pytest.raises(lib.NdError) as e:
+        lib.derivs_host(o, bad)
+    assert e.value.code == abi.ND_ERR_H_NONPOSITIVE                 # src/iterate_density.f90:99-102
+    hot = lib.Hotpath(o, 3)
+    try:
+        with pytest.raises(lib.NdError) as e:
+            hot.set_linklist()
+        assert e.value.code == abi.ND_ERR_STATE
+        hot.upload(p)
+        with pytest.raises(lib.NdError) as e:
+            hot.get_rates()
+        assert e.value.code == abi.ND_ERR_STATE
+    finally:
+        hot.close()
+    out = p.copy()
+    out.x[5, 0] = 7.0                                               # outside the periodic box: link must refuse, linkND.f90:122-125
+    o2 = abi.NdOptions.from_buffer_copy(o)
+    with pytest.raises(lib.NdError):
+        lib.derivs_host(o2, out)
+
+
+# ---- size-independent properties at sizes the oracle cannot do in seconds -------------------------------------------------
+@pytest.fixture(scope="module")
+def big():
+    o, p = setups.orszag_tang(ndim=3, nx=128, zfrac=0.125, perturb_amp=0.2, evolved=True)   # 128 x 128 x 16 = 262144
+    o.device_ghosts = 1
+    o.want_aux = 0
+    s = lib.derivs_host(o, p)
+    return o, p, s
+
+
+def test_big_momentum_conservation(big):
+    o, p, s = big
+    n = p.npart
+    mf = p.pmass[:n, None] * p.force[:n]
+    assert np.all(np.abs(mf.sum(axis=0)) <= 1e-12 * np.abs(mf).sum())
+    assert np.allclose(s["fmean"], mf.sum(axis=0), rtol=0, atol=1e-12 * np.abs(mf).sum())
+
+
+def test_big_h_rho_consistency_and_neighbours(big):
+    o, p, s = big
+    n = p.npart
+    assert np.max(np.abs(p.hh[:n] - o.hfact * (p.pmass[:n] / p.rho[:n]) ** (1 / 3.0)) / p.hh[:n]) < 3 * o.tolh
+    assert 30 <= s["nneigh_min"] and s["nneigh_max"] <= 120
+    assert np.all(np.isfinite(p.force[:n])) and np.all(np.isfinite(p.dBevoldt[:n]))
+    # ghost rows carry their parent's density state
+    nt = s["ntotal"]
+    par = p.ireal[n:nt] - 1
+    assert np.array_equal(p.rho[n:nt], p.rho[par]) and np.array_equal(p.hh[n:nt], p.hh[par])
+    assert np.all(p.force[n:nt] == 0)
+
+
+def test_big_matches_oracle_on_a_sampled_subvolume(big):
+    """Full-size run vs oracle: compare where the oracle is affordable by re-running the oracle on the same input at
+    this size once (262k particles, ~5 s single core)."""
+    o, p, s = big
+    o2, p2 = setups.orszag_tang(ndim=3, nx=128, zfrac=0.125, perturb_amp=0.2, evolved=True)
+    o2.device_ghosts = 1
+    o2.want_aux = 0
+    so, _ = oracle.derivs(o2, p2)
+    parity.assert_parity(p, p2, s, so, o2, aux=False)
