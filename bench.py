@@ -209,6 +209,16 @@ def run_single(args):
         p.arrays[k][...] = v
     p.ntotal = n
     del p0
+    # derivs overwrites hh with the converged smoothing lengths; every step must start from the same guess
+    L = lib.load()
+    import ctypes as C
+    import numpy as np
+    nb = p.arrays["hh"].nbytes
+    ptr = L.ndspmhd_b200_host_alloc(nb)
+    guess = np.frombuffer((C.c_char * nb).from_address(ptr), dtype=np.float64, count=p.idim)
+    guess[...] = p.arrays["hh"]
+    p.arrays["hh_guess"] = guess
+    p.__dict__["_pinned"].append(ptr)
     hot = lib.Hotpath(o, 3, dev)
     stream = torch.cuda.ExternalStream(hot.stream(), device=dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)

@@ -30,7 +30,7 @@ struct nd_ctx {
   ndt::KernelTables *T = nullptr;
   TabRec *d_tab = nullptr; TabRec2 *d_tab2 = nullptr; double *d_tabdrag = nullptr;
   // sizes
-  int npart = 0, ntotal = 0, cap = 0;
+  int npart = 0, ntotal = 0, cap = 0, nown = 0;   // nown <= npart: rows this context computes (the rest of [0,npart) are halo copies)
   bool uploaded = false, linked = false, density_done = false, prim_done = false, rates_done = false;
   // ---- original-order arrays (row r = Fortran index r+1) ----
   double *x = nullptr, *vel = nullptr, *pmass = nullptr, *hh = nullptr, *en = nullptr, *Bevol = nullptr, *alpha = nullptr, *psi = nullptr;
@@ -43,6 +43,7 @@ struct nd_ctx {
          *curlB = nullptr, *graddivv = nullptr, *del2u = nullptr;
   // ---- sorted-order arrays ----
   double4 *posh = nullptr, *vm = nullptr, *bpsi = nullptr, *thermo = nullptr, *gal = nullptr;
+  double *srho = nullptr;
   double4 *sF = nullptr, *sdB = nullptr, *sC = nullptr, *sP = nullptr, *sV = nullptr;
   int *typ = nullptr, *perm = nullptr, *permtmp = nullptr, *inv = nullptr, *cellOf = nullptr, *cellOfOrig = nullptr, *redo = nullptr, *list = nullptr,
       *scanout = nullptr, *ghostcount = nullptr;
@@ -50,6 +51,8 @@ struct nd_ctx {
   // ---- cell grid ----
   int *cellStart = nullptr, *cellCount = nullptr; int cellcap = 0;
   int *blocksums = nullptr; int blocksumcap = 0;
+  // ---- neighbour lists (nd_device.cuh): one chunk of targets at a time ----
+  unsigned *nbr = nullptr; int *lcnt = nullptr; size_t nbrcap = 0; int lcntcap = 0, lmax = 0;
   int ncellsx[3] = {1, 1, 1}, ncells = 0;
   double xminpart[3] = {0, 0, 0}, dxcell = 0, hhmax = 0;
   // ---- small device scratch: reduction keys, flags ----
@@ -301,7 +304,7 @@ template <int NDIM> __global__ void k_gather_sorted(GatherArgs A) {
   const int st = (r < A.npart) ? r : A.ireal[r] - 1;   // ghosts carry their parent's properties (makeghost -> copy_particle)
   double p[3] = {0, 0, 0};
   for (int d = 0; d < NDIM; d++) p[d] = A.x[(size_t)r * NDIM + d];
-  A.posh[s] = make_double4(p[0], p[1], p[2], A.hh[st]);
+  A.posh[s] = make_double4(p[0], p[1], p[2], 1.0 / A.hh[st]);   // h1(i) = 1./hh(i)
   A.vm[s] = make_double4(A.vel[(size_t)r * 3], A.vel[(size_t)r * 3 + 1], A.vel[(size_t)r * 3 + 2], A.pmass[st]);
   A.typ[s] = A.itype[r];
   A.cellOf[s] = A.cellOfOrig[r];
@@ -311,7 +314,7 @@ __global__ void k_refresh_h(const int *perm, const int *ireal, const double *hh,
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= ntotal) return;
   const int r = perm[s];
-  posh[s].w = hh[(r < npart) ? r : ireal[r] - 1];
+  posh[s].w = 1.0 / hh[(r < npart) ? r : ireal[r] - 1];
 }
 __global__ void k_compact(const int *redo, const int *scan, int n, int *list) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -418,7 +421,8 @@ __global__ void k_c2p_ghost(C2PArgs A) {                                        
 // =====================================================================================================
 struct RGatherArgs {
   const int *perm, *ireal; const double *hh, *pmass, *rho, *pr, *spsound, *uu, *gradh, *alpha, *psi, *Bfield;
-  double4 *posh, *vm, *bpsi, *thermo, *gal; int npart, ntotal, imhd; unsigned long long *stress_key; int imagforce; double Bconstmax;
+  double4 *posh, *vm, *bpsi, *thermo, *gal; double *srho; int npart, ntotal, imhd; unsigned long long *stress_key; int imagforce; double Bconstmax, pext;
+  int *err;
 };
 __global__ void k_rates_gather(RGatherArgs A) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -426,9 +430,12 @@ __global__ void k_rates_gather(RGatherArgs A) {
   if (s < A.ntotal) {
     const int r = A.perm[s];
     const int st = (r < A.npart) ? r : A.ireal[r] - 1;
-    A.posh[s].w = A.hh[st];
+    const double h = A.hh[st], rho = A.rho[st];
+    if (h <= 0.) atomicCAS(A.err, 0, ND_ERR_H_NONPOSITIVE);                         // :384-387
+    A.posh[s].w = 1.0 / h;
     A.vm[s].w = A.pmass[st];
-    A.thermo[s] = make_double4(A.rho[st], A.pr[st], A.spsound[st], A.uu[st]);
+    A.srho[s] = rho;
+    A.thermo[s] = make_double4(1.0 / rho, fmax(A.pr[st] - A.pext, 0.), A.spsound[st], A.uu[st]);   // rho1i, :325; pri = max(pr - pext, 0), :328
     A.gal[s] = make_double4(A.gradh[st], A.alpha[(size_t)st * 3], A.alpha[(size_t)st * 3 + 1], A.alpha[(size_t)st * 3 + 2]);
     if (A.imhd != 0) {
       const double bx = A.Bfield[(size_t)st * 3], by = A.Bfield[(size_t)st * 3 + 1], bz = A.Bfield[(size_t)st * 3 + 2];
@@ -445,7 +452,7 @@ __global__ void k_rates_gather(RGatherArgs A) {
 
 struct FinalArgs {
   const int *perm, *typ; const double4 *posh, *vm, *bpsi, *thermo, *gal; RatesSums S; RatesOpts O;
-  const double *drhodt_in, *Bevol, *dens; const unsigned long long *vsigmax_key;
+  const double *drhodt_in, *Bevol, *dens, *hh, *rho, *pr; const unsigned long long *vsigmax_key;
   double *force, *dudt, *dendt, *dBevoldt, *daldt, *dpsidt, *gradpsi, *divB, *curlB, *graddivv, *del2u, *drhodt, *dhdt;
   RatesRed R; int npart, ntotal;
 };
@@ -458,7 +465,7 @@ __global__ void k_rates_final(FinalArgs A) {
       const RatesOpts &O = A.O;
       const double4 F = A.S.F[s], dB4 = A.S.dB[s], C = A.S.C[s], P = A.S.P[s], V = A.S.V[s];
       const double4 p = A.posh[s], v = A.vm[s], th = A.thermo[s], g = A.gal[s];
-      const double rhoi = th.x, rho1i = 1. / rhoi, hi = p.w;
+      const double rhoi = A.rho[i], rho1i = th.x, hi = A.hh[i], pri = A.pr[i];
       const double vsigmax = dkey_inv(*A.vsigmax_key);
       const double vsig2max = (O.imhd != 0 && O.idivbzero >= 2) ? vsigmax * vsigmax : 0.;           // :518-520
       double fx = F.x, fy = F.y, fz = F.z, dudt = F.w;
@@ -493,11 +500,11 @@ __global__ void k_rates_final(FinalArgs A) {
       if (O.iresist > 0 && O.iresist != 2 && O.etamhd > DBL_MIN) dtforce = hi * hi / O.etamhd;       // :808-815
       double dendt;
       if (O.iener == 3) {                                                                            // :820-826 (+ pair part :1829)
-        dudt = dudt + th.y * (rho1i * rho1i) * drhodti;
+        dudt = dudt + pri * (rho1i * rho1i) * drhodti;
         dendt = ((v.x * fx + v.y * fy) + v.z * fz) + dudt;
         // NOTE: the reference overwrites the pair-summed dendt here (:824); P.w is therefore discarded
       } else if (O.iener > 0 && O.iav >= 0) {                                                        // :832-835
-        dudt = dudt + th.y * (rho1i * rho1i) * drhodti;
+        dudt = dudt + pri * (rho1i * rho1i) * drhodti;
         dendt = dudt;
       } else dendt = dudt;                                                                           // :837
       if (ti == T_DUST) dendt = 0.;                                                                  // :839
@@ -589,7 +596,7 @@ void register_rows(nd_ctx *c) {
   R1(rho); R1(gradh); R1(drhodt); R1(dhdt); R1(rhoalt); R1(gradhn); R1(gradsoft); R1(gradgradh); RI(numneigh);
   R1(dens); R1(uu); R1(pr); R1(spsound); R3(Bfield);
   R3(force); R1(dudt); R1(dendt); R3(dBevoldt); R3(daldt); R1(dpsidt); R3(gradpsi); R1(divB); R3(curlB); R3(graddivv); R1(del2u);
-  R4(posh); R4(vm); R4(bpsi); R4(thermo); R4(gal); R4(sF); R4(sdB); R4(sC); R4(sP); R4(sV);
+  R1(srho); R4(posh); R4(vm); R4(bpsi); R4(thermo); R4(gal); R4(sF); R4(sdB); R4(sC); R4(sP); R4(sV);
   RI(typ); RI(perm); RI(permtmp); RI(inv); RI(cellOf); RI(cellOfOrig); RI(redo); RI(list); RI(ghostcount);
 #undef R3
 #undef R1
@@ -642,7 +649,7 @@ Grid make_grid(nd_ctx *c) {
   Grid G;
   G.cellStart = c->cellStart; G.cellOf = c->cellOf; G.perm = c->perm; G.posh = c->posh; G.vm = c->vm; G.typ = c->typ;
   G.nx = c->ncellsx[0]; G.ny = c->ncellsx[1]; G.nz = c->ncellsx[2]; G.ncells = c->ncells;
-  G.npart = c->npart; G.ntotal = c->ntotal;
+  G.npart = c->npart; G.ntotal = c->ntotal; G.nown = c->nown;
   G.radkern2 = c->T->radkern2; G.dq2table = c->T->dq2table; G.ddq2table = c->T->ddq2table;
   G.tab = c->d_tab; G.tab2 = c->d_tab2; G.tabdrag = c->d_tabdrag;
   return G;
@@ -756,17 +763,60 @@ template <int NDIM> int do_link(nd_ctx *c) {
   return 0;
 }
 
-template <int NDIM, bool FIRST> int launch_density_round(nd_ctx *c, const DensityArgs &A, int n) {
+// ---- neighbour lists: capacity, chunking, overflow ----
+constexpr int LIST_CHUNK = 8 << 20;   // targets per list build: bounds the list buffer to chunk * lmax * 4 bytes
+
+int ensure_lists(nd_ctx *c, int ntargets) {
+  if (c->lmax == 0) {   // first guess: ~2.2x the mean neighbour number of the kernel at hfact = 1.2; grown on overflow
+    const double v = c->ndim == 1 ? 2. : c->ndim == 2 ? 3.141592653589793 : 4.1887902047863905;
+    double r = c->T->radkern * std::max(c->o.hfact, 1.0);
+    double nn = v * (c->ndim == 1 ? r : c->ndim == 2 ? r * r : r * r * r);
+    c->lmax = std::max(16, (int)(2.2 * nn) + 8);
+  }
+  const size_t need = ((size_t)(ntargets + 31) / 32) * 32 * (size_t)c->lmax;
+  if (need > c->nbrcap) {
+    if (c->nbr) cudaFree(c->nbr);
+    c->nbr = nullptr; c->nbrcap = 0;
+    CU(cudaMalloc(&c->nbr, sizeof(unsigned) * need));
+    c->nbrcap = need;
+  }
+  if (ntargets > c->lcntcap) {
+    if (c->lcnt) cudaFree(c->lcnt);
+    c->lcnt = nullptr; c->lcntcap = 0;
+    CU(cudaMalloc(&c->lcnt, sizeof(int) * ((size_t)ntargets + 32)));
+    c->lcntcap = ntargets + 32;
+  }
+  return 0;
+}
+
+// builds the lists of one chunk; on overflow grows lmax and repeats.  flags[5] is the overflow word.
+template <int NDIM, int MODE> int build_lists(nd_ctx *c, const Grid &G, ListArgs LA, NbrLists &L) {
+  for (int attempt = 0; attempt < 8; attempt++) {
+    if (int e = ensure_lists(c, LA.ntargets)) return e;
+    L.nbr = c->nbr; L.cnt = c->lcnt; L.lmax = c->lmax; L.overflow = c->flags + 5;
+    LAUNCH(c, (build_lists_kernel<NDIM, MODE>), nblocks(LA.ntargets, 128), 128, 0, G, LA, L);
+    CU(cudaMemcpyAsync(c->h_flags + 20, c->flags + 5, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const int big = c->h_flags[20];
+    if (big == 0) return 0;
+    c->lmax = big + big / 4 + 8;
+    CU(cudaMemsetAsync(c->flags + 5, 0, sizeof(int), c->stream));
+  }
+  return set_err(c, ND_ERR_NEIGHBOUR_OVERFLOW, "neighbour list overflow");
+}
+
+template <int NDIM, bool FIRST> int launch_density_round(nd_ctx *c, DensityArgs A, int n) {
   Grid G = make_grid(c);
-  const size_t smem = sizeof(unsigned) * DENS_CAP * DENS_BLOCK;
-  if (c->o.want_aux) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(density_round_kernel<NDIM, FIRST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    LAUNCH(c, (density_round_kernel<NDIM, FIRST, true>), nblocks(n, DENS_BLOCK), DENS_BLOCK, smem, G, A);
-  } else {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(density_round_kernel<NDIM, FIRST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    LAUNCH(c, (density_round_kernel<NDIM, FIRST, false>), nblocks(n, DENS_BLOCK), DENS_BLOCK, smem, G, A);
+  for (int c0 = 0; c0 < n; c0 += LIST_CHUNK) {
+    const int m = std::min(LIST_CHUNK, n - c0);
+    ListArgs LA;
+    LA.hh = c->hh; LA.targets = FIRST ? nullptr : c->list + c0; LA.s0 = c0; LA.ntargets = m; LA.numneigh = c->numneigh; LA.drag = 0;
+    LA.pair_out_i = LA.pair_out_j = nullptr; LA.pair_count = nullptr; LA.pair_cap = 0;
+    NbrLists L;
+    if (int e = build_lists<NDIM, FIRST ? LIST_DENS_FIRST : LIST_DENS_PARTIAL>(c, G, LA, L)) return e;
+    A.list = FIRST ? nullptr : c->list + c0; A.nlist = m; A.s0 = c0;
+    if (c->o.want_aux) LAUNCH(c, (density_round_kernel<NDIM, FIRST, true>), nblocks(m, DENS_BLOCK), DENS_BLOCK, 0, G, A, L);
+    else LAUNCH(c, (density_round_kernel<NDIM, FIRST, false>), nblocks(m, DENS_BLOCK), DENS_BLOCK, 0, G, A, L);
   }
   return 0;
 }
@@ -860,13 +910,19 @@ RatesOpts make_rates_opts(const nd_ctx *c) {
 
 enum { RED_DTC = 0, RED_VSIG = 1, RED_DTAV = 2, RED_TS = 3, RED_HCS = 4, RED_FH = 5, RED_DTF = 6, RED_STRESS = 7 };
 
-template <int NDIM, bool MHD, bool DRAG> int launch_rates_pair(nd_ctx *c, const RatesIn &I, const RatesOpts &O, const RatesSums &S, const RatesRed &R, int *pi, int *pj,
-                                                               unsigned long long *pc, long long cap) {
+template <int NDIM, bool MHD, bool DRAG, bool FAST> int launch_rates_pair(nd_ctx *c, const RatesIn &I, const RatesOpts &O, const RatesSums &S, const RatesRed &R, int *pi, int *pj,
+                                                                          unsigned long long *pc, long long cap) {
   Grid G = make_grid(c);
-  const size_t smem = sizeof(unsigned) * RATES_CAP * RATES_BLOCK;
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(rates_pair_kernel<NDIM, MHD, DRAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  LAUNCH(c, (rates_pair_kernel<NDIM, MHD, DRAG>), nblocks(c->ntotal, RATES_BLOCK), RATES_BLOCK, smem, G, I, O, S, R, pi, pj, pc, cap);
+  const int n = c->ntotal;
+  for (int c0 = 0; c0 < n; c0 += LIST_CHUNK) {
+    const int m = std::min(LIST_CHUNK, n - c0);
+    ListArgs LA;
+    LA.hh = c->hh; LA.targets = nullptr; LA.s0 = c0; LA.ntargets = m; LA.numneigh = nullptr; LA.drag = (DRAG && O.idrag_nature > 0) ? 1 : 0;
+    LA.pair_out_i = pi; LA.pair_out_j = pj; LA.pair_count = pc; LA.pair_cap = cap;
+    NbrLists L;
+    if (int e = build_lists<NDIM, LIST_RATES>(c, G, LA, L)) return e;
+    LAUNCH(c, (rates_pair_kernel<NDIM, MHD, DRAG, FAST>), nblocks(m, RATES_BLOCK), RATES_BLOCK, 0, G, I, O, S, R, L, c0, m);
+  }
   return 0;
 }
 
@@ -887,7 +943,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   GA.perm = c->perm; GA.ireal = c->ireal; GA.hh = c->hh; GA.pmass = c->pmass; GA.rho = c->rho; GA.pr = c->pr; GA.spsound = c->spsound; GA.uu = c->uu;
   GA.gradh = c->gradh; GA.alpha = c->alpha; GA.psi = c->psi; GA.Bfield = c->Bfield;
   GA.posh = c->posh; GA.vm = c->vm; GA.bpsi = c->bpsi; GA.thermo = c->thermo; GA.gal = c->gal; GA.npart = np; GA.ntotal = nt; GA.imhd = o.imhd;
-  GA.stress_key = c->red + RED_STRESS; GA.imagforce = o.imagforce;
+  GA.stress_key = c->red + RED_STRESS; GA.imagforce = o.imagforce; GA.srho = c->srho; GA.pext = o.pext; GA.err = c->flags + 1;
   GA.Bconstmax = std::max(o.Bconst[0], std::max(o.Bconst[1], o.Bconst[2]));
   LAUNCH(c, k_rates_gather, nblocks(nt, 256), 256, 0, GA);
   RatesOpts O = make_rates_opts(c);
@@ -896,7 +952,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
     CU(cudaStreamSynchronize(c->stream));
     O.stressmax = dkey_inv(c->h_red[0]);
   }
-  RatesIn I; I.bpsi = c->bpsi; I.thermo = c->thermo; I.gal = c->gal;
+  RatesIn I; I.bpsi = c->bpsi; I.thermo = c->thermo; I.gal = c->gal; I.srho = c->srho;
   RatesSums S; S.F = c->sF; S.dB = c->sdB; S.C = c->sC; S.P = c->sP; S.V = c->sV;
   RatesRed R;
   R.dtcourant_min = c->red + RED_DTC; R.vsigmax_max = c->red + RED_VSIG; R.dtav_min = c->red + RED_DTAV; R.ts_min = c->red + RED_TS;
@@ -905,15 +961,19 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   CU(cudaEventRecord(c->ev[3], c->stream));
   const bool mhd = o.imhd != 0, drag = (o.idust == 2);
   int e = 0;
-  if (mhd && !drag) e = launch_rates_pair<NDIM, true, false>(c, I, O, S, R, pi, pj, pc, cap);
-  else if (!mhd && !drag) e = launch_rates_pair<NDIM, false, false>(c, I, O, S, R, pi, pj, pc, cap);
-  else if (!mhd && drag) e = launch_rates_pair<NDIM, false, true>(c, I, O, S, R, pi, pj, pc, cap);
-  else e = launch_rates_pair<NDIM, true, true>(c, I, O, S, R, pi, pj, pc, cap);
+  // first-class tuple without run-time option tests (and without the dead graddivv "curl v" sums: want_aux = 0)
+  const bool fast = !drag && !o.want_aux && o.iav == 2 && (o.iener == 0 || o.iener == 2) && o.ikernav == 3 && o.iresist == 0 && o.iavlim[0] != 3 && o.iavlim[2] != 2;
+  if (mhd && fast) e = launch_rates_pair<NDIM, true, false, true>(c, I, O, S, R, pi, pj, pc, cap);
+  else if (!mhd && fast) e = launch_rates_pair<NDIM, false, false, true>(c, I, O, S, R, pi, pj, pc, cap);
+  else if (mhd && !drag) e = launch_rates_pair<NDIM, true, false, false>(c, I, O, S, R, pi, pj, pc, cap);
+  else if (!mhd && !drag) e = launch_rates_pair<NDIM, false, false, false>(c, I, O, S, R, pi, pj, pc, cap);
+  else if (!mhd && drag) e = launch_rates_pair<NDIM, false, true, false>(c, I, O, S, R, pi, pj, pc, cap);
+  else e = launch_rates_pair<NDIM, true, true, false>(c, I, O, S, R, pi, pj, pc, cap);
   if (e) return e;
   CU(cudaEventRecord(c->ev[4], c->stream));
   FinalArgs FA;
   FA.perm = c->perm; FA.typ = c->typ; FA.posh = c->posh; FA.vm = c->vm; FA.bpsi = c->bpsi; FA.thermo = c->thermo; FA.gal = c->gal; FA.S = S; FA.O = O;
-  FA.drhodt_in = c->drhodt; FA.Bevol = c->Bevol; FA.dens = c->dens; FA.vsigmax_key = c->red + RED_VSIG;
+  FA.drhodt_in = c->drhodt; FA.Bevol = c->Bevol; FA.dens = c->dens; FA.hh = c->hh; FA.rho = c->rho; FA.pr = c->pr; FA.vsigmax_key = c->red + RED_VSIG;
   FA.force = c->force; FA.dudt = c->dudt; FA.dendt = c->dendt; FA.dBevoldt = c->dBevoldt; FA.daldt = c->daldt; FA.dpsidt = c->dpsidt; FA.gradpsi = c->gradpsi;
   FA.divB = c->divB; FA.curlB = c->curlB; FA.graddivv = c->graddivv; FA.del2u = c->del2u; FA.drhodt = c->drhodt; FA.dhdt = c->dhdt;
   FA.R = R; FA.npart = np; FA.ntotal = nt;
@@ -1057,7 +1117,7 @@ int ndspmhd_b200_destroy(nd_ctx *c) {
   if (!c) return 0;
   if (c->stream) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
   for (auto &rb : c->rowbufs) if (*rb.p) { cudaFree(*rb.p); *rb.p = nullptr; }
-  void *singles[] = {c->scanout, c->cellStart, c->cellCount, c->blocksums, c->red, c->fmean, c->flags, c->d_tab, c->d_tab2, c->d_tabdrag};
+  void *singles[] = {c->nbr, c->lcnt, c->scanout, c->cellStart, c->cellCount, c->blocksums, c->red, c->fmean, c->flags, c->d_tab, c->d_tab2, c->d_tabdrag};
   for (void *p : singles) if (p) cudaFree(p);
   if (c->h_red) cudaFreeHost(c->h_red);
   if (c->h_flags) cudaFreeHost(c->h_flags);
@@ -1110,7 +1170,7 @@ int ndspmhd_b200_upload(nd_ctx *c, const nd_arrays *a, int npart, int ntotal, in
   CU(up(c->psi, a->psi, sizeof(double) * n));
   CU(up(c->rho, a->rho_in, sizeof(double) * n));
   CU(cudaStreamSynchronize(c->stream));
-  c->npart = npart; c->ntotal = ntotal;
+  c->npart = npart; c->ntotal = ntotal; c->nown = npart;
   c->uploaded = true; c->linked = c->density_done = c->prim_done = c->rates_done = false;
   return 0;
 }

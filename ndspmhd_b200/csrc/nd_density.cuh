@@ -17,88 +17,57 @@ struct DensityArgs {
   double *rho, *gradh, *drhodt, *dhdt;
   int *numneigh;
   double *rhoalt, *gradhn, *gradsoft, *gradgradh;   // AUX
-  const int *list;       // sorted slots to process (NULL in the FIRST round: slot = global thread id)
-  int nlist;
+  const int *list;       // sorted slots to process (NULL in the FIRST round: slot = s0 + thread id)
+  int nlist, s0;
   int *redo;             // [ntotal] by sorted slot: 1 = not converged, recompute next round
   int *flags;            // [0] relink requested, [1] error code, [2] rho<=1e-6 count
   int itsdensity, itsdensitymax;
   double hfact, psep, tolh, hhmax;
 };
 
+#ifndef ND_DENS_MINB
+#define ND_DENS_MINB 4
+#endif
 constexpr int DENS_BLOCK = 128;
-constexpr int DENS_CAP = 96;
 
 template <int NDIM, bool FIRST, bool AUX>
-__global__ void __launch_bounds__(DENS_BLOCK) density_round_kernel(Grid G, DensityArgs A) {
-  extern __shared__ unsigned nlist_smem[];
-  const int gid = blockIdx.x * DENS_BLOCK + threadIdx.x;
-  int s = -1;
-  if (FIRST) { if (gid < G.ntotal) s = gid; }
-  else if (gid < A.nlist) s = A.list[gid];
-  int orig = -1, ti = 0;
-  bool active = false;
-  if (s >= 0) {
-    orig = G.perm[s];
-    ti = G.typ[s];
-    active = orig < G.npart;                       // ghosts are sources only
-    if (!FIRST && ti == T_BND) active = false;     // density_sums.f90:510
-  }
+__global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel(Grid G, DensityArgs A, NbrLists L) {
+  const int t = blockIdx.x * DENS_BLOCK + threadIdx.x;
+  if (t >= A.nlist) return;
+  const int s = FIRST ? A.s0 + t : A.list[t];
+  const int orig = G.perm[s];
+  const int ti = G.typ[s];
+  bool active = orig < G.nown;                     // ghosts and halo rows are sources only
+  if (!FIRST && ti == T_BND) active = false;       // density_sums.f90:510
   double xi = 0, yi = 0, zi = 0, vxi = 0, vyi = 0, vzi = 0, mi = 0, hi = 1;
-  int celli = 0;
+  int cs0 = 0, cs1 = 0, cnt = 0;
   if (active) {
     double4 p = ld4(G.posh + s), v = ld4(G.vm + s);
     xi = p.x; yi = p.y; zi = p.z;
     vxi = v.x; vyi = v.y; vzi = v.z; mi = v.w;
-    hi = A.hh[orig];                               // current h (== p.w in the first round)
-    celli = G.cellOf[s];
+    hi = A.hh[orig];                               // current h (1/h == p.w in the first round)
+    const int celli = G.cellOf[s];
+    cs0 = __ldg(G.cellStart + celli); cs1 = __ldg(G.cellStart + celli + 1);
+    cnt = L.cnt[t];
   }
   const double hi1 = 1.0 / hi;                     // h1(i) = 1./hh(i), density_sums.f90:130
   const double hi21 = __dmul_rn(hi1, hi1);
   const double hfacwabi = powndim<NDIM>(hi1);
-  int nneigh = 0;
   double rho = 0, gradh = 0, drhodt = 0, densn = 0, gradhn = 0, gradgradh = 0;
+  const bool bnd_first = FIRST && ti == T_BND;     // :273, :321 -- fixed particles keep rho, gradh
 
-  // ---- phase 1: inclusion test (bit-exact arithmetic) ----
-  auto cull = [&](int k) -> bool {
-    const double4 pj = ld4(G.posh + k);
-    const int tj = __ldg(G.typ + k);
-    const double rij2 = dist2_exact(xi - pj.x, yi - pj.y, zi - pj.z);
-    if (FIRST) {
-      if (!types_interact(ti, tj)) return false;   // density_sums.f90:169-174
-      // The reference visits the pair once; "i" is the particle met first: lower cell index, or the later-inserted
-      // (higher index) particle of the same chain.  q2 of "i" is rij2*hi21, q2 of "j" is (rij2*hj1)*hj1 (:182-183).
-      const int cellj = __ldg(G.cellOf + k), origj = __ldg(G.perm + k);
-      const bool iam_i = (celli < cellj) || (celli == cellj && orig >= origj);
-      const double hj1 = 1.0 / pj.w;
-      double q2me, q2ot;
-      if (iam_i) { q2me = __dmul_rn(rij2, hi21); q2ot = __dmul_rn(__dmul_rn(rij2, hj1), hj1); }
-      else { q2me = __dmul_rn(__dmul_rn(rij2, hi1), hi1); q2ot = __dmul_rn(rij2, __dmul_rn(hj1, hj1)); }
-      // :189-190 with the target real: q2i<radkern2 .or. q2j<radkern2
-      const bool mine = q2me < G.radkern2;
-      if (mine || q2ot < G.radkern2) nneigh++;     // :196-197
-      return mine;                                  // terms with q2me >= radkern2 are exact zeros (table end = 0)
-    } else {
-      if (tj != ti && tj != T_BND) return false;   // density_sums.f90:517
-      const double q2i = __dmul_rn(rij2, hi21);
-      if (q2i < G.radkern2) { nneigh++; return true; }   // :528-532
-      return false;
-    }
-  };
-
-  // ---- phase 2: pair sums ----
-  auto body = [&](int k) {
-    const double4 pj = ld4(G.posh + k);
-    const double4 vj = ld4(G.vm + k);
+  // ---- pair sums over the neighbour list (built by build_lists_kernel with the reference's inclusion test) ----
+  auto body = [&](int k, const double4 &pj, const double4 &vj) {
     const double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
     const double rij2 = dist2_exact(dx, dy, dz);
     double q2i;
-    if (FIRST) {
-      const int cellj = __ldg(G.cellOf + k), origj = __ldg(G.perm + k);
-      const bool iam_i = (celli < cellj) || (celli == cellj && orig >= origj);
-      q2i = iam_i ? __dmul_rn(rij2, hi21) : __dmul_rn(__dmul_rn(rij2, hi1), hi1);
-    } else q2i = __dmul_rn(rij2, hi21);
-    const double rij = sqrt(rij2);
-    const bool self = (k == s);
+    // the reference rounds q2 of the first-met particle of a pair as rij2*hi21 and of the other as (rij2*hi1)*hi1 (:182-183)
+    if (FIRST) q2i = ((k >= cs1) || (k >= cs0 && k <= s)) ? __dmul_rn(rij2, hi21) : __dmul_rn(__dmul_rn(rij2, hi1), hi1);
+    else q2i = __dmul_rn(rij2, hi21);
+    // rij = sqrt(rij2) and dr = dx/(rij + epsilon(rij)) (:199) without a divide: 1/(r+e) = (1/r)(1 - e/r) to O((e/r)^2) ~ 1e-26
+    const double rinv = rij2 > 0. ? rsqrt(rij2) : 0.;
+    const double rij = rij2 * rinv;
+    const double rinve = rinv - 2.220446049250313e-16 * rinv * rinv;
     const double pmassj = vj.w;
     double wabi, grkerni, grgrkerni = 0.;
     if (AUX) interp_wggg(G, q2i, wabi, grkerni, grgrkerni);
@@ -107,7 +76,6 @@ __global__ void __launch_bounds__(DENS_BLOCK) density_round_kernel(Grid G, Densi
     grkerni = grkerni * hfacwabi * hi1;
     const double dwdhi = -rij * grkerni * hi1 - NDIM * wabi * hi1;   // :260
     // self pair: the symmetric loop adds weight 1/2 twice (:204-208, :274, :286); the gather adds it once in full
-    const bool bnd_first = FIRST && ti == T_BND;   // :273, :321 -- fixed particles keep rho, gradh
     if (!bnd_first) {
       rho += pmassj * wabi;
       gradh += pmassj * dwdhi;
@@ -120,22 +88,34 @@ __global__ void __launch_bounds__(DENS_BLOCK) density_round_kernel(Grid G, Densi
         gradgradh += pmassj * dwdhdhi;
       }
     }
-    if (!self) {                                   // :297-303
-      const double rinv = 1.0 / (rij + 2.220446049250313e-16);   // dr = dx/(rij + epsilon(rij)), :199
-      const double dvdotr = ((vxi - vj.x) * (dx * rinv) + (vyi - vj.y) * (dy * rinv)) + (vzi - vj.z) * (dz * rinv);
+    if (k != s) {                                  // :297-303
+      const double dvdotr = ((vxi - vj.x) * (dx * rinve) + (vyi - vj.y) * (dy * rinve)) + (vzi - vj.z) * (dz * rinve);
       drhodt += pmassj * dvdotr * grkerni;
     }
   };
+  {
+    const unsigned *col = L.nbr + ((size_t)(t >> 5) * L.lmax) * 32 + (t & 31);
+    int n = 0;
+    for (; n + 1 < cnt; n += 2) {                  // two neighbours in flight: their loads overlap the other's arithmetic
+      const int k0 = (int)col[(size_t)n * 32], k1 = (int)col[(size_t)(n + 1) * 32];
+      const double4 p0 = ld4(G.posh + k0), v0 = ld4(G.vm + k0), p1 = ld4(G.posh + k1), v1 = ld4(G.vm + k1);
+      body(k0, p0, v0);
+      body(k1, p1, v1);
+    }
+    if (n < cnt) {
+      const int k0 = (int)col[(size_t)n * 32];
+      const double4 p0 = ld4(G.posh + k0), v0 = ld4(G.vm + k0);
+      body(k0, p0, v0);
+    }
+  }
+  const int nneigh = active ? A.numneigh[orig] : 0;   // counted by build_lists_kernel (:196-197 / :532)
 
-  neighbour_walk<NDIM, DENS_CAP, DENS_BLOCK>(G, active, celli, nlist_smem, cull, body);
-
-  if (s < 0 || orig >= G.npart) return;
+  if (orig >= G.nown) return;
   if (!active) {                                   // fixed particle skipped by density_partial: stays as it was
     A.redo[s] = 0;
     return;
   }
   // ---- Newton-Raphson update, src/iterate_density.f90:163-278 ----
-  A.numneigh[orig] = nneigh;
   int redo = 0;
   if (ti != T_BND && ti != T_BNDDUST) {
     if (rho <= 1.e-6) {

@@ -22,11 +22,12 @@ struct Grid {
   const int *cellStart;     // [ncells+1] first sorted slot of each cell
   const int *cellOf;        // [ntotal]   cell of each sorted slot
   const int *perm;          // [ntotal]   sorted slot -> original row
-  const double4 *posh;      // [ntotal]   {x,y,z,h}
+  const double4 *posh;      // [ntotal]   {x,y,z,1/h}  (1/h correctly rounded: h1(i) = 1./hh(i), density_sums.f90:130)
   const double4 *vm;        // [ntotal]   {vx,vy,vz,m}
   const int *typ;           // [ntotal]
   int nx, ny, nz, ncells;
-  int npart, ntotal;
+  int npart, ntotal;        // rows [0,npart) carry their own state (targets are rows < nown), [npart,ntotal) are ghosts
+  int nown;
   double radkern2, dq2table, ddq2table;
   const TabRec *tab;        // [IKERN+1]
   const TabRec2 *tab2;      // [IKERN+1]
@@ -39,6 +40,8 @@ __device__ __forceinline__ double4 ld4(const double4 *p) {
   double2 a = __ldg(q), b = __ldg(q + 1);
   return make_double4(a.x, a.y, b.x, b.y);
 }
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // rij2 = dot_product(dx,dx) in index order without FMA contraction (src/density_sums.f90:181,
 // src/ratesND_mhd.f90:408; reference build has no FMA, src/Makefile:25).  Unused dimensions carry exact zeros.
@@ -116,61 +119,120 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Neighbour walk.  Every lane owns one target particle.  The 3^NDIM stencil of the target's cell is visited as
-// 3^(NDIM-1) x-rows; a row's three cells are contiguous in the cell-sorted arrays, so a row is one span of slots.
-// Phase 1 (cull): the lane tests the span's candidates and appends accepted slots to its private column of a
-// shared-memory list.  Phase 2 (flush): when any lane's column is full (and at the end) the warp runs the
-// expensive pair body over the lists, so the body executes with all lanes busy instead of at the ~15 % acceptance
-// rate of the raw stencil.  All lanes of a warp must call this together (warp votes inside).
+// Neighbour lists.  Finding neighbours (cheap test, ~85 % rejected, wants many resident warps) and evaluating pair terms
+// (hundreds of FP64 instructions, wants registers) are separate kernels: build_lists_kernel walks the 3^NDIM stencil of
+// the target's cell as 3^(NDIM-1) x-rows -- a row's three cells are contiguous in the cell-sorted arrays, so a row is
+// one span of slots -- applies the reference's inclusion test bit for bit and appends accepted slots to the target's
+// list; the pair kernels then run over the lists with every lane busy.
+// Layout: target t (index within the launch) owns column (t & 31) of warp block (t >> 5):
+//     nbr[((t >> 5) * lmax + n) * 32 + (t & 31)],  n < cnt[t]
+// so entry n of the 32 targets of a warp is one 128-byte line, written and read coalesced.
 // ------------------------------------------------------------------------------------------------------
-template <int NDIM, int CAP, int BLOCK, class Cull, class Body>
-__device__ __forceinline__ void neighbour_walk(const Grid &G, bool active, int cell, unsigned *list /* [CAP][BLOCK] */, Cull cull, Body body) {
-  const int tid = threadIdx.x;
-  int cnt = 0;
-  int ix = 0, iy = 0, iz = 0;
-  if (active) {
-    ix = cell % G.nx;
-    int t = cell / G.nx;
-    iy = (NDIM >= 2) ? t % G.ny : 0;
-    iz = (NDIM >= 3) ? t / G.ny : 0;
-  }
-  auto flush = [&]() {
-    int k = 0;
-    while (__any_sync(FULL, k < cnt)) {
-      if (k < cnt) body((int)list[k * BLOCK + tid]);
-      k++;
+struct NbrLists {
+  unsigned *nbr;
+  int *cnt;        // [targets in the launch]
+  int lmax;        // column capacity
+  int *overflow;   // set to the largest count seen when a column overflows (host grows lmax and repeats)
+};
+__device__ __forceinline__ size_t nbr_index(int t, int n, int lmax) { return ((size_t)(t >> 5) * lmax + n) * 32 + (t & 31); }
+
+enum { LIST_DENS_FIRST = 0, LIST_DENS_PARTIAL = 1, LIST_RATES = 2 };
+
+struct ListArgs {
+  const double *hh;        // original-order current smoothing lengths (density modes)
+  const int *targets;      // LIST_DENS_PARTIAL: sorted slots to process; else NULL (slot = s0 + t)
+  int s0, ntargets;
+  int *numneigh;           // density modes: neighbour count as the reference defines it, by original row
+  int drag;                // LIST_RATES: gas-dust pairs are kept (drag_forces)
+  int *pair_out_i, *pair_out_j; unsigned long long *pair_count; long long pair_cap;   // parity-test hook (LIST_RATES)
+};
+
+template <int NDIM, int MODE>
+__global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, NbrLists L) {
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= A.ntargets) return;
+  const int s = (MODE == LIST_DENS_PARTIAL) ? A.targets[t] : A.s0 + t;
+  const int orig = G.perm[s];
+  const int ti = G.typ[s];
+  bool active = orig < G.nown;                     // ghosts and halo rows are sources only
+  if (MODE == LIST_DENS_PARTIAL && ti == T_BND) active = false;   // density_sums.f90:510
+  if (!active) { L.cnt[t] = 0; return; }
+  const double4 p = ld4(G.posh + s);
+  const double xi = p.x, yi = p.y, zi = p.z;
+  // density: current h (the sorted record holds the h of the last link); rates: 1/h of the record (h1(i) = 1./hh(i))
+  const double hi1 = (MODE == LIST_RATES) ? p.w : 1.0 / A.hh[orig];
+  const double hi21 = __dmul_rn(hi1, hi1);
+  const int cell = G.cellOf[s];
+  const int cs0 = __ldg(G.cellStart + cell), cs1 = __ldg(G.cellStart + cell + 1);
+  const int ix = cell % G.nx;
+  const int tq = cell / G.nx;
+  const int iy = (NDIM >= 2) ? tq % G.ny : 0, iz = (NDIM >= 3) ? tq / G.ny : 0;
+  int cnt = 0, nneigh = 0;
+  unsigned *col = L.nbr + ((size_t)(t >> 5) * L.lmax) * 32 + (t & 31);
+
+  auto accept = [&](int k, const double4 &pj) -> bool {
+    const double rij2 = dist2_exact(xi - pj.x, yi - pj.y, zi - pj.z);
+    const double hj1 = pj.w;
+    if (MODE == LIST_DENS_FIRST) {
+      // The reference visits a pair once; "i" is the particle met first: the one in the lower cell, or the later-inserted
+      // (higher index) particle of the same chain.  Slots are sorted by (cell, index), so that is a slot comparison.
+      // q2 of "i" is rij2*hi21, q2 of "j" is (rij2*hj1)*hj1 (density_sums.f90:182-183).
+      const bool iam_i = (k >= cs1) || (k >= cs0 && k <= s);
+      double q2me, q2ot;
+      if (iam_i) { q2me = __dmul_rn(rij2, hi21); q2ot = __dmul_rn(__dmul_rn(rij2, hj1), hj1); }
+      else { q2me = __dmul_rn(__dmul_rn(rij2, hi1), hi1); q2ot = __dmul_rn(rij2, __dmul_rn(hj1, hj1)); }
+      const bool mine = q2me < G.radkern2;
+      if (!(mine || q2ot < G.radkern2)) return false;            // :189-190 with the target real
+      if (!types_interact(ti, __ldg(G.typ + k))) return false;   // :169-174
+      nneigh++;                                                   // :196-197
+      return mine;                                                // terms with q2me >= radkern2 are exact zeros (table end = 0)
+    } else if (MODE == LIST_DENS_PARTIAL) {
+      if (!(__dmul_rn(rij2, hi21) < G.radkern2)) return false;   // :528
+      const int tj = __ldg(G.typ + k);
+      if (tj != ti && tj != T_BND) return false;                 // :517
+      nneigh++;                                                   // :532
+      return true;
+    } else {                                                      // ratesND_mhd.f90:401-415
+      if (k == s) return false;                                  // j /= i (both-ghost pairs cannot occur: the target is real)
+      const double q2i = __dmul_rn(rij2, hi21), q2j = __dmul_rn(rij2, __dmul_rn(hj1, hj1));
+      if (!((q2i < G.radkern2) || (q2j < G.radkern2))) return false;
+      if (A.pair_out_i) {                                        // parity-test hook: record the accepted pair
+        unsigned long long n = atomicAdd(A.pair_count, 1ull);
+        if ((long long)n < A.pair_cap) { A.pair_out_i[n] = orig + 1; A.pair_out_j[n] = G.perm[k] + 1; }
+      }
+      return A.drag || types_interact(ti, __ldg(G.typ + k));     // :436-446
     }
-    cnt = 0;
   };
-  constexpr int NY = (NDIM >= 2) ? 3 : 1, NZ = (NDIM >= 3) ? 3 : 1;
+
+  constexpr int NY = (NDIM >= 2) ? 3 : 1, NZ = (NDIM >= 3) ? 3 : 1, UNROLL = 4;
 #pragma unroll 1
   for (int rz = 0; rz < NZ; rz++) {
 #pragma unroll 1
     for (int ry = 0; ry < NY; ry++) {
-      int k = 0, e = 0;
-      if (active) {
-        int cy = iy + ry - (NDIM >= 2 ? 1 : 0), cz = iz + rz - (NDIM >= 3 ? 1 : 0);
-        // padded empty border cells (src/linkND.f90:88-89) keep ix-1, ix+1, cy, cz inside the grid for populated cells
-        if (cy >= 0 && cy < G.ny && cz >= 0 && cz < G.nz) {
-          int c0 = (cz * G.ny + cy) * G.nx;
-          int xa = ix > 0 ? ix - 1 : 0, xb = ix + 1 < G.nx ? ix + 1 : G.nx - 1;
-          k = __ldg(G.cellStart + c0 + xa);
-          e = __ldg(G.cellStart + c0 + xb + 1);
-        }
-      }
-      while (__any_sync(FULL, k < e)) {
+      const int cy = iy + ry - (NDIM >= 2 ? 1 : 0), cz = iz + rz - (NDIM >= 3 ? 1 : 0);
+      // padded empty border cells (src/linkND.f90:88-89) keep ix-1, ix+1, cy, cz inside the grid for populated cells
+      if (cy < 0 || cy >= G.ny || cz < 0 || cz >= G.nz) continue;
+      const int c0 = (cz * G.ny + cy) * G.nx;
+      const int xa = ix > 0 ? ix - 1 : 0, xb = ix + 1 < G.nx ? ix + 1 : G.nx - 1;
+      int k = __ldg(G.cellStart + c0 + xa);
+      const int e = __ldg(G.cellStart + c0 + xb + 1);
+      for (; k < e; k += UNROLL) {
+        double4 pj[UNROLL];
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
-          if (k < e) {
-            if (cull(k)) { list[cnt * BLOCK + tid] = (unsigned)k; cnt++; }
-            k++;
+        for (int u = 0; u < UNROLL; u++) pj[u] = ld4(G.posh + min(k + u, e - 1));
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+          if (k + u < e && accept(k + u, pj[u])) {
+            if (cnt < L.lmax) col[(size_t)cnt * 32] = (unsigned)(k + u);
+            cnt++;
           }
         }
-        if (__any_sync(FULL, cnt > CAP - 2)) flush();
       }
     }
   }
-  flush();
+  if (cnt > L.lmax) { atomicMax(L.overflow, cnt); cnt = L.lmax; }
+  L.cnt[t] = cnt;
+  if (MODE != LIST_RATES) A.numneigh[orig] = nneigh;
 }
 
 }  // namespace ndk

@@ -23,8 +23,9 @@ struct RatesOpts {
 
 struct RatesIn {
   const double4 *bpsi;     // {Bx,By,Bz,psi}
-  const double4 *thermo;   // {rho, pr, spsound, uu}
+  const double4 *thermo;   // {1/rho, max(pr - pext, 0), spsound, uu}   (1/rho correctly rounded: rho1i = 1./rhoi, ratesND_mhd.f90:325)
   const double4 *gal;      // {gradh, alpha, alphau, alphaB}
+  const double *srho;      // rho by sorted slot (drag and phantom-AV branches only)
 };
 
 struct RatesSums {         // per sorted slot, written by the pair kernel, read by the final kernel
@@ -42,8 +43,10 @@ struct RatesRed {
   int *nclumped, *err;
 };
 
+#ifndef ND_RATES_MINB
+#define ND_RATES_MINB 2
+#endif
 constexpr int RATES_BLOCK = 128;
-constexpr int RATES_CAP = 96;
 
 __device__ __forceinline__ double get_tstop(int idrag_nature, double rhogas, double rhodust, double Kdrag) {
   // src/dust.f90:77-102
@@ -53,92 +56,79 @@ __device__ __forceinline__ double get_tstop(int idrag_nature, double rhogas, dou
   return 1.7976931348623157e308;
 }
 
-template <int NDIM, bool MHD, bool DRAG>
-__global__ void __launch_bounds__(RATES_BLOCK, 2) rates_pair_kernel(Grid G, RatesIn I, RatesOpts O, RatesSums S, RatesRed R, int *pair_out_i,
-                                                                      int *pair_out_j, unsigned long long *pair_count, long long pair_cap) {
-  extern __shared__ unsigned nlist_smem[];
-  const int s = blockIdx.x * RATES_BLOCK + threadIdx.x;
-  int orig = -1, ti = 0, celli = 0;
+// FAST = the first-class option tuple compiled without run-time option tests: iav=2, iener in {0,2}, ikernav=3, iresist=0,
+// iavlim(1) /= 3, iavlim(3) /= 2, pext folded into thermo.  Everything else runs the generic instantiation.
+template <int NDIM, bool MHD, bool DRAG, bool FAST>
+__global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(Grid G, RatesIn I, RatesOpts O, RatesSums S, RatesRed R, NbrLists L,
+                                                                                 int s0, int ntargets) {
+  const int tix = blockIdx.x * RATES_BLOCK + threadIdx.x;   // target index within this launch
+  const int s = s0 + tix;
+  const int iav = FAST ? 2 : O.iav, iener = FAST ? (O.iener != 0 ? 2 : 0) : O.iener, ikernav = FAST ? 3 : O.ikernav, iresist = FAST ? 0 : O.iresist;
+  const int iavlim0 = O.iavlim0, iavlim1 = O.iavlim1, iavlim2 = O.iavlim2;
+  int orig = -1, ti = 0, cnt = 0;
   bool active = false;
-  if (s < G.ntotal) {
+  if (tix < ntargets) {
     orig = G.perm[s];
-    active = orig < G.npart;      // rates are gathered for rows 1..npart (fixed particles included: they feed the dt minima)
+    active = orig < G.nown;       // rates are gathered for the caller's own rows (fixed particles included: they feed the dt minima)
   }
-  double xi = 0, yi = 0, zi = 0, hi = 1, vxi = 0, vyi = 0, vzi = 0, pmassi = 0;
-  double Bxi = 0, Byi = 0, Bzi = 0, psii = 0, rhoi = 1, pri = 0, spsoundi = 0, uui = 0, gradhi = 0, alphai = 0, alphaui = 0, alphaBi = 0;
+  double xi = 0, yi = 0, zi = 0, hi1 = 1, vxi = 0, vyi = 0, vzi = 0, pmassi = 0;
+  double Bxi = 0, Byi = 0, Bzi = 0, psii = 0, rho1i = 1, rhoi = 1, pri = 0, spsoundi = 0, uui = 0, gradhi = 0, alphai = 0, alphaui = 0, alphaBi = 0;
   if (active) {
     double4 p = ld4(G.posh + s), v = ld4(G.vm + s), t = ld4(I.thermo + s), g = ld4(I.gal + s);
-    xi = p.x; yi = p.y; zi = p.z; hi = p.w;
+    xi = p.x; yi = p.y; zi = p.z; hi1 = p.w;                                   // hi1 = 1./hi, :215, :389
     vxi = v.x; vyi = v.y; vzi = v.z; pmassi = v.w;
-    rhoi = t.x; pri = fmax(t.y - O.pext, 0.); spsoundi = t.z; uui = t.w;       // :328
+    rho1i = t.x; pri = t.y; spsoundi = t.z; uui = t.w;                          // :325-328
     gradhi = g.x; alphai = g.y; alphaui = g.z; alphaBi = g.w;
     if (MHD) { double4 b = ld4(I.bpsi + s); Bxi = b.x; Byi = b.y; Bzi = b.z; psii = b.w; }
     ti = G.typ[s];
-    celli = G.cellOf[s];
-    if (hi <= 0.) atomicCAS(R.err, 0, 3 /*ND_ERR_H_NONPOSITIVE*/);             // :384-387
+    rhoi = I.srho[s];
+    cnt = L.cnt[tix];
   }
-  const double rho1i = 1. / rhoi, rho21i = rho1i * rho1i;                     // :325-326
+  const double rho21i = rho1i * rho1i;                                         // :326
   const double Prho2i = pri * rho21i;                                          // :332
-  const double hi1 = 1. / hi, hi21 = __dmul_rn(hi1, hi1);                      // :215, :389
+  const double hi21 = __dmul_rn(hi1, hi1);
   const double hfacwabi = powndim<NDIM>(hi1), hfacgrkerni = hfacwabi * hi1;    // :390-391
-  double Brhoxi = 0, Brhoyi = 0, Brhozi = 0, Brho2i = 0, valfven2i = 0;
+  double Brhoxi = 0, Brhoyi = 0, Brhozi = 0, Brho2i = 0, valfven2i = 0, vsig2i = 0;
   if (MHD) {                                                                   // :362-373
     Brhoxi = Bxi * rho1i; Brhoyi = Byi * rho1i; Brhozi = Bzi * rho1i;
     const double B2i = (Bxi * Bxi + Byi * Byi) + Bzi * Bzi;
     Brho2i = B2i * rho21i;
     valfven2i = B2i * rho1i;
+    vsig2i = spsoundi * spsoundi + valfven2i;
   }
   // accumulators
   double fx = 0, fy = 0, fz = 0, dudt = 0, dBx = 0, dBy = 0, dBz = 0, divB = 0, cBx = 0, cBy = 0, cBz = 0, del2u = 0;
   double gpx = 0, gpy = 0, gpz = 0, gvx = 0, gvy = 0, gvz = 0, endiss = 0;
-  double dtcourant = 1.e6, vsigmax = 0., dtav = 1.7976931348623157e308, ts_min = 1.7976931348623157e308, h_on_csts_max = 0.;
+  // dtcourant = min over pairs of min(hi,hj)/vsigdtc = 1/max(max(1/hi,1/hj)*vsigdtc): track the denominator, divide once
+  double dtc_den = 0., dtav_den = 0., vsigmax = 0., ts_min = 1.7976931348623157e308, h_on_csts_max = 0.;
   int nclumped = 0;
   const double zero = 1.e-10;
+  const double eps = 2.220446049250313e-16;
 
-  // ---- phase 1: inclusion test, src/ratesND_mhd.f90:401-415 (bit-exact arithmetic) ----
-  auto cull = [&](int k) -> bool {
-    if (k == s) return false;                                   // j /= i (both-ghost pairs cannot occur: the target is real)
-    const double4 pj = ld4(G.posh + k);
-    const double rij2 = dist2_exact(xi - pj.x, yi - pj.y, zi - pj.z);
-    const double hj1 = 1. / pj.w;
-    const double q2i = __dmul_rn(rij2, hi21), q2j = __dmul_rn(rij2, __dmul_rn(hj1, hj1));
-    if (!((q2i < G.radkern2) || (q2j < G.radkern2))) return false;
-    if (pair_out_i) {                                           // parity-test hook: record the accepted pair
-      unsigned long long n = atomicAdd(pair_count, 1ull);
-      if ((long long)n < pair_cap) { pair_out_i[n] = orig + 1; pair_out_j[n] = G.perm[k] + 1; }
-    }
-    const int tj = __ldg(G.typ + k);
-    return types_interact(ti, tj) || (DRAG && O.idrag_nature > 0);   // :436-446
-  };
-
-  // ---- phase 2: pair terms ----
-  auto body = [&](int k) {
-    const double4 pj = ld4(G.posh + k);
-    const double4 vj = ld4(G.vm + k);
-    const double4 tj4 = ld4(I.thermo + k);
-    const int tj = __ldg(G.typ + k);
+  // ---- pair terms over the neighbour list (build_lists_kernel<LIST_RATES> applied src/ratesND_mhd.f90:401-415) ----
+  auto body = [&](int k, const double4 &pj, const double4 &vj, const double4 &tj4) {
+    const int tj = DRAG ? __ldg(G.typ + k) : 0;   // only the drag dispatch needs the neighbour's type on the fast path
     const double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
     const double rij2 = dist2_exact(dx, dy, dz);
-    const double hj = pj.w, hj1 = 1. / hj, hj21 = __dmul_rn(hj1, hj1);
+    const double hj1 = pj.w, hj21 = __dmul_rn(hj1, hj1);
     const double q2i = __dmul_rn(rij2, hi21), q2j = __dmul_rn(rij2, hj21);
-    const double rij = sqrt(rij2);
+    const double rinv = rij2 > 0. ? rsqrt(rij2) : 0.;           // rij = sqrt(rij2), dr = dx/rij (:416, :429)
+    const double rij = rij2 * rinv;
     double drx, dry, drz;
-    const double eps = 2.220446049250313e-16;
     if (rij <= eps) {                                           // :417-427 coincident particles
       drx = dry = drz = 0.;
-      if (tj == ti) {
+      if (__ldg(G.typ + k) == ti) {
         const int origj = G.perm[k];
-        if (origj >= G.npart || orig > origj) nclumped++;
+        if (origj >= G.nown || orig > origj) nclumped++;
         if (rij < 2.2250738585072014e-308 && ti != 2) atomicCAS(R.err, 0, 1 /*ND_ERR_INVALID_ARG: dx = 0*/);
       }
     } else {
-      const double r1 = 1. / rij;                               // dr = dx/rij, :429
-      drx = dx * r1; dry = dy * r1; drz = dz * r1;
+      drx = dx * rinv; dry = dy * rinv; drz = dz * rinv;
     }
     const double pmassj = vj.w;
     const double dvx = vxi - vj.x, dvy = vyi - vj.y, dvz = vzi - vj.z;
-    const double rhoj = tj4.x;
-    if (types_interact(ti, tj)) {
+    const double h1max = fmax(hi1, hj1);
+    if (!DRAG || types_interact(ti, tj)) {
       // =============================== rates_core ===============================
       const double4 gj = ld4(I.gal + k);
       double wabi, grkerni, wabj, grkernj;
@@ -148,7 +138,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, 2) rates_pair_kernel(Grid G, Rate
       interp_wg(G, q2j, wabj, grkernj);                         // :1217-1220
       grkernj = grkernj * hfacgrkernj;
       double grkern;
-      if (O.ikernav == 3) {                                     // :1227-1237
+      if (ikernav == 3) {                                       // :1227-1237
         grkerni = grkerni * gradhi;
         grkernj = grkernj * gj.x;
         grkern = 0.5 * (grkerni + grkernj);
@@ -157,9 +147,9 @@ __global__ void __launch_bounds__(RATES_BLOCK, 2) rates_pair_kernel(Grid G, Rate
         grkerni = grkern; grkernj = grkern;
       }
       const double dvdotr = (dvx * drx + dvy * dry) + dvz * drz;   // :1250
-      const double rho1j = 1. / rhoj, rho21j = rho1j * rho1j;      // :1256-1258
+      const double rho1j = tj4.x, rho21j = rho1j * rho1j;          // :1256-1258
       const double rhoav1 = 0.5 * (rho1i + rho1j);                 // :1261
-      const double prj = fmax(tj4.y - O.pext, 0.);                 // :1285
+      const double prj = tj4.y;                                    // :1285 (pext already subtracted)
       const double Prho2j = prj * rho21j;
       const double spsoundj = tj4.z, uuj = tj4.w;
       double Bxj = 0, Byj = 0, Bzj = 0, psij = 0, dBxx = 0, dByy = 0, dBzz = 0;
@@ -173,8 +163,8 @@ __global__ void __launch_bounds__(RATES_BLOCK, 2) rates_pair_kernel(Grid G, Rate
         projBi = (Bxi * drx + Byi * dry) + Bzi * drz;
         projBj = (Bxj * drx + Byj * dry) + Bzj * drz;
         projdB = (dBxx * drx + dByy * dry) + dBzz * drz;
-        projBrhoi = (Brhoxi * drx + Brhoyi * dry) + Brhozi * drz;
-        projBrhoj = (Brhoxj * drx + Brhoyj * dry) + Brhozj * drz;
+        projBrhoi = projBi * rho1i;                             // dot_product(Brhoi,dr)
+        projBrhoj = projBj * rho1j;
         const double B2j = (Bxj * Bxj + Byj * Byj) + Bzj * Bzj;
         valfven2j = B2j * rho1j;
         Brho2j = B2j * rho21j;
@@ -182,14 +172,13 @@ __global__ void __launch_bounds__(RATES_BLOCK, 2) rates_pair_kernel(Grid G, Rate
       // ---- signal velocities :1417-1465 ----
       double vsigi, vsigj, vsigB;
       if (MHD) {
-        const double vsig2i = spsoundi * spsoundi + valfven2i;
         const double vsig2j = spsoundj * spsoundj + valfven2j;
         const double vsigproji = vsig2i * vsig2i - 4. * ((spsoundi * projBi) * (spsoundi * projBi)) * rho1i;
         const double vsigprojj = vsig2j * vsig2j - 4. * ((spsoundj * projBj) * (spsoundj * projBj)) * rho1j;
         if (vsigproji < 0. || vsigprojj < 0.) atomicCAS(R.err, 0, 6 /*ND_ERR_VSIG_DET*/);
         vsigi = sqrt(0.5 * (vsig2i + sqrt(vsigproji)));
         vsigj = sqrt(0.5 * (vsig2j + sqrt(vsigprojj)));
-        if (O.iavlim2 != 2) vsigB = sqrt((dvx * dvx + dvy * dvy) + dvz * dvz);   // norm2(dvel), :1433
+        if (iavlim2 != 2) vsigB = sqrt((dvx * dvx + dvy * dvy) + dvz * dvz);   // norm2(dvel), :1433
         else vsigB = 0.5 * (vsigi + vsigj) + fabs(dvdotr);
       } else {
         vsigi = spsoundi; vsigj = spsoundj; vsigB = 0.;
@@ -198,20 +187,20 @@ __global__ void __launch_bounds__(RATES_BLOCK, 2) rates_pair_kernel(Grid G, Rate
       double vsigu = sqrt(fabs(pri - prj) * rhoav1);                            // :1459 (pequil = 0)
       const double vsigdtc = fmax(vsig, fmax(0.5 * (vsigi + vsigj + O.beta * fabs(dvdotr)), vsigB));   // :1465
       if (ti == T_DUST) { vsig = 0.; vsigu = 0.; }                              // :1472-1474
-      else {
-        const double dvsigdtc = 1. / vsigdtc;                                   // :1476-1481
+      else {                                                                    // :1476-1481
         vsigmax = fmax(vsigmax, vsigdtc);
-        if (vsigdtc > zero) dtcourant = fmin(dtcourant, fmin(hi * dvsigdtc, hj * dvsigdtc));
+        if (vsigdtc > zero) dtc_den = fmax(dtc_den, h1max * vsigdtc);
       }
       double fix = 0, fiy = 0, fiz = 0;   // forcei contribution of this pair
       double vsigav = 0.;
-      if (O.iav > 0 && O.iav != 3) {
+      if (iav > 0 && iav != 3) {
         // =============================== artificial_dissipation ===============================
         const double alphaav = 0.5 * (alphai + gj.y), alphau = 0.5 * (alphaui + gj.z), alphaB = 0.5 * (alphaBi + gj.w);   // :1712-1714
         vsigav = fmax(alphaav, fmax(alphau, alphaB)) * vsig;
-        const double term = vsig * rhoav1 * grkern;              // :1723
-        const double termu = vsigu * rhoav1 * grkern;            // :1727
-        const double termB = vsigB * rhoav1 * grkern;            // :1732
+        const double rg = rhoav1 * grkern;
+        const double term = vsig * rg;                           // :1723
+        const double termu = vsigu * rg;                         // :1727
+        const double termB = vsigB * rg;                         // :1732
         if (dvdotr < 0) {                                        // :1745-1748
           const double visc = alphaav * term * (-dvdotr);
           const double c = pmassj * visc;
@@ -219,36 +208,37 @@ __global__ void __launch_bounds__(RATES_BLOCK, 2) rates_pair_kernel(Grid G, Rate
         }
         if (MHD) {                                               // :1762-1774
           double bvx, bvy, bvz;
-          if (O.iav >= 2) { bvx = dBxx * rhoav1; bvy = dByy * rhoav1; bvz = dBzz * rhoav1; }
+          if (iav >= 2) { bvx = dBxx * rhoav1; bvy = dByy * rhoav1; bvz = dBzz * rhoav1; }
           else { bvx = (dBxx - drx * projdB) * rhoav1; bvy = (dByy - dry * projdB) * rhoav1; bvz = (dBzz - drz * projdB) * rhoav1; }
-          const double c = rhoi * pmassj, ab = alphaB * termB;
+          const double c = rhoi * pmassj, ab = alphaB * termB;   // dBevoldti + rhoi*pmassj*dBdtvisc, :1773
           dBx += c * (ab * bvx); dBy += c * (ab * bvy); dBz += c * (ab * bvz);
         }
-        if (O.iener == 3) {                                      // :1792-1830 total energy: pair part of dendt
+        if (iener == 3) {                                        // :1792-1830 total energy: pair part of dendt
           double qdiff = 0.;
           const double projvi = (vxi * drx + vyi * dry) + vzi * drz, projvj = (vj.x * drx + vj.y * dry) + vj.z * drz;
           if (dvdotr < 0) qdiff += term * alphaav * 0.5 * (projvi * projvi - projvj * projvj);
           qdiff += alphau * termu * (uui - uuj);
           if (MHD) {
             double B2i_, B2j_;
-            if (O.iav >= 2) { B2i_ = (Bxi * Bxi + Byi * Byi) + Bzi * Bzi; B2j_ = (Bxj * Bxj + Byj * Byj) + Bzj * Bzj; }
+            if (iav >= 2) { B2i_ = (Bxi * Bxi + Byi * Byi) + Bzi * Bzi; B2j_ = (Bxj * Bxj + Byj * Byj) + Bzj * Bzj; }
             else { B2i_ = ((Bxi * Bxi + Byi * Byi) + Bzi * Bzi) - projBi * projBi; B2j_ = ((Bxj * Bxj + Byj * Byj) + Bzj * Bzj) - projBj * projBj; }
             qdiff += alphaB * termB * 0.5 * (B2i_ - B2j_) * rhoav1;
           }
           endiss += pmassj * qdiff;                           // :1829
-        } else if (O.iener > 0) {                                // :1835-1875 thermal energy
+        } else if (iener > 0) {                                  // :1835-1875 thermal energy
           double vissv = 0., vissB = 0.;
           if (dvdotr < 0) { const double t = ((vxi * drx + vyi * dry) + vzi * drz) - ((vj.x * drx + vj.y * dry) + vj.z * drz); vissv = -alphaav * 0.5 * (t * t); }
           const double vissu = alphau * (uui - uuj);
           if (MHD) {
             const double dB2 = (dBxx * dBxx + dByy * dByy) + dBzz * dBzz;
-            if (O.iav >= 2) vissB = -alphaB * 0.5 * dB2 * rhoav1;
+            if (iav >= 2) vissB = -alphaB * 0.5 * dB2 * rhoav1;
             else vissB = -alphaB * 0.5 * (dB2 - projdB * projdB) * rhoav1;
           }
           dudt += pmassj * (term * vissv + termu * vissu + termB * vissB);
         }
-      } else if (O.iav == 3) {
+      } else if (iav == 3) {
         // =============================== artificial_dissipation_phantom ===============================
+        const double rhoj = __ldg(I.srho + k);
         double dudti = 0.;
         if (dvdotr < 0.) {
           const double vsi = fmax(alphai * spsoundi - O.beta * dvdotr, 0.);
@@ -264,7 +254,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, 2) rates_pair_kernel(Grid G, Rate
         const double diffu = cfaci * grkerni * (rho1i * rho1i) + cfacj * grkernj * (rho1j * rho1j);
         dudt += dudti + pmassj * diffu;
       }
-      if (vsigav > zero) dtav = fmin(dtav, fmin(hi / vsigav, hj / vsigav));     // :1500
+      if (vsigav > zero) dtav_den = fmax(dtav_den, h1max * vsigav);              // :1500
       {                                                          // pressure, :1538-1567 (phi = 1, sqrtg = 1)
         const double prterm = Prho2i * grkerni + Prho2j * grkernj;
         const double c = pmassj * prterm;
@@ -274,25 +264,25 @@ __global__ void __launch_bounds__(RATES_BLOCK, 2) rates_pair_kernel(Grid G, Rate
         // =============================== mhd_terms ===============================
         const double fiso = 0.5 * (Brho2i * grkerni + Brho2j * grkernj);        // :2526
         const double sm = O.stressmax;
-        const double fax = (Brhoxi * projBrhoi - sm * drx * rho21i) * grkerni + (Brhoxj * projBrhoj - sm * drx * rho21j) * grkernj;   // :2534-2537
-        const double fay = (Brhoyi * projBrhoi - sm * dry * rho21i) * grkerni + (Brhoyj * projBrhoj - sm * dry * rho21j) * grkernj;
-        const double faz = (Brhozi * projBrhoi - sm * drz * rho21i) * grkerni + (Brhozj * projBrhoj - sm * drz * rho21j) * grkernj;
-        fix += pmassj * (fax - fiso * drx);                      // :2541, :2629
-        fiy += pmassj * (fay - fiso * dry);
-        fiz += pmassj * (faz - fiso * drz);
-        divB -= pmassj * projdB * grkern;                        // :2552
-        const double mg = pmassj * grkern;                       // :2601-2602 curlB += pmassj*(dB x dr)*grkern
-        cBx += (dByy * drz - dBzz * dry) * mg;
+        // faniso = (Brho_i (Brho_i.dr) - stressmax dr/rho_i^2) grkern_i + (same for j), :2534-2537; the force is faniso - fiso dr
+        const double ai = projBrhoi * grkerni, aj = projBrhoj * grkernj;
+        const double sdr = sm * (rho21i * grkerni + rho21j * grkernj) + fiso;
+        fix += pmassj * ((Brhoxi * ai + Brhoxj * aj) - sdr * drx);               // :2541, :2629
+        fiy += pmassj * ((Brhoyi * ai + Brhoyj * aj) - sdr * dry);
+        fiz += pmassj * ((Brhozi * ai + Brhozj * aj) - sdr * drz);
+        const double mg = pmassj * grkern;
+        divB -= mg * projdB;                                     // :2552
+        cBx += (dByy * drz - dBzz * dry) * mg;                   // :2601-2602 curlB += pmassj*(dB x dr)*grkern
         cBy += (dBzz * drx - dBxx * drz) * mg;
         cBz += (dBxx * dry - dByy * drx) * mg;
         const double ci = pmassj * projBrhoi * grkerni;          // :2664-2665 induction (imhd = 1, 11)
         dBx -= dvx * ci; dBy -= dvy * ci; dBz -= dvz * ci;
-        if (O.iresist == 1) {                                    // :2685-2709
+        if (iresist == 1) {                                      // :2685-2709
           const double etaij = O.etamhd;                         // 0.5*(etai + etaj) with constant eta
           const double f = -2. * etaij / (rij + eps);
           const double c = rhoi * pmassj * 0.5 * ((rho1i * rho1i) * grkerni + (rho1j * rho1j) * grkernj);
           dBx -= c * (f * dBxx); dBy -= c * (f * dByy); dBz -= c * (f * dBzz);
-          if (O.iener > 0) dudt += pmassj * (-etaij * rho1i * rho1j * ((dBxx * dBxx + dByy * dByy) + dBzz * dBzz) * grkern / rij);
+          if (iener > 0) dudt += pmassj * (-etaij * rho1i * rho1j * ((dBxx * dBxx + dByy * dByy) + dBzz * dBzz) * grkern / rij);
         }
         if (O.idivbzero >= 2) {                                  // :2712-2716
           const double gradpsiterm = psii * rho21i * grkerni + psij * rho21j * grkernj;
@@ -301,18 +291,19 @@ __global__ void __launch_bounds__(RATES_BLOCK, 2) rates_pair_kernel(Grid G, Rate
         }
       }
       fx += fix; fy += fiy; fz += fiz;
-      if (O.iav > 0) {                                           // :1639-1656 switch sources
-        if (O.iavlim1 > 0) del2u += pmassj * rho1j * ((uui - uuj) / rij) * grkerni;
-        if (O.iavlim0 == 3) {
-          const double c = pmassj * rho1j / rij * dvdotr * grkerni;
+      if (iav > 0) {                                             // :1639-1656 switch sources
+        if (iavlim1 > 0) del2u += pmassj * rho1j * ((uui - uuj) * rinv) * grkerni;
+        if (iavlim0 == 3) {
+          const double c = pmassj * rho1j * rinv * dvdotr * grkerni;
           gvx += c * drx; gvy += c * dry; gvz += c * drz;
-        } else {
+        } else if (!FAST) {                                      // graddivv is only read back by the iavlim(1)=3 switch
           const double c = pmassj * grkerni;
           gvx += c * (dvx - dvdotr); gvy += c * (dvy - dvdotr); gvz += c * (dvz - dvdotr);
         }
       }
     } else if (DRAG) {
       // =============================== drag_forces ===============================
+      const double rhoj = __ldg(I.srho + k);
       const double dv2 = (dvx * dvx + dvy * dvy) + dvz * dvz;
       double ddx = drx, ddy = dry, ddz = drz;
       bool skip = false;
@@ -323,10 +314,10 @@ __global__ void __launch_bounds__(RATES_BLOCK, 2) rates_pair_kernel(Grid G, Rate
       const bool igas = (ti == T_GAS || ti == T_BND), jgas = (tj == T_GAS || tj == T_BND);
       if (!skip && (igas || jgas)) {                             // :1133-1144: kernel and sound speed of the gas particle
         const double projv = (dvx * ddx + dvy * ddy) + dvz * ddz;
-        double wab, spsoundgas, ts, hgas;
-        if (igas) { wab = interp_drag(G, q2i) * hfacwabi; spsoundgas = spsoundi; ts = get_tstop(O.idrag_nature, rhoi, rhoj, O.Kdrag); hgas = hi; }
-        else { wab = interp_drag(G, q2j) * powndim<NDIM>(hj1); spsoundgas = tj4.z; ts = get_tstop(O.idrag_nature, rhoj, rhoi, O.Kdrag); hgas = hj; }
-        h_on_csts_max = fmax(h_on_csts_max, hgas / (spsoundgas * ts));
+        double wab, spsoundgas, ts, hgas1;
+        if (igas) { wab = interp_drag(G, q2i) * hfacwabi; spsoundgas = spsoundi; ts = get_tstop(O.idrag_nature, rhoi, rhoj, O.Kdrag); hgas1 = hi1; }
+        else { wab = interp_drag(G, q2j) * powndim<NDIM>(hj1); spsoundgas = tj4.z; ts = get_tstop(O.idrag_nature, rhoj, rhoi, O.Kdrag); hgas1 = hj1; }
+        h_on_csts_max = fmax(h_on_csts_max, 1. / (hgas1 * (spsoundgas * ts)));
         ts_min = fmin(ts_min, ts);
         const double dragterm = NDIM * wab / ((rhoi + rhoj) * ts) * projv;   // :1156 (projvstar = projv)
         const double c = dragterm * pmassj;
@@ -336,7 +327,22 @@ __global__ void __launch_bounds__(RATES_BLOCK, 2) rates_pair_kernel(Grid G, Rate
     }
   };
 
-  neighbour_walk<NDIM, RATES_CAP, RATES_BLOCK>(G, active, celli, nlist_smem, cull, body);
+  if (cnt > 0) {
+    // The list column is read ND_RATES_PFD entries ahead (one coalesced 128-byte line per entry and warp) and the records of the
+    // neighbour two pairs ahead are pulled into L1 with register-free prefetches, so the pair body's own loads hit L1.
+    const unsigned *col = L.nbr + ((size_t)(tix >> 5) * L.lmax) * 32 + (tix & 31);
+    const int last = cnt - 1;
+    int k0 = (int)col[0], k1 = (int)col[(size_t)min(1, last) * 32], k2 = (int)col[(size_t)min(2, last) * 32], k3 = (int)col[(size_t)min(3, last) * 32];
+#pragma unroll 1
+    for (int n = 0; n < cnt; n++) {
+      const int k4 = (int)col[(size_t)min(n + 4, last) * 32];
+      prefetch_l1(G.posh + k2); prefetch_l1(G.vm + k2); prefetch_l1(I.thermo + k2); prefetch_l1(I.gal + k2);
+      if (MHD) prefetch_l1(I.bpsi + k2);
+      const double4 pj = ld4(G.posh + k0), vj = ld4(G.vm + k0), tj4 = ld4(I.thermo + k0);
+      body(k0, pj, vj, tj4);
+      k0 = k1; k1 = k2; k2 = k3; k3 = k4;
+    }
+  }
 
   if (active) {
     S.F[s] = make_double4(fx, fy, fz, dudt);
@@ -346,6 +352,8 @@ __global__ void __launch_bounds__(RATES_BLOCK, 2) rates_pair_kernel(Grid G, Rate
     S.V[s] = make_double4(gvx, gvy, gvz, 0.);
   }
   // block-free warp reductions into global min/max keys
+  double dtcourant = dtc_den > 0. ? fmin(1.e6, 1. / dtc_den) : 1.e6;            // initial value 1.e6, :251
+  double dtav = dtav_den > 0. ? 1. / dtav_den : 1.7976931348623157e308;
   dtcourant = warp_min(dtcourant); vsigmax = warp_max(vsigmax); dtav = warp_min(dtav);
   int ncl = nclumped;
   for (int o = 16; o; o >>= 1) ncl += __shfl_xor_sync(FULL, ncl, o);

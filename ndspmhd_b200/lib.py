@@ -18,7 +18,8 @@ from . import abi
 from .abi import NdArrays, NdOptions, NdScalars, Particles
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libndspmhd_b200.so")
+# NDSPMHD_B200_LIB: development override used by tools/ to time differently tuned builds of the same sources
+LIB_PATH = os.environ.get("NDSPMHD_B200_LIB") or os.path.join(_HERE, "libndspmhd_b200.so")
 _LIB = None
 
 _DP = C.POINTER(C.c_double)
@@ -115,7 +116,10 @@ def free_pinned(p: Particles) -> None:
 def arrays_struct(p: Particles) -> NdArrays:
     """Hand over the module arrays exactly as an ISO_C_BINDING shim would."""
     a = NdArrays()
-    a.x, a.vel, a.pmass, a.hh_in = p.ptr("x"), p.ptr("vel"), p.ptr("pmass"), p.ptr("hh")
+    a.x, a.vel, a.pmass = p.ptr("x"), p.ptr("vel"), p.ptr("pmass")
+    # the reference iterates hh in place; a caller that wants to keep its guess (bench.py repeats the same step) may park it
+    # in a separate `hh_guess` array
+    a.hh_in = p.ptr("hh_guess") if "hh_guess" in p.arrays else p.ptr("hh")
     a.itype, a.ireal = p.ptr("itype"), p.ptr("ireal")
     a.en, a.Bevol, a.alpha, a.psi, a.rho_in = p.ptr("en"), p.ptr("Bevol"), p.ptr("alpha"), p.ptr("psi"), p.ptr("rho")
     for n in ("hh", "rho", "gradh", "drhodt", "dhdt", "numneigh", "rhoalt", "gradhn", "gradsoft", "gradgradh", "dens", "uu", "pr",

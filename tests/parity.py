@@ -86,6 +86,9 @@ def assert_parity(pg, po, sg, so, opts, aux=True, rtol=RTOL, check_rates=True):
     fields = DENSITY_FIELDS + (AUX_FIELDS if aux else []) + PRIM_FIELDS
     if check_rates:
         fields = fields + RATES_FIELDS
+    if not aux and opts.iavlim[0] != 3:
+        # want_aux=0 skips the dead "curl v" sums the reference leaves in graddivv (src/ratesND_mhd.f90:1653-1654)
+        fields = [f for f in fields if f != "graddivv"]
     if opts.imhd == 0:
         fields = [f for f in fields if f not in ("Bfield", "dBevoldt", "gradpsi", "divB", "curlB", "dpsidt")]
     errs = compare(pg, po, sg, so, fields)

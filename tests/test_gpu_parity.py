@@ -24,6 +24,11 @@ CASES = {
     "ot2d_closepacked": (lambda: setups.orszag_tang(ndim=2, nx=64, lattice="cp", perturb_amp=0.2, evolved=True), 1),
     "hydro3d": (lambda: setups.hydro_box(ndim=3, nx=16, perturb_amp=0.2), 1),
     "hydro3d_noaux": (lambda: setups.hydro_box(ndim=3, nx=16, perturb_amp=0.2), 0),
+    # want_aux=0 runs the FAST instantiation of the rates kernel (first-class option tuple, no run-time option tests)
+    "ot3d_glass_noaux": (lambda: setups.orszag_tang(ndim=3, nx=16, zfrac=0.5, perturb_amp=0.2, evolved=True), 0),
+    "ot3d_isothermal_noaux": (lambda: setups.orszag_tang(ndim=3, nx=16, zfrac=0.5, perturb_amp=0.2, evolved=True, iener=0), 0),
+    "ot2d_closepacked_noaux": (lambda: setups.orszag_tang(ndim=2, nx=64, lattice="cp", perturb_amp=0.2, evolved=True), 0),
+    "briowu1d_noaux": (lambda: setups.shock1d(nright=60), 0),
     "hydro2d": (lambda: setups.hydro_box(ndim=2, nx=48, perturb_amp=0.3), 1),
     # configs[0]: 1D Brio-Wu / Sod shock tubes with fixed end particles
     "briowu1d": (lambda: setups.shock1d(nright=60), 1),
