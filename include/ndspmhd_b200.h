@@ -51,6 +51,7 @@ enum {
   ND_ERR_LINK = 9,               /* linkND.f90:73-76, :94-99, :122-125 */
   ND_ERR_NEIGHBOUR_OVERFLOW = 10,
   ND_ERR_STATE = 11,             /* calls out of order (e.g. get_rates before upload) */
+  ND_ERR_COMM = 12,              /* a transport callback failed, or another rank reported an error */
   ND_NEED_RELINK = 100           /* not an error: host-ghost mode, h grew past hhmax (iterate_density.f90:122-126, :260-262);
                                     caller must re-run set_ghost_particles, upload again and call iterate_density(resume=1) */
 };
@@ -217,6 +218,37 @@ int ndspmhd_b200_derivs(nd_ctx *c, nd_scalars *s);
 
 /* device -> host, rows [0,ntotal) of the arrays selected by `mask` (NULL pointers skipped) */
 int ndspmhd_b200_download(nd_ctx *c, nd_arrays *a, unsigned mask, int idim);
+
+/*
+ * Multi-GPU: 1-D slab decomposition along x, one context (one rank) per GPU.  The reference is serial; this is the
+ * device-side equivalent of its periodic ghosts (src/ghostND_mhd.f90:166-346) applied at slab faces: every rank keeps
+ * the particles with slab_lo <= x(1) < slab_hi, and the library appends HALO rows -- copies of the neighbours'
+ * particles within radkern*hhmax of the face, shifted with the reference's ghost arithmetic across the periodic wrap --
+ * before it makes the y/z ghosts locally.  The library owns selection, packing, row layout and the order of
+ * operations; the host supplies the transport as callbacks (torch.distributed/NCCL in ndspmhd_b200/slab.py; MPI from a
+ * Fortran host).  Per derivs: one all-reduce of hhmax, one halo exchange of the inputs (x, vel, pmass, hh, en, Bevol,
+ * alpha, psi, rho, itype), one small all-reduce per density round (unconverged count, relink flag), one halo exchange of
+ * (hh, rho, gradh) after the iteration, all-reduces of stressmax, vsigmax and the timestep scalars.
+ * Requires device_ghosts = 1 and ibound(1) in {0, 1, 3}.  With nranks = 1 the callbacks are never used.
+ */
+typedef struct nd_comm {
+  void *user;                   /* passed back to every callback */
+  int rank, nranks;
+  double slab_lo, slab_hi;      /* this rank's x interval */
+  long long nglobal;            /* real particles over all ranks (decides `density` vs `density_partial`, iterate_density.f90:131) */
+  /* in-place all-reduce of n HOST doubles; op 0 = max, 1 = min, 2 = sum */
+  int (*allreduce)(void *user, double *v, int n, int op);
+  /* byte counts handshake with the two x-neighbours: side 0 = rank-1, side 1 = rank+1 (periodic ring) */
+  int (*sendrecv_counts)(void *user, const long long sendbytes[2], long long recvbytes[2]);
+  /* payload: DEVICE buffers; sendbuf[s] -> neighbour s, recvbuf[s] <- neighbour s; ordered after/before work on `stream` */
+  int (*sendrecv)(void *user, void *const sendbuf[2], const long long sendbytes[2], void *const recvbuf[2],
+                  const long long recvbytes[2], void *stream);
+} nd_comm;
+
+/* attach (or detach with NULL) the transport; call before upload.  upload then takes only this rank's own rows. */
+int ndspmhd_b200_set_comm(nd_ctx *c, const nd_comm *comm);
+/* rows after the last link: own rows [0,nown), halo rows [nown,nsrc), ghosts [nsrc,ntotal) */
+int ndspmhd_b200_row_counts(const nd_ctx *c, int *nown, int *nsrc, int *ntotal);
 
 /* page-locked host memory for the caller's particle arrays (makes upload/download run at PCIe speed) */
 void *ndspmhd_b200_host_alloc(size_t bytes);

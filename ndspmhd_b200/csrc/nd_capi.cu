@@ -61,8 +61,12 @@ struct nd_ctx {
   int *flags = nullptr;                // [16]
   unsigned long long *h_red = nullptr; int *h_flags = nullptr; double *h_fmean = nullptr;   // pinned mirrors
   // ---- iterate_density state (kept across ND_NEED_RELINK) ----
-  int itsdensity = 0, ncalc = 0, nrelink = 0; long long ncalctotal = 0; bool redolink = false;
+  int itsdensity = 0, ncalc = 0, nrelink = 0; long long ncalctotal = 0, ncalc_g = 0; bool redolink = false;
   nd_scalars sc;
+  // ---- slab decomposition (nd_comm): halo send lists and staging buffers ----
+  nd_comm comm; bool has_comm = false;
+  int *sendlist[2] = {nullptr, nullptr}; int sendcap[2] = {0, 0}, nsend[2] = {0, 0}, nrecv[2] = {0, 0};
+  void *sendbuf[2] = {nullptr, nullptr}, *recvbuf[2] = {nullptr, nullptr}; size_t sendbufcap[2] = {0, 0}, recvbufcap[2] = {0, 0};
   cudaEvent_t ev[8];
   double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -254,6 +258,86 @@ template <int NDIM, bool WRITE> __global__ void k_ghosts(GhostArgs A) {
     }
   }
   if (!WRITE) A.count[j] = n;
+}
+
+// =====================================================================================================
+// slab halos (multi-GPU): selection, packing, unpacking.  A halo row is the copy of a neighbour rank's particle that lies
+// within radkern*hhmax of the shared slab face; across the periodic wrap its x is shifted with the reference's ghost
+// arithmetic, xperbound + (x - xbound) (src/ghostND_mhd.f90:212-225), so pair geometry is bitwise that of a single-GPU run.
+// =====================================================================================================
+struct HaloSelArgs { const double *x; int nown, ndim; double lo, hi, reach, tol; int left_on, right_on; int *flagL, *flagR, *err; };
+__global__ void k_halo_flags(HaloSelArgs A) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= A.nown) return;
+  const double xj = A.x[(size_t)j * A.ndim];
+  if (xj < A.lo - A.tol || xj > A.hi + A.tol) atomicCAS(A.err, 0, ND_ERR_INVALID_ARG);   // outside its slab: the caller must repartition
+  A.flagL[j] = (A.left_on && xj < A.lo + A.reach) ? 1 : 0;
+  A.flagR[j] = (A.right_on && xj > A.hi - A.reach) ? 1 : 0;
+}
+__global__ void k_halo_compact(const int *flag, const int *scan, int n, int *list) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n && flag[j]) list[scan[j]] = j;
+}
+// exchange 1 (inputs): [x(ndim) vel(3) pmass hh en Bevol(3) alpha(3) psi rho] as doubles, field-major, then itype as ints
+struct HaloPackArgs {
+  const int *list; int n, ndim;
+  double *x, *vel, *pmass, *hh, *en, *Bevol, *alpha, *psi, *rho, *gradh; int *itype;
+  double *buf; int row0;        // pack: buf out; unpack: rows [row0, row0+n) in
+  int shift; double xbound, xperbound;   // periodic wrap: x' = xperbound + (x - xbound)
+};
+__device__ __forceinline__ int halo1_nfields(int ndim) { return ndim + 14; }
+__global__ void k_halo_pack1(HaloPackArgs A) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= A.n) return;
+  const int j = A.list[q];
+  const size_t n = A.n;
+  int f = 0;
+  for (int d = 0; d < A.ndim; d++) {
+    double v = A.x[(size_t)j * A.ndim + d];
+    if (d == 0 && A.shift) v = __dadd_rn(A.xperbound, __dsub_rn(v, A.xbound));
+    A.buf[(f++) * n + q] = v;
+  }
+  for (int d = 0; d < 3; d++) A.buf[(f++) * n + q] = A.vel[(size_t)j * 3 + d];
+  A.buf[(f++) * n + q] = A.pmass[j];
+  A.buf[(f++) * n + q] = A.hh[j];
+  A.buf[(f++) * n + q] = A.en[j];
+  for (int d = 0; d < 3; d++) A.buf[(f++) * n + q] = A.Bevol[(size_t)j * 3 + d];
+  for (int d = 0; d < 3; d++) A.buf[(f++) * n + q] = A.alpha[(size_t)j * 3 + d];
+  A.buf[(f++) * n + q] = A.psi[j];
+  A.buf[(f++) * n + q] = A.rho[j];
+  reinterpret_cast<int *>(A.buf + (size_t)f * n)[q] = A.itype[j];
+}
+__global__ void k_halo_unpack1(HaloPackArgs A) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= A.n) return;
+  const int r = A.row0 + q;
+  const size_t n = A.n;
+  int f = 0;
+  for (int d = 0; d < A.ndim; d++) A.x[(size_t)r * A.ndim + d] = A.buf[(f++) * n + q];
+  for (int d = 0; d < 3; d++) A.vel[(size_t)r * 3 + d] = A.buf[(f++) * n + q];
+  A.pmass[r] = A.buf[(f++) * n + q];
+  A.hh[r] = A.buf[(f++) * n + q];
+  A.en[r] = A.buf[(f++) * n + q];
+  for (int d = 0; d < 3; d++) A.Bevol[(size_t)r * 3 + d] = A.buf[(f++) * n + q];
+  for (int d = 0; d < 3; d++) A.alpha[(size_t)r * 3 + d] = A.buf[(f++) * n + q];
+  A.psi[r] = A.buf[(f++) * n + q];
+  A.rho[r] = A.buf[(f++) * n + q];
+  A.itype[r] = reinterpret_cast<const int *>(A.buf + (size_t)f * n)[q];
+}
+// exchange 2 (after the density iteration): hh, rho, gradh
+__global__ void k_halo_pack2(HaloPackArgs A) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= A.n) return;
+  const int j = A.list[q];
+  const size_t n = A.n;
+  A.buf[q] = A.hh[j]; A.buf[n + q] = A.rho[j]; A.buf[2 * n + q] = A.gradh[j];
+}
+__global__ void k_halo_unpack2(HaloPackArgs A) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= A.n) return;
+  const int r = A.row0 + q;
+  const size_t n = A.n;
+  A.hh[r] = A.buf[q]; A.rho[r] = A.buf[n + q]; A.gradh[r] = A.buf[2 * n + q];
 }
 
 // =====================================================================================================
@@ -656,8 +740,17 @@ Grid make_grid(nd_ctx *c) {
 }
 
 void fill_link_scalars(nd_ctx *c);
-bool any_ghost_bound(const nd_ctx *c) { for (int d = 0; d < c->ndim; d++) if (c->o.ibound[d] >= 2) return true; return false; }
+// with slabs the x faces are halo faces: no ghosts are made in x on any rank
+int local_ibound(const nd_ctx *c, int d) { return (c->has_comm && d == 0 && c->o.ibound[0] >= 2) ? 0 : c->o.ibound[d]; }
+bool any_ghost_bound(const nd_ctx *c) { for (int d = 0; d < c->ndim; d++) if (local_ibound(c, d) >= 2) return true; return false; }
 bool any_fixed_bound(const nd_ctx *c) { for (int d = 0; d < c->ndim; d++) if (c->o.ibound[d] == 1) return true; return false; }
+bool has_copies(const nd_ctx *c) { return any_ghost_bound(c) || c->has_comm; }
+
+int comm_allreduce(nd_ctx *c, double *v, int n, int op) {
+  if (!c->has_comm) return 0;
+  if (c->comm.allreduce(c->comm.user, v, n, op)) return set_err(c, ND_ERR_COMM, "allreduce callback failed");
+  return 0;
+}
 
 int sync_flags(nd_ctx *c) {   // D2H of the flag block; returns a pending device-side error code
   CU(cudaMemcpyAsync(c->h_flags, c->flags, sizeof(int) * 16, cudaMemcpyDeviceToHost, c->stream));
@@ -665,21 +758,127 @@ int sync_flags(nd_ctx *c) {   // D2H of the flag block; returns a pending device
   return 0;
 }
 
-// ---- ghosts (device_ghosts=1) ----
-template <int NDIM> int make_ghosts(nd_ctx *c) {
-  const int np = c->npart;
-  // hhmax = maxval(hh(1:npart)), ghostND_mhd.f90:79
+// ---- hhmax = maxval(hh(1:npart)), ghostND_mhd.f90:79 (over all ranks with slabs) ----
+int compute_hhmax(nd_ctx *c) {
   CU(cudaMemsetAsync(c->red, 0, sizeof(unsigned long long) * 16, c->stream));
-  LAUNCH(c, k_max_h, std::min(nblocks(np, 256), 1184), 256, 0, c->hh, np, c->red);
+  LAUNCH(c, k_max_h, std::min(nblocks(c->nown, 256), 1184), 256, 0, c->hh, c->nown, c->red);
   CU(cudaMemcpyAsync(c->h_red, c->red, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  c->hhmax = dkey_inv(c->h_red[0]);
+  double m = c->nown > 0 ? dkey_inv(c->h_red[0]) : 0.;
+  if (int e = comm_allreduce(c, &m, 1, 0)) return e;
+  c->hhmax = m;
+  return 0;
+}
+
+template <class T> int grow_buf(nd_ctx *c, T **p, size_t *cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*p) { CU(cudaStreamSynchronize(c->stream)); cudaFree(*p); *p = nullptr; *cap = 0; }
+  const size_t n = need + need / 4 + 1024;
+  CU(cudaMalloc((void **)p, n * sizeof(T)));
+  *cap = n;
+  return 0;
+}
+
+int halo_sendrecv(nd_ctx *c, const long long sb[2], const long long rb[2]) {
+  void *const sbuf[2] = {c->sendbuf[0], c->sendbuf[1]};
+  void *const rbuf[2] = {c->recvbuf[0], c->recvbuf[1]};
+  if (c->comm.sendrecv(c->comm.user, sbuf, sb, rbuf, rb, (void *)c->stream)) return set_err(c, ND_ERR_COMM, "sendrecv callback failed");
+  return 0;
+}
+
+HaloPackArgs halo_args(nd_ctx *c) {
+  HaloPackArgs A;
+  A.ndim = c->ndim; A.x = c->x; A.vel = c->vel; A.pmass = c->pmass; A.hh = c->hh; A.en = c->en; A.Bevol = c->Bevol; A.alpha = c->alpha; A.psi = c->psi;
+  A.rho = c->rho; A.gradh = c->gradh; A.itype = c->itype; A.shift = 0; A.xbound = A.xperbound = 0.; A.row0 = 0; A.list = nullptr; A.n = 0; A.buf = nullptr;
+  return A;
+}
+
+// ---- halo exchange 1: select the rows within reach of the slab faces, ship the inputs, append them as rows [nown, npart) ----
+int halo_exchange_inputs(nd_ctx *c) {
+  const nd_options &o = c->o;
+  const int np = c->nown, rank = c->comm.rank, nr = c->comm.nranks;
+  const bool periodic = (o.ibound[0] == 3);
+  HaloSelArgs SA;
+  SA.x = c->x; SA.nown = np; SA.ndim = c->ndim; SA.lo = c->comm.slab_lo; SA.hi = c->comm.slab_hi;
+  SA.reach = c->T->radkern * c->hhmax * (1.0 + 1.e-10);
+  SA.tol = 1.e-9 * std::max(1.0, std::fabs(SA.hi - SA.lo));
+  SA.left_on = (periodic || rank > 0) ? 1 : 0; SA.right_on = (periodic || rank < nr - 1) ? 1 : 0;
+  SA.flagL = c->cellOfOrig; SA.flagR = c->ghostcount; SA.err = c->flags + 1;   // scratch: both are rewritten later in this link
+  LAUNCH(c, k_halo_flags, nblocks(np, 256), 256, 0, SA);
+  for (int side = 0; side < 2; side++) {
+    const int *flag = side == 0 ? c->cellOfOrig : c->ghostcount;
+    if (int e = exclusive_scan(c, flag, c->scanout, np)) return e;
+    int n = 0;
+    CU(cudaMemcpyAsync(&n, c->scanout + np, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    size_t cap = (size_t)c->sendcap[side];
+    if (int e = grow_buf(c, &c->sendlist[side], &cap, (size_t)n)) return e;
+    c->sendcap[side] = (int)cap;
+    LAUNCH(c, k_halo_compact, nblocks(np, 256), 256, 0, flag, c->scanout, np, c->sendlist[side]);
+    c->nsend[side] = n;
+  }
+  const long long rec = 8LL * (c->ndim + 14) + 4;
+  long long sb[2] = {c->nsend[0] * rec, c->nsend[1] * rec}, rb[2] = {0, 0};
+  if (c->comm.sendrecv_counts(c->comm.user, sb, rb)) return set_err(c, ND_ERR_COMM, "sendrecv_counts callback failed");
+  if (rb[0] % rec || rb[1] % rec) return set_err(c, ND_ERR_COMM, "halo record size mismatch between ranks");
+  c->nrecv[0] = (int)(rb[0] / rec); c->nrecv[1] = (int)(rb[1] / rec);
+  for (int side = 0; side < 2; side++) {
+    char **sp = (char **)&c->sendbuf[side], **rp = (char **)&c->recvbuf[side];
+    if (int e = grow_buf(c, sp, &c->sendbufcap[side], (size_t)sb[side] + 64)) return e;
+    if (int e = grow_buf(c, rp, &c->recvbufcap[side], (size_t)rb[side] + 64)) return e;
+  }
+  const int nsrc = np + c->nrecv[0] + c->nrecv[1];
+  if (int e = ensure_capacity(c, nsrc + nsrc / 4 + 1024, np)) return e;
+  for (int side = 0; side < 2; side++) {
+    HaloPackArgs A = halo_args(c);
+    A.list = c->sendlist[side]; A.n = c->nsend[side]; A.buf = (double *)c->sendbuf[side];
+    if (periodic && side == 0 && rank == 0) { A.shift = 1; A.xbound = o.xmin[0]; A.xperbound = o.xmax[0]; }          // ghostND_mhd.f90:212-225, xmin face
+    if (periodic && side == 1 && rank == nr - 1) { A.shift = 1; A.xbound = o.xmax[0]; A.xperbound = o.xmin[0]; }     // xmax face
+    LAUNCH(c, k_halo_pack1, nblocks(A.n, 256), 256, 0, A);
+  }
+  if (int e = halo_sendrecv(c, sb, rb)) return e;
+  int row0 = np;
+  for (int side = 0; side < 2; side++) {
+    HaloPackArgs A = halo_args(c);
+    A.n = c->nrecv[side]; A.buf = (double *)c->recvbuf[side]; A.row0 = row0;
+    LAUNCH(c, k_halo_unpack1, nblocks(A.n, 256), 256, 0, A);
+    row0 += A.n;
+  }
+  c->npart = nsrc;
+  return 0;
+}
+
+// ---- halo exchange 2: the owners' converged hh, rho, gradh for the halo rows (the rates test needs h_j: ratesND_mhd.f90:404-415) ----
+int halo_exchange_density(nd_ctx *c) {
+  long long sb[2] = {c->nsend[0] * 24LL, c->nsend[1] * 24LL}, rb[2] = {c->nrecv[0] * 24LL, c->nrecv[1] * 24LL};
+  for (int side = 0; side < 2; side++) {
+    HaloPackArgs A = halo_args(c);
+    A.list = c->sendlist[side]; A.n = c->nsend[side]; A.buf = (double *)c->sendbuf[side];
+    LAUNCH(c, k_halo_pack2, nblocks(A.n, 256), 256, 0, A);
+  }
+  if (int e = halo_sendrecv(c, sb, rb)) return e;
+  int row0 = c->nown;
+  for (int side = 0; side < 2; side++) {
+    HaloPackArgs A = halo_args(c);
+    A.n = c->nrecv[side]; A.buf = (double *)c->recvbuf[side]; A.row0 = row0;
+    LAUNCH(c, k_halo_unpack2, nblocks(A.n, 256), 256, 0, A);
+    row0 += A.n;
+  }
+  return 0;
+}
+
+// ---- ghosts (device_ghosts=1): rows [npart, ntotal) from rows [0, npart) ----
+template <int NDIM> int make_ghosts(nd_ctx *c) {
+  if (int e = compute_hhmax(c)) return e;
+  c->npart = c->nown;
+  if (c->has_comm) { if (int e = halo_exchange_inputs(c)) return e; }
+  const int np = c->npart;
   c->ntotal = np;
   if (!any_ghost_bound(c)) return 0;
   GhostArgs A;
   A.x = c->x; A.vel = c->vel; A.hh = c->hh; A.itype = c->itype; A.ireal = c->ireal; A.offset = c->scanout; A.count = c->ghostcount;
   A.npart = np; A.cap = c->cap; A.radkern = c->T->radkern; A.hhmax = c->hhmax; A.flags = c->flags;
-  for (int d = 0; d < 3; d++) { A.ibound[d] = d < NDIM ? c->o.ibound[d] : 0; A.xmin[d] = c->o.xmin[d]; A.xmax[d] = c->o.xmax[d]; }
+  for (int d = 0; d < 3; d++) { A.ibound[d] = d < NDIM ? local_ibound(c, d) : 0; A.xmin[d] = c->o.xmin[d]; A.xmax[d] = c->o.xmax[d]; }
   LAUNCH(c, (k_ghosts<NDIM, false>), nblocks(np, 256), 256, 0, A);
   if (int e = exclusive_scan(c, c->ghostcount, c->scanout, np)) return e;
   int nghost = 0;
@@ -699,7 +898,7 @@ template <int NDIM> int make_ghosts(nd_ctx *c) {
 template <int NDIM> int build_cells(nd_ctx *c) {
   const int nt = c->ntotal;
   const nd_options &o = c->o;
-  if (!any_ghost_bound(c) || !o.device_ghosts) {
+  if (!o.device_ghosts) {
     bool allle1 = !any_ghost_bound(c);
     if (allle1) {                                                                   // :70
       CU(cudaMemsetAsync(c->red, 0, sizeof(unsigned long long) * 16, c->stream));
@@ -758,7 +957,13 @@ template <int NDIM> int do_link(nd_ctx *c) {
   if (c->o.device_ghosts) { if (int e = make_ghosts<NDIM>(c)) return e; }
   if (int e = build_cells<NDIM>(c)) return e;
   if (int e = sync_flags(c)) return e;
-  if (c->h_flags[1]) { int code = c->h_flags[1]; CU(cudaMemsetAsync(c->flags, 0, sizeof(int) * 16, c->stream)); return set_err(c, code, "link: particle crossed boundary"); }
+  double ef = c->h_flags[1];
+  if (int e = comm_allreduce(c, &ef, 1, 0)) return e;   // every rank leaves together
+  if (ef != 0.) {
+    int code = c->h_flags[1] ? c->h_flags[1] : ND_ERR_COMM;
+    CU(cudaMemsetAsync(c->flags, 0, sizeof(int) * 16, c->stream));
+    return set_err(c, code, c->h_flags[1] ? "link: particle outside the boundary / its slab" : "link: another rank reported an error");
+  }
   c->linked = true;
   return 0;
 }
@@ -824,27 +1029,28 @@ template <int NDIM, bool FIRST> int launch_density_round(nd_ctx *c, DensityArgs 
 // ---- iterate_density (src/iterate_density.f90:43-360) ----
 template <int NDIM> int do_iterate_density(nd_ctx *c, int resume) {
   const nd_options &o = c->o;
-  const int np = c->npart;
+  const int np = c->nown;
+  const long long nglobal = c->has_comm ? c->comm.nglobal : (long long)np;
   const int itsdensitymax = (o.ikernav == 3 && o.ihvar != 0) ? o.maxdensits : 0;     // :77-81
   if (!resume) {
-    c->itsdensity = 0; c->ncalctotal = 0; c->ncalc = np; c->redolink = false; c->nrelink = 0;
+    c->itsdensity = 0; c->ncalctotal = 0; c->ncalc = np; c->ncalc_g = nglobal; c->redolink = false; c->nrelink = 0;
     CU(cudaMemcpyAsync(c->hhin, c->hh, sizeof(double) * np, cudaMemcpyDeviceToDevice, c->stream));   // :98
     CU(cudaMemsetAsync(c->flags, 0, sizeof(int) * 16, c->stream));
     LAUNCH(c, k_check_h, nblocks(np, 256), 256, 0, c->hh, np, c->flags);
     CU(cudaMemsetAsync(c->dhdt, 0, sizeof(double) * c->ntotal, c->stream));          // :90-97
     CU(cudaMemsetAsync(c->numneigh, 0, sizeof(int) * c->ntotal, c->stream));
   }
-  while (c->ncalc > 0 && c->itsdensity <= itsdensitymax) {                           // :119
+  while (c->ncalc_g > 0 && c->itsdensity <= itsdensitymax) {                         // :119
+    const bool first = (c->ncalc_g == nglobal);                                      // :131 `density` when every particle is (re)done
     if (c->redolink) {                                                               // :122-126
       // host-made ghosts: the caller re-runs set_ghost_particles, calls update_ghosts() and comes back with resume=1
       if (any_ghost_bound(c) && !o.device_ghosts && !resume) { fill_link_scalars(c); c->sc.itsdensity = c->itsdensity; return ND_NEED_RELINK; }
       resume = 0;
-      // remember which ROWS are still to be done (slots change with the re-sort), rebuild ghosts + grid, map back
+      // remember which ROWS are still to be done (slots change with the re-sort), rebuild halos + ghosts + grid, map back
       const int n = c->ncalc;
-      const bool partial = (n != np);
-      if (partial) LAUNCH(c, k_list_rows, nblocks(n, 256), 256, 0, c->list, n, c->perm, c->redo);   // redo[] doubles as row scratch
+      if (!first) LAUNCH(c, k_list_rows, nblocks(n, 256), 256, 0, c->list, n, c->perm, c->redo);   // redo[] doubles as row scratch
       if (int e = do_link<NDIM>(c)) return e;
-      if (partial) LAUNCH(c, k_remap_list, nblocks(n, 256), 256, 0, c->list, n, c->redo, c->inv);
+      if (!first) LAUNCH(c, k_remap_list, nblocks(n, 256), 256, 0, c->list, n, c->redo, c->inv);
       c->nrelink++;
       c->redolink = false;
     }
@@ -852,11 +1058,14 @@ template <int NDIM> int do_iterate_density(nd_ctx *c, int resume) {
     DensityArgs A;
     A.hh = c->hh; A.hhin = c->hhin; A.rho = c->rho; A.gradh = c->gradh; A.drhodt = c->drhodt; A.dhdt = c->dhdt; A.numneigh = c->numneigh;
     A.rhoalt = c->rhoalt; A.gradhn = c->gradhn; A.gradsoft = c->gradsoft; A.gradgradh = c->gradgradh;
-    A.list = c->list; A.nlist = c->ncalc; A.redo = c->redo; A.flags = c->flags;
+    A.list = c->list; A.nlist = c->ncalc; A.s0 = 0; A.redo = c->redo; A.flags = c->flags;
     A.itsdensity = c->itsdensity; A.itsdensitymax = itsdensitymax; A.hfact = o.hfact; A.psep = o.psep; A.tolh = o.tolh; A.hhmax = c->hhmax;
     CU(cudaMemsetAsync(c->redo, 0, sizeof(int) * c->ntotal, c->stream));
-    if (c->ncalc == np) {                                                            // :131-132 symmetric `density`
-      if (c->itsdensity > 1) LAUNCH(c, k_refresh_h, nblocks(c->ntotal, 256), 256, 0, c->perm, c->ireal, c->hh, c->posh, np, c->ntotal);
+    if (first) {                                                                     // :131-132 symmetric `density`
+      if (c->itsdensity > 1) {   // the neighbour count of `density` also looks at h_j (:189-190): refresh the sources' 1/h
+        if (c->has_comm) { if (int e = halo_exchange_density(c)) return e; }
+        LAUNCH(c, k_refresh_h, nblocks(c->ntotal, 256), 256, 0, c->perm, c->ireal, c->hh, c->posh, c->npart, c->ntotal);
+      }
       if (int e = launch_density_round<NDIM, true>(c, A, c->ntotal)) return e;
     } else {                                                                         // :133-134 `density_partial`
       if (int e = launch_density_round<NDIM, false>(c, A, c->ncalc)) return e;
@@ -867,17 +1076,24 @@ template <int NDIM> int do_iterate_density(nd_ctx *c, int resume) {
     CU(cudaMemcpyAsync(&c->h_flags[16], c->scanout + c->ntotal, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (int e = sync_flags(c)) return e;
     c->ncalc = c->h_flags[16];
-    if (c->h_flags[1]) { int code = c->h_flags[1]; return set_err(c, code, code == ND_ERR_RHO_NONPOSITIVE ? "error: rho <= 0 in iterate_density" : "error: h <= 0 in density call"); }
-    c->redolink = c->h_flags[0] != 0;
+    double v[3] = {(double)c->ncalc, (double)(c->h_flags[0] != 0), (double)(c->h_flags[1] != 0)};
+    if (int e = comm_allreduce(c, v, 3, 2)) return e;
+    c->ncalc_g = (long long)(v[0] + 0.5);
+    if (v[2] != 0.) {
+      const int code = c->h_flags[1] ? c->h_flags[1] : ND_ERR_COMM;
+      return set_err(c, code, code == ND_ERR_RHO_NONPOSITIVE ? "error: rho <= 0 in iterate_density" : code == ND_ERR_COMM ? "iterate_density: another rank reported an error" : "error: h <= 0 in density call");
+    }
+    c->redolink = v[1] != 0.;
     CU(cudaMemsetAsync(c->flags, 0, sizeof(int) * 4, c->stream));
   }
   if (c->itsdensity > itsdensitymax && itsdensitymax > 0) return set_err(c, ND_ERR_DENSITY_NOT_CONVERGED, "ERROR: DENSITY NOT CONVERGED");   // :349-351
-  // :310-344 copies to fixed particles and ghosts
+  // halo rows take the owners' converged values, then :310-344 copies to fixed particles and ghosts
+  if (c->has_comm) { if (int e = halo_exchange_density(c)) return e; }
   CopyArgs CA;
   CA.rho = c->rho; CA.rhoalt = c->rhoalt; CA.drhodt = c->drhodt; CA.dhdt = c->dhdt; CA.hh = c->hh; CA.gradh = c->gradh; CA.gradhn = c->gradhn;
-  CA.gradsoft = c->gradsoft; CA.itype = c->itype; CA.ireal = c->ireal; CA.npart = np; CA.ntotal = c->ntotal; CA.aux = o.want_aux != 0;
-  if (any_fixed_bound(c)) LAUNCH(c, k_copy_fixed_density, nblocks(np, 256), 256, 0, CA);
-  if (any_ghost_bound(c)) LAUNCH(c, k_copy_ghost_density, nblocks(c->ntotal - np, 256), 256, 0, CA);
+  CA.gradsoft = c->gradsoft; CA.itype = c->itype; CA.ireal = c->ireal; CA.npart = c->npart; CA.ntotal = c->ntotal; CA.aux = o.want_aux != 0;
+  if (any_fixed_bound(c)) { CopyArgs CF = CA; CF.npart = np; LAUNCH(c, k_copy_fixed_density, nblocks(np, 256), 256, 0, CF); }
+  if (any_ghost_bound(c)) LAUNCH(c, k_copy_ghost_density, nblocks(c->ntotal - c->npart, 256), 256, 0, CA);
   c->density_done = true;
   return 0;
 }
@@ -929,7 +1145,7 @@ template <int NDIM, bool MHD, bool DRAG, bool FAST> int launch_rates_pair(nd_ctx
 // ---- get_rates (src/ratesND_mhd.f90:29-979) ----
 template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long long *pc, long long cap) {
   const nd_options &o = c->o;
-  const int nt = c->ntotal, np = c->npart;
+  const int nt = c->ntotal, np = c->nown;
   // reduction keys: minima start at +huge (key of DBL_MAX), maxima at 0
   unsigned long long init[16];
   for (int k = 0; k < 16; k++) init[k] = 0x8000000000000000ull;                       // key(+0.0)
@@ -942,7 +1158,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   RGatherArgs GA;
   GA.perm = c->perm; GA.ireal = c->ireal; GA.hh = c->hh; GA.pmass = c->pmass; GA.rho = c->rho; GA.pr = c->pr; GA.spsound = c->spsound; GA.uu = c->uu;
   GA.gradh = c->gradh; GA.alpha = c->alpha; GA.psi = c->psi; GA.Bfield = c->Bfield;
-  GA.posh = c->posh; GA.vm = c->vm; GA.bpsi = c->bpsi; GA.thermo = c->thermo; GA.gal = c->gal; GA.npart = np; GA.ntotal = nt; GA.imhd = o.imhd;
+  GA.posh = c->posh; GA.vm = c->vm; GA.bpsi = c->bpsi; GA.thermo = c->thermo; GA.gal = c->gal; GA.npart = c->npart; GA.ntotal = nt; GA.imhd = o.imhd;
   GA.stress_key = c->red + RED_STRESS; GA.imagforce = o.imagforce; GA.srho = c->srho; GA.pext = o.pext; GA.err = c->flags + 1;
   GA.Bconstmax = std::max(o.Bconst[0], std::max(o.Bconst[1], o.Bconst[2]));
   LAUNCH(c, k_rates_gather, nblocks(nt, 256), 256, 0, GA);
@@ -951,6 +1167,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
     CU(cudaMemcpyAsync(c->h_red, c->red + RED_STRESS, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     O.stressmax = dkey_inv(c->h_red[0]);
+    if (int e = comm_allreduce(c, &O.stressmax, 1, 0)) return e;
   }
   RatesIn I; I.bpsi = c->bpsi; I.thermo = c->thermo; I.gal = c->gal; I.srho = c->srho;
   RatesSums S; S.F = c->sF; S.dB = c->sdB; S.C = c->sC; S.P = c->sP; S.V = c->sV;
@@ -971,6 +1188,15 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   else e = launch_rates_pair<NDIM, true, true, false>(c, I, O, S, R, pi, pj, pc, cap);
   if (e) return e;
   CU(cudaEventRecord(c->ev[4], c->stream));
+  if (c->has_comm) {   // vsigmax feeds dpsidt in the finalisation loop (:518-520, :902): all ranks need the global maximum
+    CU(cudaMemcpyAsync(c->h_red, c->red + RED_VSIG, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    double vs = dkey_inv(c->h_red[0]);
+    if (int e = comm_allreduce(c, &vs, 1, 0)) return e;
+    union { double d; unsigned long long u; } kv; kv.d = vs;
+    c->h_red[0] = kv.u | 0x8000000000000000ull;   // key of a non-negative double
+    CU(cudaMemcpyAsync(c->red + RED_VSIG, c->h_red, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+  }
   FinalArgs FA;
   FA.perm = c->perm; FA.typ = c->typ; FA.posh = c->posh; FA.vm = c->vm; FA.bpsi = c->bpsi; FA.thermo = c->thermo; FA.gal = c->gal; FA.S = S; FA.O = O;
   FA.drhodt_in = c->drhodt; FA.Bevol = c->Bevol; FA.dens = c->dens; FA.hh = c->hh; FA.rho = c->rho; FA.pr = c->pr; FA.vsigmax_key = c->red + RED_VSIG;
@@ -987,8 +1213,11 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   CU(cudaMemcpyAsync(c->h_red, c->red, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(c->h_fmean, c->fmean, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
   if (int e2 = sync_flags(c)) return e2;
-  if (c->h_flags[1]) {
-    const int code = c->h_flags[1];
+  double ef = c->h_flags[1];
+  if (int e2 = comm_allreduce(c, &ef, 1, 0)) return e2;
+  if (ef != 0.) {
+    const int code = c->h_flags[1] ? c->h_flags[1] : ND_ERR_COMM;
+    if (code == ND_ERR_COMM) return set_err(c, code, "rates: another rank reported an error");
     return set_err(c, code, code == ND_ERR_VSIG_DET ? "rates: vsig det < 0" : code == ND_ERR_H_NONPOSITIVE ? "rates: h <= 0" : "rates: dx = 0 (coincident particles of the same type)");
   }
   nd_scalars &s = c->sc;
@@ -998,6 +1227,18 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   s.ts_min = dkey_inv(c->h_red[RED_TS]);
   s.h_on_csts_max = dkey_inv(c->h_red[RED_HCS]);
   s.fhmax = dkey_inv(c->h_red[RED_FH]);
+  if (c->has_comm) {
+    double mn[3] = {s.dtcourant, s.dtav, s.ts_min}, mx[3] = {s.vsigmax, s.h_on_csts_max, s.fhmax};
+    double sm[4] = {c->h_fmean[0], c->h_fmean[1], c->h_fmean[2], (double)c->h_flags[4]};
+    double dtf = dkey_inv(c->h_red[RED_DTF]);
+    if (int e3 = comm_allreduce(c, mn, 3, 1)) return e3;
+    if (int e3 = comm_allreduce(c, mx, 3, 0)) return e3;
+    if (int e3 = comm_allreduce(c, sm, 4, 2)) return e3;
+    if (int e3 = comm_allreduce(c, &dtf, 1, 1)) return e3;
+    s.dtcourant = mn[0]; s.dtav = mn[1]; s.ts_min = mn[2]; s.vsigmax = mx[0]; s.h_on_csts_max = mx[1]; s.fhmax = mx[2];
+    c->h_fmean[0] = sm[0]; c->h_fmean[1] = sm[1]; c->h_fmean[2] = sm[2]; c->h_flags[4] = (int)(sm[3] + 0.5);
+    union { double d; unsigned long long u; } kv; kv.d = dtf; c->h_red[RED_DTF] = kv.u | 0x8000000000000000ull;
+  }
   s.stressmax = O.stressmax;
   s.vsig2max = (o.imhd != 0 && o.idivbzero >= 2) ? s.vsigmax * s.vsigmax : 0.;
   s.dtvisc = DBL_MAX;
@@ -1022,9 +1263,14 @@ int fill_density_scalars(nd_ctx *c) {
   s.itsdensity = c->itsdensity; s.ncalctotal = c->ncalctotal; s.nrelink = c->nrelink;
   int init[2] = {1 << 30, 0};
   CU(cudaMemcpyAsync(c->flags + 12, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
-  LAUNCH(c, k_minmax_neigh, std::min(nblocks(c->npart, 256), 1184), 256, 0, c->numneigh, c->npart, c->flags + 12);
+  LAUNCH(c, k_minmax_neigh, std::min(nblocks(c->nown, 256), 1184), 256, 0, c->numneigh, c->nown, c->flags + 12);
   if (int e = sync_flags(c)) return e;
-  s.nneigh_min = c->h_flags[12]; s.nneigh_max = c->h_flags[13];
+  double nmn = c->h_flags[12], nmx = c->h_flags[13], cnt[2] = {(double)c->ncalctotal, 0.};
+  if (int e = comm_allreduce(c, &nmn, 1, 1)) return e;
+  if (int e = comm_allreduce(c, &nmx, 1, 0)) return e;
+  if (int e = comm_allreduce(c, cnt, 2, 2)) return e;
+  s.nneigh_min = (int)nmn; s.nneigh_max = (int)nmx;
+  if (c->has_comm) s.ncalctotal = (long long)(cnt[0] + 0.5);
   fill_link_scalars(c);
   return 0;
 }
@@ -1117,7 +1363,7 @@ int ndspmhd_b200_destroy(nd_ctx *c) {
   if (!c) return 0;
   if (c->stream) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
   for (auto &rb : c->rowbufs) if (*rb.p) { cudaFree(*rb.p); *rb.p = nullptr; }
-  void *singles[] = {c->nbr, c->lcnt, c->scanout, c->cellStart, c->cellCount, c->blocksums, c->red, c->fmean, c->flags, c->d_tab, c->d_tab2, c->d_tabdrag};
+  void *singles[] = {c->sendlist[0], c->sendlist[1], c->sendbuf[0], c->sendbuf[1], c->recvbuf[0], c->recvbuf[1], c->nbr, c->lcnt, c->scanout, c->cellStart, c->cellCount, c->blocksums, c->red, c->fmean, c->flags, c->d_tab, c->d_tab2, c->d_tabdrag};
   for (void *p : singles) if (p) cudaFree(p);
   if (c->h_red) cudaFreeHost(c->h_red);
   if (c->h_flags) cudaFreeHost(c->h_flags);
@@ -1146,6 +1392,7 @@ int ndspmhd_b200_upload(nd_ctx *c, const nd_arrays *a, int npart, int ntotal, in
   if (!c || !a || !c->stream) return c ? set_err(c, ND_ERR_STATE, "context not initialised") : ND_ERR_INVALID_ARG;
   const nd_options &o = c->o;
   if (o.device_ghosts) ntotal = npart;
+  if (c->has_comm && !o.device_ghosts) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "slab decomposition needs device_ghosts = 1");
   if (npart < 1 || ntotal < npart || idim < ntotal) return set_err(c, ND_ERR_INVALID_ARG, "upload: need 1 <= npart <= ntotal <= idim");
   if (!a->x || !a->vel || !a->pmass || !a->hh_in || !a->itype) return set_err(c, ND_ERR_INVALID_ARG, "upload: x, vel, pmass, hh_in, itype are required");
   if (o.imhd != 0 && !a->Bevol) return set_err(c, ND_ERR_INVALID_ARG, "upload: Bevol required with imhd /= 0");
@@ -1172,6 +1419,26 @@ int ndspmhd_b200_upload(nd_ctx *c, const nd_arrays *a, int npart, int ntotal, in
   CU(cudaStreamSynchronize(c->stream));
   c->npart = npart; c->ntotal = ntotal; c->nown = npart;
   c->uploaded = true; c->linked = c->density_done = c->prim_done = c->rates_done = false;
+  return 0;
+}
+
+int ndspmhd_b200_set_comm(nd_ctx *c, const nd_comm *comm) {
+  if (!c) return ND_ERR_INVALID_ARG;
+  if (!comm || comm->nranks <= 1) { c->has_comm = false; return 0; }
+  if (!comm->allreduce || !comm->sendrecv_counts || !comm->sendrecv) return set_err(c, ND_ERR_INVALID_ARG, "set_comm: all three callbacks are required");
+  if (comm->rank < 0 || comm->rank >= comm->nranks || !(comm->slab_hi > comm->slab_lo) || comm->nglobal < 1) return set_err(c, ND_ERR_INVALID_ARG, "set_comm: bad rank / slab / nglobal");
+  if (!c->o.device_ghosts) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "slab decomposition needs device_ghosts = 1");
+  if (!(c->o.ibound[0] == 0 || c->o.ibound[0] == 1 || c->o.ibound[0] == 3)) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "slab decomposition needs ibound(1) in {0,1,3}");
+  c->comm = *comm; c->has_comm = true;
+  c->uploaded = c->linked = c->density_done = c->prim_done = c->rates_done = false;
+  return 0;
+}
+
+int ndspmhd_b200_row_counts(const nd_ctx *c, int *nown, int *nsrc, int *ntotal) {
+  if (!c) return ND_ERR_INVALID_ARG;
+  if (nown) *nown = c->nown;
+  if (nsrc) *nsrc = c->npart;
+  if (ntotal) *ntotal = c->ntotal;
   return 0;
 }
 
@@ -1240,7 +1507,7 @@ int ndspmhd_b200_download(nd_ctx *c, nd_arrays *a, unsigned mask, int idim) {
   if (!c->uploaded) return set_err(c, ND_ERR_STATE, "download before upload");
   if (idim < c->ntotal) return set_err(c, ND_ERR_INVALID_ARG, "download: idim < ntotal (re-allocate the host arrays, src/ghostND_mhd.f90:383-386)");
   CU(cudaSetDevice(c->device));
-  const size_t n = (size_t)c->ntotal;
+  const size_t n = (size_t)(c->has_comm ? c->nown : c->ntotal);   // with slabs only this rank's own rows go back
   auto dn = [&](void *dst, const void *src, size_t bytes) -> cudaError_t { return (dst && src) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess; };
   const size_t D = sizeof(double);
   if (mask & ND_DL_DENSITY) {
@@ -1259,7 +1526,7 @@ int ndspmhd_b200_download(nd_ctx *c, nd_arrays *a, unsigned mask, int idim) {
     // drhodt/dhdt are zeroed on ghosts and fixed particles by get_rates (:952-953)
     CU(dn(a->drhodt, c->drhodt, D * n)); CU(dn(a->dhdt, c->dhdt, D * n));
   }
-  if (mask & ND_DL_GHOSTS) {
+  if ((mask & ND_DL_GHOSTS) && !c->has_comm) {
     const size_t g0 = (size_t)c->npart, ng = n - g0;
     if (ng > 0) {
       if (a->x_out) CU(dn(a->x_out + g0 * c->ndim, c->x + g0 * c->ndim, D * c->ndim * ng));

@@ -32,7 +32,7 @@ EXPORTS = [
     "ndspmhd_b200_upload", "ndspmhd_b200_update_ghosts", "ndspmhd_b200_link", "ndspmhd_b200_iterate_density",
     "ndspmhd_b200_cons2prim", "ndspmhd_b200_get_rates", "ndspmhd_b200_derivs", "ndspmhd_b200_download",
     "ndspmhd_b200_host_alloc", "ndspmhd_b200_host_free", "ndspmhd_b200_last_timings", "ndspmhd_b200_launch_count",
-    "ndspmhd_b200_stream", "ndspmhd_b200_rates_pairs", "ndspmhd_b200_rewind",
+    "ndspmhd_b200_stream", "ndspmhd_b200_rates_pairs", "ndspmhd_b200_rewind", "ndspmhd_b200_set_comm", "ndspmhd_b200_row_counts",
 ]
 
 

@@ -151,8 +151,11 @@ def _alloc(ndim, x, opts, hmax_guess, extra=0):
 # C2 / C3 / C5: Orszag-Tang vortex, 2D or 3D thin slab / cube (src/setup_orszagtang2D_mhd.f90)
 # ---------------------------------------------------------------------------------------------------------
 def orszag_tang(ndim=2, nx=64, lattice="cubic", zfrac=0.125, perturb_amp=0.0, imhd=11, idivbzero=2, iener=2,
-                evolved=True, seed=268, cube=False):
+                evolved=True, seed=268, cube=False, slab=None):
     """Periodic box [-0.5,0.5]^2 (x [-zfrac/2, zfrac/2] in 3D, or a unit cube with cube=True).
+
+    slab=(rank, nranks): build only the rows of one x-slab of the same global particle set (multi-GPU runs); the return
+    value is then (options, particles, info) with info = {edges, nglobal, rows (global indices of the local rows)}.
 
     evolved=True puts non-trivial psi / alpha / energy perturbations on the particles so every term of the
     rates is exercised (the t=0 state has psi=0 and uniform alpha, u).
@@ -172,6 +175,16 @@ def orszag_tang(ndim=2, nx=64, lattice="cubic", zfrac=0.125, perturb_amp=0.0, im
     else:
         x, _ = closepacked_lattice(xmin, xmax, psep)
     x = wrap_periodic(perturb(x, psep, perturb_amp, seed), o)
+    nglobal = x.shape[0]
+    info = None
+    if slab is not None:
+        from .slab import owner_of, slab_edges
+
+        rank, nranks = slab
+        edges = slab_edges(x[:, 0], nranks, xmin[0], xmax[0])
+        rows = np.nonzero(owner_of(x[:, 0], edges) == rank)[0]
+        x = np.ascontiguousarray(x[rows])
+        info = {"edges": edges, "nglobal": nglobal, "rows": rows}
     n = x.shape[0]
     const = 4.0 * PI
     betazero, machzero, vzero = 10.0 / 3.0, 1.0, 1.0
@@ -180,9 +193,9 @@ def orszag_tang(ndim=2, nx=64, lattice="cubic", zfrac=0.125, perturb_amp=0.0, im
     denszero = o.gamma * przero * machzero
     uuzero = przero / ((o.gamma - 1.0) * denszero)
     vol = np.prod([xmax[d] - xmin[d] for d in range(ndim)])
-    massp = denszero * vol / n
+    massp = denszero * vol / nglobal
     hguess = o.hfact * (massp / denszero) ** (1.0 / ndim)
-    p = _alloc(ndim, x, o, hguess)
+    p = _alloc(ndim, x, o, hguess, extra=(n // 4 + 4096) if slab is not None else 0)
     p.pmass[:n] = massp
     p.vel[:n, 0] = -vzero * np.sin(2.0 * PI * (x[:, 1] - xmin[1]))
     p.vel[:n, 1] = vzero * np.sin(2.0 * PI * (x[:, 0] - xmin[0]))
@@ -205,6 +218,8 @@ def orszag_tang(ndim=2, nx=64, lattice="cubic", zfrac=0.125, perturb_amp=0.0, im
         p.alpha[:n, 0] = 0.1 + 0.9 * (0.5 + 0.5 * np.sin(4.0 * PI * x[:, 1])) ** 2
         p.alpha[:n, 1] = 0.5 * (0.5 + 0.5 * np.cos(2.0 * PI * x[:, 0]))
         p.alpha[:n, 2] = 1.0 - 0.5 * (0.5 + 0.5 * np.cos(4.0 * PI * x[:, 0])) ** 2
+    if slab is not None:
+        return o, p, info
     return o, p
 
 

@@ -1,0 +1,225 @@
+"""Multi-GPU host side: x-slab decomposition, one rank (process) per GPU, transport over torch.distributed.
+
+The reference is serial (docs/about.rst:12); its only notion of "image particles" is the periodic ghost of
+src/ghostND_mhd.f90:166-346.  The library (csrc/nd_capi.cu: halo_exchange_inputs / halo_exchange_density) applies the same
+rule at slab faces and owns selection, packing and row layout; this module supplies the transport it calls back into
+(include/ndspmhd_b200.h, `nd_comm`):
+
+    allreduce(v[n], op)            small host-side all-reduces (hhmax, unconverged count, stressmax, vsigmax, dt's)
+    sendrecv_counts(send[2])       byte-count handshake with the two x-neighbours (periodic ring)
+    sendrecv(sendbuf[2], recvbuf[2])   the halo payload, device buffers, NCCL send/recv over NVLink
+
+`SlabComm` works on CUDA tensors with the NCCL backend and on CPU tensors with gloo (tests/test_slab_host.py runs the
+latter with world_size 2 and 3).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .abi import NdOptions, Particles
+
+OP_MAX, OP_MIN, OP_SUM = 0, 1, 2
+
+_ALLREDUCE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_int)
+_COUNTS = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong))
+_SENDRECV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_void_p),
+                        C.POINTER(C.c_longlong), C.c_void_p)
+
+
+class NdComm(C.Structure):
+    """ctypes mirror of `nd_comm` (include/ndspmhd_b200.h)."""
+
+    _fields_ = [("user", C.c_void_p), ("rank", C.c_int), ("nranks", C.c_int), ("slab_lo", C.c_double), ("slab_hi", C.c_double),
+                ("nglobal", C.c_longlong), ("allreduce", _ALLREDUCE), ("sendrecv_counts", _COUNTS), ("sendrecv", _SENDRECV)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# partition
+# ---------------------------------------------------------------------------------------------------------------------
+def slab_edges(x0: np.ndarray, nranks: int, xmin: float, xmax: float) -> np.ndarray:
+    """Slab faces along x with equal particle counts: faces sit half-way between the two particles either side of each
+    quantile, so no particle lies on a face.  Returns nranks+1 edges with edges[0] = xmin, edges[-1] = xmax."""
+    n = x0.shape[0]
+    edges = np.empty(nranks + 1)
+    edges[0], edges[-1] = xmin, xmax
+    if nranks > 1:
+        xs = np.sort(x0)
+        for r in range(1, nranks):
+            k = (n * r) // nranks
+            edges[r] = 0.5 * (xs[k - 1] + xs[k]) if 0 < k < n else xmin + (xmax - xmin) * r / nranks
+            if not (xs[k - 1] < edges[r] <= xs[k]) and 0 < k < n:   # duplicate coordinates at the quantile: fall back to xs[k]
+                edges[r] = xs[k]
+    return edges
+
+
+def owner_of(x0: np.ndarray, edges: np.ndarray) -> np.ndarray:
+    """Rank owning each particle: edges[r] <= x < edges[r+1] (the last slab is closed at xmax)."""
+    r = np.searchsorted(edges, x0, side="right") - 1
+    return np.clip(r, 0, len(edges) - 2).astype(np.int32)
+
+
+def take_rows(p: Particles, rows: np.ndarray, extra: int = 0) -> Particles:
+    """A rank's own particles, in global index order, with room for `extra` more rows."""
+    n = int(rows.shape[0])
+    q = Particles(p.ndim, n, n + extra)
+    for k, v in p.arrays.items():
+        q.arrays[k][:n] = v[rows]
+    q.ntotal = n
+    return q
+
+
+def halo_select_numpy(x0: np.ndarray, lo: float, hi: float, reach: float, left_on: bool, right_on: bool):
+    """numpy restatement of k_halo_flags: rows sent to the -x and +x neighbours."""
+    left = np.nonzero(left_on & (x0 < lo + reach))[0]
+    right = np.nonzero(right_on & (x0 > hi - reach))[0]
+    return left, right
+
+
+def wrap_shift(x: np.ndarray, xbound: float, xperbound: float) -> np.ndarray:
+    """src/ghostND_mhd.f90:212-225: xnew = xperbound + (x - xbound), in that order of operations."""
+    return xperbound + (x - xbound)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# transport
+# ---------------------------------------------------------------------------------------------------------------------
+class _DevPtr:
+    """Wraps a raw device pointer so torch.as_tensor can view it (CUDA array interface v2)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class SlabComm:
+    """The three `nd_comm` callbacks over torch.distributed.  device='cuda' (NCCL) or 'cpu' (gloo)."""
+
+    def __init__(self, group=None, device: str = "cuda", stream_ptr: int = 0):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.nranks = dist.get_world_size(group)
+        self.device = device
+        self.left = (self.rank - 1) % self.nranks
+        self.right = (self.rank + 1) % self.nranks
+        self.stream_ptr = stream_ptr
+        self.n_allreduce = self.n_sendrecv = 0
+        self.bytes_sent = 0
+
+    # ---- python-level API (also what the gloo tests exercise) ----
+    def allreduce(self, vals, op: int):
+        torch, dist = self.torch, self.dist
+        t = torch.tensor(list(vals), dtype=torch.float64, device=self.device)
+        rop = {OP_MAX: dist.ReduceOp.MAX, OP_MIN: dist.ReduceOp.MIN, OP_SUM: dist.ReduceOp.SUM}[op]
+        dist.all_reduce(t, op=rop, group=self.group)
+        self.n_allreduce += 1
+        return t.cpu().tolist()
+
+    def exchange_counts(self, send_left: int, send_right: int):
+        """Returns (bytes arriving from the left neighbour, bytes arriving from the right neighbour)."""
+        torch, dist = self.torch, self.dist
+        mine = torch.tensor([send_left, send_right], dtype=torch.int64, device=self.device)
+        allc = [torch.zeros(2, dtype=torch.int64, device=self.device) for _ in range(self.nranks)]
+        dist.all_gather(allc, mine, group=self.group)
+        allc = [a.cpu().tolist() for a in allc]
+        # what my left neighbour sends to ITS right is for me, and vice versa
+        return int(allc[self.left][1]), int(allc[self.right][0])
+
+    def sendrecv_tensors(self, send_left, send_right, recv_left, recv_right):
+        """uint8 tensors (or None for empty).  Matching order for a 2-rank ring, where both neighbours are the same peer:
+        every rank posts [send->right, send->left, recv<-left, recv<-right]; sends and receives between one pair of ranks
+        are matched in posting order, so the peer's first send (to ITS right = my left side) meets my first recv."""
+        dist = self.dist
+        ops = []
+        if send_right is not None and send_right.numel():
+            ops.append(dist.P2POp(dist.isend, send_right, self._peer(self.right), self.group))
+        if send_left is not None and send_left.numel():
+            ops.append(dist.P2POp(dist.isend, send_left, self._peer(self.left), self.group))
+        if recv_left is not None and recv_left.numel():
+            ops.append(dist.P2POp(dist.irecv, recv_left, self._peer(self.left), self.group))
+        if recv_right is not None and recv_right.numel():
+            ops.append(dist.P2POp(dist.irecv, recv_right, self._peer(self.right), self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        self.n_sendrecv += 1
+        self.bytes_sent += (send_left.numel() if send_left is not None else 0) + (send_right.numel() if send_right is not None else 0)
+
+    def _peer(self, group_rank: int) -> int:
+        return self.dist.get_global_rank(self.group, group_rank) if self.group is not None else group_rank
+
+    # ---- C callbacks ----
+    def _view(self, ptr: int, nbytes: int):
+        torch = self.torch
+        if nbytes == 0 or not ptr:
+            return None
+        if self.device == "cpu":
+            buf = (C.c_ubyte * nbytes).from_address(ptr)
+            return torch.from_numpy(np.frombuffer(buf, dtype=np.uint8))
+        return torch.as_tensor(_DevPtr(ptr, nbytes), device=self.device)
+
+    def callbacks(self):
+        torch = self.torch
+
+        def _allreduce(user, v, n, op):
+            try:
+                out = self.allreduce([v[i] for i in range(n)], op)
+                for i in range(n):
+                    v[i] = out[i]
+                return 0
+            except Exception as e:  # pragma: no cover - reported through the C error path
+                print("ndspmhd_b200.slab allreduce failed:", e, flush=True)
+                return 1
+
+        def _counts(user, sb, rb):
+            try:
+                rb[0], rb[1] = self.exchange_counts(sb[0], sb[1])
+                return 0
+            except Exception as e:  # pragma: no cover
+                print("ndspmhd_b200.slab sendrecv_counts failed:", e, flush=True)
+                return 1
+
+        def _sendrecv(user, sbuf, sb, rbuf, rb, stream):
+            try:
+                views = [self._view(sbuf[0], sb[0]), self._view(sbuf[1], sb[1]), self._view(rbuf[0], rb[0]), self._view(rbuf[1], rb[1])]
+                if self.device == "cpu":
+                    self.sendrecv_tensors(*views)
+                else:
+                    # order the NCCL transfers after the pack kernels and before the unpack kernels on the library's stream
+                    with torch.cuda.stream(torch.cuda.ExternalStream(int(stream))):
+                        self.sendrecv_tensors(*views)
+                return 0
+            except Exception as e:  # pragma: no cover
+                print("ndspmhd_b200.slab sendrecv failed:", e, flush=True)
+                return 1
+
+        self._cb = (_ALLREDUCE(_allreduce), _COUNTS(_counts), _SENDRECV(_sendrecv))   # keep alive
+        return self._cb
+
+
+def attach(hot, comm: SlabComm, slab_lo: float, slab_hi: float, nglobal: int) -> None:
+    """Registers the transport with a Hotpath context (ndspmhd_b200_set_comm)."""
+    cb = comm.callbacks()
+    nc = NdComm()
+    nc.user = None
+    nc.rank, nc.nranks = comm.rank, comm.nranks
+    nc.slab_lo, nc.slab_hi = slab_lo, slab_hi
+    nc.nglobal = nglobal
+    nc.allreduce, nc.sendrecv_counts, nc.sendrecv = cb
+    hot._comm_struct = nc
+    hot._comm = comm
+    L = hot.L
+    L.ndspmhd_b200_set_comm.argtypes = [C.c_void_p, C.POINTER(NdComm)]
+    hot._chk(L.ndspmhd_b200_set_comm(hot.ctx, C.byref(nc)))
+
+
+def row_counts(hot):
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    hot.L.ndspmhd_b200_row_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    hot.L.ndspmhd_b200_row_counts(hot.ctx, C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value

@@ -1,0 +1,136 @@
+"""bench.py's N > 1 leg: the same workload, x-slab partitioned over the ranks of one node (strong scaling by default).
+
+Launched as `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N`; one rank per GPU, NCCL.
+Timing: barrier + torch.cuda.synchronize() either side of exactly K steps, CUDA events on the library's stream, MAX over
+ranks; rank 0 prints the JSON line.  value = global particles / max time.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+
+def run(args, METRIC, UNIT, config_dict, ClockSampler, measured_peaks):
+    import torch
+    import torch.distributed as dist
+
+    from . import abi, lib, setups, slab
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"bench.py --gpus {args.gpus} must be launched with torchrun --nproc-per-node {args.gpus} (WORLD_SIZE={world})")
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    weak = args.scaling == "weak"
+    if weak:
+        raise SystemExit("weak scaling is not implemented for the slab bench: the Orszag-Tang box is fixed; use --scaling strong")
+    o, p0, info = setups.orszag_tang(ndim=3, nx=args.nx, zfrac=0.125, perturb_amp=0.2, evolved=True, imhd=11, idivbzero=2, iener=2,
+                                     slab=(rank, world))
+    o.device_ghosts = 1
+    o.want_aux = 0
+    n, nglobal = p0.npart, int(info["nglobal"])
+    lo, hi = float(info["edges"][rank]), float(info["edges"][rank + 1])
+    p = lib.pinned_particles(3, n, p0.idim)
+    for k, v in p0.arrays.items():
+        p.arrays[k][...] = v
+    p.ntotal = n
+    del p0
+    guess = np.array(p.arrays["hh"], copy=True)
+    hot = lib.Hotpath(o, 3, local)
+    comm = slab.SlabComm(device="cuda")
+    slab.attach(hot, comm, lo, hi, nglobal)
+    stream = torch.cuda.ExternalStream(hot.stream(), device=local)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    mask = abi.DL_DENSITY | abi.DL_PRIM | abi.DL_RATES
+
+    def timed(fn, steps):
+        a, b = ev(), ev()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a.record(stream)
+        for _ in range(steps):
+            out = fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out
+
+    def e2e_step():
+        p.arrays["hh"][:n] = guess[:n]       # host-side restore of the guess (the integrator's predictor would do this)
+        p.ntotal = n
+        hot.upload(p)
+        s = hot.derivs()
+        hot.download(p, mask)
+        return s
+
+    for _ in range(2):
+        s = e2e_step()
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_ms, s = timed(e2e_step, e2e_steps)
+    nown, nsrc, nt = slab.row_counts(hot)
+    up_names = ["x", "vel", "pmass", "hh", "itype", "ireal", "en", "Bevol", "alpha", "psi", "rho"]
+    dn_names = ["hh", "rho", "gradh", "drhodt", "dhdt", "numneigh", "dens", "uu", "pr", "spsound", "Bfield", "force", "dudt", "dendt",
+                "dBevoldt", "daldt", "dpsidt", "gradpsi", "divB", "curlB", "graddivv", "del2u", "drhodt", "dhdt"]
+    rowbytes = lambda nm: p.arrays[nm].nbytes // p.idim
+    bytes_t = torch.tensor([sum(rowbytes(nm) for nm in up_names) * n, sum(rowbytes(nm) for nm in dn_names) * n, nsrc - nown, nt - nsrc],
+                           dtype=torch.float64, device="cuda")
+    dist.all_reduce(bytes_t, op=dist.ReduceOp.SUM)
+
+    p.arrays["hh"][:n] = guess[:n]
+    p.ntotal = n
+    hot.upload(p)
+
+    def step():
+        hot.rewind()
+        return hot.derivs()
+
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = hot.launch_count()
+    sb0 = comm.bytes_sent
+    ms, s = timed(step, args.steps)
+    launches = hot.launch_count() - l0
+    halo_bytes = torch.tensor([float(comm.bytes_sent - sb0) / args.steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(halo_bytes, op=dist.ReduceOp.SUM)
+    ck = clocks.stop()
+    phases = hot.timings()
+    ph = torch.tensor([phases[k] for k in ("link", "density", "c2p_gather", "rates_pair", "rates_final")], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+    launches_t = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(launches_t, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        pair_ms = float(ph[3].item())
+        bytes_rates = 284
+        ach = bytes_rates * (nglobal / world) / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": nglobal / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, extra={"npart": nglobal, "npart_per_rank": nglobal // world, "halo_rows_total": int(bytes_t[2].item()),
+                                               "ghost_rows_total": int(bytes_t[3].item()), "itsdensity": s["itsdensity"],
+                                               "nneigh_min": s["nneigh_min"], "nneigh_max": s["nneigh_max"],
+                                               "halo_bytes_per_step_all_ranks": float(halo_bytes.item())}),
+            "e2e": {"value": nglobal / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(bytes_t[0].item()),
+                    "d2h_bytes_per_step": int(bytes_t[1].item()), "ms_per_step": e2e_ms, "steps": e2e_steps},
+            "gpu_launches": int(launches_t.item()),
+            "clocks": ck,
+            "roofline": {"bound": "hbm", "kernel": "build_lists<RATES> + rates_pair_kernel<3,MHD,FAST> (per rank, max over ranks)", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": pair_ms},
+            "phases_ms": dict(zip(["link", "density", "c2p_gather", "rates_pair", "rates_final"], [float(v) for v in ph.tolist()])),
+            "comm": {"allreduces_per_step": comm.n_allreduce // max(1, args.steps + args.warmup + 2 + e2e_steps), "backend": "nccl send/recv + all_reduce"},
+        }
+        print(json.dumps(line), flush=True)
+    hot.close()
+    lib.free_pinned(p)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

@@ -1,0 +1,22 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): the slab-decomposed path over NCCL must reproduce the single-GPU
+result on every rank's own rows -- neighbour counts, iteration/relink counts bit-exact, fields within 1e-12 (tools/slab_check.py)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from ndspmhd_b200 import lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_slab_decomposition_matches_single_gpu(nranks):
+    if lib.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29530 + nranks), os.path.join(ROOT, "tools", "slab_check.py"), "32"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "SLAB CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
