@@ -1,0 +1,190 @@
+!------------------------------------------------------------------------------!
+! ISO_C_BINDING interface to libndspmhd_b200.so (include/ndspmhd_b200.h).
+!
+! This module is what a maintainer adds to NDSPMHD's src/ to run the per-step
+! hot path on a B200.  It is shipped as source: the image this library was built
+! in has no Fortran compiler, so these files are reviewed, not compiled, here.
+!
+! The derived types mirror the C structs field for field (bind(C) guarantees the
+! same layout).  Default `real` is c_double under the reference's build flags
+! (-fdefault-real-8, src/Makefile:27), `integer` is c_int.
+!------------------------------------------------------------------------------!
+module ndspmhd_b200
+ use, intrinsic :: iso_c_binding
+ implicit none
+
+ integer(c_int), parameter :: ND_OK = 0, ND_ERR_UNSUPPORTED_OPTION = 2, ND_NEED_RELINK = 100
+ integer(c_int), parameter :: ND_DL_DENSITY = 1, ND_DL_PRIM = 2, ND_DL_RATES = 4, ND_DL_GHOSTS = 8, ND_DL_ALL = 15
+
+ type, bind(C) :: nd_options
+    integer(c_int) :: iener,icty,iav,ikernav,ihvar,iprterm
+    integer(c_int) :: imhd,imagforce,idivbzero,iresist
+    integer(c_int) :: idust,idrag_nature
+    integer(c_int) :: ixsph,igravity,iexternal_force
+    integer(c_int) :: ikernel,ikernelalt
+    integer(c_int) :: maxdensits
+    integer(c_int) :: iavlim(3)
+    integer(c_int) :: ibound(3)
+    integer(c_int) :: usenumdens,ibiascorrection,onef_dust,use_smoothed_rhodust
+    integer(c_int) :: islope_limiter,iuse_exact_derivs,iambipolar,ivisc,iquantum,ind_timesteps
+    integer(c_int) :: nsubsteps_divB
+    integer(c_int) :: device_ghosts,want_aux
+    integer(c_int) :: reserved_i(6)
+    real(c_double) :: hfact,psep,tolh
+    real(c_double) :: gamma,polyk
+    real(c_double) :: alphamin,alphaumin,alphaBmin,beta,avdecayconst,avfact
+    real(c_double) :: psidecayfact,etamhd,Kdrag,damp,pext
+    real(c_double) :: xmin(3),xmax(3)
+    real(c_double) :: Bconst(3)
+    real(c_double) :: hhmax
+    real(c_double) :: reserved_d(8)
+ end type nd_options
+
+ type, bind(C) :: nd_arrays
+    type(c_ptr) :: x,vel,pmass,hh_in,itype,ireal,en,Bevol,alpha,psi,rho_in
+    type(c_ptr) :: hh,rho,gradh,drhodt,dhdt,numneigh,rhoalt,gradhn,gradsoft,gradgradh
+    type(c_ptr) :: dens,uu,pr,spsound,Bfield
+    type(c_ptr) :: force,dudt,dendt,dBevoldt,daldt,dpsidt,gradpsi,divB,curlB,graddivv,del2u
+    type(c_ptr) :: x_out,vel_out,ireal_out,itype_out
+    type(c_ptr) :: reserved_p(8)
+ end type nd_arrays
+
+ type, bind(C) :: nd_scalars
+    real(c_double) :: dtcourant,dtforce,dtav,dtdrag,dtvisc,vsig2max,vsigmax
+    real(c_double) :: stressmax,ts_min,h_on_csts_max,fhmax
+    real(c_double) :: hhmax,dxcell
+    real(c_double) :: fmean(3)
+    integer(c_int) :: itsdensity,nneigh_min,nneigh_max,nclumped
+    integer(c_int) :: ntotal,ncells,ncellsx(3),nrelink
+    integer(c_long_long) :: ncalctotal
+    integer(c_int) :: reserved_i(8)
+ end type nd_scalars
+
+ interface
+    integer(c_int) function ndspmhd_b200_default_options(o) bind(C,name='ndspmhd_b200_default_options')
+     import; type(nd_options), intent(out) :: o
+    end function
+    integer(c_int) function ndspmhd_b200_create(o,ndim,device,ctx) bind(C,name='ndspmhd_b200_create')
+     import; type(nd_options), intent(in) :: o; integer(c_int), value :: ndim,device; type(c_ptr), intent(out) :: ctx
+    end function
+    integer(c_int) function ndspmhd_b200_set_options(ctx,o) bind(C,name='ndspmhd_b200_set_options')
+     import; type(c_ptr), value :: ctx; type(nd_options), intent(in) :: o
+    end function
+    integer(c_int) function ndspmhd_b200_destroy(ctx) bind(C,name='ndspmhd_b200_destroy')
+     import; type(c_ptr), value :: ctx
+    end function
+    type(c_ptr) function ndspmhd_b200_last_error(ctx) bind(C,name='ndspmhd_b200_last_error')
+     import; type(c_ptr), value :: ctx
+    end function
+    integer(c_int) function ndspmhd_b200_upload(ctx,a,npart,ntotal,idim) bind(C,name='ndspmhd_b200_upload')
+     import; type(c_ptr), value :: ctx; type(nd_arrays), intent(in) :: a; integer(c_int), value :: npart,ntotal,idim
+    end function
+    integer(c_int) function ndspmhd_b200_update_ghosts(ctx,a,ntotal,idim,hhmax) bind(C,name='ndspmhd_b200_update_ghosts')
+     import; type(c_ptr), value :: ctx; type(nd_arrays), intent(in) :: a; integer(c_int), value :: ntotal,idim; real(c_double), value :: hhmax
+    end function
+    integer(c_int) function ndspmhd_b200_link(ctx) bind(C,name='ndspmhd_b200_link')
+     import; type(c_ptr), value :: ctx
+    end function
+    integer(c_int) function ndspmhd_b200_iterate_density(ctx,iresume,s) bind(C,name='ndspmhd_b200_iterate_density')
+     import; type(c_ptr), value :: ctx; integer(c_int), value :: iresume; type(nd_scalars), intent(out) :: s
+    end function
+    integer(c_int) function ndspmhd_b200_cons2prim(ctx) bind(C,name='ndspmhd_b200_cons2prim')
+     import; type(c_ptr), value :: ctx
+    end function
+    integer(c_int) function ndspmhd_b200_get_rates(ctx,s) bind(C,name='ndspmhd_b200_get_rates')
+     import; type(c_ptr), value :: ctx; type(nd_scalars), intent(out) :: s
+    end function
+    integer(c_int) function ndspmhd_b200_derivs(ctx,s) bind(C,name='ndspmhd_b200_derivs')
+     import; type(c_ptr), value :: ctx; type(nd_scalars), intent(out) :: s
+    end function
+    integer(c_int) function ndspmhd_b200_download(ctx,a,mask,idim) bind(C,name='ndspmhd_b200_download')
+     import; type(c_ptr), value :: ctx; type(nd_arrays), intent(in) :: a; integer(c_int), value :: mask,idim
+    end function
+ end interface
+
+ type(c_ptr), save :: b200_ctx = c_null_ptr     ! one context per process (the reference is single-threaded)
+ logical, save     :: b200_resident = .false.  ! .true. between the shim's link and rates calls of one derivs
+
+contains
+
+!--copies the reference's modules into the option struct (called at every derivs: options may change at run time)
+ subroutine b200_fill_options(o)
+  use dimen_mhd,    only:ndim
+  use options
+  use artvi,        only:beta,avfact,avdecayconst,alphamin,alphaumin,alphabmin
+  use eos,          only:gamma,polyk
+  use setup_params, only:hfact,psep
+  use bound,        only:xmin,xmax,hhmax,pext
+  use part,         only:Bconst
+  use timestep,     only:nsubsteps_divB
+  type(nd_options), intent(out) :: o
+  integer :: ierr
+  ierr = ndspmhd_b200_default_options(o)
+  o%iener = iener; o%icty = icty; o%iav = iav; o%ikernav = ikernav; o%ihvar = ihvar; o%iprterm = iprterm
+  o%imhd = imhd; o%imagforce = imagforce; o%idivbzero = idivbzero; o%iresist = iresist
+  o%idust = idust; o%idrag_nature = idrag_nature
+  o%ixsph = ixsph; o%igravity = igravity; o%iexternal_force = iexternal_force
+  o%ikernel = ikernel; o%ikernelalt = ikernelalt; o%maxdensits = maxdensits
+  o%iavlim(1:3) = iavlim(1:3)
+  o%ibound(:) = 0; o%ibound(1:ndim) = ibound(1:ndim)
+  o%usenumdens = merge(1,0,usenumdens); o%ibiascorrection = ibiascorrection
+  o%onef_dust = merge(1,0,onef_dust); o%use_smoothed_rhodust = merge(1,0,use_smoothed_rhodust)
+  o%islope_limiter = islope_limiter; o%iuse_exact_derivs = iuse_exact_derivs; o%iambipolar = iambipolar
+  o%ivisc = ivisc; o%iquantum = iquantum; o%ind_timesteps = 0   ! no default in defaults.f90; leapfrog never sets it
+  o%nsubsteps_divB = 0                                         ! uninitialised under leapfrog (variablesND.f90:261)
+  o%device_ghosts = 0                                          ! set_ghost_particles stays on the host in the drop-in mode
+  o%want_aux = 1
+  o%hfact = hfact; o%psep = psep; o%tolh = tolh; o%gamma = gamma; o%polyk = polyk
+  o%alphamin = alphamin; o%alphaumin = alphaumin; o%alphaBmin = alphabmin; o%beta = beta
+  o%avdecayconst = avdecayconst; o%avfact = avfact
+  o%psidecayfact = psidecayfact; o%etamhd = etamhd; o%Kdrag = Kdrag; o%damp = damp; o%pext = pext
+  o%xmin(:) = 0.; o%xmax(:) = 0.; o%xmin(1:ndim) = xmin(1:ndim); o%xmax(1:ndim) = xmax(1:ndim)
+  o%Bconst(1:3) = Bconst(1:3)
+  o%hhmax = hhmax
+ end subroutine b200_fill_options
+
+!--hands the module arrays over in their native layout; pointers are re-taken at every call because alloc() moves
+!  the arrays whenever the ghosts overflow (src/ghostND_mhd.f90:383-386)
+ subroutine b200_fill_arrays(a)
+  use part
+  use rates
+  use hterms,   only:gradh,gradhn,gradsoft,gradgradh
+  use derivB,   only:divB,curlB
+  use bound,    only:ireal
+  use linklist, only:numneigh
+  type(nd_arrays), intent(out) :: a
+  a%x = c_loc(x); a%vel = c_loc(vel); a%pmass = c_loc(pmass); a%hh_in = c_loc(hh); a%itype = c_loc(itype); a%ireal = c_loc(ireal)
+  a%en = c_loc(en); a%Bevol = c_loc(Bevol); a%alpha = c_loc(alpha); a%psi = c_loc(psi); a%rho_in = c_loc(rho)
+  a%hh = c_loc(hh); a%rho = c_loc(rho); a%gradh = c_loc(gradh); a%drhodt = c_loc(drhodt); a%dhdt = c_loc(dhdt)
+  a%numneigh = c_loc(numneigh); a%rhoalt = c_loc(rhoalt); a%gradhn = c_loc(gradhn); a%gradsoft = c_loc(gradsoft)
+  a%gradgradh = c_loc(gradgradh)
+  a%dens = c_loc(dens); a%uu = c_loc(uu); a%pr = c_loc(pr); a%spsound = c_loc(spsound); a%Bfield = c_loc(Bfield)
+  a%force = c_loc(force); a%dudt = c_loc(dudt); a%dendt = c_loc(dendt); a%dBevoldt = c_loc(dBevoldt); a%daldt = c_loc(daldt)
+  a%dpsidt = c_loc(dpsidt); a%gradpsi = c_loc(gradpsi); a%divB = c_loc(divB); a%curlB = c_loc(curlB)
+  a%graddivv = c_loc(graddivv); a%del2u = c_null_ptr
+  a%x_out = c_null_ptr; a%vel_out = c_null_ptr; a%ireal_out = c_null_ptr; a%itype_out = c_null_ptr
+  a%reserved_p(:) = c_null_ptr
+ end subroutine b200_fill_arrays
+
+!--reference error convention: print to iprint, then `call quit` (emergency dump + stop, src/ndspmhd.f90:369-386)
+ subroutine b200_check(ierr,where)
+  use loguns, only:iprint
+  integer(c_int), intent(in) :: ierr
+  character(len=*), intent(in) :: where
+  character(kind=c_char), pointer :: msg(:)
+  integer :: i
+  if (ierr == ND_OK) return
+  call c_f_pointer(ndspmhd_b200_last_error(b200_ctx), msg, [256])
+  write(iprint,"(1x,a,a,a,i4)",advance='no') 'ndspmhd_b200 error in ',where,': code ',ierr
+  write(iprint,"(1x,256a1)") (msg(i), i=1,min(256,index_of_nul(msg)-1))
+  call quit
+ contains
+  integer function index_of_nul(s)
+   character(kind=c_char), intent(in) :: s(:)
+   do index_of_nul = 1,size(s)
+      if (s(index_of_nul) == c_null_char) return
+   enddo
+  end function
+ end subroutine b200_check
+
+end module ndspmhd_b200
