@@ -227,11 +227,7 @@ def run_single(args):
     mask = abi.DL_DENSITY | abi.DL_PRIM | abi.DL_RATES
     def e2e_step():
         p.ntotal = n
-        hot.upload(p)
-        s = hot.derivs()
-        p.ntotal = s["ntotal"]
-        hot.download(p, mask)
-        return s
+        return hot.derivs_host(p, mask)     # ndspmhd_b200_derivs_host: upload + derivs + download, copies overlapped with kernels
     for _ in range(max(1, min(args.warmup, 2))):
         s = e2e_step()
     nt = s["ntotal"]
@@ -245,8 +241,8 @@ def run_single(args):
     torch.cuda.synchronize()
     e2e_ms = a.elapsed_time(b) / e2e_steps
     up_names = ["x", "vel", "pmass", "hh", "itype", "ireal", "en", "Bevol", "alpha", "psi", "rho"]
-    dn_names = ["hh", "rho", "gradh", "drhodt", "dhdt", "numneigh", "dens", "uu", "pr", "spsound", "Bfield", "force", "dudt", "dendt",
-                "dBevoldt", "daldt", "dpsidt", "gradpsi", "divB", "curlB", "graddivv", "del2u", "drhodt", "dhdt"]
+    dn_names = ["hh", "rho", "gradh", "numneigh", "dens", "uu", "pr", "spsound", "Bfield", "drhodt", "dhdt", "force", "dudt", "dendt",
+                "dBevoldt", "daldt", "dpsidt", "gradpsi", "divB", "curlB"]
     rowbytes = lambda nm: p.arrays[nm].nbytes // p.idim
     h2d = sum(rowbytes(nm) for nm in up_names) * n
     d2h = sum(rowbytes(nm) for nm in dn_names) * nt

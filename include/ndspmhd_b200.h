@@ -216,6 +216,10 @@ int ndspmhd_b200_get_rates(nd_ctx *c, nd_scalars *s);
 /* link + iterate_density + cons2prim + get_rates on the resident state = one `derivs` (src/derivs.f90:74-156) */
 int ndspmhd_b200_derivs(nd_ctx *c, nd_scalars *s);
 
+/* upload + derivs + download of the arrays selected by `mask` in one call, copies overlapped with the kernels on separate
+ * streams.  This is the call a host that keeps its state in host memory (the reference's integrators) should make. */
+int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int idim, unsigned mask, nd_scalars *s);
+
 /* device -> host, rows [0,ntotal) of the arrays selected by `mask` (NULL pointers skipped) */
 int ndspmhd_b200_download(nd_ctx *c, nd_arrays *a, unsigned mask, int idim);
 
@@ -259,6 +263,8 @@ int ndspmhd_b200_last_timings(const nd_ctx *c, double ms[8]);
 /* puts hh back to the guess handed over by the last upload (a D2D copy), so that a repeated derivs() on the resident
  * state repeats the whole smoothing-length iteration instead of starting from the converged answer */
 int ndspmhd_b200_rewind(nd_ctx *c);
+/* device self-test of the branch-free FP64 sqrt / 1/sqrt the pair kernels use (host arrays in and out) */
+int ndspmhd_b200_selftest_math(nd_ctx *c, const double *in, double *out_sqrt, double *out_rsqrt, int n);
 /* number of kernels this library launched since create (bench.py's gpu_launches) */
 long long ndspmhd_b200_launch_count(const nd_ctx *c);
 /* the CUDA stream the context launches on (cudaStream_t as void*), for event timing in bench.py */

@@ -24,7 +24,8 @@ struct RowBuf { void **p; size_t rowbytes; };   // a per-particle device array t
 struct nd_ctx {
   nd_options o;
   int ndim = 3, device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;   // compute; copy-in / copy-out of derivs_host
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[3] = {nullptr, nullptr, nullptr};
   std::string err;
   long long launches = 0;
   ndt::KernelTables *T = nullptr;
@@ -692,6 +693,8 @@ void register_rows(nd_ctx *c) {
 int ensure_capacity(nd_ctx *c, int rows, int keep) {
   if (rows <= c->cap) return 0;
   const int newcap = (int)std::min<long long>(2000000000LL, (long long)rows + rows / 8 + 1024);
+  if (c->stream_h2d) CU(cudaStreamSynchronize(c->stream_h2d));   // a pipelined upload may still be writing the old buffers
+  if (c->stream_d2h) CU(cudaStreamSynchronize(c->stream_d2h));
   for (auto &rb : c->rowbufs) {
     void *np_ = nullptr;
     CU(cudaMalloc(&np_, rb.rowbytes * (size_t)newcap));
@@ -1323,6 +1326,10 @@ int ndspmhd_b200_create(const nd_options *o, int ndim, int device, nd_ctx **out)
   CU(cudaSetDevice(device));
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (int k = 0; k < 8; k++) CU(cudaEventCreate(&c->ev[k]));
+  CU(cudaStreamCreateWithFlags(&c->stream_h2d, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; k++) CU(cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
+  for (int k = 0; k < 3; k++) CU(cudaEventCreateWithFlags(&c->ev_out[k], cudaEventDisableTiming));
   // kernel tables -> interpolation records
   std::vector<TabRec> tab(IKERN + 1);
   std::vector<TabRec2> tab2(IKERN + 1);
@@ -1369,6 +1376,10 @@ int ndspmhd_b200_destroy(nd_ctx *c) {
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->h_fmean) cudaFreeHost(c->h_fmean);
   for (int k = 0; k < 8; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+  for (int k = 0; k < 2; k++) if (c->ev_in[k]) cudaEventDestroy(c->ev_in[k]);
+  for (int k = 0; k < 3; k++) if (c->ev_out[k]) cudaEventDestroy(c->ev_out[k]);
+  if (c->stream_h2d) cudaStreamDestroy(c->stream_h2d);
+  if (c->stream_d2h) cudaStreamDestroy(c->stream_d2h);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c->T;
   delete c;
@@ -1388,8 +1399,8 @@ int ndspmhd_b200_get_kernel_tables(const nd_ctx *c, double *wij, double *grwij, 
   return 0;
 }
 
-int ndspmhd_b200_upload(nd_ctx *c, const nd_arrays *a, int npart, int ntotal, int idim) {
-  if (!c || !a || !c->stream) return c ? set_err(c, ND_ERR_STATE, "context not initialised") : ND_ERR_INVALID_ARG;
+namespace {
+int check_upload_args(nd_ctx *c, const nd_arrays *a, int npart, int &ntotal, int idim) {
   const nd_options &o = c->o;
   if (o.device_ghosts) ntotal = npart;
   if (c->has_comm && !o.device_ghosts) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "slab decomposition needs device_ghosts = 1");
@@ -1398,24 +1409,67 @@ int ndspmhd_b200_upload(nd_ctx *c, const nd_arrays *a, int npart, int ntotal, in
   if (o.imhd != 0 && !a->Bevol) return set_err(c, ND_ERR_INVALID_ARG, "upload: Bevol required with imhd /= 0");
   if (!a->en || !a->alpha) return set_err(c, ND_ERR_INVALID_ARG, "upload: en and alpha are required");
   if ((ntotal > npart || any_fixed_bound(c)) && !a->ireal) return set_err(c, ND_ERR_INVALID_ARG, "upload: ireal required with ghosts/fixed particles");
+  return 0;
+}
+// group 1: what link + density read; group 2: what cons2prim + rates read in addition
+int upload_group(nd_ctx *c, const nd_arrays *a, size_t n, int group, cudaStream_t st) {
+  auto up = [&](void *dst, const void *src, size_t bytes) -> cudaError_t { return src ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) : cudaMemsetAsync(dst, 0, bytes, st); };
+  if (group == 1) {
+    CU(up(c->x, a->x, sizeof(double) * c->ndim * n));
+    CU(up(c->vel, a->vel, sizeof(double) * 3 * n));
+    CU(up(c->pmass, a->pmass, sizeof(double) * n));
+    CU(up(c->hh, a->hh_in, sizeof(double) * n));
+    CU(cudaMemcpyAsync(c->hh0, c->hh, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    CU(up(c->itype, a->itype, sizeof(int) * n));
+    CU(up(c->ireal, a->ireal, sizeof(int) * n));
+    CU(up(c->rho, a->rho_in, sizeof(double) * n));   // fixed particles without a parent keep their density
+  } else {
+    CU(up(c->en, a->en, sizeof(double) * n));
+    CU(up(c->Bevol, a->Bevol, sizeof(double) * 3 * n));
+    CU(up(c->alpha, a->alpha, sizeof(double) * 3 * n));
+    CU(up(c->psi, a->psi, sizeof(double) * n));
+  }
+  return 0;
+}
+// phase 1: density outputs that get_rates does not touch; 2: primitives; 3: rates (+ drhodt, dhdt, zeroed on ghosts/fixed by get_rates)
+int download_group(nd_ctx *c, nd_arrays *a, size_t n, int group, unsigned mask, cudaStream_t st) {
+  auto dn = [&](void *dst, const void *src, size_t bytes) -> cudaError_t { return (dst && src) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess; };
+  const size_t D = sizeof(double);
+  if (group == 1 && (mask & ND_DL_DENSITY)) {
+    CU(dn(a->hh, c->hh, D * n)); CU(dn(a->rho, c->rho, D * n)); CU(dn(a->gradh, c->gradh, D * n)); CU(dn(a->numneigh, c->numneigh, sizeof(int) * n));
+    if (c->o.want_aux) { CU(dn(a->rhoalt, c->rhoalt, D * n)); CU(dn(a->gradhn, c->gradhn, D * n)); CU(dn(a->gradsoft, c->gradsoft, D * n)); CU(dn(a->gradgradh, c->gradgradh, D * n)); }
+  }
+  if (group == 2 && (mask & ND_DL_PRIM)) {
+    CU(dn(a->dens, c->dens, D * n)); CU(dn(a->uu, c->uu, D * n)); CU(dn(a->pr, c->pr, D * n)); CU(dn(a->spsound, c->spsound, D * n));
+    if (c->o.imhd != 0) CU(dn(a->Bfield, c->Bfield, D * 3 * n));
+  }
+  if (group == 3) {
+    if (mask & (ND_DL_DENSITY | ND_DL_RATES)) { CU(dn(a->drhodt, c->drhodt, D * n)); CU(dn(a->dhdt, c->dhdt, D * n)); }
+    if (mask & ND_DL_RATES) {
+      CU(dn(a->force, c->force, D * 3 * n)); CU(dn(a->dudt, c->dudt, D * n)); CU(dn(a->dendt, c->dendt, D * n));
+      if (c->o.imhd != 0) {
+        CU(dn(a->dBevoldt, c->dBevoldt, D * 3 * n)); CU(dn(a->dpsidt, c->dpsidt, D * n)); CU(dn(a->gradpsi, c->gradpsi, D * 3 * n)); CU(dn(a->divB, c->divB, D * n));
+        CU(dn(a->curlB, c->curlB, D * 3 * n));
+      }
+      CU(dn(a->daldt, c->daldt, D * 3 * n));
+      // graddivv holds dead "curl v" sums unless iavlim(1)=3, del2u is a local of the reference: shipped only on request
+      if (c->o.want_aux || c->o.iavlim[0] == 3) CU(dn(a->graddivv, c->graddivv, D * 3 * n));
+      if (c->o.want_aux) CU(dn(a->del2u, c->del2u, D * n));
+    }
+  }
+  return 0;
+}
+}  // namespace
+
+int ndspmhd_b200_upload(nd_ctx *c, const nd_arrays *a, int npart, int ntotal, int idim) {
+  if (!c || !a || !c->stream) return c ? set_err(c, ND_ERR_STATE, "context not initialised") : ND_ERR_INVALID_ARG;
+  if (int e = check_upload_args(c, a, npart, ntotal, idim)) return e;
   CU(cudaSetDevice(c->device));
   int want = ntotal;
-  if (o.device_ghosts && any_ghost_bound(c)) want = npart + npart / 4 + 1024;   // first guess; make_ghosts grows it if needed
+  if (c->o.device_ghosts && any_ghost_bound(c)) want = npart + npart / 4 + 1024;   // first guess; make_ghosts grows it if needed
   if (int e = ensure_capacity(c, want, 0)) return e;
-  const size_t n = (size_t)ntotal;
-  auto up = [&](void *dst, const void *src, size_t bytes) -> cudaError_t { return src ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream) : cudaMemsetAsync(dst, 0, bytes, c->stream); };
-  CU(up(c->x, a->x, sizeof(double) * c->ndim * n));
-  CU(up(c->vel, a->vel, sizeof(double) * 3 * n));
-  CU(up(c->pmass, a->pmass, sizeof(double) * n));
-  CU(up(c->hh, a->hh_in, sizeof(double) * n));
-  CU(cudaMemcpyAsync(c->hh0, c->hh, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-  CU(up(c->itype, a->itype, sizeof(int) * n));
-  CU(up(c->ireal, a->ireal, sizeof(int) * n));
-  CU(up(c->en, a->en, sizeof(double) * n));
-  CU(up(c->Bevol, a->Bevol, sizeof(double) * 3 * n));
-  CU(up(c->alpha, a->alpha, sizeof(double) * 3 * n));
-  CU(up(c->psi, a->psi, sizeof(double) * n));
-  CU(up(c->rho, a->rho_in, sizeof(double) * n));
+  if (int e = upload_group(c, a, (size_t)ntotal, 1, c->stream)) return e;
+  if (int e = upload_group(c, a, (size_t)ntotal, 2, c->stream)) return e;
   CU(cudaStreamSynchronize(c->stream));
   c->npart = npart; c->ntotal = ntotal; c->nown = npart;
   c->uploaded = true; c->linked = c->density_done = c->prim_done = c->rates_done = false;
@@ -1508,26 +1562,10 @@ int ndspmhd_b200_download(nd_ctx *c, nd_arrays *a, unsigned mask, int idim) {
   if (idim < c->ntotal) return set_err(c, ND_ERR_INVALID_ARG, "download: idim < ntotal (re-allocate the host arrays, src/ghostND_mhd.f90:383-386)");
   CU(cudaSetDevice(c->device));
   const size_t n = (size_t)(c->has_comm ? c->nown : c->ntotal);   // with slabs only this rank's own rows go back
-  auto dn = [&](void *dst, const void *src, size_t bytes) -> cudaError_t { return (dst && src) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess; };
-  const size_t D = sizeof(double);
-  if (mask & ND_DL_DENSITY) {
-    CU(dn(a->hh, c->hh, D * n)); CU(dn(a->rho, c->rho, D * n)); CU(dn(a->gradh, c->gradh, D * n)); CU(dn(a->drhodt, c->drhodt, D * n));
-    CU(dn(a->dhdt, c->dhdt, D * n)); CU(dn(a->numneigh, c->numneigh, sizeof(int) * n));
-    if (c->o.want_aux) { CU(dn(a->rhoalt, c->rhoalt, D * n)); CU(dn(a->gradhn, c->gradhn, D * n)); CU(dn(a->gradsoft, c->gradsoft, D * n)); CU(dn(a->gradgradh, c->gradgradh, D * n)); }
-  }
-  if (mask & ND_DL_PRIM) {
-    CU(dn(a->dens, c->dens, D * n)); CU(dn(a->uu, c->uu, D * n)); CU(dn(a->pr, c->pr, D * n)); CU(dn(a->spsound, c->spsound, D * n));
-    if (c->o.imhd != 0) CU(dn(a->Bfield, c->Bfield, D * 3 * n));
-  }
-  if (mask & ND_DL_RATES) {
-    CU(dn(a->force, c->force, D * 3 * n)); CU(dn(a->dudt, c->dudt, D * n)); CU(dn(a->dendt, c->dendt, D * n)); CU(dn(a->dBevoldt, c->dBevoldt, D * 3 * n));
-    CU(dn(a->daldt, c->daldt, D * 3 * n)); CU(dn(a->dpsidt, c->dpsidt, D * n)); CU(dn(a->gradpsi, c->gradpsi, D * 3 * n)); CU(dn(a->divB, c->divB, D * n));
-    CU(dn(a->curlB, c->curlB, D * 3 * n)); CU(dn(a->graddivv, c->graddivv, D * 3 * n)); CU(dn(a->del2u, c->del2u, D * n));
-    // drhodt/dhdt are zeroed on ghosts and fixed particles by get_rates (:952-953)
-    CU(dn(a->drhodt, c->drhodt, D * n)); CU(dn(a->dhdt, c->dhdt, D * n));
-  }
+  for (int g = 1; g <= 3; g++) if (int e = download_group(c, a, n, g, mask, c->stream)) return e;
   if ((mask & ND_DL_GHOSTS) && !c->has_comm) {
-    const size_t g0 = (size_t)c->npart, ng = n - g0;
+    const size_t g0 = (size_t)c->npart, ng = n - g0, D = sizeof(double);
+    auto dn = [&](void *dst, const void *src, size_t bytes) -> cudaError_t { return (dst && src) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess; };
     if (ng > 0) {
       if (a->x_out) CU(dn(a->x_out + g0 * c->ndim, c->x + g0 * c->ndim, D * c->ndim * ng));
       if (a->vel_out) CU(dn(a->vel_out + g0 * 3, c->vel + g0 * 3, D * 3 * ng));
@@ -1536,6 +1574,59 @@ int ndspmhd_b200_download(nd_ctx *c, nd_arrays *a, unsigned mask, int idim) {
     }
   }
   CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// upload + derivs + download in one call, with the copies overlapped with the kernels: the inputs of cons2prim/rates arrive
+// while the density iteration runs, the density results and primitives leave while the rates run.  Host arrays should be
+// page-locked (ndspmhd_b200_host_alloc) for the copies to be asynchronous.
+int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int idim, unsigned mask, nd_scalars *s) {
+  if (!c || !a || !c->stream) return c ? set_err(c, ND_ERR_STATE, "context not initialised") : ND_ERR_INVALID_ARG;
+  if (int e = check_upload_args(c, a, npart, ntotal, idim)) return e;
+  CU(cudaSetDevice(c->device));
+  int want = std::max(ntotal, c->ntotal);
+  if (c->o.device_ghosts && any_ghost_bound(c)) want = std::max(want, npart + npart / 4 + 1024);
+  if (int e = ensure_capacity(c, want, 0)) return e;
+  const size_t nin = (size_t)ntotal;
+  if (int e = upload_group(c, a, nin, 1, c->stream_h2d)) return e;
+  CU(cudaEventRecord(c->ev_in[0], c->stream_h2d));
+  if (int e = upload_group(c, a, nin, 2, c->stream_h2d)) return e;
+  CU(cudaEventRecord(c->ev_in[1], c->stream_h2d));
+  c->npart = npart; c->ntotal = ntotal; c->nown = npart;
+  c->uploaded = true; c->linked = c->density_done = c->prim_done = c->rates_done = false;
+  CU(cudaStreamWaitEvent(c->stream, c->ev_in[0], 0));
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  int e = DISPATCH_NDIM(c, do_link<1>(c), do_link<2>(c), do_link<3>(c));
+  if (!e) { CU(cudaEventRecord(c->ev[1], c->stream)); e = DISPATCH_NDIM(c, do_iterate_density<1>(c, 0), do_iterate_density<2>(c, 0), do_iterate_density<3>(c, 0)); }
+  if (e) { cudaStreamSynchronize(c->stream_h2d); return e; }
+  if (idim < c->ntotal) { cudaStreamSynchronize(c->stream_h2d); return set_err(c, ND_ERR_INVALID_ARG, "derivs_host: idim < ntotal after ghost generation"); }
+  const size_t nout = (size_t)(c->has_comm ? c->nown : c->ntotal);
+  CU(cudaEventRecord(c->ev_out[0], c->stream));
+  CU(cudaStreamWaitEvent(c->stream_d2h, c->ev_out[0], 0));
+  if (int e2 = download_group(c, a, nout, 1, mask, c->stream_d2h)) return e2;
+  CU(cudaStreamWaitEvent(c->stream, c->ev_in[1], 0));
+  CU(cudaEventRecord(c->ev[2], c->stream));
+  e = do_cons2prim(c);
+  if (e) { cudaStreamSynchronize(c->stream_h2d); cudaStreamSynchronize(c->stream_d2h); return e; }
+  CU(cudaEventRecord(c->ev_out[1], c->stream));
+  CU(cudaStreamWaitEvent(c->stream_d2h, c->ev_out[1], 0));
+  if (int e2 = download_group(c, a, nout, 2, mask, c->stream_d2h)) return e2;
+  e = DISPATCH_NDIM(c, do_get_rates<1>(c, nullptr, nullptr, nullptr, 0), do_get_rates<2>(c, nullptr, nullptr, nullptr, 0), do_get_rates<3>(c, nullptr, nullptr, nullptr, 0));
+  if (e) { cudaStreamSynchronize(c->stream_h2d); cudaStreamSynchronize(c->stream_d2h); return e; }
+  if (int e2 = download_group(c, a, nout, 3, mask, c->stream)) return e2;   // stream order: after the final kernel
+  if ((mask & ND_DL_GHOSTS) && !c->has_comm && c->ntotal > c->npart) {
+    const size_t g0 = (size_t)c->npart, ng = (size_t)c->ntotal - g0, D = sizeof(double);
+    if (a->x_out) CU(cudaMemcpyAsync(a->x_out + g0 * c->ndim, c->x + g0 * c->ndim, D * c->ndim * ng, cudaMemcpyDeviceToHost, c->stream_d2h));
+    if (a->vel_out) CU(cudaMemcpyAsync(a->vel_out + g0 * 3, c->vel + g0 * 3, D * 3 * ng, cudaMemcpyDeviceToHost, c->stream_d2h));
+    if (a->ireal_out) CU(cudaMemcpyAsync(a->ireal_out + g0, c->ireal + g0, sizeof(int) * ng, cudaMemcpyDeviceToHost, c->stream_d2h));
+    if (a->itype_out) CU(cudaMemcpyAsync(a->itype_out + g0, c->itype + g0, sizeof(int) * ng, cudaMemcpyDeviceToHost, c->stream_d2h));
+  }
+  if (int e2 = fill_density_scalars(c)) return e2;
+  CU(cudaStreamSynchronize(c->stream_d2h));
+  CU(cudaStreamSynchronize(c->stream));
+  float t;
+  for (int k = 0; k < 5; k++) { cudaEventElapsedTime(&t, c->ev[k], c->ev[k + 1]); c->ms[k] = t; }
+  if (s) *s = c->sc;
   return 0;
 }
 
@@ -1579,6 +1670,20 @@ int ndspmhd_b200_rewind(nd_ctx *c) {
   CU(cudaSetDevice(c->device));
   CU(cudaMemcpyAsync(c->hh, c->hh0, sizeof(double) * c->npart, cudaMemcpyDeviceToDevice, c->stream));
   c->linked = c->density_done = c->prim_done = c->rates_done = false;
+  return 0;
+}
+
+int ndspmhd_b200_selftest_math(nd_ctx *c, const double *in, double *out_sqrt, double *out_rsqrt, int n) {
+  if (!c || !in || !out_sqrt || !out_rsqrt || n < 1) return ND_ERR_INVALID_ARG;
+  CU(cudaSetDevice(c->device));
+  double *d = nullptr;
+  CU(cudaMalloc(&d, sizeof(double) * 3 * (size_t)n));
+  CU(cudaMemcpyAsync(d, in, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, k_selftest_math, nblocks(n, 256), 256, 0, d, d + n, d + 2 * (size_t)n, n);
+  CU(cudaMemcpyAsync(out_sqrt, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(out_rsqrt, d + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(d);
   return 0;
 }
 

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel
     if (FIRST) q2i = ((k >= cs1) || (k >= cs0 && k <= s)) ? __dmul_rn(rij2, hi21) : __dmul_rn(__dmul_rn(rij2, hi1), hi1);
     else q2i = __dmul_rn(rij2, hi21);
     // rij = sqrt(rij2) and dr = dx/(rij + epsilon(rij)) (:199) without a divide: 1/(r+e) = (1/r)(1 - e/r) to O((e/r)^2) ~ 1e-26
-    const double rinv = rij2 > 0. ? rsqrt(rij2) : 0.;
+    const double rinv = rsqrt_nr(rij2);          // 0 for the self pair
     const double rij = rij2 * rinv;
     const double rinve = rinv - 2.220446049250313e-16 * rinv * rinv;
     const double pmassj = vj.w;

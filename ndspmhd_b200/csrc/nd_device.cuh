@@ -41,6 +41,30 @@ __device__ __forceinline__ double4 ld4(const double4 *p) {
   return make_double4(a.x, a.y, b.x, b.y);
 }
 
+// Branch-free FP64 1/sqrt and sqrt: MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~2^-22) + two Newton steps (+ one residual
+// correction for sqrt), ~1 ulp.  CUDA's sqrt()/rsqrt() carry a slow-path branch per call, which stops ptxas from
+// interleaving the six independent square roots of a rates pair; these do not.  Arguments <= 1e-300 give 0.
+__device__ __forceinline__ double rsqrt_nr(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double t = x * y, e = fma(-t, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  t = x * y; e = fma(-t, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  return x > 1.e-300 ? y : 0.;
+}
+__device__ __forceinline__ double sqrt_nr(double x) {
+  const double y = rsqrt_nr(x);
+  double s = x * y;
+  const double d = fma(-s, s, x);
+  s = fma(0.5 * y, d, s);
+  return x > 1.e-300 ? s : 0.;
+}
+__global__ void k_selftest_math(const double *in, double *out_sqrt, double *out_rsqrt, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { out_sqrt[i] = sqrt_nr(in[i]); out_rsqrt[i] = rsqrt_nr(in[i]); }
+}
+
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // rij2 = dot_product(dx,dx) in index order without FMA contraction (src/density_sums.f90:181,

@@ -46,7 +46,10 @@ struct RatesRed {
 #ifndef ND_RATES_MINB
 #define ND_RATES_MINB 2
 #endif
-constexpr int RATES_BLOCK = 128;
+#ifndef ND_RATES_BLOCK
+#define ND_RATES_BLOCK 128
+#endif
+constexpr int RATES_BLOCK = ND_RATES_BLOCK;
 
 __device__ __forceinline__ double get_tstop(int idrag_nature, double rhogas, double rhodust, double Kdrag) {
   // src/dust.f90:77-102
@@ -112,18 +115,16 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
     const double rij2 = dist2_exact(dx, dy, dz);
     const double hj1 = pj.w, hj21 = __dmul_rn(hj1, hj1);
     const double q2i = __dmul_rn(rij2, hi21), q2j = __dmul_rn(rij2, hj21);
-    const double rinv = rij2 > 0. ? rsqrt(rij2) : 0.;           // rij = sqrt(rij2), dr = dx/rij (:416, :429)
+    // rij = sqrt(rij2), dr = dx/rij (:416, :429); coincident particles (rij <= epsilon, :417-427) get dr = 0 through rinv = 0
+    const double rinv = rij2 > 4.930380657631324e-32 ? rsqrt_nr(rij2) : 0.;
     const double rij = rij2 * rinv;
-    double drx, dry, drz;
-    if (rij <= eps) {                                           // :417-427 coincident particles
-      drx = dry = drz = 0.;
+    const double drx = dx * rinv, dry = dy * rinv, drz = dz * rinv;
+    if (rinv == 0.) {                                           // rare: bookkeeping of :417-427
       if (__ldg(G.typ + k) == ti) {
         const int origj = G.perm[k];
         if (origj >= G.nown || orig > origj) nclumped++;
-        if (rij < 2.2250738585072014e-308 && ti != 2) atomicCAS(R.err, 0, 1 /*ND_ERR_INVALID_ARG: dx = 0*/);
+        if (rij2 == 0. && ti != 2) atomicCAS(R.err, 0, 1 /*ND_ERR_INVALID_ARG: dx = 0*/);
       }
-    } else {
-      drx = dx * rinv; dry = dy * rinv; drz = dz * rinv;
     }
     const double pmassj = vj.w;
     const double dvx = vxi - vj.x, dvy = vyi - vj.y, dvz = vzi - vj.z;
@@ -176,20 +177,20 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
         const double vsigproji = vsig2i * vsig2i - 4. * ((spsoundi * projBi) * (spsoundi * projBi)) * rho1i;
         const double vsigprojj = vsig2j * vsig2j - 4. * ((spsoundj * projBj) * (spsoundj * projBj)) * rho1j;
         if (vsigproji < 0. || vsigprojj < 0.) atomicCAS(R.err, 0, 6 /*ND_ERR_VSIG_DET*/);
-        vsigi = sqrt(0.5 * (vsig2i + sqrt(vsigproji)));
-        vsigj = sqrt(0.5 * (vsig2j + sqrt(vsigprojj)));
-        if (iavlim2 != 2) vsigB = sqrt((dvx * dvx + dvy * dvy) + dvz * dvz);   // norm2(dvel), :1433
+        vsigi = sqrt_nr(0.5 * (vsig2i + sqrt_nr(vsigproji)));
+        vsigj = sqrt_nr(0.5 * (vsig2j + sqrt_nr(vsigprojj)));
+        if (iavlim2 != 2) vsigB = sqrt_nr((dvx * dvx + dvy * dvy) + dvz * dvz);   // norm2(dvel), :1433
         else vsigB = 0.5 * (vsigi + vsigj) + fabs(dvdotr);
       } else {
         vsigi = spsoundi; vsigj = spsoundj; vsigB = 0.;
       }
       double vsig = 0.5 * (fmax(vsigi + vsigj - O.beta * dvdotr, 0.0));          // :1452
-      double vsigu = sqrt(fabs(pri - prj) * rhoav1);                            // :1459 (pequil = 0)
+      double vsigu = sqrt_nr(fabs(pri - prj) * rhoav1);                            // :1459 (pequil = 0)
       const double vsigdtc = fmax(vsig, fmax(0.5 * (vsigi + vsigj + O.beta * fabs(dvdotr)), vsigB));   // :1465
       if (ti == T_DUST) { vsig = 0.; vsigu = 0.; }                              // :1472-1474
       else {                                                                    // :1476-1481
         vsigmax = fmax(vsigmax, vsigdtc);
-        if (vsigdtc > zero) dtc_den = fmax(dtc_den, h1max * vsigdtc);
+        dtc_den = fmax(dtc_den, vsigdtc > zero ? h1max * vsigdtc : 0.);
       }
       double fix = 0, fiy = 0, fiz = 0;   // forcei contribution of this pair
       double vsigav = 0.;
@@ -201,9 +202,10 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
         const double term = vsig * rg;                           // :1723
         const double termu = vsigu * rg;                         // :1727
         const double termB = vsigB * rg;                         // :1732
-        if (dvdotr < 0) {                                        // :1745-1748
+        const double approaching = dvdotr < 0. ? 1. : 0.;        // :1745-1748 as a select: no divergent branch in the pair body
+        {
           const double visc = alphaav * term * (-dvdotr);
-          const double c = pmassj * visc;
+          const double c = pmassj * visc * approaching;
           fix -= c * drx; fiy -= c * dry; fiz -= c * drz;
         }
         if (MHD) {                                               // :1762-1774
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
         if (iener == 3) {                                        // :1792-1830 total energy: pair part of dendt
           double qdiff = 0.;
           const double projvi = (vxi * drx + vyi * dry) + vzi * drz, projvj = (vj.x * drx + vj.y * dry) + vj.z * drz;
-          if (dvdotr < 0) qdiff += term * alphaav * 0.5 * (projvi * projvi - projvj * projvj);
+          qdiff += approaching * (term * alphaav * 0.5 * (projvi * projvi - projvj * projvj));
           qdiff += alphau * termu * (uui - uuj);
           if (MHD) {
             double B2i_, B2j_;
@@ -226,8 +228,9 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
           }
           endiss += pmassj * qdiff;                           // :1829
         } else if (iener > 0) {                                  // :1835-1875 thermal energy
-          double vissv = 0., vissB = 0.;
-          if (dvdotr < 0) { const double t = ((vxi * drx + vyi * dry) + vzi * drz) - ((vj.x * drx + vj.y * dry) + vj.z * drz); vissv = -alphaav * 0.5 * (t * t); }
+          double vissB = 0.;
+          const double tv = ((vxi * drx + vyi * dry) + vzi * drz) - ((vj.x * drx + vj.y * dry) + vj.z * drz);
+          const double vissv = -alphaav * 0.5 * (tv * tv) * approaching;
           const double vissu = alphau * (uui - uuj);
           if (MHD) {
             const double dB2 = (dBxx * dBxx + dByy * dByy) + dBzz * dBzz;
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
         const double diffu = cfaci * grkerni * (rho1i * rho1i) + cfacj * grkernj * (rho1j * rho1j);
         dudt += dudti + pmassj * diffu;
       }
-      if (vsigav > zero) dtav_den = fmax(dtav_den, h1max * vsigav);              // :1500
+      dtav_den = fmax(dtav_den, vsigav > zero ? h1max * vsigav : 0.);              // :1500
       {                                                          // pressure, :1538-1567 (phi = 1, sqrtg = 1)
         const double prterm = Prho2i * grkerni + Prho2j * grkernj;
         const double c = pmassj * prterm;

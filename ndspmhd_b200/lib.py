@@ -32,7 +32,7 @@ EXPORTS = [
     "ndspmhd_b200_upload", "ndspmhd_b200_update_ghosts", "ndspmhd_b200_link", "ndspmhd_b200_iterate_density",
     "ndspmhd_b200_cons2prim", "ndspmhd_b200_get_rates", "ndspmhd_b200_derivs", "ndspmhd_b200_download",
     "ndspmhd_b200_host_alloc", "ndspmhd_b200_host_free", "ndspmhd_b200_last_timings", "ndspmhd_b200_launch_count",
-    "ndspmhd_b200_stream", "ndspmhd_b200_rates_pairs", "ndspmhd_b200_rewind", "ndspmhd_b200_set_comm", "ndspmhd_b200_row_counts",
+    "ndspmhd_b200_stream", "ndspmhd_b200_rates_pairs", "ndspmhd_b200_rewind", "ndspmhd_b200_set_comm", "ndspmhd_b200_row_counts", "ndspmhd_b200_selftest_math", "ndspmhd_b200_derivs_host",
 ]
 
 
@@ -68,6 +68,7 @@ def load():
     L.ndspmhd_b200_get_rates.argtypes = [vp, C.POINTER(NdScalars)]
     L.ndspmhd_b200_derivs.argtypes = [vp, C.POINTER(NdScalars)]
     L.ndspmhd_b200_download.argtypes = [vp, C.POINTER(NdArrays), C.c_uint, C.c_int]
+    L.ndspmhd_b200_derivs_host.argtypes = [vp, C.POINTER(NdArrays), C.c_int, C.c_int, C.c_int, C.c_uint, C.POINTER(NdScalars)]
     L.ndspmhd_b200_host_alloc.argtypes = [C.c_size_t]
     L.ndspmhd_b200_host_alloc.restype = vp
     L.ndspmhd_b200_host_free.argtypes = [vp]
@@ -204,6 +205,22 @@ class Hotpath:
         self._chk(self.L.ndspmhd_b200_derivs(self.ctx, C.byref(s)))
         return s.as_dict()
 
+    def selftest_math(self, x: np.ndarray):
+        """sqrt_nr / rsqrt_nr of the pair kernels evaluated on the device for the given arguments."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        s, r = np.empty_like(x), np.empty_like(x)
+        self.L.ndspmhd_b200_selftest_math.argtypes = [C.c_void_p, _DP, _DP, _DP, C.c_int]
+        self._chk(self.L.ndspmhd_b200_selftest_math(self.ctx, x.ctypes.data_as(_DP), s.ctypes.data_as(_DP), r.ctypes.data_as(_DP), x.size))
+        return s, r
+
+    def derivs_host(self, p: Particles, mask: int = abi.DL_ALL) -> dict:
+        """upload + derivs + download in one call with the copies overlapped with the kernels (host arrays in, host arrays out)."""
+        a = arrays_struct(p)
+        s = NdScalars()
+        self._chk(self.L.ndspmhd_b200_derivs_host(self.ctx, C.byref(a), p.npart, p.ntotal, p.idim, mask, C.byref(s)))
+        p.ntotal = s.ntotal if not getattr(self, "_comm", None) else p.ntotal
+        return s.as_dict()
+
     def rewind(self) -> None:
         """Restore the smoothing-length guess of the last upload (bench hook: makes repeated derivs() do identical work)."""
         self._chk(self.L.ndspmhd_b200_rewind(self.ctx))
@@ -238,12 +255,14 @@ class Hotpath:
         return pi[: n.value].copy(), pj[: n.value].copy()
 
 
-def derivs_host(opts: NdOptions, p: Particles, device: int = 0, hot: Hotpath | None = None) -> dict:
+def derivs_host(opts: NdOptions, p: Particles, device: int = 0, hot: Hotpath | None = None, pipelined: bool = False) -> dict:
     """The call a user of the reference makes: host arrays in, host arrays out (upload + derivs + download)."""
     own = hot is None
     if own:
         hot = Hotpath(opts, p.ndim, device)
     try:
+        if pipelined:
+            return hot.derivs_host(p, abi.DL_ALL)
         hot.upload(p)
         s = hot.derivs()
         p.ntotal = s["ntotal"]

@@ -93,6 +93,21 @@ def test_quartic_quintic_kernels_parity(ikernel):
     parity.assert_parity(pg, po, sg, so, o, aux=True)
 
 
+def test_branch_free_sqrt_is_accurate_to_an_ulp():
+    rng = np.random.default_rng(5)
+    x = np.concatenate([10.0 ** rng.uniform(-280, 280, 200000), rng.uniform(0.0, 4.0, 200000), [0.0, 1.0, 4.0, 2.0, 1e-310]])
+    hot = lib.Hotpath(abi.default_options(), 3)
+    try:
+        s, r = hot.selftest_math(x)
+    finally:
+        hot.close()
+    ok = x > 1e-300
+    assert np.all(s[~ok] == 0.0) and np.all(r[~ok] == 0.0)
+    es = np.abs(s[ok] - np.sqrt(x[ok])) / np.spacing(np.sqrt(x[ok]))
+    er = np.abs(r[ok] - 1.0 / np.sqrt(x[ok])) / np.spacing(1.0 / np.sqrt(x[ok]))
+    assert es.max() <= 1.0 and er.max() <= 2.0, (es.max(), er.max())
+
+
 def test_kernel_tables_bit_exact():
     for ndim in (1, 2, 3):
         for ik, idust in ((0, 2), (2, 2), (3, 0)):
@@ -166,6 +181,30 @@ def test_phase_by_phase_calls_equal_fused_derivs():
         assert np.array_equal(getattr(p1, f), getattr(p2, f)), f
     for k in ("dtcourant", "dtforce", "vsigmax", "itsdensity", "ntotal"):
         assert s1[k] == s2[k]
+
+
+@pytest.mark.parametrize("aux", [0, 1])
+def test_pipelined_derivs_host_equals_upload_derivs_download(aux):
+    """ndspmhd_b200_derivs_host overlaps the copies with the kernels on separate streams; same bits as the serial calls."""
+    o, p = setups.orszag_tang(ndim=3, nx=24, zfrac=0.5, perturb_amp=0.2, evolved=True)
+    o.device_ghosts = 1
+    o.want_aux = aux
+    a, b = p.copy(), p.copy()
+    hot = lib.Hotpath(o, 3)
+    try:
+        sa = lib.derivs_host(o, a, hot=hot)
+        for rep in range(2):   # second pass reuses the buffers of the first
+            b = p.copy()
+            sb = lib.derivs_host(o, b, hot=hot, pipelined=True)
+    finally:
+        hot.close()
+    skip = set() if aux else {"graddivv", "del2u"}
+    for f in parity.DENSITY_FIELDS + parity.PRIM_FIELDS + parity.RATES_FIELDS:
+        if f not in skip:
+            assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert np.array_equal(a.numneigh, b.numneigh)
+    for k in ("dtcourant", "dtforce", "vsigmax", "itsdensity", "ntotal", "nneigh_max"):
+        assert sa[k] == sb[k]
 
 
 def test_host_ghost_mode_matches_device_ghost_mode():
