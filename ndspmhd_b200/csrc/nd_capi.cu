@@ -44,6 +44,7 @@ struct nd_ctx {
          *curlB = nullptr, *graddivv = nullptr, *del2u = nullptr;
   // ---- sorted-order arrays ----
   double4 *posh = nullptr, *vm = nullptr, *bpsi = nullptr, *thermo = nullptr, *gal = nullptr;
+  float4 *p32 = nullptr;   // FP32 screening records of the list builder (nd_device.cuh)
   double *srho = nullptr;
   double4 *sF = nullptr, *sdB = nullptr, *sC = nullptr, *sP = nullptr, *sV = nullptr;
   int *typ = nullptr, *perm = nullptr, *permtmp = nullptr, *inv = nullptr, *cellOf = nullptr, *cellOfOrig = nullptr, *redo = nullptr, *list = nullptr,
@@ -380,7 +381,8 @@ __global__ void k_cell_order(const int *cellStart, int ncells, const int *permtm
 
 struct GatherArgs {
   const int *perm, *cellOfOrig, *itype, *ireal; const double *x, *vel, *pmass, *hh;
-  double4 *posh, *vm; int *typ, *cellOf, *inv; int npart, ntotal;
+  double4 *posh, *vm; float4 *p32; int *typ, *cellOf, *inv; int npart, ntotal;
+  double xminpart[3], dxcell1, hhmax1;
 };
 template <int NDIM> __global__ void k_gather_sorted(GatherArgs A) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -390,16 +392,21 @@ template <int NDIM> __global__ void k_gather_sorted(GatherArgs A) {
   double p[3] = {0, 0, 0};
   for (int d = 0; d < NDIM; d++) p[d] = A.x[(size_t)r * NDIM + d];
   A.posh[s] = make_double4(p[0], p[1], p[2], 1.0 / A.hh[st]);   // h1(i) = 1./hh(i)
+  float q[3] = {0.f, 0.f, 0.f};
+  for (int d = 0; d < NDIM; d++) q[d] = (float)((p[d] - A.xminpart[d]) * A.dxcell1);
+  A.p32[s] = make_float4(q[0], q[1], q[2], screen_h2(A.hh[st], A.hhmax1));
   A.vm[s] = make_double4(A.vel[(size_t)r * 3], A.vel[(size_t)r * 3 + 1], A.vel[(size_t)r * 3 + 2], A.pmass[st]);
   A.typ[s] = A.itype[r];
   A.cellOf[s] = A.cellOfOrig[r];
   A.inv[r] = s;
 }
-__global__ void k_refresh_h(const int *perm, const int *ireal, const double *hh, double4 *posh, int npart, int ntotal) {
+__global__ void k_refresh_h(const int *perm, const int *ireal, const double *hh, double4 *posh, float4 *p32, double hhmax1, int npart, int ntotal) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= ntotal) return;
   const int r = perm[s];
-  posh[s].w = 1.0 / hh[(r < npart) ? r : ireal[r] - 1];
+  const double h = hh[(r < npart) ? r : ireal[r] - 1];
+  posh[s].w = 1.0 / h;
+  p32[s].w = screen_h2(h, hhmax1);
 }
 __global__ void k_compact(const int *redo, const int *scan, int n, int *list) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -506,7 +513,7 @@ __global__ void k_c2p_ghost(C2PArgs A) {                                        
 // =====================================================================================================
 struct RGatherArgs {
   const int *perm, *ireal; const double *hh, *pmass, *rho, *pr, *spsound, *uu, *gradh, *alpha, *psi, *Bfield;
-  double4 *posh, *vm, *bpsi, *thermo, *gal; double *srho; int npart, ntotal, imhd; unsigned long long *stress_key; int imagforce; double Bconstmax, pext;
+  double4 *posh, *vm, *bpsi, *thermo, *gal; float4 *p32; double hhmax1; double *srho; int npart, ntotal, imhd; unsigned long long *stress_key; int imagforce; double Bconstmax, pext;
   int *err;
 };
 __global__ void k_rates_gather(RGatherArgs A) {
@@ -518,6 +525,7 @@ __global__ void k_rates_gather(RGatherArgs A) {
     const double h = A.hh[st], rho = A.rho[st];
     if (h <= 0.) atomicCAS(A.err, 0, ND_ERR_H_NONPOSITIVE);                         // :384-387
     A.posh[s].w = 1.0 / h;
+    A.p32[s].w = screen_h2(h, A.hhmax1);
     A.vm[s].w = A.pmass[st];
     A.srho[s] = rho;
     A.thermo[s] = make_double4(1.0 / rho, fmax(A.pr[st] - A.pext, 0.), A.spsound[st], A.uu[st]);   // rho1i, :325; pri = max(pr - pext, 0), :328
@@ -681,6 +689,7 @@ void register_rows(nd_ctx *c) {
   R1(rho); R1(gradh); R1(drhodt); R1(dhdt); R1(rhoalt); R1(gradhn); R1(gradsoft); R1(gradgradh); RI(numneigh);
   R1(dens); R1(uu); R1(pr); R1(spsound); R3(Bfield);
   R3(force); R1(dudt); R1(dendt); R3(dBevoldt); R3(daldt); R1(dpsidt); R3(gradpsi); R1(divB); R3(curlB); R3(graddivv); R1(del2u);
+  v.push_back({(void **)&c->p32, sizeof(float4)});
   R1(srho); R4(posh); R4(vm); R4(bpsi); R4(thermo); R4(gal); R4(sF); R4(sdB); R4(sC); R4(sP); R4(sV);
   RI(typ); RI(perm); RI(permtmp); RI(inv); RI(cellOf); RI(cellOfOrig); RI(redo); RI(list); RI(ghostcount);
 #undef R3
@@ -734,7 +743,10 @@ int check_options(nd_ctx *c, const nd_options &o, int ndim) {
 
 Grid make_grid(nd_ctx *c) {
   Grid G;
-  G.cellStart = c->cellStart; G.cellOf = c->cellOf; G.perm = c->perm; G.posh = c->posh; G.vm = c->vm; G.typ = c->typ;
+  G.cellStart = c->cellStart; G.cellOf = c->cellOf; G.perm = c->perm; G.posh = c->posh; G.vm = c->vm; G.typ = c->typ; G.p32 = c->p32;
+  G.hhmax1 = 1.0 / c->hhmax;
+  // FP32 screening band (scaled units, cell = 1): 4 * 2^-23 * largest scaled coordinate + rounding of the thresholds
+  G.screen_margin = 4.f * 1.1920929e-7f * (float)std::max(c->ncellsx[0], std::max(c->ncellsx[1], c->ncellsx[2])) + 2.e-6f;
   G.nx = c->ncellsx[0]; G.ny = c->ncellsx[1]; G.nz = c->ncellsx[2]; G.ncells = c->ncells;
   G.npart = c->npart; G.ntotal = c->ntotal; G.nown = c->nown;
   G.radkern2 = c->T->radkern2; G.dq2table = c->T->dq2table; G.ddq2table = c->T->ddq2table;
@@ -951,7 +963,9 @@ template <int NDIM> int build_cells(nd_ctx *c) {
   LAUNCH(c, k_cell_order, nblocks((long long)c->ncells * 32, 256), 256, 0, c->cellStart, c->ncells, c->permtmp, c->perm);
   GatherArgs GA;
   GA.perm = c->perm; GA.cellOfOrig = c->cellOfOrig; GA.itype = c->itype; GA.ireal = c->ireal; GA.x = c->x; GA.vel = c->vel; GA.pmass = c->pmass; GA.hh = c->hh;
-  GA.posh = c->posh; GA.vm = c->vm; GA.typ = c->typ; GA.cellOf = c->cellOf; GA.inv = c->inv; GA.npart = c->npart; GA.ntotal = nt;
+  GA.posh = c->posh; GA.vm = c->vm; GA.p32 = c->p32; GA.typ = c->typ; GA.cellOf = c->cellOf; GA.inv = c->inv; GA.npart = c->npart; GA.ntotal = nt;
+  for (int d = 0; d < 3; d++) GA.xminpart[d] = c->xminpart[d];
+  GA.dxcell1 = 1.0 / c->dxcell; GA.hhmax1 = 1.0 / c->hhmax;
   LAUNCH(c, (k_gather_sorted<NDIM>), nblocks(nt, 256), 256, 0, GA);
   return 0;
 }
@@ -1067,7 +1081,7 @@ template <int NDIM> int do_iterate_density(nd_ctx *c, int resume) {
     if (first) {                                                                     // :131-132 symmetric `density`
       if (c->itsdensity > 1) {   // the neighbour count of `density` also looks at h_j (:189-190): refresh the sources' 1/h
         if (c->has_comm) { if (int e = halo_exchange_density(c)) return e; }
-        LAUNCH(c, k_refresh_h, nblocks(c->ntotal, 256), 256, 0, c->perm, c->ireal, c->hh, c->posh, c->npart, c->ntotal);
+        LAUNCH(c, k_refresh_h, nblocks(c->ntotal, 256), 256, 0, c->perm, c->ireal, c->hh, c->posh, c->p32, 1.0 / c->hhmax, c->npart, c->ntotal);
       }
       if (int e = launch_density_round<NDIM, true>(c, A, c->ntotal)) return e;
     } else {                                                                         // :133-134 `density_partial`
@@ -1161,6 +1175,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   RGatherArgs GA;
   GA.perm = c->perm; GA.ireal = c->ireal; GA.hh = c->hh; GA.pmass = c->pmass; GA.rho = c->rho; GA.pr = c->pr; GA.spsound = c->spsound; GA.uu = c->uu;
   GA.gradh = c->gradh; GA.alpha = c->alpha; GA.psi = c->psi; GA.Bfield = c->Bfield;
+  GA.p32 = c->p32; GA.hhmax1 = 1.0 / c->hhmax;
   GA.posh = c->posh; GA.vm = c->vm; GA.bpsi = c->bpsi; GA.thermo = c->thermo; GA.gal = c->gal; GA.npart = c->npart; GA.ntotal = nt; GA.imhd = o.imhd;
   GA.stress_key = c->red + RED_STRESS; GA.imagforce = o.imagforce; GA.srho = c->srho; GA.pext = o.pext; GA.err = c->flags + 1;
   GA.Bconstmax = std::max(o.Bconst[0], std::max(o.Bconst[1], o.Bconst[2]));

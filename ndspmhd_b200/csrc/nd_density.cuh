@@ -93,20 +93,12 @@ __global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel
       drhodt += pmassj * dvdotr * grkerni;
     }
   };
-  {
+  if (cnt > 0) {
     const unsigned *col = L.nbr + ((size_t)(t >> 5) * L.lmax) * 32 + (t & 31);
-    int n = 0;
-    for (; n + 1 < cnt; n += 2) {                  // two neighbours in flight: their loads overlap the other's arithmetic
-      const int k0 = (int)col[(size_t)n * 32], k1 = (int)col[(size_t)(n + 1) * 32];
-      const double4 p0 = ld4(G.posh + k0), v0 = ld4(G.vm + k0), p1 = ld4(G.posh + k1), v1 = ld4(G.vm + k1);
-      body(k0, p0, v0);
-      body(k1, p1, v1);
-    }
-    if (n < cnt) {
-      const int k0 = (int)col[(size_t)n * 32];
-      const double4 p0 = ld4(G.posh + k0), v0 = ld4(G.vm + k0);
-      body(k0, p0, v0);
-    }
+    walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
+      prefetch_l1(G.posh + k2); prefetch_l1(G.vm + k2);          // records two pairs ahead into L1, no registers held
+      body(k, ld4(G.posh + k), ld4(G.vm + k));
+    });
   }
   const int nneigh = active ? A.numneigh[orig] : 0;   // counted by build_lists_kernel (:196-197 / :532)
 

@@ -25,6 +25,8 @@ struct Grid {
   const double4 *posh;      // [ntotal]   {x,y,z,1/h}  (1/h correctly rounded: h1(i) = 1./hh(i), density_sums.f90:130)
   const double4 *vm;        // [ntotal]   {vx,vy,vz,m}
   const int *typ;           // [ntotal]
+  const float4 *p32;        // [ntotal]   FP32 screening record {(x - xminpart)/dxcell, (h/hhmax)^2}: |dX|^2 < (h/hhmax)^2  <=>  rij2/h^2 < radkern2
+  double hhmax1; float screen_margin;
   int nx, ny, nz, ncells;
   int npart, ntotal;        // rows [0,npart) carry their own state (targets are rows < nown), [npart,ntotal) are ghosts
   int nown;
@@ -34,36 +36,52 @@ struct Grid {
   const double *tabdrag;    // [2*(IKERN+1)] {w, dw}
 };
 
+// screening threshold of a particle: rij2*(1/h)^2 < radkern2 with dxcell = radkern*hhmax is |dX|^2 < (h/hhmax)^2 in cell units
+__device__ __forceinline__ float screen_h2(double h, double hhmax1) { const double t = h * hhmax1; return (float)(t * t); }
+
 __device__ __forceinline__ double4 ld4(const double4 *p) {
-  // two 128-bit read-only loads of one 32-byte aligned record
-  const double2 *q = reinterpret_cast<const double2 *>(p);
-  double2 a = __ldg(q), b = __ldg(q + 1);
-  return make_double4(a.x, a.y, b.x, b.y);
+  // one 256-bit read-only load of a 32-byte aligned record (LDG.E.256, sm_100+): one request and one sector per lane
+  double4 r;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st4(double4 *p, const double4 &v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
 }
 
-// Branch-free FP64 1/sqrt and sqrt: MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~2^-22) + two Newton steps (+ one residual
-// correction for sqrt), ~1 ulp.  CUDA's sqrt()/rsqrt() carry a slow-path branch per call, which stops ptxas from
-// interleaving the six independent square roots of a rates pair; these do not.  Arguments <= 1e-300 give 0.
+// Branch-free FP64 1/sqrt and sqrt from the MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~2^-22): one third-order step for 1/sqrt
+// (5 FP64 instructions, <= 1 ulp), one coupled Goldschmidt step + residual correction for sqrt (7 instructions, <= 0.5 ulp
+// measured).  CUDA's sqrt()/rsqrt() carry a slow-path branch per call, which stops ptxas from interleaving the six
+// independent square roots of a rates pair; these do not.  Arguments <= 1e-300 give 0.
 __device__ __forceinline__ double rsqrt_nr(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double t = x * y, e = fma(-t, y, 1.0);
-  y = fma(0.5 * y, e, y);
-  t = x * y; e = fma(-t, y, 1.0);
-  y = fma(0.5 * y, e, y);
+  const double t = x * y, e = fma(-t, y, 1.0);          // e = 1 - x y^2
+  const double q = fma(0.375, e, 0.5) * e;              // y (1 + e/2 + 3 e^2/8)
+  y = fma(y, q, y);
   return x > 1.e-300 ? y : 0.;
 }
 __device__ __forceinline__ double sqrt_nr(double x) {
-  const double y = rsqrt_nr(x);
-  double s = x * y;
-  const double d = fma(-s, s, x);
-  s = fma(0.5 * y, d, s);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double s0 = x * y, h0 = 0.5 * y;
+  const double r = fma(-s0, h0, 0.5);
+  const double s1 = fma(s0, r, s0), h1 = fma(h0, r, h0);
+  const double d = fma(-s1, s1, x);
+  const double s = fma(d, h1, s1);
   return x > 1.e-300 ? s : 0.;
 }
 __global__ void k_selftest_math(const double *in, double *out_sqrt, double *out_rsqrt, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { out_sqrt[i] = sqrt_nr(in[i]); out_rsqrt[i] = rsqrt_nr(in[i]); }
 }
+
+// cp.async (LDGSTS): 16 bytes global -> shared without passing through registers; .ca keeps the line in L1 for the other lanes
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -160,6 +178,31 @@ struct NbrLists {
 };
 __device__ __forceinline__ size_t nbr_index(int t, int n, int lmax) { return ((size_t)(t >> 5) * lmax + n) * 32 + (t & 31); }
 
+// Walks one list column.  Entries are read in batches of four, two batches (thousands of cycles) before they are needed: the
+// list streams from HBM, and a load whose consumer sits in the same basic block gets its register move hoisted right behind
+// it by ptxas, which exposes the full DRAM latency on every pair (measured: 20 % of all stall samples).  The inner loop is a
+// real loop, so the batch rotation stays at the bottom of the outer one.  f(n, k, k1, k2): entry n and the two after it.
+template <class F> __device__ __forceinline__ void walk_list(const unsigned *col, int cnt, F &&f) {
+  const int last = cnt - 1;
+  auto ld = [&](int n) { return (int)__ldcs(col + (size_t)min(n, last) * 32); };
+  int c0 = ld(0), c1 = ld(1), c2 = ld(2), c3 = ld(3);
+  int n0 = ld(4), n1 = ld(5), n2 = ld(6), n3 = ld(7);
+#pragma unroll 1
+  for (int nb = 0; nb < cnt; nb += 4) {
+    const int m0 = ld(nb + 8), m1 = ld(nb + 9), m2 = ld(nb + 10), m3 = ld(nb + 11);
+#pragma unroll 1
+    for (int u = 0; u < 4; u++) {
+      if (nb + u >= cnt) break;
+      const int k = u == 0 ? c0 : u == 1 ? c1 : u == 2 ? c2 : c3;
+      const int k1 = u == 0 ? c1 : u == 1 ? c2 : u == 2 ? c3 : n0;
+      const int k2 = u == 0 ? c2 : u == 1 ? c3 : u == 2 ? n0 : n1;
+      f(nb + u, k, k1, k2);
+    }
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    n0 = m0; n1 = m1; n2 = m2; n3 = m3;
+  }
+}
+
 enum { LIST_DENS_FIRST = 0, LIST_DENS_PARTIAL = 1, LIST_RATES = 2 };
 
 struct ListArgs {
@@ -194,7 +237,9 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
   int cnt = 0, nneigh = 0;
   unsigned *col = L.nbr + ((size_t)(t >> 5) * L.lmax) * 32 + (t & 31);
 
-  auto accept = [&](int k, const double4 &pj) -> bool {
+  // exact inclusion test in the reference's arithmetic: returns whether the candidate goes on the list
+  auto accept_exact = [&](int k) -> bool {
+    const double4 pj = ld4(G.posh + k);
     const double rij2 = dist2_exact(xi - pj.x, yi - pj.y, zi - pj.z);
     const double hj1 = pj.w;
     if (MODE == LIST_DENS_FIRST) {
@@ -217,15 +262,47 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
       nneigh++;                                                   // :532
       return true;
     } else {                                                      // ratesND_mhd.f90:401-415
-      if (k == s) return false;                                  // j /= i (both-ghost pairs cannot occur: the target is real)
       const double q2i = __dmul_rn(rij2, hi21), q2j = __dmul_rn(rij2, __dmul_rn(hj1, hj1));
-      if (!((q2i < G.radkern2) || (q2j < G.radkern2))) return false;
-      if (A.pair_out_i) {                                        // parity-test hook: record the accepted pair
-        unsigned long long n = atomicAdd(A.pair_count, 1ull);
-        if ((long long)n < A.pair_cap) { A.pair_out_i[n] = orig + 1; A.pair_out_j[n] = G.perm[k] + 1; }
-      }
-      return A.drag || types_interact(ti, __ldg(G.typ + k));     // :436-446
+      return (q2i < G.radkern2) || (q2j < G.radkern2);
     }
+  };
+  // FP32 screening in cell units: |dX|^2 against (h/hhmax)^2.  Outside a band of +-screen_margin around the thresholds the
+  // FP32 verdict provably equals the exact one (the band covers the rounding of the FP32 coordinates and thresholds); inside
+  // the band -- a 1e-4 sliver of the candidates -- the exact FP64 test above decides.  The list is therefore exactly the
+  // reference's neighbour set, at a third of the FP64 instructions per candidate.
+  const float4 pf = G.p32[s];
+  const float Ti = (MODE == LIST_RATES) ? pf.w : screen_h2(A.hh[orig], G.hhmax1);
+  const float marg = G.screen_margin;
+  auto accept = [&](int k, const float4 &qj) -> bool {
+    if (MODE == LIST_RATES && k == s) return false;               // j /= i (both-ghost pairs cannot occur: the target is real)
+    const float ddx = pf.x - qj.x, ddy = pf.y - qj.y, ddz = pf.z - qj.z;
+    const float r2 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
+    const float a = r2 - Ti, b = (MODE == LIST_DENS_PARTIAL) ? a : r2 - qj.w;
+    bool keep;
+    if (fminf(fabsf(a), fabsf(b)) <= marg) {
+      keep = accept_exact(k);
+      if (MODE != LIST_RATES) return keep;                        // the density modes count and filter types inside
+    } else {
+      const bool mine = a < 0.f;
+      if (!(mine || b < 0.f)) return false;
+      if (MODE == LIST_DENS_FIRST) {
+        if (!types_interact(ti, __ldg(G.typ + k))) return false;
+        nneigh++;
+        return mine;
+      } else if (MODE == LIST_DENS_PARTIAL) {
+        const int tj = __ldg(G.typ + k);
+        if (tj != ti && tj != T_BND) return false;
+        nneigh++;
+        return true;
+      }
+      keep = true;
+    }
+    if (!keep) return false;
+    if (A.pair_out_i) {                                          // parity-test hook: record the accepted pair
+      unsigned long long n = atomicAdd(A.pair_count, 1ull);
+      if ((long long)n < A.pair_cap) { A.pair_out_i[n] = orig + 1; A.pair_out_j[n] = G.perm[k] + 1; }
+    }
+    return A.drag || types_interact(ti, __ldg(G.typ + k));       // :436-446
   };
 
   constexpr int NY = (NDIM >= 2) ? 3 : 1, NZ = (NDIM >= 3) ? 3 : 1, UNROLL = 4;
@@ -241,12 +318,12 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
       int k = __ldg(G.cellStart + c0 + xa);
       const int e = __ldg(G.cellStart + c0 + xb + 1);
       for (; k < e; k += UNROLL) {
-        double4 pj[UNROLL];
+        float4 qj[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) pj[u] = ld4(G.posh + min(k + u, e - 1));
+        for (int u = 0; u < UNROLL; u++) qj[u] = __ldg(G.p32 + min(k + u, e - 1));
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
-          if (k + u < e && accept(k + u, pj[u])) {
+          if (k + u < e && accept(k + u, qj[u])) {
             if (cnt < L.lmax) col[(size_t)cnt * 32] = (unsigned)(k + u);
             cnt++;
           }

@@ -49,7 +49,24 @@ struct RatesRed {
 #ifndef ND_RATES_BLOCK
 #define ND_RATES_BLOCK 128
 #endif
+#ifndef ND_RATES_STAGE
+#define ND_RATES_STAGE 1   // how neighbour records reach the pair body: 0 direct 256-bit loads, 1/2 + L1 prefetch 1/2 pairs ahead, 3 cp.async to shared
+#endif
 constexpr int RATES_BLOCK = ND_RATES_BLOCK;
+constexpr int RATES_NREC = 5;    // staged records per neighbour: posh, vm, thermo, gal, bpsi
+
+// per-thread staging slots in shared memory: plane (stage, record, half) holds one 16-byte half-record per thread, so the
+// 128-bit reads of a warp are conflict-free
+__device__ __forceinline__ void stage_put(double2 *stg, int st, int rec, const double4 *src) {
+  double2 *d = stg + ((st * RATES_NREC + rec) * 2) * RATES_BLOCK + threadIdx.x;
+  cp_async16(d, src);
+  cp_async16(d + RATES_BLOCK, reinterpret_cast<const double2 *>(src) + 1);
+}
+__device__ __forceinline__ double4 stage_get(const double2 *stg, int st, int rec) {
+  const double2 *d = stg + ((st * RATES_NREC + rec) * 2) * RATES_BLOCK + threadIdx.x;
+  const double2 a = d[0], b = d[RATES_BLOCK];
+  return make_double4(a.x, a.y, b.x, b.y);
+}
 
 __device__ __forceinline__ double get_tstop(int idrag_nature, double rhogas, double rhodust, double Kdrag) {
   // src/dust.f90:77-102
@@ -64,6 +81,9 @@ __device__ __forceinline__ double get_tstop(int idrag_nature, double rhogas, dou
 template <int NDIM, bool MHD, bool DRAG, bool FAST>
 __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(Grid G, RatesIn I, RatesOpts O, RatesSums S, RatesRed R, NbrLists L,
                                                                                  int s0, int ntargets) {
+#if ND_RATES_STAGE == 3
+  __shared__ double2 stg[2 * RATES_NREC * 2 * RATES_BLOCK];   // [stage][record][half][thread], 40 KB
+#endif
   const int tix = blockIdx.x * RATES_BLOCK + threadIdx.x;   // target index within this launch
   const int s = s0 + tix;
   const int iav = FAST ? 2 : O.iav, iener = FAST ? (O.iener != 0 ? 2 : 0) : O.iener, ikernav = FAST ? 3 : O.ikernav, iresist = FAST ? 0 : O.iresist;
@@ -109,7 +129,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
   const double eps = 2.220446049250313e-16;
 
   // ---- pair terms over the neighbour list (build_lists_kernel<LIST_RATES> applied src/ratesND_mhd.f90:401-415) ----
-  auto body = [&](int k, const double4 &pj, const double4 &vj, const double4 &tj4) {
+  auto body = [&](int k, const double4 &pj, const double4 &vj, const double4 &tj4, const double4 &gj, const double4 &bj) {
     const int tj = DRAG ? __ldg(G.typ + k) : 0;   // only the drag dispatch needs the neighbour's type on the fast path
     const double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
     const double rij2 = dist2_exact(dx, dy, dz);
@@ -131,7 +151,6 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
     const double h1max = fmax(hi1, hj1);
     if (!DRAG || types_interact(ti, tj)) {
       // =============================== rates_core ===============================
-      const double4 gj = ld4(I.gal + k);
       double wabi, grkerni, wabj, grkernj;
       interp_wg(G, q2i, wabi, grkerni);                         // :1208-1211
       grkerni = grkerni * hfacgrkerni;
@@ -157,7 +176,6 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
       double projBi = 0, projBj = 0, projdB = 0, projBrhoi = 0, projBrhoj = 0, Brho2j = 0, valfven2j = 0;
       double Brhoxj = 0, Brhoyj = 0, Brhozj = 0;
       if (MHD) {                                                // :1295-1313
-        const double4 bj = ld4(I.bpsi + k);
         Bxj = bj.x; Byj = bj.y; Bzj = bj.z; psij = bj.w;
         Brhoxj = Bxj * rho1j; Brhoyj = Byj * rho1j; Brhozj = Bzj * rho1j;
         dBxx = Bxi - Bxj; dByy = Byi - Byj; dBzz = Bzi - Bzj;
@@ -331,28 +349,43 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
   };
 
   if (cnt > 0) {
-    // The list column is read ND_RATES_PFD entries ahead (one coalesced 128-byte line per entry and warp) and the records of the
-    // neighbour two pairs ahead are pulled into L1 with register-free prefetches, so the pair body's own loads hit L1.
     const unsigned *col = L.nbr + ((size_t)(tix >> 5) * L.lmax) * 32 + (tix & 31);
-    const int last = cnt - 1;
-    int k0 = (int)col[0], k1 = (int)col[(size_t)min(1, last) * 32], k2 = (int)col[(size_t)min(2, last) * 32], k3 = (int)col[(size_t)min(3, last) * 32];
-#pragma unroll 1
-    for (int n = 0; n < cnt; n++) {
-      const int k4 = (int)col[(size_t)min(n + 4, last) * 32];
-      prefetch_l1(G.posh + k2); prefetch_l1(G.vm + k2); prefetch_l1(I.thermo + k2); prefetch_l1(I.gal + k2);
-      if (MHD) prefetch_l1(I.bpsi + k2);
-      const double4 pj = ld4(G.posh + k0), vj = ld4(G.vm + k0), tj4 = ld4(I.thermo + k0);
-      body(k0, pj, vj, tj4);
-      k0 = k1; k1 = k2; k2 = k3; k3 = k4;
-    }
+    const double4 zero4 = make_double4(0., 0., 0., 0.);
+#if ND_RATES_STAGE == 3
+    // The five 32-byte records of the NEXT neighbour are copied global -> shared by cp.async while the current pair is
+    // evaluated (double buffer, no registers held across the copy); a thread only reads the slots it filled itself.
+    auto fetch = [&](int k, int st) {
+      stage_put(stg, st, 0, G.posh + k); stage_put(stg, st, 1, G.vm + k); stage_put(stg, st, 2, I.thermo + k); stage_put(stg, st, 3, I.gal + k);
+      if (MHD) stage_put(stg, st, 4, I.bpsi + k);
+      cp_async_commit();
+    };
+    fetch((int)col[0], 0);
+    walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
+      fetch(k1, (n + 1) & 1);                                   // for the last entry this refetches it; harmless
+      cp_async_wait<1>();
+      const int st = n & 1;
+      body(k, stage_get(stg, st, 0), stage_get(stg, st, 1), stage_get(stg, st, 2), stage_get(stg, st, 3), MHD ? stage_get(stg, st, 4) : zero4);
+    });
+    cp_async_wait<0>();
+#else
+    walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
+#if ND_RATES_STAGE >= 1
+      // register-free L1 prefetch of the records ND_RATES_STAGE pairs ahead
+      const int kp = ND_RATES_STAGE == 1 ? k1 : k2;
+      prefetch_l1(G.posh + kp); prefetch_l1(G.vm + kp); prefetch_l1(I.thermo + kp); prefetch_l1(I.gal + kp);
+      if (MHD) prefetch_l1(I.bpsi + kp);
+#endif
+      body(k, ld4(G.posh + k), ld4(G.vm + k), ld4(I.thermo + k), ld4(I.gal + k), MHD ? ld4(I.bpsi + k) : zero4);
+    });
+#endif
   }
 
   if (active) {
-    S.F[s] = make_double4(fx, fy, fz, dudt);
-    S.dB[s] = make_double4(dBx, dBy, dBz, divB);
-    S.C[s] = make_double4(cBx, cBy, cBz, del2u);
-    S.P[s] = make_double4(gpx, gpy, gpz, endiss);
-    S.V[s] = make_double4(gvx, gvy, gvz, 0.);
+    st4(S.F + s, make_double4(fx, fy, fz, dudt));
+    st4(S.dB + s, make_double4(dBx, dBy, dBz, divB));
+    st4(S.C + s, make_double4(cBx, cBy, cBz, del2u));
+    st4(S.P + s, make_double4(gpx, gpy, gpz, endiss));
+    st4(S.V + s, make_double4(gvx, gvy, gvz, 0.));
   }
   // block-free warp reductions into global min/max keys
   double dtcourant = dtc_den > 0. ? fmin(1.e6, 1. / dtc_den) : 1.e6;            // initial value 1.e6, :251
