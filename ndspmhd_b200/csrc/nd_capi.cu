@@ -32,6 +32,7 @@ struct nd_ctx {
   TabRec *d_tab = nullptr; TabRec2 *d_tab2 = nullptr; double *d_tabdrag = nullptr;
   // sizes
   int npart = 0, ntotal = 0, cap = 0, nown = 0;   // nown <= npart: rows this context computes (the rest of [0,npart) are halo copies)
+  bool mixed_types = true;   // false when the last link found one itype only (the list builder then skips the type rules)
   bool uploaded = false, linked = false, density_done = false, prim_done = false, rates_done = false;
   // ---- original-order arrays (row r = Fortran index r+1) ----
   double *x = nullptr, *vel = nullptr, *pmass = nullptr, *hh = nullptr, *en = nullptr, *Bevol = nullptr, *alpha = nullptr, *psi = nullptr;
@@ -381,7 +382,7 @@ __global__ void k_cell_order(const int *cellStart, int ncells, const int *permtm
 
 struct GatherArgs {
   const int *perm, *cellOfOrig, *itype, *ireal; const double *x, *vel, *pmass, *hh;
-  double4 *posh, *vm; float4 *p32; int *typ, *cellOf, *inv; int npart, ntotal;
+  double4 *posh, *vm; float4 *p32; int *typ, *cellOf, *inv, *mixed; int npart, ntotal;
   double xminpart[3], dxcell1, hhmax1;
 };
 template <int NDIM> __global__ void k_gather_sorted(GatherArgs A) {
@@ -397,6 +398,7 @@ template <int NDIM> __global__ void k_gather_sorted(GatherArgs A) {
   A.p32[s] = make_float4(q[0], q[1], q[2], screen_h2(A.hh[st], A.hhmax1));
   A.vm[s] = make_double4(A.vel[(size_t)r * 3], A.vel[(size_t)r * 3 + 1], A.vel[(size_t)r * 3 + 2], A.pmass[st]);
   A.typ[s] = A.itype[r];
+  if (A.itype[r] != A.itype[0]) *A.mixed = 1;
   A.cellOf[s] = A.cellOfOrig[r];
   A.inv[r] = s;
 }
@@ -965,7 +967,8 @@ template <int NDIM> int build_cells(nd_ctx *c) {
   GA.perm = c->perm; GA.cellOfOrig = c->cellOfOrig; GA.itype = c->itype; GA.ireal = c->ireal; GA.x = c->x; GA.vel = c->vel; GA.pmass = c->pmass; GA.hh = c->hh;
   GA.posh = c->posh; GA.vm = c->vm; GA.p32 = c->p32; GA.typ = c->typ; GA.cellOf = c->cellOf; GA.inv = c->inv; GA.npart = c->npart; GA.ntotal = nt;
   for (int d = 0; d < 3; d++) GA.xminpart[d] = c->xminpart[d];
-  GA.dxcell1 = 1.0 / c->dxcell; GA.hhmax1 = 1.0 / c->hhmax;
+  GA.dxcell1 = 1.0 / c->dxcell; GA.hhmax1 = 1.0 / c->hhmax; GA.mixed = c->flags + 6;
+  CU(cudaMemsetAsync(c->flags + 6, 0, sizeof(int), c->stream));
   LAUNCH(c, (k_gather_sorted<NDIM>), nblocks(nt, 256), 256, 0, GA);
   return 0;
 }
@@ -974,6 +977,7 @@ template <int NDIM> int do_link(nd_ctx *c) {
   if (c->o.device_ghosts) { if (int e = make_ghosts<NDIM>(c)) return e; }
   if (int e = build_cells<NDIM>(c)) return e;
   if (int e = sync_flags(c)) return e;
+  c->mixed_types = c->h_flags[6] != 0;
   double ef = c->h_flags[1];
   if (int e = comm_allreduce(c, &ef, 1, 0)) return e;   // every rank leaves together
   if (ef != 0.) {
@@ -1016,7 +1020,8 @@ template <int NDIM, int MODE> int build_lists(nd_ctx *c, const Grid &G, ListArgs
   for (int attempt = 0; attempt < 8; attempt++) {
     if (int e = ensure_lists(c, LA.ntargets)) return e;
     L.nbr = c->nbr; L.cnt = c->lcnt; L.lmax = c->lmax; L.overflow = c->flags + 5;
-    LAUNCH(c, (build_lists_kernel<NDIM, MODE>), nblocks(LA.ntargets, 128), 128, 0, G, LA, L);
+    if (c->mixed_types) LAUNCH(c, (build_lists_kernel<NDIM, MODE, true>), nblocks(LA.ntargets, 128), 128, 0, G, LA, L);
+    else LAUNCH(c, (build_lists_kernel<NDIM, MODE, false>), nblocks(LA.ntargets, 128), 128, 0, G, LA, L);
     CU(cudaMemcpyAsync(c->h_flags + 20, c->flags + 5, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     const int big = c->h_flags[20];

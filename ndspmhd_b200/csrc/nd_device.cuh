@@ -214,7 +214,8 @@ struct ListArgs {
   int *pair_out_i, *pair_out_j; unsigned long long *pair_count; long long pair_cap;   // parity-test hook (LIST_RATES)
 };
 
-template <int NDIM, int MODE>
+// TYPES = false: every row has the same itype (found at link time), so the type rules always pass and typ[] is never read.
+template <int NDIM, int MODE, bool TYPES>
 __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, NbrLists L) {
   const int t = blockIdx.x * 128 + threadIdx.x;
   if (t >= A.ntargets) return;
@@ -224,11 +225,8 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
   bool active = orig < G.nown;                     // ghosts and halo rows are sources only
   if (MODE == LIST_DENS_PARTIAL && ti == T_BND) active = false;   // density_sums.f90:510
   if (!active) { L.cnt[t] = 0; return; }
-  const double4 p = ld4(G.posh + s);
-  const double xi = p.x, yi = p.y, zi = p.z;
-  // density: current h (the sorted record holds the h of the last link); rates: 1/h of the record (h1(i) = 1./hh(i))
-  const double hi1 = (MODE == LIST_RATES) ? p.w : 1.0 / A.hh[orig];
-  const double hi21 = __dmul_rn(hi1, hi1);
+  // density: current h (the sorted record holds the h of the last link); rates: the record's (h1(i) = 1./hh(i))
+  const double hcur = (MODE == LIST_RATES) ? 0. : A.hh[orig];
   const int cell = G.cellOf[s];
   const int cs0 = __ldg(G.cellStart + cell), cs1 = __ldg(G.cellStart + cell + 1);
   const int ix = cell % G.nx;
@@ -236,11 +234,14 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
   const int iy = (NDIM >= 2) ? tq % G.ny : 0, iz = (NDIM >= 3) ? tq / G.ny : 0;
   int cnt = 0, nneigh = 0;
   unsigned *col = L.nbr + ((size_t)(t >> 5) * L.lmax) * 32 + (t & 31);
+  const bool hook = (MODE == LIST_RATES) && A.pair_out_i != nullptr;
 
-  // exact inclusion test in the reference's arithmetic: returns whether the candidate goes on the list
-  auto accept_exact = [&](int k) -> bool {
-    const double4 pj = ld4(G.posh + k);
-    const double rij2 = dist2_exact(xi - pj.x, yi - pj.y, zi - pj.z);
+  // Exact inclusion test in the reference's arithmetic (rare path, see below): sets whether the pair counts as a neighbour
+  // and whether it goes on the list.
+  auto exact = [&](int k, bool &counts, bool &store) {
+    const double4 p = ld4(G.posh + s), pj = ld4(G.posh + k);
+    const double hi1 = (MODE == LIST_RATES) ? p.w : 1.0 / hcur, hi21 = __dmul_rn(hi1, hi1);
+    const double rij2 = dist2_exact(p.x - pj.x, p.y - pj.y, p.z - pj.z);
     const double hj1 = pj.w;
     if (MODE == LIST_DENS_FIRST) {
       // The reference visits a pair once; "i" is the particle met first: the one in the lower cell, or the later-inserted
@@ -250,59 +251,49 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
       double q2me, q2ot;
       if (iam_i) { q2me = __dmul_rn(rij2, hi21); q2ot = __dmul_rn(__dmul_rn(rij2, hj1), hj1); }
       else { q2me = __dmul_rn(__dmul_rn(rij2, hi1), hi1); q2ot = __dmul_rn(rij2, __dmul_rn(hj1, hj1)); }
-      const bool mine = q2me < G.radkern2;
-      if (!(mine || q2ot < G.radkern2)) return false;            // :189-190 with the target real
-      if (!types_interact(ti, __ldg(G.typ + k))) return false;   // :169-174
-      nneigh++;                                                   // :196-197
-      return mine;                                                // terms with q2me >= radkern2 are exact zeros (table end = 0)
+      store = q2me < G.radkern2;                                  // terms with q2me >= radkern2 are exact zeros (table end = 0)
+      counts = store || q2ot < G.radkern2;                        // :189-190 with the target real
     } else if (MODE == LIST_DENS_PARTIAL) {
-      if (!(__dmul_rn(rij2, hi21) < G.radkern2)) return false;   // :528
-      const int tj = __ldg(G.typ + k);
-      if (tj != ti && tj != T_BND) return false;                 // :517
-      nneigh++;                                                   // :532
-      return true;
-    } else {                                                      // ratesND_mhd.f90:401-415
+      counts = store = __dmul_rn(rij2, hi21) < G.radkern2;        // :528
+    } else {                                                      // ratesND_mhd.f90:404-415
       const double q2i = __dmul_rn(rij2, hi21), q2j = __dmul_rn(rij2, __dmul_rn(hj1, hj1));
-      return (q2i < G.radkern2) || (q2j < G.radkern2);
+      counts = store = (q2i < G.radkern2) || (q2j < G.radkern2);
     }
   };
   // FP32 screening in cell units: |dX|^2 against (h/hhmax)^2.  Outside a band of +-screen_margin around the thresholds the
   // FP32 verdict provably equals the exact one (the band covers the rounding of the FP32 coordinates and thresholds); inside
   // the band -- a 1e-4 sliver of the candidates -- the exact FP64 test above decides.  The list is therefore exactly the
-  // reference's neighbour set, at a third of the FP64 instructions per candidate.
+  // reference's neighbour set, without FP64 arithmetic on the common path.
   const float4 pf = G.p32[s];
-  const float Ti = (MODE == LIST_RATES) ? pf.w : screen_h2(A.hh[orig], G.hhmax1);
+  const float Ti = (MODE == LIST_RATES) ? pf.w : screen_h2(hcur, G.hhmax1);
   const float marg = G.screen_margin;
-  auto accept = [&](int k, const float4 &qj) -> bool {
-    if (MODE == LIST_RATES && k == s) return false;               // j /= i (both-ghost pairs cannot occur: the target is real)
+  auto visit = [&](int k, const float4 &qj) {
     const float ddx = pf.x - qj.x, ddy = pf.y - qj.y, ddz = pf.z - qj.z;
     const float r2 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
     const float a = r2 - Ti, b = (MODE == LIST_DENS_PARTIAL) ? a : r2 - qj.w;
-    bool keep;
-    if (fminf(fabsf(a), fabsf(b)) <= marg) {
-      keep = accept_exact(k);
-      if (MODE != LIST_RATES) return keep;                        // the density modes count and filter types inside
-    } else {
-      const bool mine = a < 0.f;
-      if (!(mine || b < 0.f)) return false;
-      if (MODE == LIST_DENS_FIRST) {
-        if (!types_interact(ti, __ldg(G.typ + k))) return false;
-        nneigh++;
-        return mine;
-      } else if (MODE == LIST_DENS_PARTIAL) {
-        const int tj = __ldg(G.typ + k);
-        if (tj != ti && tj != T_BND) return false;
-        nneigh++;
-        return true;
+    bool counts = fminf(a, b) < 0.f;                              // :189-190 / :528 / ratesND_mhd.f90:415
+    bool store = (MODE == LIST_DENS_FIRST) ? (a < 0.f) : counts;
+    if (fminf(fabsf(a), fabsf(b)) <= marg) exact(k, counts, store);
+    if (MODE == LIST_RATES) {
+      if (k == s) counts = store = false;                         // j /= i (both-ghost pairs cannot occur: the target is real)
+      if (hook && store) {                                        // parity-test hook: the accepted pair before the type dispatch
+        unsigned long long n = atomicAdd(A.pair_count, 1ull);
+        if ((long long)n < A.pair_cap) { A.pair_out_i[n] = orig + 1; A.pair_out_j[n] = G.perm[k] + 1; }
       }
-      keep = true;
     }
-    if (!keep) return false;
-    if (A.pair_out_i) {                                          // parity-test hook: record the accepted pair
-      unsigned long long n = atomicAdd(A.pair_count, 1ull);
-      if ((long long)n < A.pair_cap) { A.pair_out_i[n] = orig + 1; A.pair_out_j[n] = G.perm[k] + 1; }
+    if (TYPES && counts) {
+      const int tj = __ldg(G.typ + k);
+      bool ok;
+      if (MODE == LIST_DENS_FIRST) ok = types_interact(ti, tj);   // density_sums.f90:169-174
+      else if (MODE == LIST_DENS_PARTIAL) ok = (tj == ti) || (tj == T_BND);   // :517
+      else ok = A.drag || types_interact(ti, tj);                 // ratesND_mhd.f90:436-446
+      counts = counts && ok; store = store && ok;
     }
-    return A.drag || types_interact(ti, __ldg(G.typ + k));       // :436-446
+    nneigh += counts ? 1 : 0;                                     // :196-197 / :532
+    if (store) {
+      if (cnt < L.lmax) col[(size_t)cnt * 32] = (unsigned)k;
+      cnt++;
+    }
   };
 
   constexpr int NY = (NDIM >= 2) ? 3 : 1, NZ = (NDIM >= 3) ? 3 : 1, UNROLL = 4;
@@ -317,18 +308,16 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
       const int xa = ix > 0 ? ix - 1 : 0, xb = ix + 1 < G.nx ? ix + 1 : G.nx - 1;
       int k = __ldg(G.cellStart + c0 + xa);
       const int e = __ldg(G.cellStart + c0 + xb + 1);
-      for (; k < e; k += UNROLL) {
+#pragma unroll 1
+      for (; k + UNROLL <= e; k += UNROLL) {
         float4 qj[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) qj[u] = __ldg(G.p32 + min(k + u, e - 1));
+        for (int u = 0; u < UNROLL; u++) qj[u] = __ldg(G.p32 + k + u);
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-          if (k + u < e && accept(k + u, qj[u])) {
-            if (cnt < L.lmax) col[(size_t)cnt * 32] = (unsigned)(k + u);
-            cnt++;
-          }
-        }
+        for (int u = 0; u < UNROLL; u++) visit(k + u, qj[u]);
       }
+#pragma unroll 1
+      for (; k < e; k++) visit(k, __ldg(G.p32 + k));
     }
   }
   if (cnt > L.lmax) { atomicMax(L.overflow, cnt); cnt = L.lmax; }
