@@ -71,6 +71,24 @@ __device__ __forceinline__ double sqrt_nr(double x) {
   const double s = fma(d, h1, s1);
   return x > 1.e-300 ? s : 0.;
 }
+// N independent square roots advanced in lockstep: the source order interleaves the (serial, ~9-cycle per step) chains so
+// that ptxas, which keeps close to source order under register pressure, issues them back to back instead of one after another.
+template <int N> __device__ __forceinline__ void sqrt_n(const double (&x)[N], double (&out)[N]) {
+  double y[N], s0[N], h0[N], r[N], s1[N], h1[N], d[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(x[i]));
+#pragma unroll
+  for (int i = 0; i < N; i++) { s0[i] = x[i] * y[i]; h0[i] = 0.5 * y[i]; }
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = fma(-s0[i], h0[i], 0.5);
+#pragma unroll
+  for (int i = 0; i < N; i++) { s1[i] = fma(s0[i], r[i], s0[i]); h1[i] = fma(h0[i], r[i], h0[i]); }
+#pragma unroll
+  for (int i = 0; i < N; i++) d[i] = fma(-s1[i], s1[i], x[i]);
+#pragma unroll
+  for (int i = 0; i < N; i++) out[i] = x[i] > 1.e-300 ? fma(d[i], h1[i], s1[i]) : 0.;
+}
+
 __global__ void k_selftest_math(const double *in, double *out_sqrt, double *out_rsqrt, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { out_sqrt[i] = sqrt_nr(in[i]); out_rsqrt[i] = rsqrt_nr(in[i]); }

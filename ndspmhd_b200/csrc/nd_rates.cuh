@@ -50,7 +50,7 @@ struct RatesRed {
 #define ND_RATES_BLOCK 128
 #endif
 #ifndef ND_RATES_STAGE
-#define ND_RATES_STAGE 1   // how neighbour records reach the pair body: 0 direct 256-bit loads, 1/2 + L1 prefetch 1/2 pairs ahead, 3 cp.async to shared
+#define ND_RATES_STAGE 3   // how neighbour records reach the pair body: 0 direct 256-bit loads, 1/2 + L1 prefetch 1/2 pairs ahead, 3 cp.async to shared
 #endif
 constexpr int RATES_BLOCK = ND_RATES_BLOCK;
 constexpr int RATES_NREC = 5;    // staged records per neighbour: posh, vm, thermo, gal, bpsi
@@ -151,21 +151,10 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
     const double h1max = fmax(hi1, hj1);
     if (!DRAG || types_interact(ti, tj)) {
       // =============================== rates_core ===============================
-      double wabi, grkerni, wabj, grkernj;
-      interp_wg(G, q2i, wabi, grkerni);                         // :1208-1211
-      grkerni = grkerni * hfacgrkerni;
-      const double hfacwabj = powndim<NDIM>(hj1), hfacgrkernj = hfacwabj * hj1;   // :1215-1216
-      interp_wg(G, q2j, wabj, grkernj);                         // :1217-1220
-      grkernj = grkernj * hfacgrkernj;
-      double grkern;
-      if (ikernav == 3) {                                       // :1227-1237
-        grkerni = grkerni * gradhi;
-        grkernj = grkernj * gj.x;
-        grkern = 0.5 * (grkerni + grkernj);
-      } else {                                                  // :1239-1241
-        grkern = 0.5 * (grkerni + grkernj);
-        grkerni = grkern; grkernj = grkern;
-      }
+      // kernel gradient table rows for q2i, q2j: the loads are issued here, the interpolation (their first use) comes after the
+      // signal-velocity block so that ~250 independent FP64 instructions cover the lookup latency
+      const int idxi = tab_index(q2i, G.ddq2table), idxj = tab_index(q2j, G.ddq2table);
+      const double2 rowi = __ldg(reinterpret_cast<const double2 *>(G.tab + idxi) + 1), rowj = __ldg(reinterpret_cast<const double2 *>(G.tab + idxj) + 1);
       const double dvdotr = (dvx * drx + dvy * dry) + dvz * drz;   // :1250
       const double rho1j = tj4.x, rho21j = rho1j * rho1j;          // :1256-1258
       const double rhoav1 = 0.5 * (rho1i + rho1j);                 // :1261
@@ -188,27 +177,48 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
         valfven2j = B2j * rho1j;
         Brho2j = B2j * rho21j;
       }
-      // ---- signal velocities :1417-1465 ----
-      double vsigi, vsigj, vsigB;
+      // ---- signal velocities :1417-1465 ----  (the independent square roots advance in lockstep, see sqrt_n)
+      double vsigi, vsigj, vsigB, vsigu;
+      const double pdiff = fabs(pri - prj) * rhoav1;                               // :1459 (pequil = 0)
       if (MHD) {
         const double vsig2j = spsoundj * spsoundj + valfven2j;
         const double vsigproji = vsig2i * vsig2i - 4. * ((spsoundi * projBi) * (spsoundi * projBi)) * rho1i;
         const double vsigprojj = vsig2j * vsig2j - 4. * ((spsoundj * projBj) * (spsoundj * projBj)) * rho1j;
         if (vsigproji < 0. || vsigprojj < 0.) atomicCAS(R.err, 0, 6 /*ND_ERR_VSIG_DET*/);
-        vsigi = sqrt_nr(0.5 * (vsig2i + sqrt_nr(vsigproji)));
-        vsigj = sqrt_nr(0.5 * (vsig2j + sqrt_nr(vsigprojj)));
-        if (iavlim2 != 2) vsigB = sqrt_nr((dvx * dvx + dvy * dvy) + dvz * dvz);   // norm2(dvel), :1433
+        const double a4[4] = {vsigproji, vsigprojj, (dvx * dvx + dvy * dvy) + dvz * dvz /* norm2(dvel), :1433 */, pdiff};
+        double r4[4];
+        sqrt_n<4>(a4, r4);
+        const double a2[2] = {0.5 * (vsig2i + r4[0]), 0.5 * (vsig2j + r4[1])};
+        double r2[2];
+        sqrt_n<2>(a2, r2);
+        vsigi = r2[0]; vsigj = r2[1]; vsigu = r4[3];
+        if (iavlim2 != 2) vsigB = r4[2];
         else vsigB = 0.5 * (vsigi + vsigj) + fabs(dvdotr);
       } else {
         vsigi = spsoundi; vsigj = spsoundj; vsigB = 0.;
+        vsigu = sqrt_nr(pdiff);
       }
       double vsig = 0.5 * (fmax(vsigi + vsigj - O.beta * dvdotr, 0.0));          // :1452
-      double vsigu = sqrt_nr(fabs(pri - prj) * rhoav1);                            // :1459 (pequil = 0)
       const double vsigdtc = fmax(vsig, fmax(0.5 * (vsigi + vsigj + O.beta * fabs(dvdotr)), vsigB));   // :1465
       if (ti == T_DUST) { vsig = 0.; vsigu = 0.; }                              // :1472-1474
       else {                                                                    // :1476-1481
         vsigmax = fmax(vsigmax, vsigdtc);
         dtc_den = fmax(dtc_den, vsigdtc > zero ? h1max * vsigdtc : 0.);
+      }
+      // ---- kernel gradients :1208-1241 (w = w[index] + dwdx*(q2 - index*dq2table), src/kernelND.f90:4443-4455) ----
+      double grkerni = rowi.x + rowi.y * (q2i - __dmul_rn((double)idxi, G.dq2table));
+      double grkernj = rowj.x + rowj.y * (q2j - __dmul_rn((double)idxj, G.dq2table));
+      grkerni = grkerni * hfacgrkerni;
+      const double hfacwabj = powndim<NDIM>(hj1), hfacgrkernj = hfacwabj * hj1;   // :1215-1216
+      grkernj = grkernj * hfacgrkernj;
+      double grkern;
+      if (ikernav == 3) {                                       // :1227-1237
+        grkerni = grkerni * gradhi;
+        grkernj = grkernj * gj.x;
+        grkern = 0.5 * (grkerni + grkernj);
+      } else {                                                  // :1239-1241
+        grkern = 0.5 * (grkerni + grkernj);
+        grkerni = grkern; grkernj = grkern;
       }
       double fix = 0, fiy = 0, fiz = 0;   // forcei contribution of this pair
       double vsigav = 0.;
