@@ -84,7 +84,8 @@ typedef struct nd_options {
   /* library-side switches (no reference counterpart) */
   int device_ghosts;          /* 1: library makes the ghost rows itself (restating ghostND_mhd.f90) from rows [0,npart) */
   int want_aux;               /* 1: also produce rhoalt, gradhn, gradsoft, gradgradh (dead for the first-class tuple) */
-  int reserved_i[6];
+  int idustevol;              /* options:idustevol (src/defaults.f90:98); only 0 (dust fraction itself) is supported with idust=1 */
+  int reserved_i[5];
   /* reals */
   double hfact, psep, tolh;   /* setup_params, options */
   double gamma, polyk;        /* eos */
@@ -148,14 +149,23 @@ typedef struct nd_arrays {
   double *vel_out;       /* (3,idim) */
   int    *ireal_out;     /* (idim) */
   int    *itype_out;     /* (idim) */
-  void   *reserved_p[8];
+  /* --- one-fluid dust, idust=1 (src/allocateND.f90:386-392); NULL otherwise --- */
+  const double *dustevol;    /* (idim)   in:  part:dustevol(1,:), the evolved dust variable (idustevol=0: the dust fraction) */
+  const double *dustfrac_in; /* (idim)   in:  part:dustfrac(1,:) on entry -- `density` reads the value left by the previous
+                                              conservative2primitive (src/density_sums.f90:280-282), not the one made from dustevol */
+  const double *deltav;      /* (3,idim) in:  part:deltav */
+  double *dustfrac;          /* (idim)   out: part:dustfrac after conservative2primitive (src/conservative2primitive.f90:76-113) */
+  double *rhogas;            /* (idim)   out: part:rhogas  (density sums, src/density_sums.f90:278-292) */
+  double *rhodust;           /* (idim)   out: part:rhodust(1,:) */
+  double *ddustevoldt;       /* (idim)   out: rates:ddustevoldt(1,:) */
+  double *ddeltavdt;         /* (3,idim) out: rates:ddeltavdt */
 } nd_arrays;
 
 /* download masks */
 enum {
-  ND_DL_DENSITY = 1u,   /* hh rho gradh drhodt dhdt numneigh (+aux) */
-  ND_DL_PRIM    = 2u,   /* dens uu pr spsound Bfield */
-  ND_DL_RATES   = 4u,   /* force dudt dendt dBevoldt daldt dpsidt gradpsi divB curlB graddivv del2u */
+  ND_DL_DENSITY = 1u,   /* hh rho gradh drhodt dhdt numneigh (+aux) (+rhogas rhodust with idust=1) */
+  ND_DL_PRIM    = 2u,   /* dens uu pr spsound Bfield (+dustfrac) */
+  ND_DL_RATES   = 4u,   /* force dudt dendt dBevoldt daldt dpsidt gradpsi divB curlB graddivv del2u (+ddustevoldt ddeltavdt) */
   ND_DL_GHOSTS  = 8u,   /* x_out vel_out ireal_out itype_out rows [npart,ntotal) */
   ND_DL_ALL     = 15u
 };

@@ -46,7 +46,8 @@ class NdOptions(C.Structure):
         ("iquantum", C.c_int), ("ind_timesteps", C.c_int),
         ("nsubsteps_divB", C.c_int),
         ("device_ghosts", C.c_int), ("want_aux", C.c_int),
-        ("reserved_i", C.c_int * 6),
+        ("idustevol", C.c_int),
+        ("reserved_i", C.c_int * 5),
         ("hfact", C.c_double), ("psep", C.c_double), ("tolh", C.c_double),
         ("gamma", C.c_double), ("polyk", C.c_double),
         ("alphamin", C.c_double), ("alphaumin", C.c_double), ("alphaBmin", C.c_double), ("beta", C.c_double),
@@ -73,7 +74,8 @@ class NdArrays(C.Structure):
         ("force", _DP), ("dudt", _DP), ("dendt", _DP), ("dBevoldt", _DP), ("daldt", _DP), ("dpsidt", _DP),
         ("gradpsi", _DP), ("divB", _DP), ("curlB", _DP), ("graddivv", _DP), ("del2u", _DP),
         ("x_out", _DP), ("vel_out", _DP), ("ireal_out", _IP), ("itype_out", _IP),
-        ("reserved_p", C.c_void_p * 8),
+        ("dustevol", _DP), ("dustfrac_in", _DP), ("deltav", _DP),
+        ("dustfrac", _DP), ("rhogas", _DP), ("rhodust", _DP), ("ddustevoldt", _DP), ("ddeltavdt", _DP),
     ]
 
 
@@ -134,6 +136,7 @@ def default_options(ndim: int = 3) -> NdOptions:
     o.use_smoothed_rhodust = 1
     o.iuse_exact_derivs = 0
     o.idust = 0
+    o.idustevol = 0
     o.idrag_nature = 0
     o.Kdrag = 0.0
     o.ibiascorrection = 0
@@ -179,6 +182,9 @@ _ARRAY_SPEC = {
     "daldt": (3, np.float64), "dpsidt": (1, np.float64), "gradpsi": (3, np.float64), "fmag": (3, np.float64),
     "divB": (1, np.float64), "curlB": (3, np.float64), "graddivv": (3, np.float64), "del2u": (1, np.float64),
     "xsphterm": (3, np.float64),
+    # one-fluid dust (ndust = 1, src/variablesND.f90:172)
+    "dustevol": (1, np.float64), "dustfrac": (1, np.float64), "deltav": (3, np.float64), "rhogas": (1, np.float64),
+    "rhodust": (1, np.float64), "ddustevoldt": (1, np.float64), "ddeltavdt": (3, np.float64),
 }
 
 

@@ -47,6 +47,10 @@ struct nd_ctx {
   double4 *posh = nullptr, *vm = nullptr, *bpsi = nullptr, *thermo = nullptr, *gal = nullptr;
   float4 *p32 = nullptr;   // FP32 screening records of the list builder (nd_device.cuh)
   double *srho = nullptr;
+  // ---- one-fluid dust (idust=1; allocated only then) ----
+  double *dustevol = nullptr, *dustfrac = nullptr, *deltav = nullptr, *rhogas = nullptr, *rhodust = nullptr, *ddustevoldt = nullptr, *ddeltavdt = nullptr;
+  double *sdf = nullptr;            // sorted: entry dust fraction of the row's parent (density sums)
+  double4 *dusta = nullptr, *sD = nullptr; double2 *dustb = nullptr;   // sorted rates records / sums (nd_rates.cuh)
   double4 *sF = nullptr, *sdB = nullptr, *sC = nullptr, *sP = nullptr, *sV = nullptr;
   int *typ = nullptr, *perm = nullptr, *permtmp = nullptr, *inv = nullptr, *cellOf = nullptr, *cellOfOrig = nullptr, *redo = nullptr, *list = nullptr,
       *scanout = nullptr, *ghostcount = nullptr;
@@ -383,6 +387,7 @@ __global__ void k_cell_order(const int *cellStart, int ncells, const int *permtm
 struct GatherArgs {
   const int *perm, *cellOfOrig, *itype, *ireal; const double *x, *vel, *pmass, *hh;
   double4 *posh, *vm; float4 *p32; int *typ, *cellOf, *inv, *mixed; int npart, ntotal;
+  const double *dustfrac; double *sdf;   // one-fluid dust (NULL otherwise)
   double xminpart[3], dxcell1, hhmax1;
 };
 template <int NDIM> __global__ void k_gather_sorted(GatherArgs A) {
@@ -398,6 +403,7 @@ template <int NDIM> __global__ void k_gather_sorted(GatherArgs A) {
   A.p32[s] = make_float4(q[0], q[1], q[2], screen_h2(A.hh[st], A.hhmax1));
   A.vm[s] = make_double4(A.vel[(size_t)r * 3], A.vel[(size_t)r * 3 + 1], A.vel[(size_t)r * 3 + 2], A.pmass[st]);
   A.typ[s] = A.itype[r];
+  if (A.sdf) A.sdf[s] = A.dustfrac[st];
   if (A.itype[r] != A.itype[0]) *A.mixed = 1;
   A.cellOf[s] = A.cellOfOrig[r];
   A.inv[r] = s;
@@ -454,21 +460,30 @@ struct C2PArgs {
   // fixed-particle replicas (copy_particle, src/copy_particle.f90:28-115) touch the state arrays too
   double *pmass, *rho_w, *rhoalt, *hh, *en_w, *Bevol_w, *alpha, *psi, *gradh, *gradhn, *gradsoft, *gradgradh;
   int npart, ntotal, imhd, iener; double gamma, polyk; bool aux;
+  // one-fluid dust (NULL otherwise)
+  const double *dustevol; double *dustfrac, *rhogas, *rhodust;
 };
 __global__ void k_c2p(C2PArgs A) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.npart) return;
-  const double rho = A.rho[i];
+  const double rhotot = A.rho[i];
+  double rho = rhotot;
+  if (A.dustevol) {                                                                 // :76-113 (idustevol = 0)
+    double eps = A.dustevol[i];
+    if (eps > 1.) eps = 1.;                                                         // :102-104 (the caller's dustevol is not touched)
+    A.dustfrac[i] = eps;
+    rho = rhotot * (1. - eps);                                                      // :112 dens is the GAS density; the EOS takes it (:418-424)
+  }
   A.dens[i] = rho;                                                                  // :117
   double B[3] = {0, 0, 0};
   if (A.imhd >= 11) for (int k = 0; k < 3; k++) B[k] = A.Bevol[(size_t)i * 3 + k];  // :151-152
-  else if (A.imhd >= 1) for (int k = 0; k < 3; k++) B[k] = A.Bevol[(size_t)i * 3 + k] * rho;   // :190-193
+  else if (A.imhd >= 1) for (int k = 0; k < 3; k++) B[k] = A.Bevol[(size_t)i * 3 + k] * rhotot;   // :190-193
   if (A.imhd != 0) for (int k = 0; k < 3; k++) A.Bfield[(size_t)i * 3 + k] = B[k];
   double uu;
   if (A.iener == 3) {                                                               // :329-346
     const double *v = A.vel + (size_t)i * 3;
     const double v2i = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2];
-    const double B2i = ((B[0] * B[0] + B[1] * B[1]) + B[2] * B[2]) / rho;
+    const double B2i = ((B[0] * B[0] + B[1] * B[1]) + B[2] * B[2]) / rhotot;
     uu = A.en[i] - 0.5 * v2i - 0.5 * B2i;
     if (uu < 0.) uu = 0.;
   } else uu = A.en[i];                                                              // :353-368
@@ -500,6 +515,7 @@ __global__ void k_c2p_fixed(C2PArgs A) {                                        
   A.psi[i] = A.psi[j]; A.gradh[i] = A.gradh[j];
   if (A.aux) { A.rhoalt[i] = A.rhoalt[j]; A.gradhn[i] = A.gradhn[j]; A.gradsoft[i] = A.gradsoft[j]; A.gradgradh[i] = A.gradgradh[j]; }
   A.spsound[i] = A.spsound[j]; A.pr[i] = A.pr[j]; A.dens[i] = A.dens[j];
+  if (A.dustevol) { A.dustfrac[i] = A.dustfrac[j]; A.rhogas[i] = A.rhogas[j]; A.rhodust[i] = A.rhodust[j]; }   // copy_particle.f90:84-92
 }
 __global__ void k_c2p_ghost(C2PArgs A) {                                            // :441-467
   const int i = A.npart + blockIdx.x * blockDim.x + threadIdx.x;
@@ -508,6 +524,8 @@ __global__ void k_c2p_ghost(C2PArgs A) {                                        
   if (j < 0) return;
   A.psi[i] = A.psi[j]; A.dens[i] = A.dens[j]; A.uu[i] = A.uu[j]; A.spsound[i] = A.spsound[j]; A.pr[i] = A.pr[j];
   if (A.imhd != 0) for (int k = 0; k < 3; k++) A.Bfield[(size_t)i * 3 + k] = A.Bfield[(size_t)j * 3 + k];
+  // :464, and copy_particle for all-periodic boundaries (:465) -- the only ghost configuration accepted with one-fluid dust
+  if (A.dustevol) { A.dustfrac[i] = A.dustfrac[j]; A.rhogas[i] = A.rhogas[j]; A.rhodust[i] = A.rhodust[j]; }
 }
 
 // =====================================================================================================
@@ -517,6 +535,8 @@ struct RGatherArgs {
   const int *perm, *ireal; const double *hh, *pmass, *rho, *pr, *spsound, *uu, *gradh, *alpha, *psi, *Bfield;
   double4 *posh, *vm, *bpsi, *thermo, *gal; float4 *p32; double hhmax1; double *srho; int npart, ntotal, imhd; unsigned long long *stress_key; int imagforce; double Bconstmax, pext;
   int *err;
+  // one-fluid dust (dusta NULL otherwise)
+  const double *dustfrac, *deltav, *rhogas, *rhodust; double4 *dusta; double2 *dustb; int use_smoothed_rhodust;
 };
 __global__ void k_rates_gather(RGatherArgs A) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -532,6 +552,11 @@ __global__ void k_rates_gather(RGatherArgs A) {
     A.srho[s] = rho;
     A.thermo[s] = make_double4(1.0 / rho, fmax(A.pr[st] - A.pext, 0.), A.spsound[st], A.uu[st]);   // rho1i, :325; pri = max(pr - pext, 0), :328
     A.gal[s] = make_double4(A.gradh[st], A.alpha[(size_t)st * 3], A.alpha[(size_t)st * 3 + 1], A.alpha[(size_t)st * 3 + 2]);
+    if (A.dusta) {                                                                  // :344-356
+      const double eps = A.dustfrac[st];
+      A.dusta[s] = make_double4(eps, A.deltav[(size_t)st * 3], A.deltav[(size_t)st * 3 + 1], A.deltav[(size_t)st * 3 + 2]);
+      A.dustb[s] = A.use_smoothed_rhodust ? make_double2(A.rhogas[st], A.rhodust[st]) : make_double2((1. - eps) * rho, eps * rho);
+    }
     if (A.imhd != 0) {
       const double bx = A.Bfield[(size_t)st * 3], by = A.Bfield[(size_t)st * 3 + 1], bz = A.Bfield[(size_t)st * 3 + 2];
       A.bpsi[s] = make_double4(bx, by, bz, A.psi[st]);
@@ -550,10 +575,12 @@ struct FinalArgs {
   const double *drhodt_in, *Bevol, *dens, *hh, *rho, *pr; const unsigned long long *vsigmax_key;
   double *force, *dudt, *dendt, *dBevoldt, *daldt, *dpsidt, *gradpsi, *divB, *curlB, *graddivv, *del2u, *drhodt, *dhdt;
   RatesRed R; int npart, ntotal;
+  // one-fluid dust (dusta NULL otherwise)
+  const double4 *dusta; const double2 *dustb; const int *cellStart, *cellOf; double *ddustevoldt, *ddeltavdt;
 };
 __global__ void k_rates_final(FinalArgs A) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  double fhmax = 0., dtforce = DBL_MAX, fm0 = 0., fm1 = 0., fm2 = 0.;
+  double fhmax = 0., dtforce = DBL_MAX, fm0 = 0., fm1 = 0., fm2 = 0., tsmin = DBL_MAX;
   if (s < A.ntotal) {
     const int i = A.perm[s];
     if (i < A.npart) {
@@ -593,12 +620,26 @@ __global__ void k_rates_final(FinalArgs A) {
         if (O.idivbzero >= 2) { const double r2 = rho1i * rho1i; gpx *= r2; gpy *= r2; gpz *= r2; }
       } else { dbx = dby = dbz = 0.; }
       if (O.iresist > 0 && O.iresist != 2 && O.etamhd > DBL_MIN) dtforce = hi * hi / O.etamhd;       // :808-815
+      double ddv0 = 0., ddv1 = 0., ddv2 = 0., ddust = 0., tstop = DBL_MAX;
+      if (A.dusta) {                                                                                 // :548-582 one fluid dust
+        const double4 D = A.S.D[s], da = A.dusta[s];
+        const double2 db = A.dustb[s];
+        ddv0 = D.x; ddv1 = D.y; ddv2 = D.z; ddust = D.w;
+        tstop = get_tstop(O.idrag_nature, db.x, db.y, O.Kdrag);
+        // :566 tests `dustfraci`, which the reference last assigned in the pair loop: it belongs to the LAST particle that loop
+        // visited -- the lowest-index row of the last non-empty cell, i.e. the first slot of the last slot's cell
+        const double dustfrac_stale = A.dusta[A.cellStart[A.cellOf[A.ntotal - 1]]].x;
+        double dtstop;
+        if (dustfrac_stale > 0.) { dtstop = 1. / tstop; ddv0 -= da.y * dtstop; ddv1 -= da.z * dtstop; ddv2 -= da.w * dtstop; }
+        else { dtstop = 0.; ddv0 = ddv1 = ddv2 = 0.; }
+        if (O.iener > 0) dudt = dudt + db.y * rho1i * ((da.y * da.y + da.z * da.z) + da.w * da.w) * dtstop;   // :579-582
+      }
       double dendt;
       if (O.iener == 3) {                                                                            // :820-826 (+ pair part :1829)
         dudt = dudt + pri * (rho1i * rho1i) * drhodti;
         dendt = ((v.x * fx + v.y * fy) + v.z * fz) + dudt;
         // NOTE: the reference overwrites the pair-summed dendt here (:824); P.w is therefore discarded
-      } else if (O.iener > 0 && O.iav >= 0) {                                                        // :832-835
+      } else if (O.iener > 0 && O.iav >= 0 && O.idust != 1) {                                        // :832-835
         dudt = dudt + pri * (rho1i * rho1i) * drhodti;
         dendt = dudt;
       } else dendt = dudt;                                                                           // :837
@@ -646,6 +687,11 @@ __global__ void k_rates_final(FinalArgs A) {
       o3 = A.curlB + (size_t)i * 3; o3[0] = cbx; o3[1] = cby; o3[2] = cbz;
       o3 = A.graddivv + (size_t)i * 3; o3[0] = V.x; o3[1] = V.y; o3[2] = V.z;
       A.del2u[i] = C.w;
+      if (A.dusta) {
+        A.ddustevoldt[i] = ddust;
+        o3 = A.ddeltavdt + (size_t)i * 3; o3[0] = ddv0; o3[1] = ddv1; o3[2] = ddv2;
+        tsmin = tstop;
+      }
     }
   }
   fhmax = warp_max(fhmax); dtforce = warp_min(dtforce);
@@ -654,6 +700,10 @@ __global__ void k_rates_final(FinalArgs A) {
     atomic_max_d(A.R.fhmax_max, fhmax);
     atomic_min_d(A.R.dtforce_min, dtforce);
     atomicAdd(A.R.fmean, fm0); atomicAdd(A.R.fmean + 1, fm1); atomicAdd(A.R.fmean + 2, fm2);
+  }
+  if (A.dusta) {                                                                                    // dtdrag = min(dtdrag, tstop), :561
+    tsmin = warp_min(tsmin);
+    if ((threadIdx.x & 31) == 0) atomic_min_d(A.R.ts_min, tsmin);
   }
 }
 struct ZeroArgs { double *force, *dudt, *dendt, *dBevoldt, *daldt, *dpsidt, *gradpsi, *divB, *curlB, *graddivv, *del2u, *drhodt, *dhdt; int npart, ntotal; };
@@ -694,6 +744,10 @@ void register_rows(nd_ctx *c) {
   v.push_back({(void **)&c->p32, sizeof(float4)});
   R1(srho); R4(posh); R4(vm); R4(bpsi); R4(thermo); R4(gal); R4(sF); R4(sdB); R4(sC); R4(sP); R4(sV);
   RI(typ); RI(perm); RI(permtmp); RI(inv); RI(cellOf); RI(cellOfOrig); RI(redo); RI(list); RI(ghostcount);
+  if (c->o.onef_dust) {
+    R1(dustevol); R1(dustfrac); R3(deltav); R1(rhogas); R1(rhodust); R1(ddustevoldt); R3(ddeltavdt); R1(sdf); R4(dusta); R4(sD);
+    v.push_back({(void **)&c->dustb, sizeof(double2)});
+  }
 #undef R3
 #undef R1
 #undef RI
@@ -730,11 +784,23 @@ int check_options(nd_ctx *c, const nd_options &o, int ndim) {
   if (o.imhd != 0 && o.imagforce != 2) return bad("imagforce /= 2");
   if (o.iav < 0 || o.iav > 3) return bad("iav not in 0..3");
   if (!(o.iener == 0 || o.iener == 2 || o.iener == 3)) return bad("iener not in {0,2,3}");
-  if (!(o.idust == 0 || o.idust == 2)) return bad("idust not in {0,2}");
+  if (!(o.idust == 0 || o.idust == 1 || o.idust == 2)) return bad("idust not in {0,1,2}");
   if (!(o.iresist == 0 || o.iresist == 1)) return bad("iresist not in {0,1}");
   if (o.icty != 0 || o.ixsph != 0 || o.igravity != 0 || o.iexternal_force != 0 || o.damp != 0.) return bad("icty/ixsph/igravity/iexternal_force/damp");
-  if (o.usenumdens || o.ibiascorrection || o.onef_dust || o.iuse_exact_derivs || o.iambipolar || o.ivisc || o.iquantum || o.ind_timesteps || o.islope_limiter >= 0)
-    return bad("usenumdens/ibiascorrection/onef_dust/iuse_exact_derivs/iambipolar/ivisc/iquantum/ind_timesteps/islope_limiter");
+  if (o.usenumdens || o.ibiascorrection || o.iuse_exact_derivs || o.iambipolar || o.ivisc || o.iquantum || o.ind_timesteps || o.islope_limiter >= 0)
+    return bad("usenumdens/ibiascorrection/iuse_exact_derivs/iambipolar/ivisc/iquantum/ind_timesteps/islope_limiter");
+  if ((o.idust == 1) != (o.onef_dust != 0)) return bad("onef_dust must be set exactly when idust = 1 (initialiseND_mhd.f90:148; idust = 3, 4 unsupported)");
+  if (o.idust == 1) {
+    // one-fluid dust (Laibe & Price 2014): dust fraction evolved directly, thermal energy, AV 1-3.  Ghost rows of rhogas/rhodust
+    // are only refreshed by copy_particle when every boundary is periodic (conservative2primitive.f90:465); with reflecting or
+    // mixed ghosts the reference reads stale partial sums there, which is not reproduced.
+    if (o.idustevol != 0) return bad("idustevol /= 0 with one-fluid dust");
+    if (o.iener == 3 || o.iener == 1) return bad("iener = 1, 3 with one-fluid dust (the reference stops, ratesND_mhd.f90:2044)");
+    if (o.iav < 1 || o.iav > 3) return bad("one-fluid dust needs iav in 1..3");
+    bool ghosts = false, all3 = true;
+    for (int d = 0; d < ndim; d++) { if (o.ibound[d] >= 2) ghosts = true; if (o.ibound[d] != 3) all3 = false; }
+    if (ghosts && !all3) return bad("one-fluid dust with ghost boundaries needs ibound = 3 in every dimension");
+  }
   if (o.ikernelalt != o.ikernel) return bad("ikernelalt /= ikernel");
   for (int d = 0; d < ndim; d++) {
     const int b = o.ibound[d];
@@ -968,6 +1034,7 @@ template <int NDIM> int build_cells(nd_ctx *c) {
   GA.posh = c->posh; GA.vm = c->vm; GA.p32 = c->p32; GA.typ = c->typ; GA.cellOf = c->cellOf; GA.inv = c->inv; GA.npart = c->npart; GA.ntotal = nt;
   for (int d = 0; d < 3; d++) GA.xminpart[d] = c->xminpart[d];
   GA.dxcell1 = 1.0 / c->dxcell; GA.hhmax1 = 1.0 / c->hhmax; GA.mixed = c->flags + 6;
+  GA.dustfrac = c->dustfrac; GA.sdf = c->o.onef_dust ? c->sdf : nullptr;
   CU(cudaMemsetAsync(c->flags + 6, 0, sizeof(int), c->stream));
   LAUNCH(c, (k_gather_sorted<NDIM>), nblocks(nt, 256), 256, 0, GA);
   return 0;
@@ -1042,7 +1109,7 @@ template <int NDIM, bool FIRST> int launch_density_round(nd_ctx *c, DensityArgs 
     NbrLists L;
     if (int e = build_lists<NDIM, FIRST ? LIST_DENS_FIRST : LIST_DENS_PARTIAL>(c, G, LA, L)) return e;
     A.list = FIRST ? nullptr : c->list + c0; A.nlist = m; A.s0 = c0;
-    if (c->o.want_aux) LAUNCH(c, (density_round_kernel<NDIM, FIRST, true>), nblocks(m, DENS_BLOCK), DENS_BLOCK, 0, G, A, L);
+    if (c->o.want_aux || c->o.onef_dust) LAUNCH(c, (density_round_kernel<NDIM, FIRST, true>), nblocks(m, DENS_BLOCK), DENS_BLOCK, 0, G, A, L);
     else LAUNCH(c, (density_round_kernel<NDIM, FIRST, false>), nblocks(m, DENS_BLOCK), DENS_BLOCK, 0, G, A, L);
   }
   return 0;
@@ -1080,6 +1147,7 @@ template <int NDIM> int do_iterate_density(nd_ctx *c, int resume) {
     DensityArgs A;
     A.hh = c->hh; A.hhin = c->hhin; A.rho = c->rho; A.gradh = c->gradh; A.drhodt = c->drhodt; A.dhdt = c->dhdt; A.numneigh = c->numneigh;
     A.rhoalt = c->rhoalt; A.gradhn = c->gradhn; A.gradsoft = c->gradsoft; A.gradgradh = c->gradgradh;
+    A.sdf = o.onef_dust ? c->sdf : nullptr; A.rhogas = c->rhogas; A.rhodust = c->rhodust;
     A.list = c->list; A.nlist = c->ncalc; A.s0 = 0; A.redo = c->redo; A.flags = c->flags;
     A.itsdensity = c->itsdensity; A.itsdensitymax = itsdensitymax; A.hfact = o.hfact; A.psep = o.psep; A.tolh = o.tolh; A.hhmax = c->hhmax;
     CU(cudaMemsetAsync(c->redo, 0, sizeof(int) * c->ntotal, c->stream));
@@ -1128,6 +1196,7 @@ int do_cons2prim(nd_ctx *c) {
   A.pmass = c->pmass; A.rho_w = c->rho; A.rhoalt = c->rhoalt; A.hh = c->hh; A.en_w = c->en; A.Bevol_w = c->Bevol; A.alpha = c->alpha; A.psi = c->psi;
   A.gradh = c->gradh; A.gradhn = c->gradhn; A.gradsoft = c->gradsoft; A.gradgradh = c->gradgradh;
   A.npart = c->npart; A.ntotal = c->ntotal; A.imhd = o.imhd; A.iener = o.iener; A.gamma = o.gamma; A.polyk = o.polyk; A.aux = o.want_aux != 0;
+  A.dustevol = o.onef_dust ? c->dustevol : nullptr; A.dustfrac = c->dustfrac; A.rhogas = c->rhogas; A.rhodust = c->rhodust;
   LAUNCH(c, k_c2p, nblocks(c->npart, 256), 256, 0, A);
   if (any_fixed_bound(c)) LAUNCH(c, k_c2p_fixed, nblocks(c->npart, 256), 256, 0, A);
   if (any_ghost_bound(c)) LAUNCH(c, k_c2p_ghost, nblocks(c->ntotal - c->npart, 256), 256, 0, A);
@@ -1148,7 +1217,7 @@ RatesOpts make_rates_opts(const nd_ctx *c) {
 
 enum { RED_DTC = 0, RED_VSIG = 1, RED_DTAV = 2, RED_TS = 3, RED_HCS = 4, RED_FH = 5, RED_DTF = 6, RED_STRESS = 7 };
 
-template <int NDIM, bool MHD, bool DRAG, bool FAST> int launch_rates_pair(nd_ctx *c, const RatesIn &I, const RatesOpts &O, const RatesSums &S, const RatesRed &R, int *pi, int *pj,
+template <int NDIM, bool MHD, bool DRAG, bool FAST, bool ONEF> int launch_rates_pair(nd_ctx *c, const RatesIn &I, const RatesOpts &O, const RatesSums &S, const RatesRed &R, int *pi, int *pj,
                                                                           unsigned long long *pc, long long cap) {
   Grid G = make_grid(c);
   const int n = c->ntotal;
@@ -1159,7 +1228,7 @@ template <int NDIM, bool MHD, bool DRAG, bool FAST> int launch_rates_pair(nd_ctx
     LA.pair_out_i = pi; LA.pair_out_j = pj; LA.pair_count = pc; LA.pair_cap = cap;
     NbrLists L;
     if (int e = build_lists<NDIM, LIST_RATES>(c, G, LA, L)) return e;
-    LAUNCH(c, (rates_pair_kernel<NDIM, MHD, DRAG, FAST>), nblocks(m, RATES_BLOCK), RATES_BLOCK, 0, G, I, O, S, R, L, c0, m);
+    LAUNCH(c, (rates_pair_kernel<NDIM, MHD, DRAG, FAST, ONEF>), nblocks(m, RATES_BLOCK), RATES_BLOCK, 0, G, I, O, S, R, L, c0, m);
   }
   return 0;
 }
@@ -1181,6 +1250,8 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   GA.perm = c->perm; GA.ireal = c->ireal; GA.hh = c->hh; GA.pmass = c->pmass; GA.rho = c->rho; GA.pr = c->pr; GA.spsound = c->spsound; GA.uu = c->uu;
   GA.gradh = c->gradh; GA.alpha = c->alpha; GA.psi = c->psi; GA.Bfield = c->Bfield;
   GA.p32 = c->p32; GA.hhmax1 = 1.0 / c->hhmax;
+  GA.dustfrac = c->dustfrac; GA.deltav = c->deltav; GA.rhogas = c->rhogas; GA.rhodust = c->rhodust;
+  GA.dusta = o.onef_dust ? c->dusta : nullptr; GA.dustb = c->dustb; GA.use_smoothed_rhodust = o.use_smoothed_rhodust;
   GA.posh = c->posh; GA.vm = c->vm; GA.bpsi = c->bpsi; GA.thermo = c->thermo; GA.gal = c->gal; GA.npart = c->npart; GA.ntotal = nt; GA.imhd = o.imhd;
   GA.stress_key = c->red + RED_STRESS; GA.imagforce = o.imagforce; GA.srho = c->srho; GA.pext = o.pext; GA.err = c->flags + 1;
   GA.Bconstmax = std::max(o.Bconst[0], std::max(o.Bconst[1], o.Bconst[2]));
@@ -1192,8 +1263,8 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
     O.stressmax = dkey_inv(c->h_red[0]);
     if (int e = comm_allreduce(c, &O.stressmax, 1, 0)) return e;
   }
-  RatesIn I; I.bpsi = c->bpsi; I.thermo = c->thermo; I.gal = c->gal; I.srho = c->srho;
-  RatesSums S; S.F = c->sF; S.dB = c->sdB; S.C = c->sC; S.P = c->sP; S.V = c->sV;
+  RatesIn I; I.bpsi = c->bpsi; I.thermo = c->thermo; I.gal = c->gal; I.srho = c->srho; I.dusta = c->dusta; I.dustb = c->dustb;
+  RatesSums S; S.F = c->sF; S.dB = c->sdB; S.C = c->sC; S.P = c->sP; S.V = c->sV; S.D = c->sD;
   RatesRed R;
   R.dtcourant_min = c->red + RED_DTC; R.vsigmax_max = c->red + RED_VSIG; R.dtav_min = c->red + RED_DTAV; R.ts_min = c->red + RED_TS;
   R.h_on_csts_max = c->red + RED_HCS; R.fhmax_max = c->red + RED_FH; R.dtforce_min = c->red + RED_DTF; R.fmean = c->fmean;
@@ -1202,13 +1273,15 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   const bool mhd = o.imhd != 0, drag = (o.idust == 2);
   int e = 0;
   // first-class tuple without run-time option tests (and without the dead graddivv "curl v" sums: want_aux = 0)
-  const bool fast = !drag && !o.want_aux && o.iav == 2 && (o.iener == 0 || o.iener == 2) && o.ikernav == 3 && o.iresist == 0 && o.iavlim[0] != 3 && o.iavlim[2] != 2;
-  if (mhd && fast) e = launch_rates_pair<NDIM, true, false, true>(c, I, O, S, R, pi, pj, pc, cap);
-  else if (!mhd && fast) e = launch_rates_pair<NDIM, false, false, true>(c, I, O, S, R, pi, pj, pc, cap);
-  else if (mhd && !drag) e = launch_rates_pair<NDIM, true, false, false>(c, I, O, S, R, pi, pj, pc, cap);
-  else if (!mhd && !drag) e = launch_rates_pair<NDIM, false, false, false>(c, I, O, S, R, pi, pj, pc, cap);
-  else if (!mhd && drag) e = launch_rates_pair<NDIM, false, true, false>(c, I, O, S, R, pi, pj, pc, cap);
-  else e = launch_rates_pair<NDIM, true, true, false>(c, I, O, S, R, pi, pj, pc, cap);
+  const bool fast = !drag && o.idust != 1 && !o.want_aux && o.iav == 2 && (o.iener == 0 || o.iener == 2) && o.ikernav == 3 && o.iresist == 0 && o.iavlim[0] != 3 && o.iavlim[2] != 2;
+  if (o.idust == 1 && mhd) e = launch_rates_pair<NDIM, true, false, false, true>(c, I, O, S, R, pi, pj, pc, cap);
+  else if (o.idust == 1) e = launch_rates_pair<NDIM, false, false, false, true>(c, I, O, S, R, pi, pj, pc, cap);
+  else if (mhd && fast) e = launch_rates_pair<NDIM, true, false, true, false>(c, I, O, S, R, pi, pj, pc, cap);
+  else if (!mhd && fast) e = launch_rates_pair<NDIM, false, false, true, false>(c, I, O, S, R, pi, pj, pc, cap);
+  else if (mhd && !drag) e = launch_rates_pair<NDIM, true, false, false, false>(c, I, O, S, R, pi, pj, pc, cap);
+  else if (!mhd && !drag) e = launch_rates_pair<NDIM, false, false, false, false>(c, I, O, S, R, pi, pj, pc, cap);
+  else if (!mhd && drag) e = launch_rates_pair<NDIM, false, true, false, false>(c, I, O, S, R, pi, pj, pc, cap);
+  else e = launch_rates_pair<NDIM, true, true, false, false>(c, I, O, S, R, pi, pj, pc, cap);
   if (e) return e;
   CU(cudaEventRecord(c->ev[4], c->stream));
   if (c->has_comm) {   // vsigmax feeds dpsidt in the finalisation loop (:518-520, :902): all ranks need the global maximum
@@ -1226,6 +1299,8 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   FA.force = c->force; FA.dudt = c->dudt; FA.dendt = c->dendt; FA.dBevoldt = c->dBevoldt; FA.daldt = c->daldt; FA.dpsidt = c->dpsidt; FA.gradpsi = c->gradpsi;
   FA.divB = c->divB; FA.curlB = c->curlB; FA.graddivv = c->graddivv; FA.del2u = c->del2u; FA.drhodt = c->drhodt; FA.dhdt = c->dhdt;
   FA.R = R; FA.npart = np; FA.ntotal = nt;
+  FA.dusta = o.onef_dust ? c->dusta : nullptr; FA.dustb = c->dustb; FA.cellStart = c->cellStart; FA.cellOf = c->cellOf;
+  FA.ddustevoldt = c->ddustevoldt; FA.ddeltavdt = c->ddeltavdt;
   LAUNCH(c, k_rates_final, nblocks(nt, 256), 256, 0, FA);
   ZeroArgs ZA;
   ZA.force = c->force; ZA.dudt = c->dudt; ZA.dendt = c->dendt; ZA.dBevoldt = c->dBevoldt; ZA.daldt = c->daldt; ZA.dpsidt = c->dpsidt; ZA.gradpsi = c->gradpsi;
@@ -1269,6 +1344,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   if (s.fhmax > 0.) s.dtforce = std::min(s.dtforce, std::sqrt(1. / s.fhmax));        // :938-943
   s.dtdrag = DBL_MAX;
   if (o.idust == 2 && o.idrag_nature != 0 && (o.Kdrag > 0. || o.idrag_nature > 1)) s.dtdrag = std::min(s.dtdrag, s.ts_min);   // :543-547
+  else if (o.idust == 1) { s.dtdrag = std::min(s.dtdrag, s.ts_min); s.ts_min = DBL_MAX; }   // :561: the key carried min tstop; module ts_min is two-fluid only
   for (int k = 0; k < 3; k++) s.fmean[k] = c->h_fmean[k];
   s.nclumped = c->h_flags[4];
   c->rates_done = true;
@@ -1428,6 +1504,8 @@ int check_upload_args(nd_ctx *c, const nd_arrays *a, int npart, int &ntotal, int
   if (!a->x || !a->vel || !a->pmass || !a->hh_in || !a->itype) return set_err(c, ND_ERR_INVALID_ARG, "upload: x, vel, pmass, hh_in, itype are required");
   if (o.imhd != 0 && !a->Bevol) return set_err(c, ND_ERR_INVALID_ARG, "upload: Bevol required with imhd /= 0");
   if (!a->en || !a->alpha) return set_err(c, ND_ERR_INVALID_ARG, "upload: en and alpha are required");
+  if (o.onef_dust && (!a->dustevol || !a->dustfrac_in || !a->deltav)) return set_err(c, ND_ERR_INVALID_ARG, "upload: dustevol, dustfrac_in, deltav required with idust = 1");
+  if (o.onef_dust && c->has_comm) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "one-fluid dust is not available with the slab decomposition");
   if ((ntotal > npart || any_fixed_bound(c)) && !a->ireal) return set_err(c, ND_ERR_INVALID_ARG, "upload: ireal required with ghosts/fixed particles");
   return 0;
 }
@@ -1443,11 +1521,13 @@ int upload_group(nd_ctx *c, const nd_arrays *a, size_t n, int group, cudaStream_
     CU(up(c->itype, a->itype, sizeof(int) * n));
     CU(up(c->ireal, a->ireal, sizeof(int) * n));
     CU(up(c->rho, a->rho_in, sizeof(double) * n));   // fixed particles without a parent keep their density
+    if (c->o.onef_dust) CU(up(c->dustfrac, a->dustfrac_in, sizeof(double) * n));   // read by the density sums (density_sums.f90:280-282)
   } else {
     CU(up(c->en, a->en, sizeof(double) * n));
     CU(up(c->Bevol, a->Bevol, sizeof(double) * 3 * n));
     CU(up(c->alpha, a->alpha, sizeof(double) * 3 * n));
     CU(up(c->psi, a->psi, sizeof(double) * n));
+    if (c->o.onef_dust) { CU(up(c->dustevol, a->dustevol, sizeof(double) * n)); CU(up(c->deltav, a->deltav, sizeof(double) * 3 * n)); }
   }
   return 0;
 }
@@ -1459,9 +1539,11 @@ int download_group(nd_ctx *c, nd_arrays *a, size_t n, int group, unsigned mask, 
     CU(dn(a->hh, c->hh, D * n)); CU(dn(a->rho, c->rho, D * n)); CU(dn(a->gradh, c->gradh, D * n)); CU(dn(a->numneigh, c->numneigh, sizeof(int) * n));
     if (c->o.want_aux) { CU(dn(a->rhoalt, c->rhoalt, D * n)); CU(dn(a->gradhn, c->gradhn, D * n)); CU(dn(a->gradsoft, c->gradsoft, D * n)); CU(dn(a->gradgradh, c->gradgradh, D * n)); }
   }
+  if (group == 2 && (mask & ND_DL_DENSITY) && c->o.onef_dust) { CU(dn(a->rhogas, c->rhogas, D * n)); CU(dn(a->rhodust, c->rhodust, D * n)); }   // ghost rows are final after c2p
   if (group == 2 && (mask & ND_DL_PRIM)) {
     CU(dn(a->dens, c->dens, D * n)); CU(dn(a->uu, c->uu, D * n)); CU(dn(a->pr, c->pr, D * n)); CU(dn(a->spsound, c->spsound, D * n));
     if (c->o.imhd != 0) CU(dn(a->Bfield, c->Bfield, D * 3 * n));
+    if (c->o.onef_dust) CU(dn(a->dustfrac, c->dustfrac, D * n));
   }
   if (group == 3) {
     if (mask & (ND_DL_DENSITY | ND_DL_RATES)) { CU(dn(a->drhodt, c->drhodt, D * n)); CU(dn(a->dhdt, c->dhdt, D * n)); }
@@ -1475,6 +1557,7 @@ int download_group(nd_ctx *c, nd_arrays *a, size_t n, int group, unsigned mask, 
       // graddivv holds dead "curl v" sums unless iavlim(1)=3, del2u is a local of the reference: shipped only on request
       if (c->o.want_aux || c->o.iavlim[0] == 3) CU(dn(a->graddivv, c->graddivv, D * 3 * n));
       if (c->o.want_aux) CU(dn(a->del2u, c->del2u, D * n));
+      if (c->o.onef_dust) { CU(dn(a->ddustevoldt, c->ddustevoldt, D * n)); CU(dn(a->ddeltavdt, c->ddeltavdt, D * 3 * n)); }
     }
   }
   return 0;

@@ -23,6 +23,8 @@ struct DensityArgs {
   int *flags;            // [0] relink requested, [1] error code, [2] rho<=1e-6 count
   int itsdensity, itsdensitymax;
   double hfact, psep, tolh, hhmax;
+  // one-fluid dust (AUX instantiation only; sdf NULL otherwise): rhogas, rhodust sums of src/density_sums.f90:278-292, :569-573
+  const double *sdf; double *rhogas, *rhodust;
 };
 
 #ifndef ND_DENS_MINB
@@ -53,7 +55,8 @@ __global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel
   const double hi1 = 1.0 / hi;                     // h1(i) = 1./hh(i), density_sums.f90:130
   const double hi21 = __dmul_rn(hi1, hi1);
   const double hfacwabi = powndim<NDIM>(hi1);
-  double rho = 0, gradh = 0, drhodt = 0, densn = 0, gradhn = 0, gradgradh = 0;
+  double rho = 0, gradh = 0, drhodt = 0, densn = 0, gradhn = 0, gradgradh = 0, rhogas = 0, rhodust = 0;
+  const bool onef = AUX && A.sdf != nullptr;
   const bool bnd_first = FIRST && ti == T_BND;     // :273, :321 -- fixed particles keep rho, gradh
 
   // ---- pair sums over the neighbour list (built by build_lists_kernel with the reference's inclusion test) ----
@@ -86,6 +89,11 @@ __global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel
         const double dwdhdhi = NDIM * (NDIM + 1) * wabi * (hi1 * hi1) + 2. * (NDIM + 1) * rij * (hi1 * hi1) * grkerni +
                                (rij * rij) * (hi1 * hi1) * grgrkerni;        // :265
         gradgradh += pmassj * dwdhdhi;
+        if (onef) {
+          const double dfj = __ldg(A.sdf + k);
+          rhodust += pmassj * dfj * wabi;
+          rhogas += pmassj * (1. - dfj) * wabi;
+        }
       }
     }
     if (k != s) {                                  // :297-303
@@ -138,6 +146,7 @@ __global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel
       const double d2hdrho2i = hi * (NDIM + 1) / ((rho * NDIM) * (rho * NDIM));   // :206
       A.gradgradh[orig] = rho * (d2hdrho2i * dwdhsumi + (dhdrhoi * dhdrhoi) * gradgradh);
       A.gradsoft[orig] = 0.;                                          // :204 with igravity = 0
+      if (onef) { A.rhogas[orig] = rhogas; A.rhodust[orig] = rhodust; }
     }
     if (!converged) {
       redo = 1;

@@ -26,6 +26,8 @@ struct RatesIn {
   const double4 *thermo;   // {1/rho, max(pr - pext, 0), spsound, uu}   (1/rho correctly rounded: rho1i = 1./rhoi, ratesND_mhd.f90:325)
   const double4 *gal;      // {gradh, alpha, alphau, alphaB}
   const double *srho;      // rho by sorted slot (drag and phantom-AV branches only)
+  const double4 *dusta;    // one-fluid dust: {dustfrac, deltav xyz}
+  const double2 *dustb;    // one-fluid dust: {rhogas, rhodust} (smoothed sums or rho*(1-eps), rho*eps: ratesND_mhd.f90:346-352)
 };
 
 struct RatesSums {         // per sorted slot, written by the pair kernel, read by the final kernel
@@ -34,6 +36,7 @@ struct RatesSums {         // per sorted slot, written by the pair kernel, read 
   double4 *C;              // {curlB xyz, del2u}
   double4 *P;              // {gradpsi xyz, total-energy dissipation pair sum (iener=3)}
   double4 *V;              // {graddivv xyz, -}
+  double4 *D;              // one-fluid dust: {ddeltavdt xyz, ddustevoldt}
 };
 
 // global reductions (order-preserving u64 keys, see dkey)
@@ -78,7 +81,8 @@ __device__ __forceinline__ double get_tstop(int idrag_nature, double rhogas, dou
 
 // FAST = the first-class option tuple compiled without run-time option tests: iav=2, iener in {0,2}, ikernav=3, iresist=0,
 // iavlim(1) /= 3, iavlim(3) /= 2, pext folded into thermo.  Everything else runs the generic instantiation.
-template <int NDIM, bool MHD, bool DRAG, bool FAST>
+// ONEF = one-fluid dust (idust=1): dust_derivs (:2726-2807) and artificial_dissipation_dust (:1969-2148) on the generic path.
+template <int NDIM, bool MHD, bool DRAG, bool FAST, bool ONEF>
 __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(Grid G, RatesIn I, RatesOpts O, RatesSums S, RatesRed R, NbrLists L,
                                                                                  int s0, int ntargets) {
 #if ND_RATES_STAGE == 3
@@ -107,6 +111,16 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
     rhoi = I.srho[s];
     cnt = L.cnt[tix];
   }
+  double dustfraci = 0., rhogasi = rhoi, rhodusti = 0., dvix = 0., dviy = 0., dviz = 0., deltav2i = 0., rhogrhodonrhoi = 0.;
+  if (ONEF && active) {                                                        // :344-356
+    const double4 da = ld4(I.dusta + s);
+    const double2 db = __ldg(I.dustb + s);
+    dustfraci = da.x; dvix = da.y; dviy = da.z; dviz = da.w;
+    rhogasi = db.x; rhodusti = db.y;
+    deltav2i = (dvix * dvix + dviy * dviy) + dviz * dviz;
+    rhogrhodonrhoi = rhogasi * rhodusti * rho1i;
+  }
+  double fgx = 0, fgy = 0, fgz = 0, ddvx = 0, ddvy = 0, ddvz = 0, ddust = 0;      // gas-only force sum, ddeltavdt, ddustevoldt
   const double rho21i = rho1i * rho1i;                                         // :326
   const double Prho2i = pri * rho21i;                                          // :332
   const double hi21 = __dmul_rn(hi1, hi1);
@@ -158,6 +172,21 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
       const double dvdotr = (dvx * drx + dvy * dry) + dvz * drz;   // :1250
       const double rho1j = tj4.x, rho21j = rho1j * rho1j;          // :1256-1258
       const double rhoav1 = 0.5 * (rho1i + rho1j);                 // :1261
+      double dustfracj = 0., rhogasj = 0., rhodustj = 0., dvjx = 0., dvjy = 0., dvjz = 0., deltav2j = 0., rhogrhodonrhoj = 0.;
+      double projdvgas = dvdotr, projdeltavi = 0., projdeltavj = 0.;
+      if (ONEF) {                                                  // :1262-1280
+        const double4 da = ld4(I.dusta + k);
+        const double2 db = __ldg(I.dustb + k);
+        dustfracj = da.x; dvjx = da.y; dvjy = da.z; dvjz = da.w;
+        rhogasj = db.x; rhodustj = db.y;
+        rhogrhodonrhoj = rhogasj * rhodustj * rho1j;
+        deltav2j = (dvjx * dvjx + dvjy * dvjy) + dvjz * dvjz;
+        const double gx = (vxi - dustfraci * dvix) - (vj.x - dustfracj * dvjx), gy = (vyi - dustfraci * dviy) - (vj.y - dustfracj * dvjy),
+                     gz = (vzi - dustfraci * dviz) - (vj.z - dustfracj * dvjz);
+        projdvgas = (gx * drx + gy * dry) + gz * drz;
+        projdeltavi = (dvix * drx + dviy * dry) + dviz * drz;
+        projdeltavj = (dvjx * drx + dvjy * dry) + dvjz * drz;
+      }
       const double prj = tj4.y;                                    // :1285 (pext already subtracted)
       const double Prho2j = prj * rho21j;
       const double spsoundj = tj4.z, uuj = tj4.w;
@@ -199,7 +228,8 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
         vsigu = sqrt_nr(pdiff);
       }
       double vsig = 0.5 * (fmax(vsigi + vsigj - O.beta * dvdotr, 0.0));          // :1452
-      const double vsigdtc = fmax(vsig, fmax(0.5 * (vsigi + vsigj + O.beta * fabs(dvdotr)), vsigB));   // :1465
+      double vsigdtc = fmax(vsig, fmax(0.5 * (vsigi + vsigj + O.beta * fabs(dvdotr)), vsigB));   // :1465
+      if (ONEF) vsigdtc = vsigdtc + sqrt(deltav2i + deltav2j);                                   // :1466-1468
       if (ti == T_DUST) { vsig = 0.; vsigu = 0.; }                              // :1472-1474
       else {                                                                    // :1476-1481
         vsigmax = fmax(vsigmax, vsigdtc);
@@ -222,7 +252,49 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
       }
       double fix = 0, fiy = 0, fiz = 0;   // forcei contribution of this pair
       double vsigav = 0.;
-      if (iav > 0 && iav != 3) {
+      if (ONEF && iav > 0) {
+        // =============================== artificial_dissipation_dust (iav = 1, 2, 3) ===============================
+        const double alphaav = 0.5 * (alphai + gj.y), alphau = 0.5 * (alphaui + gj.z), alphaB = 0.5 * (alphaBi + gj.w);
+        vsigav = fmax(alphaav, alphau) * vsig;                   // :1984
+        const double dustfracav = 0.5 * (dustfraci + dustfracj);
+        const double projdvgasav = dvdotr - dustfracav * (projdeltavi - projdeltavj);
+        const double ddx_ = dvix - dvjx, ddy_ = dviy - dvjy, ddz_ = dviz - dvjz;
+        const double projddeltav = (ddx_ * drx + ddy_ * dry) + ddz_ * drz;
+        const double dpmomdotr = (iav == 3) ? projdvgasav : (iav == 2) ? projdvgas : dvdotr;   // :1993-1999
+        const double term = vsig * rhoav1 * grkern;
+        double termv = term;
+        const bool allpairs = (iav == 1);
+        if (iav == 2 || iav == 3) termv = termv * (1. - dustfracav);
+        const double termu = vsigu * rhoav1 * grkern * (1. - dustfracav);
+        const bool on = (projdvgas < 0.) || allpairs;
+        if (on) {                                                // :2023-2038
+          const double visc = alphaav * termv * dpmomdotr;
+          const double c = pmassj * visc;
+          if (iav == 1 || iav == 3) { fx += c * drx; fy += c * dry; fz += c * drz; }   // fextra: acts on the whole fluid
+          else { fix += c * drx; fiy += c * dry; fiz += c * drz; }
+        }
+        if (iener > 0) {                                         // :2049-2146
+          double vissv = 0., vissdv = 0., termdv = 0.;
+          if (on) vissv = (iav == 3) ? -alphaav * 0.5 * (projdvgasav * projdvgasav) : (iav == 2) ? -alphaav * 0.5 * (projdvgas * projdvgas) : -alphaav * 0.5 * (dvdotr * dvdotr);
+          const double vissu = (iener == 1) ? 0. : alphau * (uui - uuj);
+          const double faci = 1. / (dustfraci * (1. - dustfraci));   // :2078-2079
+          if (iav == 1 || iav == 3) {
+            if (iav == 1) { vissdv = -0.5 * ((ddx_ * ddx_ + ddy_ * ddy_) + ddz_ * ddz_); termdv = alphaav * vsig * rhoav1 * dustfracav * grkern; }
+            else { vissdv = 0.; termdv = alphaav * vsig * rhoav1 * dustfracav * grkern * (1. - dustfracav); }
+            if (iav == 3) { const double c = faci * pmassj * termdv * (-projdvgasav); ddvx += c * drx; ddvy += c * dry; ddvz += c * drz; }
+            else { const double c = faci * pmassj * termdv; ddvx += c * ddx_; ddvy += c * ddy_; ddvz += c * ddz_; }
+          } else if (iav == 2 && projddeltav < 0.) {             // :2111-2125
+            const double vsigdv = 0.5 * (spsoundi + spsoundj);
+            termdv = alphaav * vsigdv * rhoav1 * grkern * dustfracav * (1. - dustfracav);
+            const double c = faci * pmassj * termdv * projddeltav;
+            ddvx += c * drx; ddvy += c * dry; ddvz += c * drz;
+            vissdv = -0.5 * (projddeltav * projddeltav);
+          }
+          dudt += (rhoi / rhogasi) * pmassj * (termv * vissv + termu * vissu + termdv * vissdv);   // :2133-2138
+          const double vsigeps = 0.5 * (spsoundi + spsoundj);    // :2140-2145
+          ddust += pmassj * (alphaB * rhoav1 * vsigeps * (dustfraci - dustfracj) * grkern);
+        }
+      } else if (iav > 0 && iav != 3) {
         // =============================== artificial_dissipation ===============================
         const double alphaav = 0.5 * (alphai + gj.y), alphau = 0.5 * (alphaui + gj.z), alphaB = 0.5 * (alphaBi + gj.w);   // :1712-1714
         vsigav = fmax(alphaav, fmax(alphau, alphaB)) * vsig;
@@ -321,6 +393,17 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
           gpx -= c * drx; gpy -= c * dry; gpz -= c * drz;
         }
       }
+      if (ONEF) {
+        // =============================== dust_derivs (idustevol = 0) ===============================
+        ddust -= pmassj * (rhogrhodonrhoi * projdeltavi * rho21i * grkerni + rhogrhodonrhoj * projdeltavj * rho21j * grkernj);   // :2753-2758
+        const double dterm = 0.5 * ((rhogasi - rhodusti) * rho1i * deltav2i - (rhogasj - rhodustj) * rho1j * deltav2j);          // :2767-2769
+        const double c = rho1i * pmassj * grkerni;               // :2776 (the -rho/rhogas*forcei term follows the pair loop, :460)
+        ddvx += c * (dvx * projdeltavi + dterm * drx); ddvy += c * (dvy * projdeltavi + dterm * dry); ddvz += c * (dvz * projdeltavi + dterm * drz);
+        const double pi_ = rhogrhodonrhoi * projdeltavi * rho21i * grkerni, pj_ = rhogrhodonrhoj * projdeltavj * rho21j * grkernj;   // :2792-2795
+        fx -= pmassj * (pi_ * dvix + pj_ * dvjx); fy -= pmassj * (pi_ * dviy + pj_ * dvjy); fz -= pmassj * (pi_ * dviz + pj_ * dvjz);
+        if (iener > 0) dudt += pmassj * (pri * rho1i / rhogasi * projdvgas - rhodusti * rho21i * (uui - uuj) * projdeltavi) * grkerni;   // :2801-2803
+        fgx += fix; fgy += fiy; fgz += fiz;
+      }
       fx += fix; fy += fiy; fz += fiz;
       if (iav > 0) {                                             // :1639-1656 switch sources
         if (iavlim1 > 0) del2u += pmassj * rho1j * ((uui - uuj) * rinv) * grkerni;
@@ -396,6 +479,10 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
     st4(S.C + s, make_double4(cBx, cBy, cBz, del2u));
     st4(S.P + s, make_double4(gpx, gpy, gpz, endiss));
     st4(S.V + s, make_double4(gvx, gvy, gvz, 0.));
+    if (ONEF) {                                                  // ddeltavdt(:,i) - rhoi/rhogasi*forcei(:), :460
+      const double c = rhoi / rhogasi;
+      st4(S.D + s, make_double4(ddvx - c * fgx, ddvy - c * fgy, ddvz - c * fgz, ddust));
+    }
   }
   // block-free warp reductions into global min/max keys
   double dtcourant = dtc_den > 0. ? fmin(1.e6, 1. / dtc_den) : 1.e6;            // initial value 1.e6, :251

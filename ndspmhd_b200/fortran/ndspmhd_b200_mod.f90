@@ -29,7 +29,8 @@ module ndspmhd_b200
     integer(c_int) :: islope_limiter,iuse_exact_derivs,iambipolar,ivisc,iquantum,ind_timesteps
     integer(c_int) :: nsubsteps_divB
     integer(c_int) :: device_ghosts,want_aux
-    integer(c_int) :: reserved_i(6)
+    integer(c_int) :: idustevol
+    integer(c_int) :: reserved_i(5)
     real(c_double) :: hfact,psep,tolh
     real(c_double) :: gamma,polyk
     real(c_double) :: alphamin,alphaumin,alphaBmin,beta,avdecayconst,avfact
@@ -46,7 +47,7 @@ module ndspmhd_b200
     type(c_ptr) :: dens,uu,pr,spsound,Bfield
     type(c_ptr) :: force,dudt,dendt,dBevoldt,daldt,dpsidt,gradpsi,divB,curlB,graddivv,del2u
     type(c_ptr) :: x_out,vel_out,ireal_out,itype_out
-    type(c_ptr) :: reserved_p(8)
+    type(c_ptr) :: dustevol,dustfrac_in,deltav,dustfrac,rhogas,rhodust,ddustevoldt,ddeltavdt
  end type nd_arrays
 
  type, bind(C) :: nd_scalars
@@ -122,7 +123,7 @@ contains
   ierr = ndspmhd_b200_default_options(o)
   o%iener = iener; o%icty = icty; o%iav = iav; o%ikernav = ikernav; o%ihvar = ihvar; o%iprterm = iprterm
   o%imhd = imhd; o%imagforce = imagforce; o%idivbzero = idivbzero; o%iresist = iresist
-  o%idust = idust; o%idrag_nature = idrag_nature
+  o%idust = idust; o%idrag_nature = idrag_nature; o%idustevol = idustevol
   o%ixsph = ixsph; o%igravity = igravity; o%iexternal_force = iexternal_force
   o%ikernel = ikernel; o%ikernelalt = ikernelalt; o%maxdensits = maxdensits
   o%iavlim(1:3) = iavlim(1:3)
@@ -163,7 +164,14 @@ contains
   a%dpsidt = c_loc(dpsidt); a%gradpsi = c_loc(gradpsi); a%divB = c_loc(divB); a%curlB = c_loc(curlB)
   a%graddivv = c_loc(graddivv); a%del2u = c_null_ptr
   a%x_out = c_null_ptr; a%vel_out = c_null_ptr; a%ireal_out = c_null_ptr; a%itype_out = c_null_ptr
-  a%reserved_p(:) = c_null_ptr
+  if (onef_dust) then   ! one-fluid dust arrays only exist then (src/allocateND.f90:386-392)
+     a%dustevol = c_loc(dustevol); a%dustfrac_in = c_loc(dustfrac); a%deltav = c_loc(deltav)
+     a%dustfrac = c_loc(dustfrac); a%rhogas = c_loc(rhogas); a%rhodust = c_loc(rhodust)
+     a%ddustevoldt = c_loc(ddustevoldt); a%ddeltavdt = c_loc(ddeltavdt)
+  else
+     a%dustevol = c_null_ptr; a%dustfrac_in = c_null_ptr; a%deltav = c_null_ptr; a%dustfrac = c_null_ptr
+     a%rhogas = c_null_ptr; a%rhodust = c_null_ptr; a%ddustevoldt = c_null_ptr; a%ddeltavdt = c_null_ptr
+  endif
  end subroutine b200_fill_arrays
 
 !--reference error convention: print to iprint, then `call quit` (emergency dump + stop, src/ndspmhd.f90:369-386)

@@ -128,6 +128,10 @@ def arrays_struct(p: Particles) -> NdArrays:
               "del2u"):
         setattr(a, n, p.ptr(n))
     a.x_out, a.vel_out, a.ireal_out, a.itype_out = p.ptr("x"), p.ptr("vel"), p.ptr("ireal"), p.ptr("itype")
+    # one-fluid dust: part:dustfrac is read on entry (density sums) and rewritten by conservative2primitive, like the module array
+    a.dustevol, a.dustfrac_in, a.deltav = p.ptr("dustevol"), p.ptr("dustfrac"), p.ptr("deltav")
+    for n in ("dustfrac", "rhogas", "rhodust", "ddustevoldt", "ddeltavdt"):
+        setattr(a, n, p.ptr(n))
     return a
 
 

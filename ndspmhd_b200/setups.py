@@ -328,3 +328,30 @@ def dustybox(ndim=3, nx=16, perturb_amp=0.05, Kdrag=1.0, idrag_nature=1, seed=7,
     uu = np.where(np.arange(n) < ngas, 1.0, 0.0)
     _finish(p, o, dens, uu, None)
     return o, p
+
+
+# ---------------------------------------------------------------------------------------------------------
+# C4 variant: one-fluid dust (idust=1), the dusty wave of src/setup_wave_x_ND_dust.f90:95-150 on a periodic box, with a
+# perturbed dust fraction and a non-zero differential velocity so that every one-fluid term is live
+# ---------------------------------------------------------------------------------------------------------
+def dustywave_onefluid(ndim=3, nx=12, perturb_amp=0.1, dust_to_gas=1.0, Kdrag=1.0, idrag_nature=1, iav=2, mhd=False, seed=3,
+                       use_smoothed_rhodust=True):
+    o, p = orszag_tang(ndim=ndim, nx=nx, perturb_amp=perturb_amp, imhd=11 if mhd else 0, idivbzero=2 if mhd else 0, iener=2,
+                       evolved=True, seed=seed, cube=(ndim == 3))
+    o.idust, o.onef_dust, o.idustevol = 1, 1, 0
+    o.idrag_nature, o.Kdrag = idrag_nature, Kdrag
+    o.use_smoothed_rhodust = 1 if use_smoothed_rhodust else 0
+    o.iav = iav
+    n = p.npart
+    x0 = p.x[:n, 0]
+    eps0 = dust_to_gas / (1.0 + dust_to_gas)                                   # :148
+    eps = eps0 * (1.0 + 0.1 * np.sin(2.0 * PI * x0) * np.cos(2.0 * PI * p.x[:n, min(1, ndim - 1)]))
+    p.dustfrac[:n] = eps                                                        # the value the previous c2p left behind
+    p.dustevol[:n] = eps * (1.0 + 0.02 * np.cos(4.0 * PI * x0))               # idustevol = 0: the evolved variable has moved on
+    p.deltav[:n, 0] = 0.05 * np.sin(2.0 * PI * x0)
+    p.deltav[:n, 1] = 0.02 * np.cos(2.0 * PI * x0)
+    p.deltav[:n, 2] = -0.01 * np.sin(4.0 * PI * x0)
+    p.pmass[:n] = p.pmass[:n] / (1.0 - eps0)                                   # :150 total (gas + dust) mass
+    p.rho[:n] = p.rho[:n] / (1.0 - eps0)
+    p.hh[:n] = o.hfact * (p.pmass[:n] / p.rho[:n]) ** (1.0 / ndim)
+    return o, p

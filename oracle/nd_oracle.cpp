@@ -315,6 +315,12 @@ void copy_particle(St &S, int i, int j) {
   A1(divB, i) = A1(divB, j);
   for (int k = 1; k <= 3; k++) V3(curlB, k, i) = V3(curlB, k, j);
   for (int k = 1; k <= 3; k++) V3(graddivv, k, i) = V3(graddivv, k, j);
+  if (o.onef_dust) {                                            // :84-92
+    A1(dustfrac, i) = A1(dustfrac, j); A1(dustevol, i) = A1(dustevol, j); A1(ddustevoldt, i) = A1(ddustevoldt, j);
+    for (int k = 1; k <= 3; k++) V3(deltav, k, i) = V3(deltav, k, j);
+    for (int k = 1; k <= 3; k++) V3(ddeltavdt, k, i) = V3(ddeltavdt, k, j);
+    A1(rhodust, i) = A1(rhodust, j); A1(rhogas, i) = A1(rhogas, j);
+  }
 }
 
 // src/ghostND_mhd.f90:363-431 makeghost
@@ -552,6 +558,7 @@ void density(St &S, double *rho, double *drhodt, double *densn, double *dndt, do
     if (A1(itype, i) != ND_ITYPE_BND && A1(itype, i) != ND_ITYPE_BNDDUST) {
       rho[i - 1] = 0.; drhodt[i - 1] = 0.; densn[i - 1] = 0.; dndt[i - 1] = 0.; delsqn[i - 1] = 0.;
       gradh[i - 1] = 0.; gradhn[i - 1] = 0.; gradsoft[i - 1] = 0.; gradgradh[i - 1] = 0.;
+      if (o.onef_dust) { A1(rhogas, i) = 0.; A1(rhodust, i) = 0.; }   // :123-126
     }
   }
   for (int i = 1; i <= ntotal; i++) h1[i] = 1. / A1(hh, i);    // :129-131
@@ -563,6 +570,7 @@ void density(St &S, double *rho, double *drhodt, double *densn, double *dndt, do
     while (i != -1) {                                           // :148
       idone = idone + 1;
       double pmassi = A1(pmass, i);
+      double dustfraci = o.onef_dust ? A1(dustfrac, i) : 0.;    // :153 (ndust = 1)
       double xi[3] = {0, 0, 0}, veli[3];
       for (int k = 1; k <= ndim; k++) xi[k - 1] = X_(k, i);
       for (int k = 1; k <= 3; k++) veli[k - 1] = V3(vel, k, i);
@@ -613,10 +621,19 @@ void density(St &S, double *rho, double *drhodt, double *densn, double *dndt, do
           if (itypei != ND_ITYPE_BND) {                         // :273-283
             rho[i - 1] = rho[i - 1] + pmassj * wabi * weight;
             densn[i - 1] = densn[i - 1] + wabalti * weight;
+            if (o.onef_dust) {                                  // :278-282
+              double dustfracj = A1(dustfrac, j);
+              A1(rhodust, i) = A1(rhodust, i) + pmassj * A1(dustfrac, j) * wabi * weight;
+              A1(rhogas, i) = A1(rhogas, i) + pmassj * (1. - dustfracj) * wabi * weight;
+            }
           }
           if (itypej != ND_ITYPE_BND) {                         // :285-293
             rho[j - 1] = rho[j - 1] + pmassi * wabj * weight;
             densn[j - 1] = densn[j - 1] + wabaltj * weight;
+            if (o.onef_dust) {                                  // :289-292
+              A1(rhodust, j) = A1(rhodust, j) + pmassi * A1(dustfrac, i) * wabj * weight;
+              A1(rhogas, j) = A1(rhogas, j) + pmassi * (1. - dustfraci) * wabj * weight;
+            }
           }
           if (i != j) {                                         // :297-303
             double dvel[3], dvdotr = 0.;
@@ -657,6 +674,7 @@ void density_partial(St &S, double *rho, double *drhodt, double *densn, double *
     rho[i - 1] = 0.; drhodt[i - 1] = 0.; densn[i - 1] = 0.; dndt[i - 1] = 0.; delsqn[i - 1] = 0.;
     gradh[i - 1] = 0.; gradhn[i - 1] = 0.; gradsoft[i - 1] = 0.; gradgradh[i - 1] = 0.;
     A1(numneigh, i) = 0;
+    if (S.o->onef_dust) { A1(rhodust, i) = 0.; A1(rhogas, i) = 0.; }   // :470-473
   }
   int icellprev = 0, nneigh = 0;
   for (int ipart = 1; ipart <= nlist; ipart++) {                // :480
@@ -700,6 +718,11 @@ void density_partial(St &S, double *rho, double *drhodt, double *densn, double *
         rho[i - 1] = rho[i - 1] + pmassj * wabi;                // :566-568
         densn[i - 1] = densn[i - 1] + wabalti;
         delsqn[i - 1] = delsqn[i - 1] + grgrkerni;
+        if (S.o->onef_dust) {                                   // :569-573
+          double dustfracj = A1(dustfrac, j);
+          A1(rhodust, i) = A1(rhodust, i) + pmassj * A1(dustfrac, j) * wabi;
+          A1(rhogas, i) = A1(rhogas, i) + pmassj * (1. - dustfracj) * wabi;
+        }
         if (i != j) {                                           // :577-581
           double dvel[3], dvdotr = 0.;
           for (int k = 1; k <= 3; k++) dvel[k - 1] = veli[k - 1] - V3(vel, k, j);
@@ -846,7 +869,14 @@ int conservative2primitive(St &S) {
   const nd_options &o = *S.o;
   const int npart = S.npart, ntotal = S.ntotal;
   for (int i = 1; i <= S.idim; i++) A1(sqrtg, i) = 1.;          // :72
-  for (int i = 1; i <= S.idim; i++) A1(dens, i) = A1(rho, i);   // :117
+  if (o.onef_dust) {                                            // :76-113 (idustevol = 0)
+    for (int i = 1; i <= npart; i++) {
+      A1(dustfrac, i) = A1(dustevol, i);
+      if (A1(dustfrac, i) > 1.) { A1(dustfrac, i) = 1.; A1(dustevol, i) = 1.; }   // :102-108 (dustevolin is integrator state)
+    }
+    for (int i = 1; i <= npart; i++) A1(dens, i) = A1(rho, i) * (1. - A1(dustfrac, i));   // :112: dens is the GAS density
+  } else
+    for (int i = 1; i <= S.idim; i++) A1(dens, i) = A1(rho, i); // :117
   if (o.imhd >= 11) {                                           // :151-152
     for (int i = 1; i <= S.idim; i++) for (int k = 1; k <= 3; k++) V3(Bfield, k, i) = V3(Bevol, k, i);
   } else if (o.imhd >= 1 && o.imhd <= 9) {                      // :190-193
@@ -868,7 +898,7 @@ int conservative2primitive(St &S) {
   } else {                                                      // :353-368
     for (int i = 1; i <= S.idim; i++) A1(uu, i) = A1(en, i);
   }
-  equation_of_state(S, S.a.rho);                                // :418
+  equation_of_state(S, o.onef_dust ? S.a.dens : S.a.rho);       // :418-424
   bool anyeq1 = false, anygt1 = false, all3 = true;
   for (int d = 0; d < S.ndim; d++) { if (o.ibound[d] == 1) anyeq1 = true; if (o.ibound[d] > 1) anygt1 = true; if (o.ibound[d] != 3) all3 = false; }
   if (anyeq1) {                                                 // :424-437
@@ -885,6 +915,7 @@ int conservative2primitive(St &S) {
       A1(dens, i) = A1(dens, j);
       A1(uu, i) = A1(uu, j); A1(spsound, i) = A1(spsound, j); A1(pr, i) = A1(pr, j);
       for (int k = 1; k <= 3; k++) V3(Bfield, k, i) = V3(Bfield, k, j);
+      if (o.onef_dust) A1(dustfrac, i) = A1(dustfrac, j);       // :464
       if (all3) copy_particle(S, i, j);
     }
   }
@@ -920,7 +951,9 @@ int get_rates(St &S, std::vector<int> *pairs_i, std::vector<int> *pairs_j) {
   if (o.imhd != 0 && o.imagforce != 2) return fail(S, ND_ERR_UNSUPPORTED_OPTION, "rates: imagforce");
   if (o.iav < 0 || o.iav > 3) return fail(S, ND_ERR_UNSUPPORTED_OPTION, "rates: iav");
   if (!(o.iener == 0 || o.iener == 2 || o.iener == 3)) return fail(S, ND_ERR_UNSUPPORTED_OPTION, "rates: iener");
-  if (!(o.idust == 0 || o.idust == 2)) return fail(S, ND_ERR_UNSUPPORTED_OPTION, "rates: idust");
+  if (!(o.idust == 0 || o.idust == 1 || o.idust == 2)) return fail(S, ND_ERR_UNSUPPORTED_OPTION, "rates: idust");
+  if ((o.idust == 1) != (o.onef_dust != 0)) return fail(S, ND_ERR_UNSUPPORTED_OPTION, "rates: onef_dust must be set with idust=1 only");
+  if (o.idust == 1 && (o.idustevol != 0 || o.iener == 3 || o.iav == 0)) return fail(S, ND_ERR_UNSUPPORTED_OPTION, "rates: one-fluid dust needs idustevol=0, iener/=3, iav>0");
   if (o.iresist != 0 && o.iresist != 1) return fail(S, ND_ERR_UNSUPPORTED_OPTION, "rates: iresist");
   if (o.icty != 0 || o.ixsph != 0 || o.igravity != 0 || o.iexternal_force != 0 || o.damp != 0.) return fail(S, ND_ERR_UNSUPPORTED_OPTION, "rates: option");
 
@@ -940,6 +973,7 @@ int get_rates(St &S, std::vector<int> *pairs_i, std::vector<int> *pairs_j) {
     if (o.imhd > 0) for (int k = 1; k <= 3; k++) V3(curlB, k, i) = 0.;
     del2u[i - 1] = 0.;
     h1[i] = 1. / A1(hh, i);
+    if (o.onef_dust) { A1(ddustevoldt, i) = 0.; for (int k = 1; k <= 3; k++) V3(ddeltavdt, k, i) = 0.; }   // :222-225
   }
   // :231-245 stressmax
   double stressmax = 0.;
@@ -956,6 +990,9 @@ int get_rates(St &S, std::vector<int> *pairs_i, std::vector<int> *pairs_j) {
   double Bi[3] = {0, 0, 0}, Bj[3] = {0, 0, 0}, Brhoi[3] = {0, 0, 0}, Brhoj[3] = {0, 0, 0};
   double Brho2i = 0., Brho2j = 0., valfven2i = 0., valfven2j = 0., projBi = 0., projBj = 0., projBrhoi = 0., projBrhoj = 0., alphaBi = 0.;
   double etai = 0., etaj = 0.;
+  // one-fluid dust locals (ndust = 1).  dustfraci keeps the value of the LAST particle of the pair loop when the
+  // finalisation loop tests it (:566) -- the reference never reassigns it there.
+  double dustfraci = 0., rhodusti = 0., rhogasi = 0., deltavi[3] = {0, 0, 0}, deltav2i = 0., rhogrhodonrhoi = 0.;
   int nneigh = 0;
   for (int icell = 1; icell <= S.ncellsloop; icell++) {         // :304
     get_neighbour_list(S, icell, listneigh.data(), nneigh);
@@ -981,6 +1018,14 @@ int get_rates(St &S, std::vector<int> *pairs_i, std::vector<int> *pairs_j) {
       alphaBi = V3(alpha, 3, i);
       const double phii = 1.0, phii1 = 1. / phii;
       double sqrtgi = A1(sqrtg, i);
+      if (o.onef_dust) {                                        // :344-360
+        dustfraci = A1(dustfrac, i);
+        if (o.use_smoothed_rhodust) { rhodusti = A1(rhodust, i); rhogasi = A1(rhogas, i); }
+        else { rhodusti = dustfraci * rhoi; rhogasi = (1. - dustfraci) * rhoi; }
+        for (int k = 0; k < 3; k++) deltavi[k] = V3(deltav, k + 1, i);
+        deltav2i = dot3(deltavi, deltavi);
+        rhogrhodonrhoi = rhogasi * rhodusti * rho1i;
+      } else { rhogasi = rhoi; rhodusti = 0.; deltav2i = 0.; }
       if (o.imhd != 0) {                                        // :362-380
         for (int k = 0; k < 3; k++) Bi[k] = V3(Bfield, k + 1, i);
         for (int k = 0; k < 3; k++) Brhoi[k] = Bi[k] * rho1i;
@@ -1052,6 +1097,21 @@ int get_rates(St &S, std::vector<int> *pairs_i, std::vector<int> *pairs_j) {
           double rho1j = 1. / rhoj;
           double rho21j = rho1j * rho1j;
           double rhoav1 = 0.5 * (rho1i + rho1j);                // :1261
+          double dustfracj = 0., rhodustj = 0., rhogasj = rhoj, rhogrhodonrhoj = 0., deltavj[3] = {0, 0, 0}, deltav2j = 0.;
+          double projdvgas = dvdotr, projdeltavi = 0., projdeltavj = 0.;
+          if (o.onef_dust) {                                    // :1262-1284
+            dustfracj = A1(dustfrac, j);
+            if (o.use_smoothed_rhodust) { rhodustj = A1(rhodust, j); rhogasj = A1(rhogas, j); }
+            else { rhodustj = rhoj * dustfracj; rhogasj = (1. - dustfracj) * rhoj; }
+            rhogrhodonrhoj = rhogasj * rhodustj * rho1j;
+            for (int k = 0; k < 3; k++) deltavj[k] = V3(deltav, k + 1, j);
+            deltav2j = dot3(deltavj, deltavj);
+            double dvgas[3];
+            for (int k = 0; k < 3; k++) dvgas[k] = (veli[k] - dustfraci * deltavi[k]) - (velj[k] - dustfracj * deltavj[k]);
+            projdvgas = dot3(dvgas, dr);
+            projdeltavi = dot3(deltavi, dr);
+            projdeltavj = dot3(deltavj, dr);
+          }
           double prj = std::max(A1(pr, j) - o.pext, 0.);
           double prnetj = prj - 0.;
           double Prho2j = prj * rho21j;
@@ -1095,6 +1155,7 @@ int get_rates(St &S, std::vector<int> *pairs_i, std::vector<int> *pairs_j) {
           vsig = 0.5 * (std::max(vsigi + vsigj - o.beta * dvdotr, 0.0));   // :1452
           vsigu = std::sqrt(std::fabs(prneti - prnetj) * rhoav1);          // :1459
           vsigdtc = std::max(vsig, std::max(0.5 * (vsigi + vsigj + o.beta * std::fabs(dvdotr)), vsigB));   // :1465
+          if (o.idust == 1) vsigdtc = vsigdtc + std::sqrt(deltav2i + deltav2j);                            // :1466-1468
           if (A1(itype, i) == ND_ITYPE_DUST) {                  // :1472-1482
             vsig = 0.; vsigu = 0.;
           } else {
@@ -1102,7 +1163,74 @@ int get_rates(St &S, std::vector<int> *pairs_i, std::vector<int> *pairs_j) {
             vsigmax = std::max(vsigmax, vsigdtc);
             if (vsigdtc > zero) S.dtcourant = std::min(S.dtcourant, std::min(hi * dvsigdtc, hj * dvsigdtc));
           }
-          if (o.iav > 0 && o.iav != 3) {
+          if (o.iav > 0 && o.idust == 1) {
+            // ===================== artificial_dissipation_dust :1969-2148 (iav = 1, 2, 3; iener /= 3) =====================
+            double alphaav = 0.5 * (alphai + V3(alpha, 1, j));
+            double alphau = 0.5 * (alphaui + V3(alpha, 2, j));
+            double alphaB = 0.5 * (alphaBi + V3(alpha, 3, j));
+            vsigav = std::max(alphaav, alphau) * vsig;          // :1984
+            double dustfracav = 0.5 * (dustfraci + dustfracj);
+            double projdvgasav = dvdotr - dustfracav * (projdeltavi - projdeltavj);
+            double ddeltav[3];
+            for (int k = 0; k < 3; k++) ddeltav[k] = deltavi[k] - deltavj[k];
+            double projddeltav = dot3(ddeltav, dr);
+            double dpmomdotr = (o.iav == 3) ? projdvgasav : (o.iav == 2) ? projdvgas : dvdotr;   // :1993-1999
+            double term = vsig * rhoav1 * grkern;
+            double termv = term;
+            const bool allpairs = (o.iav == 1);                 // :2005-2007
+            if (o.iav == 2 || o.iav == 3) termv = termv * (1. - dustfracav);
+            double termu = vsigu * rhoav1 * grkern * (1. - dustfracav);
+            if (projdvgas < 0 || allpairs) {                    // :2023-2038
+              double visc = alphaav * termv * dpmomdotr;
+              if (o.iav == 1 || o.iav == 3) {
+                for (int k = 0; k < 3; k++) fextrai[k] = fextrai[k] + pmassj * visc * dr[k];
+                for (int k = 0; k < 3; k++) fextraj[k] = fextraj[k] - pmassi * visc * dr[k];
+              } else {
+                for (int k = 0; k < 3; k++) forcei[k] = forcei[k] + pmassj * visc * dr[k];
+                for (int k = 0; k < 3; k++) forcej[k] = forcej[k] - pmassi * visc * dr[k];
+              }
+            }
+            if (o.iener > 0) {                                  // :2049-2146
+              double vissv, vissu, vissdv = 0., termdv = 0.;
+              if (projdvgas < 0 || allpairs) {
+                if (o.iav == 3) vissv = -alphaav * 0.5 * (projdvgasav * projdvgasav);
+                else if (o.iav == 2) vissv = -alphaav * 0.5 * (projdvgas * projdvgas);
+                else vissv = -alphaav * 0.5 * (dvdotr * dvdotr);
+              } else vissv = 0.;
+              if (o.iener == 1) vissu = 0.;
+              else vissu = alphau * (A1(uu, i) - A1(uu, j));
+              double faci = 1. / (dustfraci * (1. - dustfraci));   // :2078-2079
+              double facj = 1. / (dustfracj * (1. - dustfracj));
+              if (o.iav == 1 || o.iav == 3) {
+                if (o.iav == 1) { vissdv = -0.5 * dot3(ddeltav, ddeltav); termdv = alphaav * vsig * rhoav1 * dustfracav * grkern; }
+                else { vissdv = 0.; termdv = alphaav * vsig * rhoav1 * dustfracav * grkern * (1. - dustfracav); }
+                if (o.iav == 3) {
+                  for (int k = 0; k < 3; k++) V3(ddeltavdt, k + 1, i) = V3(ddeltavdt, k + 1, i) + faci * pmassj * termdv * (-projdvgasav) * dr[k];
+                  for (int k = 0; k < 3; k++) V3(ddeltavdt, k + 1, j) = V3(ddeltavdt, k + 1, j) - facj * pmassi * termdv * (-projdvgasav) * dr[k];
+                } else {
+                  for (int k = 0; k < 3; k++) V3(ddeltavdt, k + 1, i) = V3(ddeltavdt, k + 1, i) + faci * pmassj * termdv * (ddeltav[k]);
+                  for (int k = 0; k < 3; k++) V3(ddeltavdt, k + 1, j) = V3(ddeltavdt, k + 1, j) - facj * pmassi * termdv * (ddeltav[k]);
+                }
+              } else if (o.iav == 2) {                          // :2111-2125
+                termdv = 0.; vissdv = 0.;
+                if (projddeltav < 0.) {
+                  double vsigdv = 0.5 * (spsoundi + spsoundj);
+                  termdv = alphaav * vsigdv * rhoav1 * grkern * dustfracav * (1. - dustfracav);
+                  for (int k = 0; k < 3; k++) V3(ddeltavdt, k + 1, i) = V3(ddeltavdt, k + 1, i) + faci * pmassj * termdv * (projddeltav) * dr[k];
+                  for (int k = 0; k < 3; k++) V3(ddeltavdt, k + 1, j) = V3(ddeltavdt, k + 1, j) - facj * pmassi * termdv * (projddeltav) * dr[k];
+                  vissdv = -0.5 * (projddeltav * projddeltav);
+                }
+              }
+              faci = rhoi / rhogasi;                            // :2133-2138 (damp = 0)
+              facj = rhoj / rhogasj;
+              A1(dudt, i) = A1(dudt, i) + faci * pmassj * (termv * (vissv) + termu * vissu + termdv * vissdv);
+              A1(dudt, j) = A1(dudt, j) + facj * pmassi * (termv * (vissv) - termu * vissu + termdv * vissdv);
+              double vsigeps = 0.5 * (spsoundi + spsoundj);     // :2140-2145
+              double diffeps = alphaB * rhoav1 * vsigeps * (dustfraci - dustfracj) * grkern;
+              A1(ddustevoldt, i) = A1(ddustevoldt, i) + pmassj * diffeps;
+              A1(ddustevoldt, j) = A1(ddustevoldt, j) - pmassi * diffeps;
+            }
+          } else if (o.iav > 0 && o.iav != 3) {
             // ===================== artificial_dissipation :1700-1894 =====================
             double alphaav = 0.5 * (alphai + V3(alpha, 1, j));
             double alphau = 0.5 * (alphaui + V3(alpha, 2, j));
@@ -1223,6 +1351,33 @@ int get_rates(St &S, std::vector<int> *pairs_i, std::vector<int> *pairs_j) {
               for (int k = 0; k < 3; k++) V3(gradpsi, k + 1, j) = V3(gradpsi, k + 1, j) + pmassi * gradpsiterm * dr[k];
             }
           }
+          if (o.idust == 1) {
+            // ===================== dust_derivs :2726-2807 (idustevol = 0) =====================
+            {
+              double termi = rhogrhodonrhoi * projdeltavi * rho21i * grkerni;
+              double termj = rhogrhodonrhoj * projdeltavj * rho21j * grkernj;
+              double term = termi + termj;
+              A1(ddustevoldt, i) = A1(ddustevoldt, i) - pmassj * term;
+              A1(ddustevoldt, j) = A1(ddustevoldt, j) + pmassi * term;
+            }
+            double termi = (rhogasi - rhodusti) * rho1i * deltav2i;   // :2767-2769 high Mach number term
+            double termj = (rhogasj - rhodustj) * rho1j * deltav2j;
+            double dterm = 0.5 * (termi - termj);
+            for (int k = 0; k < 3; k++)                         // :2776-2777 (the forcei term is added after the pair loop, :460)
+              V3(ddeltavdt, k + 1, i) = V3(ddeltavdt, k + 1, i) + rho1i * pmassj * (dvel[k] * projdeltavi + dterm * dr[k]) * grkerni;
+            for (int k = 0; k < 3; k++)
+              V3(ddeltavdt, k + 1, j) = V3(ddeltavdt, k + 1, j) + rho1j * pmassi * (dvel[k] * projdeltavj + dterm * dr[k]) * grkernj - rhoj / rhogasj * forcej[k];
+            double prdustterm[3];                               // :2792-2796 anisotropic pressure
+            for (int k = 0; k < 3; k++)
+              prdustterm[k] = rhogrhodonrhoi * deltavi[k] * projdeltavi * rho21i * grkerni + rhogrhodonrhoj * deltavj[k] * projdeltavj * rho21j * grkernj;
+            for (int k = 0; k < 3; k++) fextrai[k] = fextrai[k] - pmassj * (prdustterm[k]);
+            for (int k = 0; k < 3; k++) fextraj[k] = fextraj[k] + pmassi * (prdustterm[k]);
+            if (o.iener > 0) {                                  // :2801-2805
+              double du = A1(uu, i) - A1(uu, j);
+              A1(dudt, i) = A1(dudt, i) + pmassj * (pri * rho1i / rhogasi * projdvgas - rhodusti * rho21i * du * projdeltavi) * grkerni;
+              A1(dudt, j) = A1(dudt, j) + pmassi * (prj * rho1j / rhogasj * projdvgas - rhodustj * rho21j * du * projdeltavj) * grkernj;
+            }
+          }
           for (int k = 0; k < 3; k++) V3(force, k + 1, j) = V3(force, k + 1, j) + fextraj[k] + forcej[k];   // :1600
           if (o.iav > 0) {                                      // :1639-1656
             if (o.iavlim[1] > 0) {
@@ -1289,6 +1444,7 @@ int get_rates(St &S, std::vector<int> *pairs_i, std::vector<int> *pairs_j) {
       // :458-459
       for (int k = 0; k < 3; k++) V3(force, k + 1, i) = V3(force, k + 1, i) + fextrai[k] + forcei[k];
       for (int k = 0; k < 3; k++) V3(dBevoldt, k + 1, i) = V3(dBevoldt, k + 1, i) + dBevoldti[k];
+      if (o.idust == 1) for (int k = 0; k < 3; k++) V3(ddeltavdt, k + 1, i) = V3(ddeltavdt, k + 1, i) - rhoi / rhogasi * forcei[k];   // :460
       i = S.ll[i];
     }
   }
@@ -1309,6 +1465,24 @@ int get_rates(St &S, std::vector<int> *pairs_i, std::vector<int> *pairs_j) {
     double rhoi = A1(rho, i);
     double rho1i = 1. / rhoi;
     if (o.idust == 2 && o.idrag_nature != 0 && (o.Kdrag > 0. || o.idrag_nature > 1)) S.dtdrag = std::min(S.dtdrag, ts_min);   // :543-547
+    else if (o.idust == 1) {                                    // :548-582 one fluid dust
+      if (o.use_smoothed_rhodust) { rhodusti = A1(rhodust, i); rhogasi = A1(rhogas, i); }
+      else { rhodusti = rhoi * A1(dustfrac, i); rhogasi = (1. - A1(dustfrac, i)) * rhoi; }
+      double tstop = get_tstop(o.idrag_nature, rhogasi, rhodusti, A1(spsound, i), o.Kdrag);
+      S.dtdrag = std::min(S.dtdrag, tstop);
+      double dtstop;
+      if (dustfraci > 0.) {                                     // :566 -- dustfraci is NOT particle i's (see above)
+        dtstop = 1. / tstop;
+        for (int k = 1; k <= 3; k++) V3(ddeltavdt, k, i) = V3(ddeltavdt, k, i) - V3(deltav, k, i) * dtstop;
+      } else {
+        dtstop = 0.;
+        for (int k = 1; k <= 3; k++) V3(ddeltavdt, k, i) = 0.;
+      }
+      if (o.iener > 0) {                                        // :579-582
+        deltav2i = dot3(&V3(deltav, 1, i), &V3(deltav, 1, i));
+        A1(dudt, i) = A1(dudt, i) + rhodusti * rho1i * deltav2i * dtstop;
+      }
+    }
     if (o.imhd != 0) {                                          // :630-649
       if (o.imhd > 0) for (int k = 1; k <= 3; k++) V3(curlB, k, i) = V3(curlB, k, i) * rho1i;
       A1(divB, i) = A1(divB, i) * rho1i;
@@ -1337,7 +1511,7 @@ int get_rates(St &S, std::vector<int> *pairs_i, std::vector<int> *pairs_j) {
     if (o.iener == 3) {                                         // :820-826
       A1(dudt, i) = A1(dudt, i) + A1(pr, i) * (rho1i * rho1i) * A1(drhodt, i);
       A1(dendt, i) = dot3(&V3(vel, 1, i), &V3(force, 1, i)) + A1(dudt, i);
-    } else if (o.iener > 0 && o.iav >= 0) {                     // :832-835
+    } else if (o.iener > 0 && o.iav >= 0 && o.idust != 1) {     // :832-835
       A1(dudt, i) = A1(dudt, i) + A1(pr, i) * (rho1i * rho1i) * A1(drhodt, i);
       A1(dendt, i) = A1(dudt, i);
     } else {

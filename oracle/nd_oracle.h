@@ -28,6 +28,8 @@ typedef struct ndo_arrays {
   double *dens, *uu, *pr, *spsound, *Bfield, *sqrtg;
   double *force, *dudt, *dendt, *dBevoldt, *daldt, *dpsidt, *gradpsi, *fmag, *divB, *curlB,
          *graddivv, *del2u, *xsphterm;
+  /* one-fluid dust (idust=1): dustfrac is in/out like the module array (read by `density`, rewritten by c2p) */
+  double *dustevol, *dustfrac, *deltav, *rhogas, *rhodust, *ddustevoldt, *ddeltavdt;
 } ndo_arrays;
 
 enum { NDO_GHOSTS = 1, NDO_LINK = 2, NDO_DENSITY = 4, NDO_C2P = 8, NDO_RATES = 16, NDO_ALL = 31 };

@@ -25,7 +25,8 @@ _D_NAMES = ["x", "vel", "pmass", "hh", "en", "Bevol", "alpha", "psi", "rho"]
 _I_NAMES = ["itype", "ireal"]
 _D2_NAMES = ["gradh", "gradhn", "gradsoft", "gradgradh", "rhoalt", "drhodt", "dhdt"]
 _D3_NAMES = ["dens", "uu", "pr", "spsound", "Bfield", "sqrtg", "force", "dudt", "dendt", "dBevoldt", "daldt", "dpsidt",
-             "gradpsi", "fmag", "divB", "curlB", "graddivv", "del2u", "xsphterm"]
+             "gradpsi", "fmag", "divB", "curlB", "graddivv", "del2u", "xsphterm",
+             "dustevol", "dustfrac", "deltav", "rhogas", "rhodust", "ddustevoldt", "ddeltavdt"]
 
 
 class NdoArrays(C.Structure):

@@ -20,6 +20,9 @@ DENSITY_FIELDS = ["hh", "rho", "gradh", "drhodt", "dhdt"]
 AUX_FIELDS = ["rhoalt", "gradhn", "gradgradh"]
 PRIM_FIELDS = ["dens", "uu", "pr", "spsound", "Bfield"]
 RATES_FIELDS = ["force", "dudt", "dendt", "dBevoldt", "daldt", "dpsidt", "gradpsi", "divB", "curlB", "graddivv", "del2u"]
+# one-fluid dust (idust=1): rhogas/rhodust from the density sums, dustfrac from c2p, the two extra rates
+DUST_DENSITY_FIELDS = ["rhogas", "rhodust", "dustfrac"]
+DUST_RATES_FIELDS = ["ddustevoldt", "ddeltavdt"]
 SCALARS = ["dtcourant", "dtforce", "dtav", "dtdrag", "vsigmax", "vsig2max", "stressmax", "fhmax", "hhmax", "dxcell", "ts_min",
            "h_on_csts_max"]
 INT_SCALARS = ["itsdensity", "nneigh_min", "nneigh_max", "ntotal", "ncells", "ncellsx", "ncalctotal", "nclumped"]
@@ -40,6 +43,7 @@ def natural_scales(p, n):
         "drhodt": rho * v / h, "dhdt": v, "force": (cs * cs + va2) / h, "dudt": (u + vs * vs) * vs / h, "dendt": (u + vs * vs) * vs / h,
         "dBevoldt": B * vs / h, "daldt": vs / h, "dpsidt": vs * vs * B / h + psi * vs / h, "gradpsi": psi / h * max(rho, 1.0), "divB": B / h,
         "curlB": B / h, "graddivv": rho * v / h, "del2u": u / (h * h),
+        "ddustevoldt": vs / h, "ddeltavdt": (cs * cs + va2) / h,
     }
 
 
@@ -94,11 +98,15 @@ def assert_parity(pg, po, sg, so, opts, aux=True, rtol=RTOL, check_rates=True):
         fields = [f for f in fields if f != "del2u"]
     if opts.imhd == 0:
         fields = [f for f in fields if f not in ("Bfield", "dBevoldt", "gradpsi", "divB", "curlB", "dpsidt")]
+    if opts.idust == 1:
+        fields = fields + DUST_DENSITY_FIELDS + (DUST_RATES_FIELDS if check_rates else [])
     errs = compare(pg, po, sg, so, fields)
     bad = {k: v for k, v in errs.items() if not (v <= rtol)}
     assert not bad, f"fields beyond {rtol:g}: {bad}  (all: {errs})"
     # density outputs on ghost rows are copies of the parent (iterate_density.f90:330-344)
-    gerrs = compare(pg, po, sg, so, ["hh", "rho", "gradh"], rows=nt)
+    # (one-fluid dust: dustfrac, rhogas, rhodust of ghost rows are the parent's after conservative2primitive.f90:464-465; the
+    #  reference leaves unnormalised partial pair sums in ddustevoldt/ddeltavdt of ghost rows, which are not compared)
+    gerrs = compare(pg, po, sg, so, ["hh", "rho", "gradh"] + (DUST_DENSITY_FIELDS if opts.idust == 1 else []), rows=nt)
     bad = {k: v for k, v in gerrs.items() if not (v <= rtol)}
     assert not bad, f"ghost rows beyond {rtol:g}: {bad}"
     if check_rates:

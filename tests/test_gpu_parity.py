@@ -38,6 +38,13 @@ CASES = {
     "dustybox3d": (lambda: setups.dustybox(ndim=3, nx=12), 1),
     "dustybox3d_coincident": (lambda: setups.dustybox(ndim=3, nx=10, coincident=True), 1),
     "dustybox3d_const_ts": (lambda: setups.dustybox(ndim=3, nx=10, idrag_nature=2, Kdrag=0.3), 1),
+    # configs[3] variant: one-fluid dust, dust_derivs + artificial_dissipation_dust
+    "onefluid_dust3d": (lambda: setups.dustywave_onefluid(ndim=3, nx=12), 1),
+    "onefluid_dust3d_unsmoothed": (lambda: setups.dustywave_onefluid(ndim=3, nx=10, use_smoothed_rhodust=False), 1),
+    "onefluid_dust3d_mhd": (lambda: setups.dustywave_onefluid(ndim=3, nx=10, mhd=True), 1),
+    "onefluid_dust3d_const_ts": (lambda: setups.dustywave_onefluid(ndim=3, nx=10, idrag_nature=2, Kdrag=0.2), 1),
+    "onefluid_dust2d_iav1": (lambda: setups.dustywave_onefluid(ndim=2, nx=32, iav=1), 1),
+    "onefluid_dust3d_iav3": (lambda: setups.dustywave_onefluid(ndim=3, nx=10, iav=3), 1),
 }
 
 

@@ -296,3 +296,62 @@ def test_fixed_particles_keep_their_state_and_have_zero_rates():
     xl = (p.x[:n, 0] > -0.4) & (p.x[:n, 0] < -0.1)
     xr = (p.x[:n, 0] > 0.1) & (p.x[:n, 0] < 0.4)
     assert np.max(np.abs(p.rho[:n][xl] - 1.0)) < 2e-3 and np.max(np.abs(p.rho[:n][xr] - 0.125)) < 2e-3 * 0.125 * 8
+
+
+# ---------------------------------------------------------------------------------------------------------
+# one-fluid dust (idust=1): the reference's own "should be zero" debug sums
+# ---------------------------------------------------------------------------------------------------------
+def _onefluid_energy_sum(p, smoothed):
+    """esum of src/ratesND_mhd.f90:913-917: total energy rate of the one-fluid mixture."""
+    n = p.npart
+    m, rho, eps = p.pmass[:n], p.rho[:n], p.dustfrac[:n]
+    rg, rd = (p.rhogas[:n], p.rhodust[:n]) if smoothed else (rho * (1 - eps), rho * eps)
+    t = m * ((p.vel[:n] * p.force[:n]).sum(1) + rg * rd / rho ** 2 * (p.deltav[:n] * p.ddeltavdt[:n]).sum(1)
+             + ((1 - 2 * eps) * 0.5 * (p.deltav[:n] ** 2).sum(1) - p.uu[:n]) * p.ddustevoldt[:n] + rg / rho * p.dudt[:n])
+    return t.sum(), np.abs(t).sum()
+
+
+@pytest.mark.parametrize("ndim,nx", [(3, 8), (2, 24)])
+def test_onefluid_dust_conserves_momentum_and_dust_mass(ndim, nx):
+    o, p = setups.dustywave_onefluid(ndim=ndim, nx=nx)
+    oracle.derivs(o, p)
+    n = p.npart
+    m = p.pmass[:n]
+    f = m[:, None] * p.force[:n]
+    assert np.all(np.abs(f.sum(0)) <= 1e-13 * np.abs(f).sum())                       # sum m f = 0 (:678)
+    d = m * p.ddustevoldt[:n]
+    assert abs(d.sum()) <= 1e-13 * np.abs(d).sum()                                   # dust mass: sum m d(eps)/dt = 0 (derivs.f90:225-232)
+    assert np.all(np.abs(p.rhogas[:n] + p.rhodust[:n] - p.rho[:n]) <= 1e-14 * p.rho[:n])   # the two density sums partition rho
+    assert np.array_equal(p.dustfrac[:n], p.dustevol[:n])                            # idustevol = 0 (conservative2primitive.f90:91)
+    assert np.allclose(p.dens[:n], p.rho[:n] * (1 - p.dustfrac[:n]), rtol=1e-15)     # dens is the gas density (:112)
+
+
+@pytest.mark.parametrize("iav", [1, 2])
+def test_onefluid_dust_energy_identity(iav):
+    """With a dust fraction consistent with rho_g, rho_d (unsmoothed) and no dust-fraction diffusion (alpha_B = 0) the
+    reference's debug sum (ratesND_mhd.f90:908-917, 'should be zero if conserving energy') vanishes to round-off with
+    viscosity, conductivity, drag heating and the deltav dissipation all active."""
+    o, p = setups.dustywave_onefluid(ndim=3, nx=8, iav=iav, use_smoothed_rhodust=False)
+    n = p.npart
+    p.dustevol[:n] = p.dustfrac[:n]
+    p.alpha[:n, 0], p.alpha[:n, 1], p.alpha[:n, 2] = 0.7, 0.4, 0.0
+    oracle.derivs(o, p)
+    e, scale = _onefluid_energy_sum(p, smoothed=False)
+    assert abs(e) <= 1e-13 * scale, (e, scale)
+
+
+def test_onefluid_dust_drag_terms():
+    """Uniform lattice, uniform dust fraction and deltav: every pair sum cancels, leaving the local drag terms of
+    ratesND_mhd.f90:561-582: d(deltav)/dt = -deltav/ts, du/dt = rho_d/rho deltav^2/ts, dtdrag = ts = rho_d rho_g/(K rho)."""
+    o, p = setups.dustywave_onefluid(ndim=3, nx=8, perturb_amp=0.0, Kdrag=2.0)
+    n = p.npart
+    eps = 0.5
+    p.dustfrac[:n] = eps; p.dustevol[:n] = eps
+    p.deltav[:n] = np.array([0.03, -0.01, 0.02]); p.vel[:n] = 0.0
+    p.en[:n] = 1.0; p.alpha[:n] = 0.0
+    s, _ = oracle.derivs(o, p)
+    rg, rd, rho = p.rhogas[:n], p.rhodust[:n], p.rho[:n]
+    ts = rd * rg / (2.0 * rho)
+    assert np.allclose(p.ddeltavdt[:n], -p.deltav[:n] / ts[:, None], rtol=1e-9, atol=1e-12)
+    assert np.allclose(p.dudt[:n], rd / rho * (p.deltav[:n] ** 2).sum(1) / ts, rtol=1e-9)
+    assert np.isclose(s["dtdrag"], ts.min(), rtol=1e-14)
