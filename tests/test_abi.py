@@ -32,8 +32,8 @@ def test_library_exports_every_declared_symbol():
 def test_header_is_plain_c_and_struct_layout_matches_ctypes():
     """Compile the header as C (gcc) and compare sizeof/offsetof with the ctypes mirror."""
     fields = {
-        "nd_options": ["iener", "iavlim", "ibound", "device_ghosts", "hfact", "gamma", "xmin", "Bconst", "hhmax", "reserved_d"],
-        "nd_arrays": ["x", "rho_in", "hh", "dens", "force", "del2u", "x_out", "reserved_p"],
+        "nd_options": ["iener", "iavlim", "ibound", "device_ghosts", "idustevol", "hfact", "gamma", "xmin", "Bconst", "hhmax", "reserved_d"],
+        "nd_arrays": ["x", "rho_in", "hh", "dens", "force", "del2u", "x_out", "dustevol", "dustfrac_in", "dustfrac", "ddeltavdt"],
         "nd_scalars": ["dtcourant", "fmean", "itsdensity", "ncellsx", "nrelink", "ncalctotal", "reserved_i"],
     }
     prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
