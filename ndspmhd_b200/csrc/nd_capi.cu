@@ -835,6 +835,19 @@ int comm_allreduce(nd_ctx *c, double *v, int n, int op) {
   return 0;
 }
 
+// several maxima and minima in ONE all-reduce (min x = -max(-x)): every callback round trip costs ~0.1 ms of host latency
+int comm_allreduce_maxmin(nd_ctx *c, double *mx, int nmx, double *mn, int nmn) {
+  if (!c->has_comm) return 0;
+  double v[16];
+  if (nmx + nmn > 16) return set_err(c, ND_ERR_INVALID_ARG, "comm_allreduce_maxmin: too many values");
+  for (int k = 0; k < nmx; k++) v[k] = mx[k];
+  for (int k = 0; k < nmn; k++) v[nmx + k] = -mn[k];
+  if (int e = comm_allreduce(c, v, nmx + nmn, 0)) return e;
+  for (int k = 0; k < nmx; k++) mx[k] = v[k];
+  for (int k = 0; k < nmn; k++) mn[k] = -v[nmx + k];
+  return 0;
+}
+
 int sync_flags(nd_ctx *c) {   // D2H of the flag block; returns a pending device-side error code
   CU(cudaMemcpyAsync(c->h_flags, c->flags, sizeof(int) * 16, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -1311,13 +1324,6 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   CU(cudaMemcpyAsync(c->h_red, c->red, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(c->h_fmean, c->fmean, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
   if (int e2 = sync_flags(c)) return e2;
-  double ef = c->h_flags[1];
-  if (int e2 = comm_allreduce(c, &ef, 1, 0)) return e2;
-  if (ef != 0.) {
-    const int code = c->h_flags[1] ? c->h_flags[1] : ND_ERR_COMM;
-    if (code == ND_ERR_COMM) return set_err(c, code, "rates: another rank reported an error");
-    return set_err(c, code, code == ND_ERR_VSIG_DET ? "rates: vsig det < 0" : code == ND_ERR_H_NONPOSITIVE ? "rates: h <= 0" : "rates: dx = 0 (coincident particles of the same type)");
-  }
   nd_scalars &s = c->sc;
   s.dtcourant = dkey_inv(c->h_red[RED_DTC]);
   s.vsigmax = dkey_inv(c->h_red[RED_VSIG]);
@@ -1325,17 +1331,21 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   s.ts_min = dkey_inv(c->h_red[RED_TS]);
   s.h_on_csts_max = dkey_inv(c->h_red[RED_HCS]);
   s.fhmax = dkey_inv(c->h_red[RED_FH]);
-  if (c->has_comm) {
-    double mn[3] = {s.dtcourant, s.dtav, s.ts_min}, mx[3] = {s.vsigmax, s.h_on_csts_max, s.fhmax};
+  double ef = c->h_flags[1];
+  if (c->has_comm) {   // two all-reduces: {error flag, maxima, minima} and the sums
+    double mx[4] = {ef, s.vsigmax, s.h_on_csts_max, s.fhmax}, mn[4] = {s.dtcourant, s.dtav, s.ts_min, dkey_inv(c->h_red[RED_DTF])};
     double sm[4] = {c->h_fmean[0], c->h_fmean[1], c->h_fmean[2], (double)c->h_flags[4]};
-    double dtf = dkey_inv(c->h_red[RED_DTF]);
-    if (int e3 = comm_allreduce(c, mn, 3, 1)) return e3;
-    if (int e3 = comm_allreduce(c, mx, 3, 0)) return e3;
+    if (int e3 = comm_allreduce_maxmin(c, mx, 4, mn, 4)) return e3;
     if (int e3 = comm_allreduce(c, sm, 4, 2)) return e3;
-    if (int e3 = comm_allreduce(c, &dtf, 1, 1)) return e3;
-    s.dtcourant = mn[0]; s.dtav = mn[1]; s.ts_min = mn[2]; s.vsigmax = mx[0]; s.h_on_csts_max = mx[1]; s.fhmax = mx[2];
+    ef = mx[0]; s.vsigmax = mx[1]; s.h_on_csts_max = mx[2]; s.fhmax = mx[3];
+    s.dtcourant = mn[0]; s.dtav = mn[1]; s.ts_min = mn[2];
     c->h_fmean[0] = sm[0]; c->h_fmean[1] = sm[1]; c->h_fmean[2] = sm[2]; c->h_flags[4] = (int)(sm[3] + 0.5);
-    union { double d; unsigned long long u; } kv; kv.d = dtf; c->h_red[RED_DTF] = kv.u | 0x8000000000000000ull;
+    union { double d; unsigned long long u; } kv; kv.d = mn[3]; c->h_red[RED_DTF] = kv.u | 0x8000000000000000ull;
+  }
+  if (ef != 0.) {
+    const int code = c->h_flags[1] ? c->h_flags[1] : ND_ERR_COMM;
+    if (code == ND_ERR_COMM) return set_err(c, code, "rates: another rank reported an error");
+    return set_err(c, code, code == ND_ERR_VSIG_DET ? "rates: vsig det < 0" : code == ND_ERR_H_NONPOSITIVE ? "rates: h <= 0" : "rates: dx = 0 (coincident particles of the same type)");
   }
   s.stressmax = O.stressmax;
   s.vsig2max = (o.imhd != 0 && o.idivbzero >= 2) ? s.vsigmax * s.vsigmax : 0.;
@@ -1365,9 +1375,8 @@ int fill_density_scalars(nd_ctx *c) {
   LAUNCH(c, k_minmax_neigh, std::min(nblocks(c->nown, 256), 1184), 256, 0, c->numneigh, c->nown, c->flags + 12);
   if (int e = sync_flags(c)) return e;
   double nmn = c->h_flags[12], nmx = c->h_flags[13], cnt[2] = {(double)c->ncalctotal, 0.};
-  if (int e = comm_allreduce(c, &nmn, 1, 1)) return e;
-  if (int e = comm_allreduce(c, &nmx, 1, 0)) return e;
-  if (int e = comm_allreduce(c, cnt, 2, 2)) return e;
+  if (int e = comm_allreduce_maxmin(c, &nmx, 1, &nmn, 1)) return e;
+  if (int e = comm_allreduce(c, cnt, 1, 2)) return e;
   s.nneigh_min = (int)nmn; s.nneigh_max = (int)nmx;
   if (c->has_comm) s.ncalctotal = (long long)(cnt[0] + 0.5);
   fill_link_scalars(c);

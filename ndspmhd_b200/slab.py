@@ -112,21 +112,47 @@ class SlabComm:
         self.bytes_sent = 0
 
     # ---- python-level API (also what the gloo tests exercise) ----
+    def _scratch(self):
+        """Reused device / pinned-host staging for the small collectives (allocation and tensor construction per call cost more
+        than the collective itself)."""
+        if getattr(self, "_dev", None) is None:
+            torch = self.torch
+            pin = self.device != "cpu"
+            self._host = torch.zeros(32, dtype=torch.float64, pin_memory=pin)
+            self._dev = torch.zeros(32, dtype=torch.float64, device=self.device) if pin else self._host
+            self._ihost = torch.zeros(2 * self.nranks, dtype=torch.int64, pin_memory=pin)
+            self._idev = torch.zeros(2 * self.nranks, dtype=torch.int64, device=self.device) if pin else self._ihost
+            self._imine = torch.zeros(2, dtype=torch.int64, device=self.device)
+            self._rops = {OP_MAX: self.dist.ReduceOp.MAX, OP_MIN: self.dist.ReduceOp.MIN, OP_SUM: self.dist.ReduceOp.SUM}
+        return self._host, self._dev
+
     def allreduce(self, vals, op: int):
         torch, dist = self.torch, self.dist
-        t = torch.tensor(list(vals), dtype=torch.float64, device=self.device)
-        rop = {OP_MAX: dist.ReduceOp.MAX, OP_MIN: dist.ReduceOp.MIN, OP_SUM: dist.ReduceOp.SUM}[op]
-        dist.all_reduce(t, op=rop, group=self.group)
+        host, dev = self._scratch()
+        n = len(vals)
+        for i in range(n):
+            host[i] = vals[i]
+        if dev is not host:
+            dev[:n].copy_(host[:n], non_blocking=True)
+        dist.all_reduce(dev[:n], op=self._rops[op], group=self.group)
+        if dev is not host:
+            host[:n].copy_(dev[:n], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         self.n_allreduce += 1
-        return t.cpu().tolist()
+        return host[:n].tolist()
 
     def exchange_counts(self, send_left: int, send_right: int):
         """Returns (bytes arriving from the left neighbour, bytes arriving from the right neighbour)."""
         torch, dist = self.torch, self.dist
-        mine = torch.tensor([send_left, send_right], dtype=torch.int64, device=self.device)
-        allc = [torch.zeros(2, dtype=torch.int64, device=self.device) for _ in range(self.nranks)]
-        dist.all_gather(allc, mine, group=self.group)
-        allc = [a.cpu().tolist() for a in allc]
+        self._scratch()
+        self._ihost[0], self._ihost[1] = send_left, send_right
+        self._imine.copy_(self._ihost[:2], non_blocking=True)
+        dist.all_gather_into_tensor(self._idev, self._imine, group=self.group) if self.device != "cpu" else \
+            dist.all_gather(list(self._idev.view(self.nranks, 2).unbind(0)), self._imine, group=self.group)
+        if self._idev is not self._ihost:
+            self._ihost.copy_(self._idev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        allc = self._ihost.view(self.nranks, 2)
         # what my left neighbour sends to ITS right is for me, and vice versa
         return int(allc[self.left][1]), int(allc[self.right][0])
 
