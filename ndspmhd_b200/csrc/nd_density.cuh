@@ -30,6 +30,9 @@ struct DensityArgs {
 #ifndef ND_DENS_MINB
 #define ND_DENS_MINB 4
 #endif
+#ifndef ND_DENS_PF
+#define ND_DENS_PF 3   // neighbour record staging of the density kernel: 0 none, 1/2 L1 prefetch 1/2 pairs ahead, 3 two pairs per trip
+#endif
 constexpr int DENS_BLOCK = 128;
 
 template <int NDIM, bool FIRST, bool AUX>
@@ -103,10 +106,23 @@ __global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel
   };
   if (cnt > 0) {
     const unsigned *col = L.nbr + ((size_t)(t >> 5) * L.lmax) * 32 + (t & 31);
+#if ND_DENS_PF == 3
+    // two neighbours per trip: their four record loads are issued together and overlap the other's arithmetic
+    walk_list2(col, cnt, [&](int ka, int kb, bool twob) {
+      const double4 pa = ld4(G.posh + ka), va = ld4(G.vm + ka), pb = ld4(G.posh + kb), vb = ld4(G.vm + kb);
+      body(ka, pa, va);
+      if (twob) body(kb, pb, vb);
+    });
+#else
     walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
+#if ND_DENS_PF == 2
       prefetch_l1(G.posh + k2); prefetch_l1(G.vm + k2);          // records two pairs ahead into L1, no registers held
+#elif ND_DENS_PF == 1
+      prefetch_l1(G.posh + k1); prefetch_l1(G.vm + k1);
+#endif
       body(k, ld4(G.posh + k), ld4(G.vm + k));
     });
+#endif
   }
   const int nneigh = active ? A.numneigh[orig] : 0;   // counted by build_lists_kernel (:196-197 / :532)
 

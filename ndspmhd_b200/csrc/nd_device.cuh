@@ -221,6 +221,25 @@ template <class F> __device__ __forceinline__ void walk_list(const unsigned *col
   }
 }
 
+// Same batching, two entries per trip: f(ka, kb, has_b).
+template <class F> __device__ __forceinline__ void walk_list2(const unsigned *col, int cnt, F &&f) {
+  const int last = cnt - 1;
+  auto ld = [&](int n) { return (int)__ldcs(col + (size_t)min(n, last) * 32); };
+  int c0 = ld(0), c1 = ld(1), c2 = ld(2), c3 = ld(3);
+  int n0 = ld(4), n1 = ld(5), n2 = ld(6), n3 = ld(7);
+#pragma unroll 1
+  for (int nb = 0; nb < cnt; nb += 4) {
+    const int m0 = ld(nb + 8), m1 = ld(nb + 9), m2 = ld(nb + 10), m3 = ld(nb + 11);
+#pragma unroll 1
+    for (int u = 0; u < 4; u += 2) {
+      if (nb + u >= cnt) break;
+      f(u == 0 ? c0 : c2, u == 0 ? c1 : c3, nb + u + 1 < cnt);
+    }
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    n0 = m0; n1 = m1; n2 = m2; n3 = m3;
+  }
+}
+
 enum { LIST_DENS_FIRST = 0, LIST_DENS_PARTIAL = 1, LIST_RATES = 2 };
 
 struct ListArgs {
