@@ -29,7 +29,8 @@ struct nd_ctx {
   std::string err;
   long long launches = 0;
   ndt::KernelTables *T = nullptr;
-  TabRec *d_tab = nullptr; TabRec2 *d_tab2 = nullptr; double *d_tabdrag = nullptr;
+  TabRec *d_tab = nullptr; TabRec2 *d_tab2 = nullptr; double *d_tabdrag = nullptr; double2 *d_tabg = nullptr;
+  int num_sms = 148;
   // sizes
   int npart = 0, ntotal = 0, cap = 0, nown = 0;   // nown <= npart: rows this context computes (the rest of [0,npart) are halo copies)
   bool mixed_types = true;   // false when the last link found one itype only (the list builder then skips the type rules)
@@ -818,7 +819,7 @@ Grid make_grid(nd_ctx *c) {
   G.nx = c->ncellsx[0]; G.ny = c->ncellsx[1]; G.nz = c->ncellsx[2]; G.ncells = c->ncells;
   G.npart = c->npart; G.ntotal = c->ntotal; G.nown = c->nown;
   G.radkern2 = c->T->radkern2; G.dq2table = c->T->dq2table; G.ddq2table = c->T->ddq2table;
-  G.tab = c->d_tab; G.tab2 = c->d_tab2; G.tabdrag = c->d_tabdrag;
+  G.tab = c->d_tab; G.tab2 = c->d_tab2; G.tabdrag = c->d_tabdrag; G.tabg = c->d_tabg;
   return G;
 }
 
@@ -1241,7 +1242,23 @@ template <int NDIM, bool MHD, bool DRAG, bool FAST, bool ONEF> int launch_rates_
     LA.pair_out_i = pi; LA.pair_out_j = pj; LA.pair_count = pc; LA.pair_cap = cap;
     NbrLists L;
     if (int e = build_lists<NDIM, LIST_RATES>(c, G, LA, L)) return e;
-    LAUNCH(c, (rates_pair_kernel<NDIM, MHD, DRAG, FAST, ONEF>), nblocks(m, RATES_BLOCK), RATES_BLOCK, 0, G, I, O, S, R, L, c0, m);
+    // persistent blocks: one per resident slot (the 64 KB shared-memory table is loaded once per block)
+    static int resident = 0, carveout = 100;
+    auto kfn = rates_pair_kernel<NDIM, MHD, DRAG, FAST, ONEF>;
+    CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, RATES_SMEM_BYTES));   // attributes are per device
+    if (!resident) {
+      CU(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      int per_sm = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, RATES_BLOCK, RATES_SMEM_BYTES));
+      if (per_sm < 1) return set_err(c, ND_ERR_CUDA, "rates_pair_kernel does not fit on an SM");
+      resident = per_sm * c->num_sms;
+      // leave the rest of the 256 KB L1/shared array to L1: the neighbour gather lives on its hit rate
+      carveout = std::min(100, (int)((per_sm * (size_t)(RATES_SMEM_BYTES + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
+      if (getenv("NDSPMHD_B200_DEBUG")) fprintf(stderr, "rates_pair_kernel: %d blocks/SM x %d SMs, %d B dynamic smem, carveout %d%%\n", per_sm, c->num_sms, RATES_SMEM_BYTES, carveout);
+    }
+    CU(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+    CU(cudaMemsetAsync(c->flags + 8, 0, sizeof(int), c->stream));
+    LAUNCH(c, (rates_pair_kernel<NDIM, MHD, DRAG, FAST, ONEF>), ND_RATES_PERSIST ? std::min(nblocks(m, RATES_BLOCK), resident) : nblocks(m, RATES_BLOCK), RATES_BLOCK, RATES_SMEM_BYTES, G, I, O, S, R, L, c0, m);
   }
   return 0;
 }
@@ -1281,7 +1298,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   RatesRed R;
   R.dtcourant_min = c->red + RED_DTC; R.vsigmax_max = c->red + RED_VSIG; R.dtav_min = c->red + RED_DTAV; R.ts_min = c->red + RED_TS;
   R.h_on_csts_max = c->red + RED_HCS; R.fhmax_max = c->red + RED_FH; R.dtforce_min = c->red + RED_DTF; R.fmean = c->fmean;
-  R.nclumped = c->flags + 4; R.err = c->flags + 1;
+  R.nclumped = c->flags + 4; R.err = c->flags + 1; R.sched = c->flags + 8;
   CU(cudaEventRecord(c->ev[3], c->stream));
   const bool mhd = o.imhd != 0, drag = (o.idust == 2);
   int e = 0;
@@ -1429,6 +1446,7 @@ int ndspmhd_b200_create(const nd_options *o, int ndim, int device, nd_ctx **out)
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_err(c, ND_ERR_NO_DEVICE, "no CUDA device: the NDSPMHD hot path has no CPU fallback in this library");
   if (device < 0 || device >= ndev) return set_err(c, ND_ERR_INVALID_ARG, "bad device ordinal");
   CU(cudaSetDevice(device));
+  CU(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (int k = 0; k < 8; k++) CU(cudaEventCreate(&c->ev[k]));
   CU(cudaStreamCreateWithFlags(&c->stream_h2d, cudaStreamNonBlocking));
@@ -1449,6 +1467,12 @@ int ndspmhd_b200_create(const nd_options *o, int ndim, int device, nd_ctx **out)
   CU(cudaMalloc(&c->d_tab, sizeof(TabRec) * (IKERN + 1)));
   CU(cudaMalloc(&c->d_tab2, sizeof(TabRec2) * (IKERN + 1)));
   CU(cudaMalloc(&c->d_tabdrag, sizeof(double) * 2 * (IKERN + 1)));
+  {
+    std::vector<double2> tabg(IKERN + 1);
+    for (int i = 0; i <= IKERN; i++) tabg[i] = make_double2(tab[i].g, tab[i].dg);
+    CU(cudaMalloc(&c->d_tabg, sizeof(double2) * (IKERN + 1)));
+    CU(cudaMemcpy(c->d_tabg, tabg.data(), sizeof(double2) * (IKERN + 1), cudaMemcpyHostToDevice));
+  }
   CU(cudaMemcpy(c->d_tab, tab.data(), sizeof(TabRec) * (IKERN + 1), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(c->d_tab2, tab2.data(), sizeof(TabRec2) * (IKERN + 1), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(c->d_tabdrag, tabd.data(), sizeof(double) * 2 * (IKERN + 1), cudaMemcpyHostToDevice));
@@ -1475,7 +1499,7 @@ int ndspmhd_b200_destroy(nd_ctx *c) {
   if (!c) return 0;
   if (c->stream) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
   for (auto &rb : c->rowbufs) if (*rb.p) { cudaFree(*rb.p); *rb.p = nullptr; }
-  void *singles[] = {c->sendlist[0], c->sendlist[1], c->sendbuf[0], c->sendbuf[1], c->recvbuf[0], c->recvbuf[1], c->nbr, c->lcnt, c->scanout, c->cellStart, c->cellCount, c->blocksums, c->red, c->fmean, c->flags, c->d_tab, c->d_tab2, c->d_tabdrag};
+  void *singles[] = {c->sendlist[0], c->sendlist[1], c->sendbuf[0], c->sendbuf[1], c->recvbuf[0], c->recvbuf[1], c->nbr, c->lcnt, c->scanout, c->cellStart, c->cellCount, c->blocksums, c->red, c->fmean, c->flags, c->d_tab, c->d_tab2, c->d_tabdrag, c->d_tabg};
   for (void *p : singles) if (p) cudaFree(p);
   if (c->h_red) cudaFreeHost(c->h_red);
   if (c->h_flags) cudaFreeHost(c->h_flags);

@@ -44,6 +44,7 @@ struct RatesRed {
   unsigned long long *dtcourant_min, *vsigmax_max, *dtav_min, *ts_min, *h_on_csts_max, *fhmax_max, *dtforce_min;
   double *fmean;           // [3]
   int *nclumped, *err;
+  int *sched;              // work counter of the persistent warps (zeroed before each launch)
 };
 
 #ifndef ND_RATES_MINB
@@ -53,10 +54,19 @@ struct RatesRed {
 #define ND_RATES_BLOCK 128
 #endif
 #ifndef ND_RATES_STAGE
-#define ND_RATES_STAGE 3   // how neighbour records reach the pair body: 0 direct 256-bit loads, 1/2 + L1 prefetch 1/2 pairs ahead, 3 cp.async to shared
+#define ND_RATES_STAGE 5   // how neighbour records reach the pair body: 0 direct 256-bit loads, 1/2 + L1 prefetch 1/2 pairs ahead, 3 cp.async to shared, 4/5/6 register pipeline
 #endif
 constexpr int RATES_BLOCK = ND_RATES_BLOCK;
 constexpr int RATES_NREC = 5;    // staged records per neighbour: posh, vm, thermo, gal, bpsi
+#ifndef ND_RATES_TABSMEM
+#define ND_RATES_TABSMEM 1   // kernel-gradient table rows in shared memory (TMA bulk copy per block) instead of global loads
+#endif
+#ifndef ND_RATES_PERSIST
+#define ND_RATES_PERSIST 1   // persistent blocks (one table load per block); every warp draws 32-target units from a global counter
+#endif
+constexpr int RATES_TABG_BYTES = (IKERN + 1) * 16;                       // {grad W, slope} rows, 64016 B
+constexpr int RATES_TAB_BYTES = ND_RATES_TABSMEM ? ((16 + RATES_TABG_BYTES + 127) / 128) * 128 : 0;
+constexpr int RATES_SMEM_BYTES = RATES_TAB_BYTES + (ND_RATES_STAGE == 3 ? 2 * RATES_NREC * 2 * RATES_BLOCK * 16 : 0);
 
 // per-thread staging slots in shared memory: plane (stage, record, half) holds one 16-byte half-record per thread, so the
 // 128-bit reads of a warp are conflict-free
@@ -85,13 +95,53 @@ __device__ __forceinline__ double get_tstop(int idrag_nature, double rhogas, dou
 template <int NDIM, bool MHD, bool DRAG, bool FAST, bool ONEF>
 __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(Grid G, RatesIn I, RatesOpts O, RatesSums S, RatesRed R, NbrLists L,
                                                                                  int s0, int ntargets) {
+  // dynamic shared memory: [0,16) mbarrier, then the {grad W, slope} rows of the kernel table (64 KB; every pair does two
+  // random lookups, which as global loads cost ~30 L1 wavefronts each and were the largest long-scoreboard stall), then the
+  // cp.async staging slots.  The table arrives by one TMA bulk copy per block; blocks are persistent (grid = resident blocks)
+  // so it is loaded once per SM slot, not once per 128 targets.
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
+  const double2 *tabs = reinterpret_cast<const double2 *>(smem_raw + 16);
 #if ND_RATES_STAGE == 3
-  __shared__ double2 stg[2 * RATES_NREC * 2 * RATES_BLOCK];   // [stage][record][half][thread], 40 KB
+  double2 *stg = reinterpret_cast<double2 *>(smem_raw + RATES_TAB_BYTES);   // [stage][record][half][thread], 40 KB
 #endif
-  const int tix = blockIdx.x * RATES_BLOCK + threadIdx.x;   // target index within this launch
-  const int s = s0 + tix;
+#if ND_RATES_TABSMEM
+  if (threadIdx.x == 0) {
+    mbar_init(mbar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(mbar, RATES_TABG_BYTES);
+    bulk_g2s(smem_raw + 16, G.tabg, RATES_TABG_BYTES, mbar);
+  }
+  __syncthreads();
+  mbar_wait(mbar, 0);
+#endif
   const int iav = FAST ? 2 : O.iav, iener = FAST ? (O.iener != 0 ? 2 : 0) : O.iener, ikernav = FAST ? 3 : O.ikernav, iresist = FAST ? 0 : O.iresist;
   const int iavlim0 = O.iavlim0, iavlim1 = O.iavlim1, iavlim2 = O.iavlim2;
+  const double zero = 1.e-10;
+  const double eps = 2.220446049250313e-16;
+  // block-wide reductions are carried across the chunks of a persistent block and flushed once
+  double dtc_den = 0., dtav_den = 0., vsigmax = 0., ts_min = 1.7976931348623157e308, h_on_csts_max = 0.;
+  int nclumped = 0;
+  // Work unit = the 32 targets of one list column block.  Persistent warps draw units from a global counter (a static
+  // round-robin of 128-target chunks over blocks measured 8.9 ms against 6.5 ms for one block per chunk: unit costs differ
+  // widely -- ghost-only units are free -- and a block waits for its slowest warp); the non-persistent launch maps
+  // unit = global warp index.
+  const int nunits = (ntargets + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int trip = 0;; trip++) {
+    int unit;
+#if ND_RATES_PERSIST
+    unit = 0;
+    if (lane == 0) unit = atomicAdd(R.sched, 1);
+    unit = __shfl_sync(FULL, unit, 0);
+#else
+    unit = (blockIdx.x * RATES_BLOCK + threadIdx.x) >> 5;
+    if (trip > 0) break;
+#endif
+    if (unit >= nunits) break;
+  const int tix = unit * 32 + lane;   // target index within this launch
+  const int s = s0 + tix;
   int orig = -1, ti = 0, cnt = 0;
   bool active = false;
   if (tix < ntargets) {
@@ -137,10 +187,6 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
   double fx = 0, fy = 0, fz = 0, dudt = 0, dBx = 0, dBy = 0, dBz = 0, divB = 0, cBx = 0, cBy = 0, cBz = 0, del2u = 0;
   double gpx = 0, gpy = 0, gpz = 0, gvx = 0, gvy = 0, gvz = 0, endiss = 0;
   // dtcourant = min over pairs of min(hi,hj)/vsigdtc = 1/max(max(1/hi,1/hj)*vsigdtc): track the denominator, divide once
-  double dtc_den = 0., dtav_den = 0., vsigmax = 0., ts_min = 1.7976931348623157e308, h_on_csts_max = 0.;
-  int nclumped = 0;
-  const double zero = 1.e-10;
-  const double eps = 2.220446049250313e-16;
 
   // ---- pair terms over the neighbour list (build_lists_kernel<LIST_RATES> applied src/ratesND_mhd.f90:401-415) ----
   auto body = [&](int k, const double4 &pj, const double4 &vj, const double4 &tj4, const double4 &gj, const double4 &bj) {
@@ -168,7 +214,11 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
       // kernel gradient table rows for q2i, q2j: the loads are issued here, the interpolation (their first use) comes after the
       // signal-velocity block so that ~250 independent FP64 instructions cover the lookup latency
       const int idxi = tab_index(q2i, G.ddq2table), idxj = tab_index(q2j, G.ddq2table);
-      const double2 rowi = __ldg(reinterpret_cast<const double2 *>(G.tab + idxi) + 1), rowj = __ldg(reinterpret_cast<const double2 *>(G.tab + idxj) + 1);
+      #if ND_RATES_TABSMEM
+      const double2 rowi = tabs[idxi], rowj = tabs[idxj];
+#else
+      const double2 rowi = __ldg(G.tabg + idxi), rowj = __ldg(G.tabg + idxj);
+#endif
       const double dvdotr = (dvx * drx + dvy * dry) + dvz * drz;   // :1250
       const double rho1j = tj4.x, rho21j = rho1j * rho1j;          // :1256-1258
       const double rhoav1 = 0.5 * (rho1i + rho1j);                 // :1261
@@ -460,6 +510,65 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
       body(k, stage_get(stg, st, 0), stage_get(stg, st, 1), stage_get(stg, st, 2), stage_get(stg, st, 3), MHD ? stage_get(stg, st, 4) : zero4);
     });
     cp_async_wait<0>();
+#elif ND_RATES_STAGE == 7
+    // Register software pipeline, all five records one pair ahead in two alternating register sets (A, B): the body is
+    // instantiated twice per trip so no set is ever copied (the rotating single-set form costs 40 register moves a pair).
+    struct Rec5 { double4 p, v, t, g, b; };
+    auto load5 = [&](int k) { Rec5 r; r.p = ld4(G.posh + k); r.v = ld4(G.vm + k); r.t = ld4(I.thermo + k); r.g = ld4(I.gal + k); r.b = MHD ? ld4(I.bpsi + k) : zero4; return r; };
+    {
+      const int last = cnt - 1;
+      auto ld = [&](int n) { return (int)__ldcs(col + (size_t)min(n, last) * 32); };
+      // list entries are read one batch of four (thousands of cycles) ahead
+      int c0 = ld(0), c1 = ld(1), c2 = ld(2), c3 = ld(3);
+      Rec5 A = load5(c0), B;
+#pragma unroll 1
+      for (int nb = 0; nb < cnt; nb += 4) {
+        const int n0 = ld(nb + 4), n1 = ld(nb + 5), n2 = ld(nb + 6), n3 = ld(nb + 7);
+#pragma unroll 1
+        for (int v = 0; v < 2; v++) {
+          const int n = nb + 2 * v;
+          if (n >= cnt) break;
+          const int ka = v ? c2 : c0, kb = v ? c3 : c1, kn = v ? n0 : c2;
+          B = load5(kb);
+          body(ka, A.p, A.v, A.t, A.g, A.b);
+          A = load5(kn);                                        // past the end these reload the last entry; harmless
+          if (n + 1 < cnt) body(kb, B.p, B.v, B.t, B.g, B.b);
+        }
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      }
+    }
+#elif ND_RATES_STAGE >= 4
+    // Register software pipeline: the records the body touches first are loaded one pair ahead (4: posh + vm, 5: all five,
+    // 6: posh only); the rest are issued at the top of the body and have the distance/rsqrt chain to arrive.
+    if (ONEF) {   // the one-fluid dust instantiations have no registers to spare: direct loads
+      walk_list(col, cnt, [&](int n, int k, int k1, int k2) { body(k, ld4(G.posh + k), ld4(G.vm + k), ld4(I.thermo + k), ld4(I.gal + k), MHD ? ld4(I.bpsi + k) : zero4); });
+    } else {
+    const int kf = (int)col[0];
+    double4 pn = ld4(G.posh + kf);
+#if ND_RATES_STAGE != 6
+    double4 vn = ld4(G.vm + kf);
+#endif
+#if ND_RATES_STAGE == 5
+    double4 tn = ld4(I.thermo + kf), gn = ld4(I.gal + kf), bn = MHD ? ld4(I.bpsi + kf) : zero4;
+#endif
+    walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
+      const double4 pc = pn;
+      pn = ld4(G.posh + k1);
+#if ND_RATES_STAGE != 6
+      const double4 vc = vn;
+      vn = ld4(G.vm + k1);
+#else
+      const double4 vc = ld4(G.vm + k);
+#endif
+#if ND_RATES_STAGE == 5
+      const double4 tc = tn, gc = gn, bc = bn;
+      tn = ld4(I.thermo + k1); gn = ld4(I.gal + k1); bn = MHD ? ld4(I.bpsi + k1) : zero4;
+      body(k, pc, vc, tc, gc, bc);
+#else
+      body(k, pc, vc, ld4(I.thermo + k), ld4(I.gal + k), MHD ? ld4(I.bpsi + k) : zero4);
+#endif
+    });
+    }
 #else
     walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
 #if ND_RATES_STAGE >= 1
@@ -484,6 +593,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
       st4(S.D + s, make_double4(ddvx - c * fgx, ddvy - c * fgy, ddvz - c * fgz, ddust));
     }
   }
+  }   // persistent chunk loop
   // block-free warp reductions into global min/max keys
   double dtcourant = dtc_den > 0. ? fmin(1.e6, 1. / dtc_den) : 1.e6;            // initial value 1.e6, :251
   double dtav = dtav_den > 0. ? 1. / dtav_den : 1.7976931348623157e308;
