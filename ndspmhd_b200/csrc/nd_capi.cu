@@ -363,25 +363,36 @@ template <int NDIM> __global__ void k_cell_index(CellArgs A) {
   }
   if (bad) atomicCAS(&A.flags[1], 0, ND_ERR_LINK);                                      // :122-125
   const int cell = ic[0] + A.ncellsx[0] * (ic[1] + A.ncellsx[1] * ic[2]);               // :127-135
-  A.cellOfOrig[r] = cell;
-  atomicAdd(&A.cellCount[cell], 1);
+  // fine bin along x inside the cell (sort key only; the cell is the reference's)
+  const double tx = (A.x[(size_t)r * NDIM] - A.xminpart[0]) / A.dxcell;
+  int fb = bad ? 0 : __double2int_rz((tx - (double)ic[0]) * CELL_FX);
+  fb = fb < 0 ? 0 : (fb > CELL_FX - 1 ? CELL_FX - 1 : fb);
+  const int fine = cell * CELL_FX + fb;
+  A.cellOfOrig[r] = fine;
+  atomicAdd(&A.cellCount[fine], 1);
 }
-__global__ void k_cell_scatter(const int *cellOfOrig, int ntotal, const int *cellStart, int *cellFill, int *permtmp) {
+__global__ void k_cell_scatter(const int *fineOfOrig, int ntotal, const int *fineStart, int *fineFill, int *permtmp) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= ntotal) return;
-  const int cell = cellOfOrig[r];
-  permtmp[cellStart[cell] + atomicAdd(&cellFill[cell], 1)] = r;
+  const int fine = fineOfOrig[r];
+  permtmp[fineStart[fine] + atomicAdd(&fineFill[fine], 1)] = r;
 }
-// one warp per cell: order the cell's rows by original index (rank sort) so the result is run-to-run deterministic
-__global__ void k_cell_order(const int *cellStart, int ncells, const int *permtmp, int *perm) {
+// one warp per cell: order the rows of each of its fine bins by original index (rank sort) so the result is run-to-run deterministic
+__global__ void k_cell_order(const int *fineStart, int ncells, const int *permtmp, int *perm) {
   const int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (cell >= ncells) return;
-  const int a = cellStart[cell], n = cellStart[cell + 1] - a;
+  const int *fs = fineStart + (size_t)cell * CELL_FX;
+  const int a = fs[0], n = fs[CELL_FX] - a;
   for (int e = lane; e < n; e += 32) {
-    const int mine = permtmp[a + e];
+    const int pos = a + e;
+    int b = 0;
+#pragma unroll
+    for (int q = 1; q < CELL_FX; q++) b += (pos >= fs[q]);
+    const int ba = fs[b], bn = fs[b + 1] - ba;
+    const int mine = permtmp[pos];
     int rank = 0;
-    for (int f = 0; f < n; f++) rank += (permtmp[a + f] < mine);
-    perm[a + rank] = mine;
+    for (int f = 0; f < bn; f++) rank += (permtmp[ba + f] < mine);
+    perm[ba + rank] = mine;
   }
 }
 
@@ -406,7 +417,7 @@ template <int NDIM> __global__ void k_gather_sorted(GatherArgs A) {
   A.typ[s] = A.itype[r];
   if (A.sdf) A.sdf[s] = A.dustfrac[st];
   if (A.itype[r] != A.itype[0]) *A.mixed = 1;
-  A.cellOf[s] = A.cellOfOrig[r];
+  A.cellOf[s] = A.cellOfOrig[r] / CELL_FX;
   A.inv[r] = s;
 }
 __global__ void k_refresh_h(const int *perm, const int *ireal, const double *hh, double4 *posh, float4 *p32, double hhmax1, int npart, int ntotal) {
@@ -577,7 +588,7 @@ struct FinalArgs {
   double *force, *dudt, *dendt, *dBevoldt, *daldt, *dpsidt, *gradpsi, *divB, *curlB, *graddivv, *del2u, *drhodt, *dhdt;
   RatesRed R; int npart, ntotal;
   // one-fluid dust (dusta NULL otherwise)
-  const double4 *dusta; const double2 *dustb; const int *cellStart, *cellOf; double *ddustevoldt, *ddeltavdt;
+  const double4 *dusta; const double2 *dustb; const int *fineStart, *cellOf; double *ddustevoldt, *ddeltavdt;
 };
 __global__ void k_rates_final(FinalArgs A) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -629,7 +640,11 @@ __global__ void k_rates_final(FinalArgs A) {
         tstop = get_tstop(O.idrag_nature, db.x, db.y, O.Kdrag);
         // :566 tests `dustfraci`, which the reference last assigned in the pair loop: it belongs to the LAST particle that loop
         // visited -- the lowest-index row of the last non-empty cell, i.e. the first slot of the last slot's cell
-        const double dustfrac_stale = A.dusta[A.cellStart[A.cellOf[A.ntotal - 1]]].x;
+        // (slots inside a cell are ordered by (fine bin, index): search the cell for its lowest row)
+        const int lastcell = A.cellOf[A.ntotal - 1];
+        int sl = A.fineStart[(size_t)lastcell * CELL_FX];
+        for (int q = sl + 1, qe = A.fineStart[(size_t)(lastcell + 1) * CELL_FX]; q < qe; q++) if (A.perm[q] < A.perm[sl]) sl = q;
+        const double dustfrac_stale = A.dusta[sl].x;
         double dtstop;
         if (dustfrac_stale > 0.) { dtstop = 1. / tstop; ddv0 -= da.y * dtstop; ddv1 -= da.z * dtstop; ddv2 -= da.w * dtstop; }
         else { dtstop = 0.; ddv0 = ddv1 = ddv2 = 0.; }
@@ -812,10 +827,11 @@ int check_options(nd_ctx *c, const nd_options &o, int ndim) {
 
 Grid make_grid(nd_ctx *c) {
   Grid G;
-  G.cellStart = c->cellStart; G.cellOf = c->cellOf; G.perm = c->perm; G.posh = c->posh; G.vm = c->vm; G.typ = c->typ; G.p32 = c->p32;
+  G.fineStart = c->cellStart; G.cellOf = c->cellOf; G.perm = c->perm; G.posh = c->posh; G.vm = c->vm; G.typ = c->typ; G.p32 = c->p32;
   G.hhmax1 = 1.0 / c->hhmax;
   // FP32 screening band (scaled units, cell = 1): 4 * 2^-23 * largest scaled coordinate + rounding of the thresholds
   G.screen_margin = 4.f * 1.1920929e-7f * (float)std::max(c->ncellsx[0], std::max(c->ncellsx[1], c->ncellsx[2])) + 2.e-6f;
+  G.cull_margin = 16.f * G.screen_margin + 1.e-5f;
   G.nx = c->ncellsx[0]; G.ny = c->ncellsx[1]; G.nz = c->ncellsx[2]; G.ncells = c->ncells;
   G.npart = c->npart; G.ntotal = c->ntotal; G.nown = c->nown;
   G.radkern2 = c->T->radkern2; G.dq2table = c->T->dq2table; G.ddq2table = c->T->ddq2table;
@@ -1027,20 +1043,21 @@ template <int NDIM> int build_cells(nd_ctx *c) {
     c->ncellsx[d] = (int)q + 1;                                                     // :93
     nc *= c->ncellsx[d];
   }
-  if (nc > 1500000000LL) return set_err(c, ND_ERR_LINK, "link: too many cells");
+  if (nc * CELL_FX > 1500000000LL) return set_err(c, ND_ERR_LINK, "link: too many cells");
   c->ncells = (int)nc;
-  if (c->ncells + 2 > c->cellcap) {
-    c->cellcap = c->ncells + c->ncells / 4 + 1024;
+  const int nfine = c->ncells * CELL_FX;   // cellStart / cellCount are indexed by fine bin (cell * CELL_FX + bin along x)
+  if (nfine + 2 > c->cellcap) {
+    c->cellcap = nfine + nfine / 4 + 1024;
     if (int e = dev_alloc(c, &c->cellStart, (size_t)c->cellcap + 1)) return e;
     if (int e = dev_alloc(c, &c->cellCount, (size_t)c->cellcap + 1)) return e;
   }
-  CU(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * ((size_t)c->ncells + 1), c->stream));
+  CU(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * ((size_t)nfine + 1), c->stream));
   CellArgs CA;
   CA.x = c->x; CA.ntotal = nt; CA.dxcell = c->dxcell; CA.cellOfOrig = c->cellOfOrig; CA.cellCount = c->cellCount; CA.flags = c->flags;
   for (int d = 0; d < 3; d++) { CA.xminpart[d] = c->xminpart[d]; CA.ncellsx[d] = c->ncellsx[d]; }
   LAUNCH(c, (k_cell_index<NDIM>), nblocks(nt, 256), 256, 0, CA);
-  if (int e = exclusive_scan(c, c->cellCount, c->cellStart, c->ncells)) return e;
-  CU(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * ((size_t)c->ncells + 1), c->stream));
+  if (int e = exclusive_scan(c, c->cellCount, c->cellStart, nfine)) return e;
+  CU(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * ((size_t)nfine + 1), c->stream));
   LAUNCH(c, k_cell_scatter, nblocks(nt, 256), 256, 0, c->cellOfOrig, nt, c->cellStart, c->cellCount, c->permtmp);
   LAUNCH(c, k_cell_order, nblocks((long long)c->ncells * 32, 256), 256, 0, c->cellStart, c->ncells, c->permtmp, c->perm);
   GatherArgs GA;
@@ -1329,7 +1346,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   FA.force = c->force; FA.dudt = c->dudt; FA.dendt = c->dendt; FA.dBevoldt = c->dBevoldt; FA.daldt = c->daldt; FA.dpsidt = c->dpsidt; FA.gradpsi = c->gradpsi;
   FA.divB = c->divB; FA.curlB = c->curlB; FA.graddivv = c->graddivv; FA.del2u = c->del2u; FA.drhodt = c->drhodt; FA.dhdt = c->dhdt;
   FA.R = R; FA.npart = np; FA.ntotal = nt;
-  FA.dusta = o.onef_dust ? c->dusta : nullptr; FA.dustb = c->dustb; FA.cellStart = c->cellStart; FA.cellOf = c->cellOf;
+  FA.dusta = o.onef_dust ? c->dusta : nullptr; FA.dustb = c->dustb; FA.fineStart = c->cellStart; FA.cellOf = c->cellOf;
   FA.ddustevoldt = c->ddustevoldt; FA.ddeltavdt = c->ddeltavdt;
   LAUNCH(c, k_rates_final, nblocks(nt, 256), 256, 0, FA);
   ZeroArgs ZA;

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel
     vxi = v.x; vyi = v.y; vzi = v.z; mi = v.w;
     hi = A.hh[orig];                               // current h (1/h == p.w in the first round)
     const int celli = G.cellOf[s];
-    cs0 = __ldg(G.cellStart + celli); cs1 = __ldg(G.cellStart + celli + 1);
+    cs0 = cell_begin(G, celli); cs1 = cell_begin(G, celli + 1);
     cnt = L.cnt[t];
   }
   const double hi1 = 1.0 / hi;                     // h1(i) = 1./hh(i), density_sums.f90:130
@@ -67,7 +67,10 @@ __global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel
     const double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
     const double rij2 = dist2_exact(dx, dy, dz);
     double q2i;
-    // the reference rounds q2 of the first-met particle of a pair as rij2*hi21 and of the other as (rij2*hi1)*hi1 (:182-183)
+    // the reference rounds q2 of the first-met particle of a pair as rij2*hi21 and of the other as (rij2*hi1)*hi1 (:182-183);
+    // inside a cell "first met" is decided here by slot order, (fine bin, index), where the reference's chain order is the
+    // index alone: a last-bit difference of q2 for some same-cell pairs, far inside the 1e-12 tolerance (the neighbour SET is
+    // decided exactly by build_lists_kernel, which compares the original rows)
     if (FIRST) q2i = ((k >= cs1) || (k >= cs0 && k <= s)) ? __dmul_rn(rij2, hi21) : __dmul_rn(__dmul_rn(rij2, hi1), hi1);
     else q2i = __dmul_rn(rij2, hi21);
     // rij = sqrt(rij2) and dr = dx/(rij + epsilon(rij)) (:199) without a divide: 1/(r+e) = (1/r)(1 - e/r) to O((e/r)^2) ~ 1e-26

@@ -6,6 +6,9 @@
 namespace ndk {
 
 constexpr int IKERN = 4000;
+// Sorted order: (cell, fine x bin, original index).  A cell row (fixed y, z) is contiguous and its fine bins ascend in x, so a
+// neighbour search can clip every row of the stencil to the chord of the search sphere instead of scanning three whole cells.
+constexpr int CELL_FX = 4;
 constexpr unsigned FULL = 0xffffffffu;
 
 // particle types, src/variablesND.f90:165-171
@@ -19,14 +22,14 @@ struct __align__(16) TabRec2 { double gg, dgg; };
 
 // Everything a pair kernel needs to find neighbours; passed by value.
 struct Grid {
-  const int *cellStart;     // [ncells+1] first sorted slot of each cell
+  const int *fineStart;     // [ncells*CELL_FX+1] first sorted slot of each fine bin (a cell is cut into CELL_FX bins along x)
   const int *cellOf;        // [ntotal]   cell of each sorted slot
   const int *perm;          // [ntotal]   sorted slot -> original row
   const double4 *posh;      // [ntotal]   {x,y,z,1/h}  (1/h correctly rounded: h1(i) = 1./hh(i), density_sums.f90:130)
   const double4 *vm;        // [ntotal]   {vx,vy,vz,m}
   const int *typ;           // [ntotal]
   const float4 *p32;        // [ntotal]   FP32 screening record {(x - xminpart)/dxcell, (h/hhmax)^2}: |dX|^2 < (h/hhmax)^2  <=>  rij2/h^2 < radkern2
-  double hhmax1; float screen_margin;
+  double hhmax1; float screen_margin, cull_margin;
   int nx, ny, nz, ncells;
   int npart, ntotal;        // rows [0,npart) carry their own state (targets are rows < nown), [npart,ntotal) are ghosts
   int nown;
@@ -175,6 +178,8 @@ __device__ __forceinline__ bool types_interact(int ti, int tj) {
          (tj == T_DUST && ti == T_BNDDUST);
 }
 
+__device__ __forceinline__ int cell_begin(const Grid &G, int cell) { return __ldg(G.fineStart + (size_t)cell * CELL_FX); }
+
 // order-preserving double <-> u64 keys for atomicMin/Max
 __device__ __forceinline__ unsigned long long dkey(double v) {
   unsigned long long b = (unsigned long long)__double_as_longlong(v);
@@ -287,7 +292,7 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
   // density: current h (the sorted record holds the h of the last link); rates: the record's (h1(i) = 1./hh(i))
   const double hcur = (MODE == LIST_RATES) ? 0. : A.hh[orig];
   const int cell = G.cellOf[s];
-  const int cs0 = __ldg(G.cellStart + cell), cs1 = __ldg(G.cellStart + cell + 1);
+  const int cs0 = cell_begin(G, cell), cs1 = cell_begin(G, cell + 1);
   const int ix = cell % G.nx;
   const int tq = cell / G.nx;
   const int iy = (NDIM >= 2) ? tq % G.ny : 0, iz = (NDIM >= 3) ? tq / G.ny : 0;
@@ -306,7 +311,8 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
       // The reference visits a pair once; "i" is the particle met first: the one in the lower cell, or the later-inserted
       // (higher index) particle of the same chain.  Slots are sorted by (cell, index), so that is a slot comparison.
       // q2 of "i" is rij2*hi21, q2 of "j" is (rij2*hj1)*hj1 (density_sums.f90:182-183).
-      const bool iam_i = (k >= cs1) || (k >= cs0 && k <= s);
+      // Inside a cell the slots are ordered by (fine bin, index), so the same-cell case compares the original rows.
+      const bool iam_i = (k >= cs1) || (k >= cs0 && G.perm[k] <= orig);
       double q2me, q2ot;
       if (iam_i) { q2me = __dmul_rn(rij2, hi21); q2ot = __dmul_rn(__dmul_rn(rij2, hj1), hj1); }
       else { q2me = __dmul_rn(__dmul_rn(rij2, hi1), hi1); q2ot = __dmul_rn(rij2, __dmul_rn(hj1, hj1)); }
@@ -356,6 +362,12 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
   };
 
   constexpr int NY = (NDIM >= 2) ? 3 : 1, NZ = (NDIM >= 3) ? 3 : 1, UNROLL = 4;
+  // Chord clipping.  In cell units (dxcell = radkern*hhmax) no accepted or counted pair is farther than Rc: 1 when the
+  // neighbour's h can decide (h_j <= hhmax), (h_i/hhmax) when only the target's does.  A stencil row at transverse distance d
+  // from the target can only hold such pairs within |dx| <= sqrt(Rc^2 - d^2): the scan covers just the fine bins that
+  // overlap that interval.  cull_margin covers the FP32 rounding of the cell-unit coordinates (bins are cut in FP64).
+  const float Rc2 = ((MODE == LIST_DENS_PARTIAL) ? Ti : 1.f) + G.cull_margin;
+  const float fy = (NDIM >= 2) ? pf.y - (float)iy : 0.f, fz = (NDIM >= 3) ? pf.z - (float)iz : 0.f;   // position inside the cell, [0,1)
 #pragma unroll 1
   for (int rz = 0; rz < NZ; rz++) {
 #pragma unroll 1
@@ -363,10 +375,20 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
       const int cy = iy + ry - (NDIM >= 2 ? 1 : 0), cz = iz + rz - (NDIM >= 3 ? 1 : 0);
       // padded empty border cells (src/linkND.f90:88-89) keep ix-1, ix+1, cy, cz inside the grid for populated cells
       if (cy < 0 || cy >= G.ny || cz < 0 || cz >= G.nz) continue;
+      float dty = 0.f, dtz = 0.f;
+      if (NDIM >= 2) dty = ry == 1 ? 0.f : (ry == 0 ? fy : 1.f - fy);
+      if (NDIM >= 3) dtz = rz == 1 ? 0.f : (rz == 0 ? fz : 1.f - fz);
+      dty = fmaxf(dty, 0.f); dtz = fmaxf(dtz, 0.f);
+      const float R2 = Rc2 - (dty * dty + dtz * dtz);
+      if (R2 < 0.f) continue;
+      const float R = sqrtf(R2) + G.cull_margin;
       const int c0 = (cz * G.ny + cy) * G.nx;
       const int xa = ix > 0 ? ix - 1 : 0, xb = ix + 1 < G.nx ? ix + 1 : G.nx - 1;
-      int k = __ldg(G.cellStart + c0 + xa);
-      const int e = __ldg(G.cellStart + c0 + xb + 1);
+      int blo = __float2int_rd((pf.x - R) * (float)CELL_FX), bhi = __float2int_rd((pf.x + R) * (float)CELL_FX);
+      blo = max(blo, xa * CELL_FX); bhi = min(bhi, xb * CELL_FX + CELL_FX - 1);
+      if (bhi < blo) continue;
+      int k = __ldg(G.fineStart + (size_t)c0 * CELL_FX + blo);
+      const int e = __ldg(G.fineStart + (size_t)c0 * CELL_FX + bhi + 1);
 #pragma unroll 1
       for (; k + UNROLL <= e; k += UNROLL) {
         float4 qj[UNROLL];
