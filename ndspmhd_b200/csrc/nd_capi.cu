@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include "../../include/ndspmhd_b200.h"
 #include "nd_tables.h"
+#include <chrono>
 #include "nd_device.cuh"
 #include "nd_density.cuh"
 #include "nd_rates.cuh"
@@ -99,6 +100,15 @@ inline int nblocks(long long n, int b) { return (int)((n + b - 1) / b); }
       (c)->launches++;                                               \
     }                                                                \
   } while (0)
+
+// Scalars travel device -> host as stores of a one-warp kernel into page-locked host memory (directly addressable under
+// unified addressing), not as cudaMemcpy: a memcpy queues on the D2H copy engine behind whatever bulk download
+// ndspmhd_b200_derivs_host has in flight (measured: a 27 ms stall per step at 16.8M particles), a store does not.
+__global__ void k_to_host(const int *src, int *dst_pinned, int nwords) {
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst_pinned[i] = src[i];
+  __threadfence_system();
+}
+#define SMALL_D2H(c, dst_pinned, src, bytes) LAUNCH(c, k_to_host, 1, 32, 0, reinterpret_cast<const int *>(src), reinterpret_cast<int *>(dst_pinned), (int)((bytes) / sizeof(int)))
 
 // =====================================================================================================
 // primitives: exclusive scan of ints, reductions
@@ -866,7 +876,7 @@ int comm_allreduce_maxmin(nd_ctx *c, double *mx, int nmx, double *mn, int nmn) {
 }
 
 int sync_flags(nd_ctx *c) {   // D2H of the flag block; returns a pending device-side error code
-  CU(cudaMemcpyAsync(c->h_flags, c->flags, sizeof(int) * 16, cudaMemcpyDeviceToHost, c->stream));
+  SMALL_D2H(c, c->h_flags, c->flags, sizeof(int) * 16);
   CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -875,7 +885,7 @@ int sync_flags(nd_ctx *c) {   // D2H of the flag block; returns a pending device
 int compute_hhmax(nd_ctx *c) {
   CU(cudaMemsetAsync(c->red, 0, sizeof(unsigned long long) * 16, c->stream));
   LAUNCH(c, k_max_h, std::min(nblocks(c->nown, 256), 1184), 256, 0, c->hh, c->nown, c->red);
-  CU(cudaMemcpyAsync(c->h_red, c->red, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  SMALL_D2H(c, c->h_red, c->red, sizeof(unsigned long long));
   CU(cudaStreamSynchronize(c->stream));
   double m = c->nown > 0 ? dkey_inv(c->h_red[0]) : 0.;
   if (int e = comm_allreduce(c, &m, 1, 0)) return e;
@@ -921,9 +931,9 @@ int halo_exchange_inputs(nd_ctx *c) {
   for (int side = 0; side < 2; side++) {
     const int *flag = side == 0 ? c->cellOfOrig : c->ghostcount;
     if (int e = exclusive_scan(c, flag, c->scanout, np)) return e;
-    int n = 0;
-    CU(cudaMemcpyAsync(&n, c->scanout + np, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SMALL_D2H(c, c->h_flags + 24, c->scanout + np, sizeof(int));
     CU(cudaStreamSynchronize(c->stream));
+    const int n = c->h_flags[24];
     size_t cap = (size_t)c->sendcap[side];
     if (int e = grow_buf(c, &c->sendlist[side], &cap, (size_t)n)) return e;
     c->sendcap[side] = (int)cap;
@@ -994,9 +1004,9 @@ template <int NDIM> int make_ghosts(nd_ctx *c) {
   for (int d = 0; d < 3; d++) { A.ibound[d] = d < NDIM ? local_ibound(c, d) : 0; A.xmin[d] = c->o.xmin[d]; A.xmax[d] = c->o.xmax[d]; }
   LAUNCH(c, (k_ghosts<NDIM, false>), nblocks(np, 256), 256, 0, A);
   if (int e = exclusive_scan(c, c->ghostcount, c->scanout, np)) return e;
-  int nghost = 0;
-  CU(cudaMemcpyAsync(&nghost, c->scanout + np, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  SMALL_D2H(c, c->h_flags + 25, c->scanout + np, sizeof(int));
   CU(cudaStreamSynchronize(c->stream));
+  const int nghost = c->h_flags[25];
   if (int e = ensure_capacity(c, np + nghost, np)) return e;
   A.x = c->x; A.vel = c->vel; A.hh = c->hh; A.itype = c->itype; A.ireal = c->ireal; A.offset = c->scanout; A.count = c->ghostcount; A.cap = c->cap;
   // ensure_capacity may have reallocated scanout: redo the scan in that case (cheap)
@@ -1016,7 +1026,7 @@ template <int NDIM> int build_cells(nd_ctx *c) {
     if (allle1) {                                                                   // :70
       CU(cudaMemsetAsync(c->red, 0, sizeof(unsigned long long) * 16, c->stream));
       LAUNCH(c, k_max_h, std::min(nblocks(c->npart, 256), 1184), 256, 0, c->hh, c->npart, c->red);
-      CU(cudaMemcpyAsync(c->h_red, c->red, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      SMALL_D2H(c, c->h_red, c->red, sizeof(unsigned long long));
       CU(cudaStreamSynchronize(c->stream));
       c->hhmax = dkey_inv(c->h_red[0]);
     } else if (!o.device_ghosts) c->hhmax = o.hhmax;                                // set by the host's set_ghost_particles
@@ -1029,7 +1039,7 @@ template <int NDIM> int build_cells(nd_ctx *c) {
   for (int k = 0; k < 3; k++) init[k] = ~0ull;
   CU(cudaMemcpyAsync(c->red, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
   LAUNCH(c, (k_minmax_x<NDIM>), std::min(nblocks(nt, 256), 1184), 256, 0, c->x, nt, c->red);
-  CU(cudaMemcpyAsync(c->h_red, c->red, sizeof(unsigned long long) * 6, cudaMemcpyDeviceToHost, c->stream));
+  SMALL_D2H(c, c->h_red, c->red, sizeof(unsigned long long) * 6);
   CU(cudaStreamSynchronize(c->stream));
   long long nc = 1;
   c->ncellsx[0] = c->ncellsx[1] = c->ncellsx[2] = 1;
@@ -1120,7 +1130,7 @@ template <int NDIM, int MODE> int build_lists(nd_ctx *c, const Grid &G, ListArgs
     L.nbr = c->nbr; L.cnt = c->lcnt; L.lmax = c->lmax; L.overflow = c->flags + 5;
     if (c->mixed_types) LAUNCH(c, (build_lists_kernel<NDIM, MODE, true>), nblocks(LA.ntargets, 128), 128, 0, G, LA, L);
     else LAUNCH(c, (build_lists_kernel<NDIM, MODE, false>), nblocks(LA.ntargets, 128), 128, 0, G, LA, L);
-    CU(cudaMemcpyAsync(c->h_flags + 20, c->flags + 5, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SMALL_D2H(c, c->h_flags + 20, c->flags + 5, sizeof(int));
     CU(cudaStreamSynchronize(c->stream));
     const int big = c->h_flags[20];
     if (big == 0) return 0;
@@ -1194,7 +1204,7 @@ template <int NDIM> int do_iterate_density(nd_ctx *c, int resume) {
     c->ncalctotal += c->ncalc;                                                       // :154
     if (int e = exclusive_scan(c, c->redo, c->scanout, c->ntotal)) return e;
     LAUNCH(c, k_compact, nblocks(c->ntotal, 256), 256, 0, c->redo, c->scanout, c->ntotal, c->list);
-    CU(cudaMemcpyAsync(&c->h_flags[16], c->scanout + c->ntotal, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SMALL_D2H(c, &c->h_flags[16], c->scanout + c->ntotal, sizeof(int));
     if (int e = sync_flags(c)) return e;
     c->ncalc = c->h_flags[16];
     double v[3] = {(double)c->ncalc, (double)(c->h_flags[0] != 0), (double)(c->h_flags[1] != 0)};
@@ -1305,7 +1315,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   LAUNCH(c, k_rates_gather, nblocks(nt, 256), 256, 0, GA);
   RatesOpts O = make_rates_opts(c);
   if (o.imhd != 0) {   // stressmax feeds the pair kernel by value: one 8-byte D2H
-    CU(cudaMemcpyAsync(c->h_red, c->red + RED_STRESS, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    SMALL_D2H(c, c->h_red, c->red + RED_STRESS, sizeof(unsigned long long));
     CU(cudaStreamSynchronize(c->stream));
     O.stressmax = dkey_inv(c->h_red[0]);
     if (int e = comm_allreduce(c, &O.stressmax, 1, 0)) return e;
@@ -1332,7 +1342,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   if (e) return e;
   CU(cudaEventRecord(c->ev[4], c->stream));
   if (c->has_comm) {   // vsigmax feeds dpsidt in the finalisation loop (:518-520, :902): all ranks need the global maximum
-    CU(cudaMemcpyAsync(c->h_red, c->red + RED_VSIG, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    SMALL_D2H(c, c->h_red, c->red + RED_VSIG, sizeof(unsigned long long));
     CU(cudaStreamSynchronize(c->stream));
     double vs = dkey_inv(c->h_red[0]);
     if (int e = comm_allreduce(c, &vs, 1, 0)) return e;
@@ -1355,8 +1365,8 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   LAUNCH(c, k_rates_zero_ghosts, nblocks(nt - np, 256), 256, 0, ZA);
   CU(cudaEventRecord(c->ev[5], c->stream));
   // scalars back to the host (module timestep)
-  CU(cudaMemcpyAsync(c->h_red, c->red, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(c->h_fmean, c->fmean, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
+  SMALL_D2H(c, c->h_red, c->red, sizeof(unsigned long long) * 16);
+  SMALL_D2H(c, c->h_fmean, c->fmean, sizeof(double) * 4);
   if (int e2 = sync_flags(c)) return e2;
   nd_scalars &s = c->sc;
   s.dtcourant = dkey_inv(c->h_red[RED_DTC]);
@@ -1736,6 +1746,7 @@ int ndspmhd_b200_download(nd_ctx *c, nd_arrays *a, unsigned mask, int idim) {
 int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int idim, unsigned mask, nd_scalars *s) {
   if (!c || !a || !c->stream) return c ? set_err(c, ND_ERR_STATE, "context not initialised") : ND_ERR_INVALID_ARG;
   if (int e = check_upload_args(c, a, npart, ntotal, idim)) return e;
+  const auto t_enter = std::chrono::steady_clock::now();
   CU(cudaSetDevice(c->device));
   int want = std::max(ntotal, c->ntotal);
   if (c->o.device_ghosts && any_ghost_bound(c)) want = std::max(want, npart + npart / 4 + 1024);
@@ -1779,6 +1790,10 @@ int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int
   CU(cudaStreamSynchronize(c->stream));
   float t;
   for (int k = 0; k < 5; k++) { cudaEventElapsedTime(&t, c->ev[k], c->ev[k + 1]); c->ms[k] = t; }
+  if (getenv("NDSPMHD_B200_DEBUG")) {
+    const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
+    fprintf(stderr, "derivs_host: wall %.1f ms; kernels link %.1f density %.1f c2p %.1f rates_pair %.1f final %.1f\n", wall, c->ms[0], c->ms[1], c->ms[2], c->ms[3], c->ms[4]);
+  }
   if (s) *s = c->sc;
   return 0;
 }
