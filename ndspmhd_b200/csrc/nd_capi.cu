@@ -30,7 +30,7 @@ struct nd_ctx {
   std::string err;
   long long launches = 0;
   ndt::KernelTables *T = nullptr;
-  TabRec *d_tab = nullptr; TabRec2 *d_tab2 = nullptr; double *d_tabdrag = nullptr; double2 *d_tabg = nullptr;
+  TabRec *d_tab = nullptr; TabRec2 *d_tab2 = nullptr; double *d_tabdrag = nullptr; double2 *d_tabg = nullptr, *d_tabw = nullptr;
   int num_sms = 148;
   // sizes
   int npart = 0, ntotal = 0, cap = 0, nown = 0;   // nown <= npart: rows this context computes (the rest of [0,npart) are halo copies)
@@ -845,7 +845,7 @@ Grid make_grid(nd_ctx *c) {
   G.nx = c->ncellsx[0]; G.ny = c->ncellsx[1]; G.nz = c->ncellsx[2]; G.ncells = c->ncells;
   G.npart = c->npart; G.ntotal = c->ntotal; G.nown = c->nown;
   G.radkern2 = c->T->radkern2; G.dq2table = c->T->dq2table; G.ddq2table = c->T->ddq2table;
-  G.tab = c->d_tab; G.tab2 = c->d_tab2; G.tabdrag = c->d_tabdrag; G.tabg = c->d_tabg;
+  G.tab = c->d_tab; G.tab2 = c->d_tab2; G.tabdrag = c->d_tabdrag; G.tabg = c->d_tabg; G.tabw = c->d_tabw;
   return G;
 }
 
@@ -1150,8 +1150,22 @@ template <int NDIM, bool FIRST> int launch_density_round(nd_ctx *c, DensityArgs 
     NbrLists L;
     if (int e = build_lists<NDIM, FIRST ? LIST_DENS_FIRST : LIST_DENS_PARTIAL>(c, G, LA, L)) return e;
     A.list = FIRST ? nullptr : c->list + c0; A.nlist = m; A.s0 = c0;
-    if (c->o.want_aux || c->o.onef_dust) LAUNCH(c, (density_round_kernel<NDIM, FIRST, true>), nblocks(m, DENS_BLOCK), DENS_BLOCK, 0, G, A, L);
+    A.sched = c->flags + 9;
+    const bool aux = c->o.want_aux || c->o.onef_dust;
+#if ND_DENS_TABSMEM
+    // persistent blocks, one per SM (128 KB of shared-memory tables each); warps draw 32-target units from flags[9]
+    auto kaux = density_round_kernel<NDIM, FIRST, true>;
+    auto kfast = density_round_kernel<NDIM, FIRST, false>;
+    CU(cudaFuncSetAttribute(kaux, cudaFuncAttributeMaxDynamicSharedMemorySize, DENS_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(kfast, cudaFuncAttributeMaxDynamicSharedMemorySize, DENS_SMEM_BYTES));
+    CU(cudaMemsetAsync(c->flags + 9, 0, sizeof(int), c->stream));
+    const int grid = std::min(nblocks(m, DENS_BLOCK), c->num_sms);
+    if (aux) LAUNCH(c, kaux, grid, DENS_BLOCK, DENS_SMEM_BYTES, G, A, L);
+    else LAUNCH(c, kfast, grid, DENS_BLOCK, DENS_SMEM_BYTES, G, A, L);
+#else
+    if (aux) LAUNCH(c, (density_round_kernel<NDIM, FIRST, true>), nblocks(m, DENS_BLOCK), DENS_BLOCK, 0, G, A, L);
     else LAUNCH(c, (density_round_kernel<NDIM, FIRST, false>), nblocks(m, DENS_BLOCK), DENS_BLOCK, 0, G, A, L);
+#endif
   }
   return 0;
 }
@@ -1499,6 +1513,9 @@ int ndspmhd_b200_create(const nd_options *o, int ndim, int device, nd_ctx **out)
     for (int i = 0; i <= IKERN; i++) tabg[i] = make_double2(tab[i].g, tab[i].dg);
     CU(cudaMalloc(&c->d_tabg, sizeof(double2) * (IKERN + 1)));
     CU(cudaMemcpy(c->d_tabg, tabg.data(), sizeof(double2) * (IKERN + 1), cudaMemcpyHostToDevice));
+    for (int i = 0; i <= IKERN; i++) tabg[i] = make_double2(tab[i].w, tab[i].dw);
+    CU(cudaMalloc(&c->d_tabw, sizeof(double2) * (IKERN + 1)));
+    CU(cudaMemcpy(c->d_tabw, tabg.data(), sizeof(double2) * (IKERN + 1), cudaMemcpyHostToDevice));
   }
   CU(cudaMemcpy(c->d_tab, tab.data(), sizeof(TabRec) * (IKERN + 1), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(c->d_tab2, tab2.data(), sizeof(TabRec2) * (IKERN + 1), cudaMemcpyHostToDevice));
@@ -1526,7 +1543,7 @@ int ndspmhd_b200_destroy(nd_ctx *c) {
   if (!c) return 0;
   if (c->stream) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
   for (auto &rb : c->rowbufs) if (*rb.p) { cudaFree(*rb.p); *rb.p = nullptr; }
-  void *singles[] = {c->sendlist[0], c->sendlist[1], c->sendbuf[0], c->sendbuf[1], c->recvbuf[0], c->recvbuf[1], c->nbr, c->lcnt, c->scanout, c->cellStart, c->cellCount, c->blocksums, c->red, c->fmean, c->flags, c->d_tab, c->d_tab2, c->d_tabdrag, c->d_tabg};
+  void *singles[] = {c->sendlist[0], c->sendlist[1], c->sendbuf[0], c->sendbuf[1], c->recvbuf[0], c->recvbuf[1], c->nbr, c->lcnt, c->scanout, c->cellStart, c->cellCount, c->blocksums, c->red, c->fmean, c->flags, c->d_tab, c->d_tab2, c->d_tabdrag, c->d_tabg, c->d_tabw};
   for (void *p : singles) if (p) cudaFree(p);
   if (c->h_red) cudaFreeHost(c->h_red);
   if (c->h_flags) cudaFreeHost(c->h_flags);

@@ -25,20 +25,28 @@ struct DensityArgs {
   double hfact, psep, tolh, hhmax;
   // one-fluid dust (AUX instantiation only; sdf NULL otherwise): rhogas, rhodust sums of src/density_sums.f90:278-292, :569-573
   const double *sdf; double *rhogas, *rhodust;
+  int *sched;            // work counter of the persistent warps (zeroed before each launch)
 };
 
-#ifndef ND_DENS_MINB
-#define ND_DENS_MINB 4
-#endif
 #ifndef ND_DENS_PF
-#define ND_DENS_PF 3   // neighbour record staging of the density kernel: 0 none, 1/2 L1 prefetch 1/2 pairs ahead, 3 two pairs per trip
+#define ND_DENS_PF 4   // neighbour records: 0 direct loads, 1/2 + L1 prefetch 1/2 pairs ahead, 3 two pairs per trip, 4 register pipeline one pair ahead
 #endif
-constexpr int DENS_BLOCK = 128;
+#ifndef ND_DENS_TABSMEM
+#define ND_DENS_TABSMEM 1   // {W, slope} and {grad W, slope} rows in shared memory (two TMA bulk copies per persistent block)
+#endif
+#ifndef ND_DENS_BLOCK
+#define ND_DENS_BLOCK (ND_DENS_TABSMEM ? 512 : 128)
+#endif
+#ifndef ND_DENS_MINB
+#define ND_DENS_MINB (ND_DENS_TABSMEM ? 1 : 4)
+#endif
+constexpr int DENS_BLOCK = ND_DENS_BLOCK;
+constexpr int DENS_TAB_BYTES = (IKERN + 1) * 16;                         // one {value, slope} table, 64016 B
+constexpr int DENS_TAB_STRIDE = ((DENS_TAB_BYTES + 127) / 128) * 128;
+constexpr int DENS_SMEM_BYTES = ND_DENS_TABSMEM ? 128 + 2 * DENS_TAB_STRIDE : 0;
 
 template <int NDIM, bool FIRST, bool AUX>
-__global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel(Grid G, DensityArgs A, NbrLists L) {
-  const int t = blockIdx.x * DENS_BLOCK + threadIdx.x;
-  if (t >= A.nlist) return;
+__device__ __forceinline__ void density_target(const Grid &G, const DensityArgs &A, const NbrLists &L, int t, const double2 *tabw, const double2 *tabg) {
   const int s = FIRST ? A.s0 + t : A.list[t];
   const int orig = G.perm[s];
   const int ti = G.typ[s];
@@ -79,8 +87,19 @@ __global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel
     const double rinve = rinv - 2.220446049250313e-16 * rinv * rinv;
     const double pmassj = vj.w;
     double wabi, grkerni, grgrkerni = 0.;
+#if ND_DENS_TABSMEM
+    {
+      const int idx = tab_index(q2i, G.ddq2table);
+      const double2 rw = tabw[idx], rg = tabg[idx];
+      const double dxx = q2i - __dmul_rn((double)idx, G.dq2table);
+      wabi = rw.x + rw.y * dxx;
+      grkerni = rg.x + rg.y * dxx;
+      if (AUX) { const double2 r2 = __ldg(reinterpret_cast<const double2 *>(G.tab2 + idx)); grgrkerni = r2.x + r2.y * dxx; }
+    }
+#else
     if (AUX) interp_wggg(G, q2i, wabi, grkerni, grgrkerni);
     else interp_wg(G, q2i, wabi, grkerni);
+#endif
     wabi = wabi * hfacwabi;                        // :237-241 / :549-553
     grkerni = grkerni * hfacwabi * hi1;
     const double dwdhi = -rij * grkerni * hi1 - NDIM * wabi * hi1;   // :260
@@ -109,7 +128,15 @@ __global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel
   };
   if (cnt > 0) {
     const unsigned *col = L.nbr + ((size_t)(t >> 5) * L.lmax) * 32 + (t & 31);
-#if ND_DENS_PF == 3
+#if ND_DENS_PF == 4
+    // register pipeline: the next neighbour's two records load while this pair is evaluated
+    double4 pn = ld4(G.posh + (int)col[0]), vn = ld4(G.vm + (int)col[0]);
+    walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
+      const double4 pc = pn, vc = vn;
+      pn = ld4(G.posh + k1); vn = ld4(G.vm + k1);
+      body(k, pc, vc);
+    });
+#elif ND_DENS_PF == 3
     // two neighbours per trip: their four record loads are issued together and overlap the other's arithmetic
     walk_list2(col, cnt, [&](int ka, int kb, bool twob) {
       const double4 pa = ld4(G.posh + ka), va = ld4(G.vm + ka), pb = ld4(G.posh + kb), vb = ld4(G.vm + kb);
@@ -182,6 +209,40 @@ __global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel
     A.drhodt[orig] = drhodt;                                          // density_sums.f90:300 runs for fixed particles too
   }
   A.redo[s] = redo;
+}
+
+template <int NDIM, bool FIRST, bool AUX>
+__global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel(Grid G, DensityArgs A, NbrLists L) {
+#if ND_DENS_TABSMEM
+  // One persistent block per SM: the two interpolation tables (128 KB) arrive by TMA bulk copies, then every warp draws
+  // 32-target units from a global counter until the work is gone.
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
+  const double2 *tabw = reinterpret_cast<const double2 *>(smem_raw + 128);
+  const double2 *tabg = reinterpret_cast<const double2 *>(smem_raw + 128 + DENS_TAB_STRIDE);
+  if (threadIdx.x == 0) {
+    mbar_init(mbar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(mbar, 2 * DENS_TAB_BYTES);
+    bulk_g2s(smem_raw + 128, G.tabw, DENS_TAB_BYTES, mbar);
+    bulk_g2s(smem_raw + 128 + DENS_TAB_STRIDE, G.tabg, DENS_TAB_BYTES, mbar);
+  }
+  __syncthreads();
+  mbar_wait(mbar, 0);
+  const int nunits = (A.nlist + 31) >> 5;
+#pragma unroll 1
+  for (;;) {
+    int unit = 0;
+    if ((threadIdx.x & 31) == 0) unit = atomicAdd(A.sched, 1);
+    unit = __shfl_sync(FULL, unit, 0);
+    if (unit >= nunits) break;
+    const int t = unit * 32 + (threadIdx.x & 31);
+    if (t < A.nlist) density_target<NDIM, FIRST, AUX>(G, A, L, t, tabw, tabg);
+  }
+#else
+  const int t = blockIdx.x * DENS_BLOCK + threadIdx.x;
+  if (t < A.nlist) density_target<NDIM, FIRST, AUX>(G, A, L, t, nullptr, nullptr);
+#endif
 }
 
 }  // namespace ndk

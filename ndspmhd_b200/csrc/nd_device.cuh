@@ -36,7 +36,8 @@ struct Grid {
   double radkern2, dq2table, ddq2table;
   const TabRec *tab;        // [IKERN+1]
   const TabRec2 *tab2;      // [IKERN+1]
-  const double2 *tabg;      // [IKERN+1] {g, dg} of tab, contiguous: the rates kernel's shared-memory copy (one TMA bulk copy)
+  const double2 *tabg;      // [IKERN+1] {g, dg} of tab, contiguous: the pair kernels' shared-memory copy (one TMA bulk copy)
+  const double2 *tabw;      // [IKERN+1] {w, dw} of tab, likewise (density kernel)
   const double *tabdrag;    // [2*(IKERN+1)] {w, dw}
 };
 
