@@ -255,7 +255,7 @@ def run_single(args):
         return hot.derivs()
     for _ in range(args.warmup):
         s = step()
-    phases = {k: 0.0 for k in ("link", "density", "c2p_gather", "rates_pair", "rates_final")}
+    phases = {k: 0.0 for k in ("link", "density", "c2p_gather", "rates_pair", "rates_final", "rates_pair_kernel")}
     clocks = ClockSampler(dev)
     clocks.start()
     l0 = hot.launch_count()
@@ -274,15 +274,16 @@ def run_single(args):
         phases[k] /= args.steps
     value = n / (ms * 1e-3)
     peak, peak_src = measured_peaks()
-    pair_ms = phases["rates_pair"]
+    pair_ms = phases.pop("rates_pair_kernel")       # CUDA events around the pair kernel's launch alone, on the library's stream
     achieved = BYTES_RATES * n / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else 0.0
-    traffic = None
+    traffic, ncu_extra = None, {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
             if int(tj.get("nx", 0)) == args.nx:
                 traffic = tj.get("rates_pair_kernel_dram_bytes_per_launch")
+                ncu_extra = {k: tj[k] for k in ("fp64_pipe_active_pct", "issue_active_pct", "l1tex_throughput_pct", "ncu_report") if k in tj}
         except Exception:
             pass
     line = {
@@ -296,7 +297,8 @@ def run_single(args):
         "clocks": ck,
         "roofline": {"bound": "hbm", "kernel": "rates_pair_kernel<3,MHD>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": BYTES_RATES * n, "kernel_ms": pair_ms,
+                     "algorithmic_bytes_per_launch": BYTES_RATES * n, "kernel_ms": pair_ms, "kernel_share_of_step": pair_ms / ms,
+                     "ncu": ncu_extra,
                      "whole_step_GBps": BYTES_TOTAL * n / (ms * 1e-3) / 1e9, "whole_step_frac": BYTES_TOTAL * n / (ms * 1e-3) / 1e9 / peak,
                      "note": "FP64 pairwise gather: the FP64 pipe and L1/shared gather bandwidth bind long before HBM (DESIGN.md); no tensor cores"},
         "phases_ms": phases,

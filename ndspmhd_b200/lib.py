@@ -233,7 +233,8 @@ class Hotpath:
     def timings(self):
         ms = (C.c_double * 8)()
         self.L.ndspmhd_b200_last_timings(self.ctx, ms)
-        return dict(zip(["link", "density", "c2p_gather", "rates_pair", "rates_final"], list(ms)[:5]))
+        # phases between events on the library's stream; "rates_pair" = list build + pair kernel, "rates_pair_kernel" = the kernel alone
+        return dict(zip(["link", "density", "c2p_gather", "rates_pair", "rates_final", "rates_pair_kernel"], list(ms)[:6]))
 
     def launch_count(self) -> int:
         return int(self.L.ndspmhd_b200_launch_count(self.ctx))
