@@ -264,6 +264,29 @@ int ndspmhd_b200_set_comm(nd_ctx *c, const nd_comm *comm);
 /* rows after the last link: own rows [0,nown), halo rows [nown,nsrc), ghosts [nsrc,ntotal) */
 int ndspmhd_b200_row_counts(const nd_ctx *c, int *nown, int *nsrc, int *ntotal);
 
+/*
+ * Leapfrog integrator on the RESIDENT state: one call = `call step`
+ * (src/stepND_leapfrog_mhd.f90:39-300) -- predictor (:108-163), `call derivs` (:167), corrector (:171-209),
+ * `call boundary` (:216 -> src/boundaryND.f90:65-93, particles crossing a periodic domain), new timestep (:239-253).
+ * Between dumps no particle array crosses PCIe.  Needs a prior upload + derivs (the reference enters `step` with the
+ * rates of the previous call) and, with ghost boundaries, device_ghosts = 1.
+ * nd_step_opts mirrors module timestep (C_cour, C_force, dtfixed: src/variablesND.f90:255-273); `damp` is nd_options.damp.
+ * *dt_inout: in = dt of this step, out = dt of the next: min(C_force*dtforce, C_cour*dtcourant, 0.9*dtdrag, C_force*dtvisc).
+ */
+typedef struct nd_step_opts {
+  double C_cour, C_force;
+  int dtfixed;
+  int reserved;
+} nd_step_opts;
+int ndspmhd_b200_step(nd_ctx *c, const nd_step_opts *so, double *dt_inout, nd_scalars *s);
+
+/* the evolved state after steps: host arrays for rows [0,npart), Fortran layout; NULL pointers are skipped */
+typedef struct nd_state_out {
+  double *x, *vel, *hh, *en, *Bevol, *alpha, *psi, *rho;
+  double *dustevol, *deltav;   /* idust = 1 */
+} nd_state_out;
+int ndspmhd_b200_download_state(nd_ctx *c, const nd_state_out *st, int idim);
+
 /* page-locked host memory for the caller's particle arrays (makes upload/download run at PCIe speed) */
 void *ndspmhd_b200_host_alloc(size_t bytes);
 void ndspmhd_b200_host_free(void *p);

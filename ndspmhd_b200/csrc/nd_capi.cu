@@ -77,6 +77,7 @@ struct nd_ctx {
   int *sendlist[2] = {nullptr, nullptr}; int sendcap[2] = {0, 0}, nsend[2] = {0, 0}, nrecv[2] = {0, 0};
   void *sendbuf[2] = {nullptr, nullptr}, *recvbuf[2] = {nullptr, nullptr}; size_t sendbufcap[2] = {0, 0}, recvbufcap[2] = {0, 0};
   cudaEvent_t ev[8];
+  double *stepbuf = nullptr; size_t stepbufrows = 0;   // leapfrog `*in` copies (ndspmhd_b200_step), rows [0,npart)
   cudaEvent_t ev_pair[2] = {nullptr, nullptr};   // around the rates pair kernel alone (the roofline's kernel time)
   double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -743,6 +744,116 @@ __global__ void k_rates_zero_ghosts(ZeroArgs A) {                               
     if (A.dBevoldt) A.dBevoldt[(size_t)i * 3 + k] = 0.;
   }
   A.dudt[i] = 0.; A.dendt[i] = 0.; A.dpsidt[i] = 0.; A.divB[i] = 0.; A.del2u[i] = 0.; A.drhodt[i] = 0.; A.dhdt[i] = 0.;
+}
+
+// =====================================================================================================
+// leapfrog integrator: `step`, src/stepND_leapfrog_mhd.f90:39-300, and the periodic wrap of
+// `boundary`, src/boundaryND.f90:65-93.  Element-wise over rows [0,npart); the `*in` copies live in one buffer of
+// STEP_NIN(+dust) planes of npart doubles.
+// =====================================================================================================
+struct StepArgs {
+  double *x, *vel, *Bevol, *rho, *hh, *en, *alpha, *psi, *dustevol, *deltav;                     // state (in place)
+  const double *force, *dBevoldt, *drhodt, *dhdt, *dendt, *daldt, *dpsidt, *ddustevoldt, *ddeltavdt;   // rates of the last derivs
+  const int *itype, *ireal;
+  double *in;            // `*in` planes
+  size_t n;              // plane stride = npart
+  int npart, ndim;
+  int imhd, iresist, icty, ihvar, iener, idivbzero, idust, onef, iavlim[3], ibound[3];
+  double dt, damp, xmin[3], xmax[3];
+  int *flags;
+};
+// plane offsets (in units of n doubles)
+enum { SP_X = 0, SP_VEL = 3, SP_BEVOL = 6, SP_RHO = 9, SP_HH = 10, SP_EN = 11, SP_ALPHA = 12, SP_PSI = 15, SP_FORCE = 16, SP_DBEVOL = 19, SP_DRHO = 22,
+       SP_DH = 23, SP_DEN = 24, SP_DAL = 25, SP_DPSI = 28, STEP_NIN = 29, SP_DUSTEVOL = 29, SP_DDUSTEVOL = 30, SP_DELTAV = 31, SP_DDELTAV = 34, STEP_NIN_DUST = 37 };
+
+__global__ void k_step_save(StepArgs A) {                                                 // :70-100
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.npart) return;
+  double *in = A.in + i; const size_t n = A.n;
+  for (int d = 0; d < A.ndim; d++) in[(SP_X + d) * n] = A.x[(size_t)i * A.ndim + d];
+  for (int d = 0; d < 3; d++) {
+    in[(SP_VEL + d) * n] = A.vel[(size_t)i * 3 + d]; in[(SP_BEVOL + d) * n] = A.Bevol[(size_t)i * 3 + d]; in[(SP_ALPHA + d) * n] = A.alpha[(size_t)i * 3 + d];
+    in[(SP_FORCE + d) * n] = A.force[(size_t)i * 3 + d]; in[(SP_DBEVOL + d) * n] = A.dBevoldt[(size_t)i * 3 + d]; in[(SP_DAL + d) * n] = A.daldt[(size_t)i * 3 + d];
+  }
+  in[SP_RHO * n] = A.rho[i]; in[SP_HH * n] = A.hh[i]; in[SP_EN * n] = A.en[i]; in[SP_PSI * n] = A.psi[i];
+  in[SP_DRHO * n] = A.drhodt[i]; in[SP_DH * n] = A.dhdt[i]; in[SP_DEN * n] = A.dendt[i]; in[SP_DPSI * n] = A.dpsidt[i];
+  if (A.onef) {
+    in[SP_DUSTEVOL * n] = A.dustevol[i]; in[SP_DDUSTEVOL * n] = A.ddustevoldt[i];
+    if (A.idust == 1) for (int d = 0; d < 3; d++) { in[(SP_DELTAV + d) * n] = A.deltav[(size_t)i * 3 + d]; in[(SP_DDELTAV + d) * n] = A.ddeltavdt[(size_t)i * 3 + d]; }
+  }
+}
+__device__ __forceinline__ bool step_fixed(int it) { return it == T_BND || it == 11 /*itypebnd2*/ || it == T_BNDDUST; }
+
+__global__ void k_step_predict(StepArgs A) {                                              // :108-163
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.npart) return;
+  const double *in = A.in + i; const size_t n = A.n;
+  const double dt = A.dt;
+  const int it = A.itype[i];
+  if (step_fixed(it)) {
+    if (it == 11) { atomicCAS(&A.flags[1], 0, ND_ERR_UNSUPPORTED_OPTION); return; }       // itypebnd2: cylindrical fixed particles
+    const int j = A.ireal[i];
+    const double *pin = (j > 0) ? A.in + (j - 1) : in;                                    // :112-117
+    for (int d = 0; d < A.ndim; d++) A.x[(size_t)i * A.ndim + d] = in[(SP_X + d) * n] + dt * pin[(SP_VEL + d) * n] + 0.5 * dt * dt * pin[(SP_FORCE + d) * n];
+    // Bevol, rho, hh, en, alpha, psi (and the dust variables) are reset to their `in` values, i.e. left as they are (:130-142)
+  } else {
+    for (int d = 0; d < A.ndim; d++) A.x[(size_t)i * A.ndim + d] = in[(SP_X + d) * n] + dt * in[(SP_VEL + d) * n] + 0.5 * dt * dt * in[(SP_FORCE + d) * n];   // :145
+    for (int d = 0; d < 3; d++) A.vel[(size_t)i * 3 + d] = (in[(SP_VEL + d) * n] + dt * in[(SP_FORCE + d) * n]) / (1. + A.damp);                              // :146
+    if (A.imhd != 0 && A.iresist != 2) for (int d = 0; d < 3; d++) A.Bevol[(size_t)i * 3 + d] = in[(SP_BEVOL + d) * n] + dt * in[(SP_DBEVOL + d) * n];
+    double rho = in[SP_RHO * n];
+    if (A.icty >= 1) { rho = in[SP_RHO * n] + dt * in[SP_DRHO * n]; A.rho[i] = rho; }
+    if (A.ihvar == 1) A.hh[i] = in[SP_HH * n] * pow(in[SP_RHO * n] / rho, 1. / A.ndim);   // :151
+    else if (A.ihvar == 2 || A.ihvar == 3) A.hh[i] = in[SP_HH * n] + dt * in[SP_DH * n];
+    if (A.iener != 0) A.en[i] = in[SP_EN * n] + dt * in[SP_DEN * n];
+    for (int d = 0; d < 3; d++) if (A.iavlim[d] != 0) A.alpha[(size_t)i * 3 + d] = fmin(in[(SP_ALPHA + d) * n] + dt * in[(SP_DAL + d) * n], 1.0);
+    if (A.idivbzero >= 2) A.psi[i] = in[SP_PSI * n] + dt * in[SP_DPSI * n];
+    if (A.onef) {
+      A.dustevol[i] = in[SP_DUSTEVOL * n] + dt * in[SP_DDUSTEVOL * n];
+      if (A.idust == 1) for (int d = 0; d < 3; d++) A.deltav[(size_t)i * 3 + d] = in[(SP_DELTAV + d) * n] + dt * in[(SP_DDELTAV + d) * n];
+    }
+  }
+}
+__global__ void k_step_correct(StepArgs A) {                                              // :171-209, then boundaryND.f90:65-93
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.npart) return;
+  const double *in = A.in + i; const size_t n = A.n;
+  const double dt = A.dt, hdt = 0.5 * A.dt;
+  const int it = A.itype[i];
+  if (step_fixed(it)) {
+    if (it == T_BND || it == T_BNDDUST) for (int d = 0; d < 3; d++) A.vel[(size_t)i * 3 + d] = in[(SP_VEL + d) * n];
+    for (int d = 0; d < 3; d++) { A.Bevol[(size_t)i * 3 + d] = in[(SP_BEVOL + d) * n]; A.alpha[(size_t)i * 3 + d] = in[(SP_ALPHA + d) * n]; }
+    A.rho[i] = in[SP_RHO * n]; A.hh[i] = in[SP_HH * n]; A.en[i] = in[SP_EN * n]; A.psi[i] = in[SP_PSI * n];   // derivs rewrote rho, hh of fixed rows
+    if (A.idust == 1 || A.idust == 3 || A.idust == 4) {
+      if (A.onef) A.dustevol[i] = in[SP_DUSTEVOL * n];
+      if (A.idust == 1) for (int d = 0; d < 3; d++) A.deltav[(size_t)i * 3 + d] = in[(SP_DELTAV + d) * n];
+    }
+  } else {
+    for (int d = 0; d < 3; d++) A.vel[(size_t)i * 3 + d] = (in[(SP_VEL + d) * n] + hdt * (A.force[(size_t)i * 3 + d] + in[(SP_FORCE + d) * n])) / (1. + A.damp);   // :187
+    if (A.imhd != 0) for (int d = 0; d < 3; d++) {
+      if (A.iresist == 2) A.Bevol[(size_t)i * 3 + d] = in[(SP_BEVOL + d) * n] + dt * A.dBevoldt[(size_t)i * 3 + d];
+      else A.Bevol[(size_t)i * 3 + d] = in[(SP_BEVOL + d) * n] + hdt * (A.dBevoldt[(size_t)i * 3 + d] + in[(SP_DBEVOL + d) * n]);
+    }
+    if (A.icty >= 1) A.rho[i] = in[SP_RHO * n] + hdt * (A.drhodt[i] + in[SP_DRHO * n]);
+    if (A.ihvar == 2) {
+      const double h = in[SP_HH * n] + hdt * (A.dhdt[i] + in[SP_DH * n]);
+      A.hh[i] = h;
+      if (h <= 0.) atomicCAS(&A.flags[1], 0, ND_ERR_H_NONPOSITIVE);                        // :197-200
+    }
+    if (A.iener != 0) A.en[i] = in[SP_EN * n] + hdt * (A.dendt[i] + in[SP_DEN * n]);
+    for (int d = 0; d < 3; d++) if (A.iavlim[d] != 0) A.alpha[(size_t)i * 3 + d] = fmin(in[(SP_ALPHA + d) * n] + hdt * (A.daldt[(size_t)i * 3 + d] + in[(SP_DAL + d) * n]), 1.0);
+    if (A.idivbzero >= 2) A.psi[i] = in[SP_PSI * n] + hdt * (A.dpsidt[i] + in[SP_DPSI * n]);
+    if (A.onef) {
+      A.dustevol[i] = in[SP_DUSTEVOL * n] + hdt * (A.ddustevoldt[i] + in[SP_DDUSTEVOL * n]);
+      if (A.idust == 1) for (int d = 0; d < 3; d++) A.deltav[(size_t)i * 3 + d] = in[(SP_DELTAV + d) * n] + hdt * (A.ddeltavdt[(size_t)i * 3 + d] + in[(SP_DDELTAV + d) * n]);
+    }
+  }
+  // particles cross the periodic domain, boundaryND.f90:65-93 (`if (any(ibound.ne.0)) call boundary`, :216)
+  for (int d = 0; d < A.ndim; d++) if (A.ibound[d] == 3) {
+    double xx = A.x[(size_t)i * A.ndim + d];
+    if (xx > A.xmax[d]) xx = A.xmin[d] + xx - A.xmax[d];
+    else if (xx < A.xmin[d]) xx = A.xmax[d] - (A.xmin[d] - xx);
+    A.x[(size_t)i * A.ndim + d] = xx;
+  }
 }
 
 // =====================================================================================================
@@ -1552,6 +1663,7 @@ int ndspmhd_b200_destroy(nd_ctx *c) {
   if (c->h_red) cudaFreeHost(c->h_red);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->h_fmean) cudaFreeHost(c->h_fmean);
+  if (c->stepbuf) cudaFree(c->stepbuf);
   for (int k = 0; k < 8; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
   for (int k = 0; k < 2; k++) if (c->ev_pair[k]) cudaEventDestroy(c->ev_pair[k]);
   for (int k = 0; k < 2; k++) if (c->ev_in[k]) cudaEventDestroy(c->ev_in[k]);
@@ -1899,6 +2011,72 @@ int ndspmhd_b200_rates_pairs(nd_ctx *c, int *pair_i, int *pair_j, long long cap,
   cudaFree(di); cudaFree(dj); cudaFree(dc);
   *npairs = (long long)n;
   return e;
+}
+
+/* ---- leapfrog step on the resident state ---- */
+int ndspmhd_b200_step(nd_ctx *c, const nd_step_opts *so, double *dt_inout, nd_scalars *s) {
+  if (!c || !so || !dt_inout) return ND_ERR_INVALID_ARG;
+  if (!c->uploaded || !c->rates_done) return set_err(c, ND_ERR_STATE, "step needs a prior upload + derivs (the reference enters `step` with the rates of the previous call)");
+  const nd_options &o = c->o;
+  if (o.imhd < 0 || o.idivbzero == 10 || o.idustevol != 0) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "step: imhd < 0, idivbzero = 10 and idustevol /= 0 are not supported");
+  bool ghost_bound = false;
+  for (int d = 0; d < c->ndim; d++) if (o.ibound[d] >= 2) ghost_bound = true;
+  if (ghost_bound && !o.device_ghosts) return set_err(c, ND_ERR_STATE, "step on the resident state needs device_ghosts = 1 (derivs regenerates the ghosts, src/derivs.f90:78)");
+  if (c->has_comm) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "step: slab-decomposed contexts need particle migration, not available yet");
+  CU(cudaSetDevice(c->device));
+  const int np = c->npart;
+  const int planes = o.onef_dust ? STEP_NIN_DUST : STEP_NIN;
+  if (c->stepbufrows < (size_t)np) {
+    if (c->stepbuf) cudaFree(c->stepbuf);
+    c->stepbuf = nullptr; c->stepbufrows = 0;
+    CU(cudaMalloc(&c->stepbuf, sizeof(double) * (size_t)STEP_NIN_DUST * (size_t)np));
+    c->stepbufrows = (size_t)np;
+  }
+  auto args = [&]() {
+    StepArgs A;
+    A.x = c->x; A.vel = c->vel; A.Bevol = c->Bevol; A.rho = c->rho; A.hh = c->hh; A.en = c->en; A.alpha = c->alpha; A.psi = c->psi;
+    A.dustevol = c->dustevol; A.deltav = c->deltav;
+    A.force = c->force; A.dBevoldt = c->dBevoldt; A.drhodt = c->drhodt; A.dhdt = c->dhdt; A.dendt = c->dendt; A.daldt = c->daldt; A.dpsidt = c->dpsidt;
+    A.ddustevoldt = c->ddustevoldt; A.ddeltavdt = c->ddeltavdt;
+    A.itype = c->itype; A.ireal = c->ireal; A.in = c->stepbuf; A.n = (size_t)np; A.npart = np; A.ndim = c->ndim;
+    A.imhd = o.imhd; A.iresist = o.iresist; A.icty = o.icty; A.ihvar = o.ihvar; A.iener = o.iener; A.idivbzero = o.idivbzero; A.idust = o.idust; A.onef = o.onef_dust;
+    for (int d = 0; d < 3; d++) { A.iavlim[d] = o.iavlim[d]; A.ibound[d] = d < c->ndim ? o.ibound[d] : 0; A.xmin[d] = o.xmin[d]; A.xmax[d] = o.xmax[d]; }
+    A.dt = *dt_inout; A.damp = o.damp; A.flags = c->flags;
+    return A;
+  };
+  (void)planes;
+  StepArgs A = args();
+  LAUNCH(c, k_step_save, nblocks(np, 256), 256, 0, A);
+  LAUNCH(c, k_step_predict, nblocks(np, 256), 256, 0, A);
+  c->linked = c->density_done = c->prim_done = c->rates_done = false;
+  c->ntotal = ghost_bound ? np : c->ntotal;                    // the ghost rows are stale: derivs makes new ones from rows [0,npart)
+  if (int e = ndspmhd_b200_derivs(c, s)) return e;
+  A = args();                                                  // derivs may have re-allocated the arrays (more ghosts)
+  LAUNCH(c, k_step_correct, nblocks(np, 256), 256, 0, A);
+  if (int e = sync_flags(c)) return e;
+  if (c->h_flags[1]) {
+    const int code = c->h_flags[1];
+    CU(cudaMemsetAsync(c->flags, 0, sizeof(int) * 16, c->stream));
+    return set_err(c, code, code == ND_ERR_H_NONPOSITIVE ? "step: hh -ve" : "step: itypebnd2 (cylindrical fixed particles) is not supported");
+  }
+  // new timestep, :239-253
+  if (!so->dtfixed) *dt_inout = std::min(std::min(so->C_force * c->sc.dtforce, so->C_cour * c->sc.dtcourant), std::min(0.9 * c->sc.dtdrag, so->C_force * c->sc.dtvisc));
+  return 0;
+}
+
+/* evolved state of rows [0,npart) back to the host arrays (NULL pointers skipped) */
+int ndspmhd_b200_download_state(nd_ctx *c, const nd_state_out *st, int idim) {
+  if (!c || !st) return ND_ERR_INVALID_ARG;
+  if (!c->uploaded) return set_err(c, ND_ERR_STATE, "download_state before upload");
+  if (idim < c->npart) return set_err(c, ND_ERR_INVALID_ARG, "download_state: idim < npart");
+  CU(cudaSetDevice(c->device));
+  const size_t n = (size_t)c->npart, D = sizeof(double);
+  auto dn = [&](void *dst, const void *src, size_t bytes) -> cudaError_t { return (dst && src) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess; };
+  CU(dn(st->x, c->x, D * c->ndim * n)); CU(dn(st->vel, c->vel, D * 3 * n)); CU(dn(st->hh, c->hh, D * n)); CU(dn(st->en, c->en, D * n));
+  CU(dn(st->Bevol, c->Bevol, D * 3 * n)); CU(dn(st->alpha, c->alpha, D * 3 * n)); CU(dn(st->psi, c->psi, D * n)); CU(dn(st->rho, c->rho, D * n));
+  if (c->o.onef_dust) { CU(dn(st->dustevol, c->dustevol, D * n)); CU(dn(st->deltav, c->deltav, D * 3 * n)); }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
 }
 
 }  // extern "C"

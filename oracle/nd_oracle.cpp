@@ -1712,4 +1712,112 @@ long long ndo_linklist_pairs(const nd_options *o, int ndim, ndo_arrays *a, int n
   return n;
 }
 
+/* One leapfrog step: `step` (src/stepND_leapfrog_mhd.f90:39-300) with its `call derivs` (:167) and `call boundary`
+ * (:216 -> src/boundaryND.f90:65-93, periodic wrap only), restated loop for loop.  On entry the rates arrays hold the
+ * result of the previous derivs.  Not supported (error 2): itypebnd2 rows (cylindrical fixed particles), imhd < 0,
+ * idivbzero = 10, particle splitting, idustevol /= 0. */
+int ndo_step(const nd_options *o, int ndim, ndo_arrays *a, int npart, int *ntotal, int idim, double *dt_inout, double C_cour, double C_force,
+             int dtfixed, nd_scalars *s) {
+  g_err.clear();
+  if (o->imhd < 0 || o->idivbzero == 10 || o->idustevol != 0) { g_err = "ndo_step: unsupported option"; return ND_ERR_UNSUPPORTED_OPTION; }
+  const double dt = *dt_inout, hdt = 0.5 * dt;                                            // :68
+  const double dndim = 1. / ndim;
+  const bool onef = o->onef_dust != 0;
+  const size_t N = (size_t)npart;
+  std::vector<double> xin(N * ndim), velin(N * 3), Bevolin(N * 3), rhoin(N), hhin(N), enin(N), alphain(N * 3), psiin(N), forcein(N * 3),
+      dBevoldtin(N * 3), drhodtin(N), dhdtin(N), dendtin(N), daldtin(N * 3), dpsidtin(N), dustevolin, ddustevoldtin, deltavin, ddeltavdtin;
+  if (onef) { dustevolin.resize(N); ddustevoldtin.resize(N); deltavin.resize(N * 3); ddeltavdtin.resize(N * 3); }
+  for (int i = 0; i < npart; i++) {                                                       // :70-100
+    for (int d = 0; d < ndim; d++) xin[(size_t)i * ndim + d] = a->x[(size_t)i * ndim + d];
+    for (int d = 0; d < 3; d++) {
+      velin[(size_t)i * 3 + d] = a->vel[(size_t)i * 3 + d]; Bevolin[(size_t)i * 3 + d] = a->Bevol[(size_t)i * 3 + d];
+      alphain[(size_t)i * 3 + d] = a->alpha[(size_t)i * 3 + d]; forcein[(size_t)i * 3 + d] = a->force[(size_t)i * 3 + d];
+      dBevoldtin[(size_t)i * 3 + d] = a->dBevoldt[(size_t)i * 3 + d]; daldtin[(size_t)i * 3 + d] = a->daldt[(size_t)i * 3 + d];
+    }
+    rhoin[i] = a->rho[i]; hhin[i] = a->hh[i]; enin[i] = a->en[i]; psiin[i] = a->psi[i];
+    drhodtin[i] = a->drhodt[i]; dhdtin[i] = a->dhdt[i]; dendtin[i] = a->dendt[i]; dpsidtin[i] = a->dpsidt[i];
+    if (onef) {
+      dustevolin[i] = a->dustevol[i]; ddustevoldtin[i] = a->ddustevoldt[i];
+      if (o->idust == 1) for (int d = 0; d < 3; d++) { deltavin[(size_t)i * 3 + d] = a->deltav[(size_t)i * 3 + d]; ddeltavdtin[(size_t)i * 3 + d] = a->ddeltavdt[(size_t)i * 3 + d]; }
+    }
+  }
+  // ---- predictor :108-163 ----
+  for (int i = 0; i < npart; i++) {
+    const int it = a->itype[i];
+    if (it == ND_ITYPE_BND || it == ND_ITYPE_BND2 || it == ND_ITYPE_BNDDUST) {
+      if (it == ND_ITYPE_BND2) { g_err = "ndo_step: itypebnd2 not supported"; return ND_ERR_UNSUPPORTED_OPTION; }
+      const int j = a->ireal[i];                                                          // 1-based
+      const size_t r = (j > 0) ? (size_t)(j - 1) : (size_t)i;                             // :112-117
+      for (int d = 0; d < ndim; d++) a->x[(size_t)i * ndim + d] = xin[(size_t)i * ndim + d] + dt * velin[r * 3 + d] + 0.5 * dt * dt * forcein[r * 3 + d];
+      for (int d = 0; d < 3; d++) { a->Bevol[(size_t)i * 3 + d] = Bevolin[(size_t)i * 3 + d]; a->alpha[(size_t)i * 3 + d] = alphain[(size_t)i * 3 + d]; }
+      a->rho[i] = rhoin[i]; a->hh[i] = hhin[i]; a->en[i] = enin[i]; a->psi[i] = psiin[i];  // :135-139
+      if (o->idust == 1 || o->idust == 3 || o->idust == 4) {
+        if (onef) a->dustevol[i] = dustevolin[i];
+        if (o->idust == 1) for (int d = 0; d < 3; d++) a->deltav[(size_t)i * 3 + d] = deltavin[(size_t)i * 3 + d];
+      }
+    } else {
+      for (int d = 0; d < ndim; d++) a->x[(size_t)i * ndim + d] = xin[(size_t)i * ndim + d] + dt * velin[(size_t)i * 3 + d] + 0.5 * dt * dt * forcein[(size_t)i * 3 + d];   // :145
+      for (int d = 0; d < 3; d++) a->vel[(size_t)i * 3 + d] = (velin[(size_t)i * 3 + d] + dt * forcein[(size_t)i * 3 + d]) / (1. + o->damp);                           // :146
+      if (o->imhd != 0 && o->iresist != 2) for (int d = 0; d < 3; d++) a->Bevol[(size_t)i * 3 + d] = Bevolin[(size_t)i * 3 + d] + dt * dBevoldtin[(size_t)i * 3 + d];
+      if (o->icty >= 1) a->rho[i] = rhoin[i] + dt * drhodtin[i];
+      if (o->ihvar == 1) a->hh[i] = hhin[i] * pow(rhoin[i] / a->rho[i], dndim);            // :151
+      else if (o->ihvar == 2 || o->ihvar == 3) a->hh[i] = hhin[i] + dt * dhdtin[i];
+      if (o->iener != 0) a->en[i] = enin[i] + dt * dendtin[i];
+      for (int d = 0; d < 3; d++) if (o->iavlim[d] != 0) a->alpha[(size_t)i * 3 + d] = std::min(alphain[(size_t)i * 3 + d] + dt * daldtin[(size_t)i * 3 + d], 1.0);
+      if (o->idivbzero >= 2) a->psi[i] = psiin[i] + dt * dpsidtin[i];
+      if (onef) {
+        a->dustevol[i] = dustevolin[i] + dt * ddustevoldtin[i];
+        if (o->idust == 1) for (int d = 0; d < 3; d++) a->deltav[(size_t)i * 3 + d] = deltavin[(size_t)i * 3 + d] + dt * ddeltavdtin[(size_t)i * 3 + d];
+      }
+    }
+  }
+  // ---- derivs :167 ----
+  if (int e = ndo_derivs(o, ndim, a, npart, ntotal, idim, NDO_ALL, s, nullptr)) return e;
+  // ---- corrector :171-209 ----
+  for (int i = 0; i < npart; i++) {
+    const int it = a->itype[i];
+    if (it == ND_ITYPE_BND || it == ND_ITYPE_BND2 || it == ND_ITYPE_BNDDUST) {
+      for (int d = 0; d < 3; d++) { a->vel[(size_t)i * 3 + d] = velin[(size_t)i * 3 + d]; a->Bevol[(size_t)i * 3 + d] = Bevolin[(size_t)i * 3 + d]; a->alpha[(size_t)i * 3 + d] = alphain[(size_t)i * 3 + d]; }
+      a->rho[i] = rhoin[i]; a->hh[i] = hhin[i]; a->en[i] = enin[i]; a->psi[i] = psiin[i];
+      if (o->idust == 1 || o->idust == 3 || o->idust == 4) {
+        if (onef) a->dustevol[i] = dustevolin[i];
+        if (o->idust == 1) for (int d = 0; d < 3; d++) a->deltav[(size_t)i * 3 + d] = deltavin[(size_t)i * 3 + d];
+      }
+    } else {
+      for (int d = 0; d < 3; d++) a->vel[(size_t)i * 3 + d] = (velin[(size_t)i * 3 + d] + hdt * (a->force[(size_t)i * 3 + d] + forcein[(size_t)i * 3 + d])) / (1. + o->damp);   // :187
+      if (o->imhd != 0) {
+        for (int d = 0; d < 3; d++) {
+          if (o->iresist == 2) a->Bevol[(size_t)i * 3 + d] = Bevolin[(size_t)i * 3 + d] + dt * a->dBevoldt[(size_t)i * 3 + d];
+          else a->Bevol[(size_t)i * 3 + d] = Bevolin[(size_t)i * 3 + d] + hdt * (a->dBevoldt[(size_t)i * 3 + d] + dBevoldtin[(size_t)i * 3 + d]);
+        }
+      }
+      if (o->icty >= 1) a->rho[i] = rhoin[i] + hdt * (a->drhodt[i] + drhodtin[i]);
+      if (o->ihvar == 2) {
+        a->hh[i] = hhin[i] + hdt * (a->dhdt[i] + dhdtin[i]);
+        if (a->hh[i] <= 0.) { g_err = "step: hh -ve"; return ND_ERR_H_NONPOSITIVE; }        // :197-200
+      }
+      if (o->iener != 0) a->en[i] = enin[i] + hdt * (a->dendt[i] + dendtin[i]);
+      for (int d = 0; d < 3; d++) if (o->iavlim[d] != 0) a->alpha[(size_t)i * 3 + d] = std::min(alphain[(size_t)i * 3 + d] + hdt * (a->daldt[(size_t)i * 3 + d] + daldtin[(size_t)i * 3 + d]), 1.0);
+      if (o->idivbzero >= 2) a->psi[i] = psiin[i] + hdt * (a->dpsidt[i] + dpsidtin[i]);
+      if (onef) {
+        a->dustevol[i] = dustevolin[i] + hdt * (a->ddustevoldt[i] + ddustevoldtin[i]);
+        if (o->idust == 1) for (int d = 0; d < 3; d++) a->deltav[(size_t)i * 3 + d] = deltavin[(size_t)i * 3 + d] + hdt * (a->ddeltavdt[(size_t)i * 3 + d] + ddeltavdtin[(size_t)i * 3 + d]);
+      }
+    }
+  }
+  // ---- boundary (src/boundaryND.f90:65-93): particles cross the periodic domain ----
+  bool any3 = false, any_nonzero = false;
+  for (int d = 0; d < ndim; d++) { if (o->ibound[d] == 3) any3 = true; if (o->ibound[d] != 0) any_nonzero = true; }
+  if (any_nonzero && any3) {
+    for (int i = 0; i < npart; i++) for (int d = 0; d < ndim; d++) if (o->ibound[d] == 3) {
+      double &xx = a->x[(size_t)i * ndim + d];
+      if (xx > o->xmax[d]) xx = o->xmin[d] + xx - o->xmax[d];
+      else if (xx < o->xmin[d]) xx = o->xmax[d] - (o->xmin[d] - xx);
+    }
+  }
+  // ---- new timestep :239-253 ----
+  if (!dtfixed) *dt_inout = std::min(std::min(C_force * s->dtforce, C_cour * s->dtcourant), std::min(0.9 * s->dtdrag, C_force * s->dtvisc));
+  return 0;
+}
+
 }  // extern "C"

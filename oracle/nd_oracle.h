@@ -39,6 +39,12 @@ enum { NDO_GHOSTS = 1, NDO_LINK = 2, NDO_DENSITY = 4, NDO_C2P = 8, NDO_RATES = 1
 int ndo_derivs(const nd_options *o, int ndim, ndo_arrays *a, int npart, int *ntotal, int idim,
                int phases, nd_scalars *s, double *ms);
 
+/* one leapfrog `step` (src/stepND_leapfrog_mhd.f90:39-300) incl. its `call derivs` and the periodic wrap of `boundary`
+ * (src/boundaryND.f90:65-93): on entry the rates arrays hold the previous derivs; *dt_inout in = this step's dt, out = the next
+ * (:253) unless dtfixed.  `s` (required) receives the scalars of the inner derivs. */
+int ndo_step(const nd_options *o, int ndim, ndo_arrays *a, int npart, int *ntotal, int idim, double *dt_inout, double C_cour, double C_force,
+             int dtfixed, nd_scalars *s);
+
 /* kernel tables as built by setkernels/setkerndrag (src/kernelND.f90:127-4289) */
 int ndo_kernel_tables(int ikernel, int ikerneldrag, int ndim, double *wij, double *grwij, double *grgrwij,
                       double *wijdrag, double *radkern2, double *dq2table);
