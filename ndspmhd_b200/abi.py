@@ -79,6 +79,15 @@ class NdArrays(C.Structure):
     ]
 
 
+class NdStepOpts(C.Structure):
+    """module timestep: C_cour, C_force, dtfixed (src/variablesND.f90:255-273; defaults src/defaults.f90: C_cour=0.3, C_force=0.25)."""
+    _fields_ = [("C_cour", C.c_double), ("C_force", C.c_double), ("dtfixed", C.c_int), ("reserved", C.c_int)]
+
+
+class NdStateOut(C.Structure):
+    _fields_ = [(n, _DP) for n in ("x", "vel", "hh", "en", "Bevol", "alpha", "psi", "rho", "dustevol", "deltav")]
+
+
 class NdScalars(C.Structure):
     _fields_ = [
         ("dtcourant", C.c_double), ("dtforce", C.c_double), ("dtav", C.c_double), ("dtdrag", C.c_double), ("dtvisc", C.c_double),

@@ -847,7 +847,12 @@ __global__ void k_step_correct(StepArgs A) {                                    
       if (A.idust == 1) for (int d = 0; d < 3; d++) A.deltav[(size_t)i * 3 + d] = in[(SP_DELTAV + d) * n] + hdt * (A.ddeltavdt[(size_t)i * 3 + d] + in[(SP_DDELTAV + d) * n]);
     }
   }
-  // particles cross the periodic domain, boundaryND.f90:65-93 (`if (any(ibound.ne.0)) call boundary`, :216)
+}
+// particles cross the periodic domain: `boundary`, src/boundaryND.f90:65-93 -- called at the top of derivs (src/derivs.f90:74, before
+// the ghosts: set_ghost_particles makes no ghost of a particle on or over the boundary) and after the corrector (:216)
+__global__ void k_step_boundary(StepArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.npart) return;
   for (int d = 0; d < A.ndim; d++) if (A.ibound[d] == 3) {
     double xx = A.x[(size_t)i * A.ndim + d];
     if (xx > A.xmax[d]) xx = A.xmin[d] + xx - A.xmax[d];
@@ -2048,11 +2053,13 @@ int ndspmhd_b200_step(nd_ctx *c, const nd_step_opts *so, double *dt_inout, nd_sc
   StepArgs A = args();
   LAUNCH(c, k_step_save, nblocks(np, 256), 256, 0, A);
   LAUNCH(c, k_step_predict, nblocks(np, 256), 256, 0, A);
+  LAUNCH(c, k_step_boundary, nblocks(np, 256), 256, 0, A);     // src/derivs.f90:74
   c->linked = c->density_done = c->prim_done = c->rates_done = false;
   c->ntotal = ghost_bound ? np : c->ntotal;                    // the ghost rows are stale: derivs makes new ones from rows [0,npart)
   if (int e = ndspmhd_b200_derivs(c, s)) return e;
   A = args();                                                  // derivs may have re-allocated the arrays (more ghosts)
   LAUNCH(c, k_step_correct, nblocks(np, 256), 256, 0, A);
+  LAUNCH(c, k_step_boundary, nblocks(np, 256), 256, 0, A);     // :216
   if (int e = sync_flags(c)) return e;
   if (c->h_flags[1]) {
     const int code = c->h_flags[1];

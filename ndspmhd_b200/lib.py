@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 from . import abi
-from .abi import NdArrays, NdOptions, NdScalars, Particles
+from .abi import NdArrays, NdOptions, NdScalars, NdStateOut, NdStepOpts, Particles
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # NDSPMHD_B200_LIB: development override used by tools/ to time differently tuned builds of the same sources
@@ -33,6 +33,7 @@ EXPORTS = [
     "ndspmhd_b200_cons2prim", "ndspmhd_b200_get_rates", "ndspmhd_b200_derivs", "ndspmhd_b200_download",
     "ndspmhd_b200_host_alloc", "ndspmhd_b200_host_free", "ndspmhd_b200_last_timings", "ndspmhd_b200_launch_count",
     "ndspmhd_b200_stream", "ndspmhd_b200_rates_pairs", "ndspmhd_b200_rewind", "ndspmhd_b200_set_comm", "ndspmhd_b200_row_counts", "ndspmhd_b200_selftest_math", "ndspmhd_b200_derivs_host",
+    "ndspmhd_b200_step", "ndspmhd_b200_download_state",
 ]
 
 
@@ -80,6 +81,8 @@ def load():
     L.ndspmhd_b200_stream.argtypes = [vp]
     L.ndspmhd_b200_stream.restype = vp
     L.ndspmhd_b200_rates_pairs.argtypes = [vp, _IP, _IP, C.c_longlong, C.POINTER(C.c_longlong)]
+    L.ndspmhd_b200_step.argtypes = [vp, C.POINTER(NdStepOpts), _DP, C.POINTER(NdScalars)]
+    L.ndspmhd_b200_download_state.argtypes = [vp, C.POINTER(NdStateOut), C.c_int]
     _LIB = L
     return L
 
@@ -208,6 +211,22 @@ class Hotpath:
         s = NdScalars()
         self._chk(self.L.ndspmhd_b200_derivs(self.ctx, C.byref(s)))
         return s.as_dict()
+
+    def step(self, dt: float, C_cour: float = 0.3, C_force: float = 0.25, dtfixed: bool = False):
+        """`call step` (src/stepND_leapfrog_mhd.f90:39) on the resident state: predictor, derivs, corrector, periodic wrap.
+        Returns (dt for the next step, scalars of the inner derivs)."""
+        so = NdStepOpts(C_cour, C_force, int(dtfixed), 0)
+        d = C.c_double(dt)
+        s = NdScalars()
+        self._chk(self.L.ndspmhd_b200_step(self.ctx, C.byref(so), C.byref(d), C.byref(s)))
+        return d.value, s.as_dict()
+
+    def download_state(self, p: Particles):
+        """x, vel, hh, en, Bevol, alpha, psi, rho (+ dustevol, deltav) of rows [0,npart) into the host arrays of `p`."""
+        st = NdStateOut()
+        for n in ("x", "vel", "hh", "en", "Bevol", "alpha", "psi", "rho", "dustevol", "deltav"):
+            setattr(st, n, p.ptr(n))
+        self._chk(self.L.ndspmhd_b200_download_state(self.ctx, C.byref(st), p.idim))
 
     def selftest_math(self, x: np.ndarray):
         """sqrt_nr / rsqrt_nr of the pair kernels evaluated on the device for the given arguments."""

@@ -1771,7 +1771,20 @@ int ndo_step(const nd_options *o, int ndim, ndo_arrays *a, int npart, int *ntota
       }
     }
   }
-  // ---- derivs :167 ----
+  // ---- derivs :167; it opens with `if (any(ibound.ne.0)) call boundary` (src/derivs.f90:74), so particles the predictor moved out of a
+  //      periodic domain are wrapped before the ghosts are made (set_ghost_particles makes no ghost of a particle on or over the
+  //      boundary, src/ghostND_mhd.f90:204) ----
+  auto boundary = [&]() {                                                                 // src/boundaryND.f90:65-93
+    bool any3 = false;
+    for (int d = 0; d < ndim; d++) if (o->ibound[d] == 3) any3 = true;
+    if (!any3) return;
+    for (int i = 0; i < npart; i++) for (int d = 0; d < ndim; d++) if (o->ibound[d] == 3) {
+      double &xx = a->x[(size_t)i * ndim + d];
+      if (xx > o->xmax[d]) xx = o->xmin[d] + xx - o->xmax[d];
+      else if (xx < o->xmin[d]) xx = o->xmax[d] - (o->xmin[d] - xx);
+    }
+  };
+  boundary();
   if (int e = ndo_derivs(o, ndim, a, npart, ntotal, idim, NDO_ALL, s, nullptr)) return e;
   // ---- corrector :171-209 ----
   for (int i = 0; i < npart; i++) {
@@ -1805,16 +1818,7 @@ int ndo_step(const nd_options *o, int ndim, ndo_arrays *a, int npart, int *ntota
       }
     }
   }
-  // ---- boundary (src/boundaryND.f90:65-93): particles cross the periodic domain ----
-  bool any3 = false, any_nonzero = false;
-  for (int d = 0; d < ndim; d++) { if (o->ibound[d] == 3) any3 = true; if (o->ibound[d] != 0) any_nonzero = true; }
-  if (any_nonzero && any3) {
-    for (int i = 0; i < npart; i++) for (int d = 0; d < ndim; d++) if (o->ibound[d] == 3) {
-      double &xx = a->x[(size_t)i * ndim + d];
-      if (xx > o->xmax[d]) xx = o->xmin[d] + xx - o->xmax[d];
-      else if (xx < o->xmin[d]) xx = o->xmax[d] - (o->xmin[d] - xx);
-    }
-  }
+  boundary();                                                                             // :216
   // ---- new timestep :239-253 ----
   if (!dtfixed) *dt_inout = std::min(std::min(C_force * s->dtforce, C_cour * s->dtcourant), std::min(0.9 * s->dtdrag, C_force * s->dtvisc));
   return 0;

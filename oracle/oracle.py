@@ -49,6 +49,9 @@ def lib():
         _LIB.ndo_derivs.restype = C.c_int
         _LIB.ndo_derivs.argtypes = [C.POINTER(NdOptions), C.c_int, C.POINTER(NdoArrays), C.c_int, _IP, C.c_int, C.c_int,
                                     C.POINTER(NdScalars), _DP]
+        _LIB.ndo_step.restype = C.c_int
+        _LIB.ndo_step.argtypes = [C.POINTER(NdOptions), C.c_int, C.POINTER(NdoArrays), C.c_int, _IP, C.c_int, _DP, C.c_double, C.c_double, C.c_int,
+                                  C.POINTER(NdScalars)]
         _LIB.ndo_kernel_tables.restype = C.c_int
         _LIB.ndo_kernel_tables.argtypes = [C.c_int, C.c_int, C.c_int, _DP, _DP, _DP, _DP, _DP, _DP]
         _LIB.ndo_interpolate.restype = C.c_int
@@ -89,6 +92,21 @@ def derivs(opts: NdOptions, p: Particles, phases: int = NDO_ALL):
     if e != 0:
         raise OracleError(e, L.ndo_last_error().decode())
     return s.as_dict(), list(ms)
+
+
+def step(opts: NdOptions, p: Particles, dt: float, C_cour: float = 0.3, C_force: float = 0.25, dtfixed: bool = False):
+    """One leapfrog `step` (src/stepND_leapfrog_mhd.f90:39-300) on the host arrays of `p`, which must hold the rates of a previous
+    derivs.  Returns (dt for the next step, scalars of the inner derivs)."""
+    L = lib()
+    a = _arrays(p)
+    nt = C.c_int(p.ntotal)
+    s = NdScalars()
+    d = C.c_double(dt)
+    e = L.ndo_step(C.byref(opts), p.ndim, C.byref(a), p.npart, C.byref(nt), p.idim, C.byref(d), C_cour, C_force, int(dtfixed), C.byref(s))
+    p.ntotal = nt.value
+    if e != 0:
+        raise OracleError(e, L.ndo_last_error().decode())
+    return d.value, s.as_dict()
 
 
 def kernel_tables(ikernel: int, ikerneldrag: int, ndim: int):
