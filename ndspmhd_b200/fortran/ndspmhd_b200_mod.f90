@@ -61,6 +61,15 @@ module ndspmhd_b200
     integer(c_int) :: reserved_i(8)
  end type nd_scalars
 
+ type, bind(C) :: nd_step_opts
+    real(c_double) :: C_cour,C_force
+    integer(c_int) :: dtfixed,reserved
+ end type nd_step_opts
+
+ type, bind(C) :: nd_state_out
+    type(c_ptr) :: x,vel,hh,en,Bevol,alpha,psi,rho,dustevol,deltav
+ end type nd_state_out
+
  interface
     integer(c_int) function ndspmhd_b200_default_options(o) bind(C,name='ndspmhd_b200_default_options')
      import; type(nd_options), intent(out) :: o
@@ -100,6 +109,12 @@ module ndspmhd_b200
     end function
     integer(c_int) function ndspmhd_b200_download(ctx,a,mask,idim) bind(C,name='ndspmhd_b200_download')
      import; type(c_ptr), value :: ctx; type(nd_arrays), intent(in) :: a; integer(c_int), value :: mask,idim
+    end function
+    integer(c_int) function ndspmhd_b200_step(ctx,so,dt,s) bind(C,name='ndspmhd_b200_step')
+     import; type(c_ptr), value :: ctx; type(nd_step_opts), intent(in) :: so; real(c_double), intent(inout) :: dt; type(nd_scalars), intent(out) :: s
+    end function
+    integer(c_int) function ndspmhd_b200_download_state(ctx,st,idim) bind(C,name='ndspmhd_b200_download_state')
+     import; type(c_ptr), value :: ctx; type(nd_state_out), intent(in) :: st; integer(c_int), value :: idim
     end function
  end interface
 
