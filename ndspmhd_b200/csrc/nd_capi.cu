@@ -3,6 +3,7 @@
 #include "../../include/ndspmhd_b200.h"
 #include "nd_tables.h"
 #include <chrono>
+#include <functional>
 #include "nd_device.cuh"
 #include "nd_density.cuh"
 #include "nd_rates.cuh"
@@ -77,6 +78,11 @@ struct nd_ctx {
   int *sendlist[2] = {nullptr, nullptr}; int sendcap[2] = {0, 0}, nsend[2] = {0, 0}, nrecv[2] = {0, 0};
   void *sendbuf[2] = {nullptr, nullptr}, *recvbuf[2] = {nullptr, nullptr}; size_t sendbufcap[2] = {0, 0}, recvbufcap[2] = {0, 0};
   cudaEvent_t ev[8];
+  // rates in row chunks (ndspmhd_b200_derivs_host): chunk q = original rows [q*rows, (q+1)*rows) so that its results can be
+  // downloaded while the next chunk's pair kernel runs
+  int rate_chunks = 1; int *rlist = nullptr; size_t rlistcap = 0;
+  std::function<int(int, int, int)> on_rates_chunk;
+  std::vector<cudaEvent_t> chunk_events;   // (chunk, row0, row1) after the chunk's finalisation is enqueued
   double *stepbuf = nullptr; size_t stepbufrows = 0;   // leapfrog `*in` copies (ndspmhd_b200_step), rows [0,npart)
   cudaEvent_t ev_pair[2] = {nullptr, nullptr};   // around the rates pair kernel alone (the roofline's kernel time)
   double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -599,11 +605,13 @@ struct FinalArgs {
   const double *drhodt_in, *Bevol, *dens, *hh, *rho, *pr; const unsigned long long *vsigmax_key;
   double *force, *dudt, *dendt, *dBevoldt, *daldt, *dpsidt, *gradpsi, *divB, *curlB, *graddivv, *del2u, *drhodt, *dhdt;
   RatesRed R; int npart, ntotal;
+  const int *targets; int ntargets;   // row-chunked finalisation: the chunk's target slots (NULL: every slot)
   // one-fluid dust (dusta NULL otherwise)
   const double4 *dusta; const double2 *dustb; const int *fineStart, *cellOf; double *ddustevoldt, *ddeltavdt;
 };
 __global__ void k_rates_final(FinalArgs A) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = A.targets ? (t < A.ntargets ? A.targets[t] : A.ntotal) : t;
   double fhmax = 0., dtforce = DBL_MAX, fm0 = 0., fm1 = 0., fm2 = 0., tsmin = DBL_MAX;
   if (s < A.ntotal) {
     const int i = A.perm[s];
@@ -734,6 +742,25 @@ __global__ void k_rates_final(FinalArgs A) {
     if ((threadIdx.x & 31) == 0) atomic_min_d(A.R.ts_min, tsmin);
   }
 }
+// Row-chunked rates: dpsidt needs the maximum signal velocity over ALL pairs (:518-520, :902), known only after the last chunk.
+__global__ void k_rates_dpsidt(const double *divB, const double *psi, const double *hh, const int *itype, const unsigned long long *vsigmax_key,
+                               double psidecayfact, int imhd, int idivbzero, double *dpsidt, int npart) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npart) return;
+  const double vsigmax = dkey_inv(*vsigmax_key);
+  const double vsig2max = (imhd != 0 && idivbzero >= 2) ? vsigmax * vsigmax : 0.;
+  double v = 0.;
+  if (idivbzero >= 2 && idivbzero <= 7) v = -vsig2max * divB[i] - psidecayfact * psi[i] * vsigmax / hh[i];
+  const int ti = itype[i];
+  if (ti == T_BND || ti == T_BNDDUST) v = 0.;
+  dpsidt[i] = v;
+}
+// flags the sorted slots whose original row lies in [row0,row1) (rows below nown only): the chunk's targets, in slot order
+__global__ void k_chunk_flags(const int *perm, int ntotal, int row0, int row1, int *flag) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < ntotal) { const int r = perm[s]; flag[s] = (r >= row0 && r < row1) ? 1 : 0; }
+}
+
 struct ZeroArgs { double *force, *dudt, *dendt, *dBevoldt, *daldt, *dpsidt, *gradpsi, *divB, *curlB, *graddivv, *del2u, *drhodt, *dhdt; int npart, ntotal; };
 __global__ void k_rates_zero_ghosts(ZeroArgs A) {                                    // :949-965 for rows > npart
   const int i = A.npart + blockIdx.x * blockDim.x + threadIdx.x;
@@ -1390,13 +1417,13 @@ RatesOpts make_rates_opts(const nd_ctx *c) {
 enum { RED_DTC = 0, RED_VSIG = 1, RED_DTAV = 2, RED_TS = 3, RED_HCS = 4, RED_FH = 5, RED_DTF = 6, RED_STRESS = 7 };
 
 template <int NDIM, bool MHD, bool DRAG, bool FAST, bool ONEF> int launch_rates_pair(nd_ctx *c, const RatesIn &I, const RatesOpts &O, const RatesSums &S, const RatesRed &R, int *pi, int *pj,
-                                                                          unsigned long long *pc, long long cap) {
+                                                                          unsigned long long *pc, long long cap, const int *targets, int ntargets) {
   Grid G = make_grid(c);
-  const int n = c->ntotal;
+  const int n = targets ? ntargets : c->ntotal;
   for (int c0 = 0; c0 < n; c0 += LIST_CHUNK) {
     const int m = std::min(LIST_CHUNK, n - c0);
     ListArgs LA;
-    LA.hh = c->hh; LA.targets = nullptr; LA.s0 = c0; LA.ntargets = m; LA.numneigh = nullptr; LA.drag = (DRAG && O.idrag_nature > 0) ? 1 : 0;
+    LA.hh = c->hh; LA.targets = targets ? targets + c0 : nullptr; LA.s0 = c0; LA.ntargets = m; LA.numneigh = nullptr; LA.drag = (DRAG && O.idrag_nature > 0) ? 1 : 0;
     LA.pair_out_i = pi; LA.pair_out_j = pj; LA.pair_count = pc; LA.pair_cap = cap;
     NbrLists L;
     if (int e = build_lists<NDIM, LIST_RATES>(c, G, LA, L)) return e;
@@ -1417,7 +1444,7 @@ template <int NDIM, bool MHD, bool DRAG, bool FAST, bool ONEF> int launch_rates_
     CU(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
     CU(cudaMemsetAsync(c->flags + 8, 0, sizeof(int), c->stream));
     if (c0 == 0) CU(cudaEventRecord(c->ev_pair[0], c->stream));   // the first chunk's launch is the one timed (the only one below 32 Mi rows)
-    LAUNCH(c, (rates_pair_kernel<NDIM, MHD, DRAG, FAST, ONEF>), ND_RATES_PERSIST ? std::min(nblocks(m, RATES_BLOCK), resident) : nblocks(m, RATES_BLOCK), RATES_BLOCK, RATES_SMEM_BYTES, G, I, O, S, R, L, c0, m);
+    LAUNCH(c, (rates_pair_kernel<NDIM, MHD, DRAG, FAST, ONEF>), ND_RATES_PERSIST ? std::min(nblocks(m, RATES_BLOCK), resident) : nblocks(m, RATES_BLOCK), RATES_BLOCK, RATES_SMEM_BYTES, G, I, O, S, R, L, c0, m, targets ? targets + c0 : nullptr);
     if (c0 == 0) CU(cudaEventRecord(c->ev_pair[1], c->stream));
   }
   return 0;
@@ -1461,37 +1488,66 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   R.nclumped = c->flags + 4; R.err = c->flags + 1; R.sched = c->flags + 8;
   CU(cudaEventRecord(c->ev[3], c->stream));
   const bool mhd = o.imhd != 0, drag = (o.idust == 2);
-  int e = 0;
   // first-class tuple without run-time option tests (and without the dead graddivv "curl v" sums: want_aux = 0)
   const bool fast = !drag && o.idust != 1 && !o.want_aux && o.iav == 2 && (o.iener == 0 || o.iener == 2) && o.ikernav == 3 && o.iresist == 0 && o.iavlim[0] != 3 && o.iavlim[2] != 2;
-  if (o.idust == 1 && mhd) e = launch_rates_pair<NDIM, true, false, false, true>(c, I, O, S, R, pi, pj, pc, cap);
-  else if (o.idust == 1) e = launch_rates_pair<NDIM, false, false, false, true>(c, I, O, S, R, pi, pj, pc, cap);
-  else if (mhd && fast) e = launch_rates_pair<NDIM, true, false, true, false>(c, I, O, S, R, pi, pj, pc, cap);
-  else if (!mhd && fast) e = launch_rates_pair<NDIM, false, false, true, false>(c, I, O, S, R, pi, pj, pc, cap);
-  else if (mhd && !drag) e = launch_rates_pair<NDIM, true, false, false, false>(c, I, O, S, R, pi, pj, pc, cap);
-  else if (!mhd && !drag) e = launch_rates_pair<NDIM, false, false, false, false>(c, I, O, S, R, pi, pj, pc, cap);
-  else if (!mhd && drag) e = launch_rates_pair<NDIM, false, true, false, false>(c, I, O, S, R, pi, pj, pc, cap);
-  else e = launch_rates_pair<NDIM, true, true, false, false>(c, I, O, S, R, pi, pj, pc, cap);
-  if (e) return e;
-  CU(cudaEventRecord(c->ev[4], c->stream));
-  if (c->has_comm) {   // vsigmax feeds dpsidt in the finalisation loop (:518-520, :902): all ranks need the global maximum
-    SMALL_D2H(c, c->h_red, c->red + RED_VSIG, sizeof(unsigned long long));
-    CU(cudaStreamSynchronize(c->stream));
-    double vs = dkey_inv(c->h_red[0]);
-    if (int e = comm_allreduce(c, &vs, 1, 0)) return e;
-    union { double d; unsigned long long u; } kv; kv.d = vs;
-    c->h_red[0] = kv.u | 0x8000000000000000ull;   // key of a non-negative double
-    CU(cudaMemcpyAsync(c->red + RED_VSIG, c->h_red, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
-  }
+  auto pair = [&](const int *targets, int ntargets) -> int {
+    if (o.idust == 1 && mhd) return launch_rates_pair<NDIM, true, false, false, true>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (o.idust == 1) return launch_rates_pair<NDIM, false, false, false, true>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (mhd && fast) return launch_rates_pair<NDIM, true, false, true, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (!mhd && fast) return launch_rates_pair<NDIM, false, false, true, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (mhd && !drag) return launch_rates_pair<NDIM, true, false, false, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (!mhd && !drag) return launch_rates_pair<NDIM, false, false, false, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (!mhd && drag) return launch_rates_pair<NDIM, false, true, false, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    return launch_rates_pair<NDIM, true, true, false, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+  };
   FinalArgs FA;
   FA.perm = c->perm; FA.typ = c->typ; FA.posh = c->posh; FA.vm = c->vm; FA.bpsi = c->bpsi; FA.thermo = c->thermo; FA.gal = c->gal; FA.S = S; FA.O = O;
   FA.drhodt_in = c->drhodt; FA.Bevol = c->Bevol; FA.dens = c->dens; FA.hh = c->hh; FA.rho = c->rho; FA.pr = c->pr; FA.vsigmax_key = c->red + RED_VSIG;
   FA.force = c->force; FA.dudt = c->dudt; FA.dendt = c->dendt; FA.dBevoldt = c->dBevoldt; FA.daldt = c->daldt; FA.dpsidt = c->dpsidt; FA.gradpsi = c->gradpsi;
   FA.divB = c->divB; FA.curlB = c->curlB; FA.graddivv = c->graddivv; FA.del2u = c->del2u; FA.drhodt = c->drhodt; FA.dhdt = c->dhdt;
-  FA.R = R; FA.npart = np; FA.ntotal = nt;
+  FA.R = R; FA.npart = np; FA.ntotal = nt; FA.targets = nullptr; FA.ntargets = 0;
   FA.dusta = o.onef_dust ? c->dusta : nullptr; FA.dustb = c->dustb; FA.fineStart = c->cellStart; FA.cellOf = c->cellOf;
   FA.ddustevoldt = c->ddustevoldt; FA.ddeltavdt = c->ddeltavdt;
-  LAUNCH(c, k_rates_final, nblocks(nt, 256), 256, 0, FA);
+  const int nchunk = (c->rate_chunks > 1 && !c->has_comm && !pi) ? c->rate_chunks : 1;
+  if (nchunk == 1) {
+    if (int e = pair(nullptr, 0)) return e;
+    CU(cudaEventRecord(c->ev[4], c->stream));
+    if (c->has_comm) {   // vsigmax feeds dpsidt in the finalisation loop (:518-520, :902): all ranks need the global maximum
+      SMALL_D2H(c, c->h_red, c->red + RED_VSIG, sizeof(unsigned long long));
+      CU(cudaStreamSynchronize(c->stream));
+      double vs = dkey_inv(c->h_red[0]);
+      if (int e = comm_allreduce(c, &vs, 1, 0)) return e;
+      union { double d; unsigned long long u; } kv; kv.d = vs;
+      c->h_red[0] = kv.u | 0x8000000000000000ull;   // key of a non-negative double
+      CU(cudaMemcpyAsync(c->red + RED_VSIG, c->h_red, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+    }
+    LAUNCH(c, k_rates_final, nblocks(nt, 256), 256, 0, FA);
+  } else {
+    // Row chunks: chunk q gathers and finalises the targets whose ORIGINAL row lies in [q*rows, (q+1)*rows); its output rows are
+    // then complete (except dpsidt) and contiguous in the caller's arrays, so on_rates_chunk can start their download while the
+    // next chunk's pair kernel runs.  Results are those of the single launch bit for bit: every target's sums are its own.
+    if (c->rlistcap < (size_t)nt) {
+      if (c->rlist) cudaFree(c->rlist);
+      c->rlist = nullptr; c->rlistcap = 0;
+      CU(cudaMalloc(&c->rlist, sizeof(int) * ((size_t)c->cap + 1)));
+      c->rlistcap = (size_t)c->cap + 1;
+    }
+    const int rows = (np + nchunk - 1) / nchunk;
+    for (int q = 0; q < nchunk; q++) {
+      const int r0 = q * rows, r1 = std::min(np, r0 + rows);
+      if (r1 <= r0) continue;
+      LAUNCH(c, k_chunk_flags, nblocks(nt, 256), 256, 0, c->perm, nt, r0, r1, c->redo);
+      if (int e = exclusive_scan(c, c->redo, c->scanout, nt)) return e;
+      LAUNCH(c, k_compact, nblocks(nt, 256), 256, 0, c->redo, c->scanout, nt, c->rlist);
+      const int m = r1 - r0;                         // every row below nown has exactly one slot
+      if (int e = pair(c->rlist, m)) return e;
+      FA.targets = c->rlist; FA.ntargets = m;
+      LAUNCH(c, k_rates_final, nblocks(m, 256), 256, 0, FA);
+      if (c->on_rates_chunk) { if (int e = c->on_rates_chunk(q, r0, r1)) return e; }
+    }
+    CU(cudaEventRecord(c->ev[4], c->stream));
+    LAUNCH(c, k_rates_dpsidt, nblocks(np, 256), 256, 0, c->divB, c->psi, c->hh, c->itype, c->red + RED_VSIG, o.psidecayfact, o.imhd, o.idivbzero, c->dpsidt, np);
+  }
   ZeroArgs ZA;
   ZA.force = c->force; ZA.dudt = c->dudt; ZA.dendt = c->dendt; ZA.dBevoldt = c->dBevoldt; ZA.daldt = c->daldt; ZA.dpsidt = c->dpsidt; ZA.gradpsi = c->gradpsi;
   ZA.divB = c->divB; ZA.curlB = c->curlB; ZA.graddivv = c->graddivv; ZA.del2u = c->del2u; ZA.drhodt = c->drhodt; ZA.dhdt = c->dhdt; ZA.npart = np; ZA.ntotal = nt;
@@ -1669,6 +1725,8 @@ int ndspmhd_b200_destroy(nd_ctx *c) {
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->h_fmean) cudaFreeHost(c->h_fmean);
   if (c->stepbuf) cudaFree(c->stepbuf);
+  if (c->rlist) cudaFree(c->rlist);
+  for (auto x : c->chunk_events) cudaEventDestroy(x);
   for (int k = 0; k < 8; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
   for (int k = 0; k < 2; k++) if (c->ev_pair[k]) cudaEventDestroy(c->ev_pair[k]);
   for (int k = 0; k < 2; k++) if (c->ev_in[k]) cudaEventDestroy(c->ev_in[k]);
@@ -1731,6 +1789,27 @@ int upload_group(nd_ctx *c, const nd_arrays *a, size_t n, int group, cudaStream_
   return 0;
 }
 // phase 1: density outputs that get_rates does not touch; 2: primitives; 3: rates (+ drhodt, dhdt, zeroed on ghosts/fixed by get_rates)
+// rows [r0,r1) of the arrays get_rates writes (download group 3); dpsidt separately when the rates ran in row chunks
+int download_rates_rows(nd_ctx *c, nd_arrays *a, size_t r0, size_t r1, unsigned mask, cudaStream_t st, bool with_dpsidt) {
+  if (r1 <= r0) return 0;
+  const size_t D = sizeof(double), n = r1 - r0;
+  auto dn = [&](double *dst, const double *src, size_t w) -> cudaError_t {
+    return (dst && src) ? cudaMemcpyAsync(dst + r0 * w, src + r0 * w, D * w * n, cudaMemcpyDeviceToHost, st) : cudaSuccess;
+  };
+  if (mask & (ND_DL_DENSITY | ND_DL_RATES)) { CU(dn(a->drhodt, c->drhodt, 1)); CU(dn(a->dhdt, c->dhdt, 1)); }
+  if (mask & ND_DL_RATES) {
+    CU(dn(a->force, c->force, 3)); CU(dn(a->dudt, c->dudt, 1)); CU(dn(a->dendt, c->dendt, 1));
+    if (c->o.imhd != 0) {
+      CU(dn(a->dBevoldt, c->dBevoldt, 3)); if (with_dpsidt) CU(dn(a->dpsidt, c->dpsidt, 1)); CU(dn(a->gradpsi, c->gradpsi, 3)); CU(dn(a->divB, c->divB, 1));
+      CU(dn(a->curlB, c->curlB, 3));
+    }
+    CU(dn(a->daldt, c->daldt, 3));
+    if (c->o.want_aux || c->o.iavlim[0] == 3) CU(dn(a->graddivv, c->graddivv, 3));
+    if (c->o.want_aux) CU(dn(a->del2u, c->del2u, 1));
+    if (c->o.onef_dust) { CU(dn(a->ddustevoldt, c->ddustevoldt, 1)); CU(dn(a->ddeltavdt, c->ddeltavdt, 3)); }
+  }
+  return 0;
+}
 int download_group(nd_ctx *c, nd_arrays *a, size_t n, int group, unsigned mask, cudaStream_t st) {
   auto dn = [&](void *dst, const void *src, size_t bytes) -> cudaError_t { return (dst && src) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess; };
   const size_t D = sizeof(double);
@@ -1915,9 +1994,30 @@ int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int
   CU(cudaEventRecord(c->ev_out[1], c->stream));
   CU(cudaStreamWaitEvent(c->stream_d2h, c->ev_out[1], 0));
   if (int e2 = download_group(c, a, nout, 2, mask, c->stream_d2h)) return e2;
+  // The rates run in row chunks (do_get_rates) so that a chunk's rows go down the wire while the next chunk's pair kernel
+  // runs; what is left after the last kernel is one chunk, dpsidt and the (zero) ghost rows instead of the whole 168 B/row.
+  int nchunk = 1;
+  if (!c->has_comm && (mask & ND_DL_RATES)) {
+    if (const char *ev = getenv("NDSPMHD_B200_RATE_CHUNKS")) nchunk = std::max(1, std::min(64, atoi(ev)));
+    else if (c->npart >= (1 << 20)) nchunk = 4;
+  }
+  std::vector<cudaEvent_t> &cev = c->chunk_events;
+  while ((int)cev.size() < nchunk) { cudaEvent_t x; CU(cudaEventCreateWithFlags(&x, cudaEventDisableTiming)); cev.push_back(x); }
+  c->rate_chunks = nchunk;
+  int cb_err = 0;
+  c->on_rates_chunk = [&](int q, int r0, int r1) -> int {
+    if (cudaEventRecord(cev[q], c->stream) != cudaSuccess || cudaStreamWaitEvent(c->stream_d2h, cev[q], 0) != cudaSuccess) { cb_err = 1; return set_err(c, ND_ERR_CUDA, "derivs_host: chunk event"); }
+    return download_rates_rows(c, a, (size_t)r0, (size_t)r1, mask, c->stream_d2h, false);
+  };
   e = DISPATCH_NDIM(c, do_get_rates<1>(c, nullptr, nullptr, nullptr, 0), do_get_rates<2>(c, nullptr, nullptr, nullptr, 0), do_get_rates<3>(c, nullptr, nullptr, nullptr, 0));
-  if (e) { cudaStreamSynchronize(c->stream_h2d); cudaStreamSynchronize(c->stream_d2h); return e; }
-  if (int e2 = download_group(c, a, nout, 3, mask, c->stream)) return e2;   // stream order: after the final kernel
+  c->rate_chunks = 1; c->on_rates_chunk = nullptr;
+  if (e || cb_err) { cudaStreamSynchronize(c->stream_h2d); cudaStreamSynchronize(c->stream_d2h); return e ? e : ND_ERR_CUDA; }
+  if (nchunk == 1) {
+    if (int e2 = download_group(c, a, nout, 3, mask, c->stream)) return e2;   // stream order: after the final kernel
+  } else {                                                                    // stream order: after k_rates_dpsidt / k_rates_zero_ghosts
+    if ((mask & ND_DL_RATES) && c->o.imhd != 0 && a->dpsidt) CU(cudaMemcpyAsync(a->dpsidt, c->dpsidt, sizeof(double) * nout, cudaMemcpyDeviceToHost, c->stream));
+    if (int e2 = download_rates_rows(c, a, (size_t)c->npart, nout, mask, c->stream, false)) return e2;
+  }
   if ((mask & ND_DL_GHOSTS) && !c->has_comm && c->ntotal > c->npart) {
     const size_t g0 = (size_t)c->npart, ng = (size_t)c->ntotal - g0, D = sizeof(double);
     if (a->x_out) CU(cudaMemcpyAsync(a->x_out + g0 * c->ndim, c->x + g0 * c->ndim, D * c->ndim * ng, cudaMemcpyDeviceToHost, c->stream_d2h));
@@ -2033,6 +2133,8 @@ int ndspmhd_b200_step(nd_ctx *c, const nd_step_opts *so, double *dt_inout, nd_sc
   const int planes = o.onef_dust ? STEP_NIN_DUST : STEP_NIN;
   if (c->stepbufrows < (size_t)np) {
     if (c->stepbuf) cudaFree(c->stepbuf);
+  if (c->rlist) cudaFree(c->rlist);
+  for (auto x : c->chunk_events) cudaEventDestroy(x);
     c->stepbuf = nullptr; c->stepbufrows = 0;
     CU(cudaMalloc(&c->stepbuf, sizeof(double) * (size_t)STEP_NIN_DUST * (size_t)np));
     c->stepbufrows = (size_t)np;

@@ -272,7 +272,7 @@ enum { LIST_DENS_FIRST = 0, LIST_DENS_PARTIAL = 1, LIST_RATES = 2 };
 
 struct ListArgs {
   const double *hh;        // original-order current smoothing lengths (density modes)
-  const int *targets;      // LIST_DENS_PARTIAL: sorted slots to process; else NULL (slot = s0 + t)
+  const int *targets;      // LIST_DENS_PARTIAL, optionally LIST_RATES: sorted slots to process; else NULL (slot = s0 + t)
   int s0, ntargets;
   int *numneigh;           // density modes: neighbour count as the reference defines it, by original row
   int drag;                // LIST_RATES: gas-dust pairs are kept (drag_forces)
@@ -284,7 +284,7 @@ template <int NDIM, int MODE, bool TYPES>
 __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, NbrLists L) {
   const int t = blockIdx.x * 128 + threadIdx.x;
   if (t >= A.ntargets) return;
-  const int s = (MODE == LIST_DENS_PARTIAL) ? A.targets[t] : A.s0 + t;
+  const int s = (MODE == LIST_DENS_PARTIAL || (MODE == LIST_RATES && A.targets)) ? A.targets[t] : A.s0 + t;
   const int orig = G.perm[s];
   const int ti = G.typ[s];
   bool active = orig < G.nown;                     // ghosts and halo rows are sources only

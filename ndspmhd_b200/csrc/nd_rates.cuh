@@ -94,7 +94,7 @@ __device__ __forceinline__ double get_tstop(int idrag_nature, double rhogas, dou
 // ONEF = one-fluid dust (idust=1): dust_derivs (:2726-2807) and artificial_dissipation_dust (:1969-2148) on the generic path.
 template <int NDIM, bool MHD, bool DRAG, bool FAST, bool ONEF>
 __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(Grid G, RatesIn I, RatesOpts O, RatesSums S, RatesRed R, NbrLists L,
-                                                                                 int s0, int ntargets) {
+                                                                                 int s0, int ntargets, const int *targets) {
   // dynamic shared memory: [0,16) mbarrier, then the {grad W, slope} rows of the kernel table (64 KB; every pair does two
   // random lookups, which as global loads cost ~30 L1 wavefronts each and were the largest long-scoreboard stall), then the
   // cp.async staging slots.  The table arrives by one TMA bulk copy per block; blocks are persistent (grid = resident blocks)
@@ -141,10 +141,11 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
 #endif
     if (unit >= nunits) break;
   const int tix = unit * 32 + lane;   // target index within this launch
-  const int s = s0 + tix;
+  int s = s0 + tix;                                  // target slot: a contiguous range, or the entries of a target list
   int orig = -1, ti = 0, cnt = 0;
   bool active = false;
   if (tix < ntargets) {
+    if (targets) s = targets[tix];
     orig = G.perm[s];
     active = orig < G.nown;       // rates are gathered for the caller's own rows (fixed particles included: they feed the dt minima)
   }

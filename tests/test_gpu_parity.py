@@ -214,6 +214,30 @@ def test_pipelined_derivs_host_equals_upload_derivs_download(aux):
         assert sa[k] == sb[k]
 
 
+@pytest.mark.parametrize("name,chunks", [("ot3d_glass", 3), ("briowu1d", 4), ("dustybox3d", 2), ("onefluid_dust3d_mhd", 5), ("ot2d_closepacked", 7)])
+def test_row_chunked_rates_equal_the_single_launch(name, chunks, monkeypatch):
+    """ndspmhd_b200_derivs_host runs the rates in chunks of original rows so that a chunk's results download while the next
+    chunk's pair kernel runs (4 chunks above 1 Mi particles; forced here).  Every target's sums are its own and dpsidt is made
+    from the global vsigmax after the last chunk, so the outputs must equal the single launch bit for bit."""
+    o, p = CASES[name][0]()
+    o.device_ghosts = 1
+    o.want_aux = 1
+    a, b = p.copy(), p.copy()
+    hot = lib.Hotpath(o, p.ndim)
+    try:
+        monkeypatch.setenv("NDSPMHD_B200_RATE_CHUNKS", "1")
+        sa = lib.derivs_host(o, a, hot=hot, pipelined=True)
+        monkeypatch.setenv("NDSPMHD_B200_RATE_CHUNKS", str(chunks))
+        sb = lib.derivs_host(o, b, hot=hot, pipelined=True)
+    finally:
+        hot.close()
+    fields = parity.DENSITY_FIELDS + parity.PRIM_FIELDS + parity.RATES_FIELDS + (parity.DUST_RATES_FIELDS if o.idust == 1 else [])
+    for f in fields:
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    for k in ("dtcourant", "dtforce", "dtav", "vsigmax", "fhmax", "itsdensity", "ntotal", "nclumped"):
+        assert sa[k] == sb[k], k
+    assert np.allclose(sa["fmean"], sb["fmean"], rtol=0, atol=1e-13 * (1 + np.max(np.abs(a.force))))   # atomics: order differs
+
 def test_host_ghost_mode_matches_device_ghost_mode():
     """device_ghosts=0: the caller (Fortran set_ghost_particles) supplies rows npart+1..ntotal and bound:hhmax."""
     o, p = setups.orszag_tang(ndim=3, nx=16, zfrac=0.5, perturb_amp=0.0, evolved=True)
