@@ -287,6 +287,23 @@ typedef struct nd_state_out {
 } nd_state_out;
 int ndspmhd_b200_download_state(nd_ctx *c, const nd_state_out *st, int idim);
 
+/*
+ * Per-step diagnostics on the resident state: the sums of `evwrite`, src/evwrite_mhd.f90:27-320, called
+ * every step by the reference (src/evolve.f90:62,165) -- as device reductions (fixed-order, run-to-run deterministic) so
+ * that a simulation stepping on the device does not have to download the particles to write its .ev line.
+ * Not produced: fdotBav/fdotBmax/force_err_av/force_err_max (they need fmagarray:fmag, which the hot path does not keep)
+ * and epot (external forces / self-gravity are outside the supported tuple: 0).
+ */
+typedef struct nd_evwrite {
+  double ekin, etherm, emag, epot, etot, momtot, angtot, rhomax, rhomean, rhomin;   /* :296-301 columns 2-10 */
+  double emagp, crosshel, betamhdmin, betamhdav, divBav, divBmax, divBtot;           /* MHD columns */
+  double omegamhdav, omegamhdmax, fracdivBok, fluxtotmag;
+  double ekiny, dmomtot, totmassgas, totmassdust;                                    /* hydro / one-fluid dust columns */
+  double mom[3], dmom[3], ang[3], fluxtot[3];
+  double reserved[8];
+} nd_evwrite;
+int ndspmhd_b200_evwrite(nd_ctx *c, nd_evwrite *ev);
+
 /* page-locked host memory for the caller's particle arrays (makes upload/download run at PCIe speed) */
 void *ndspmhd_b200_host_alloc(size_t bytes);
 void ndspmhd_b200_host_free(void *p);

@@ -88,6 +88,24 @@ class NdStateOut(C.Structure):
     _fields_ = [(n, _DP) for n in ("x", "vel", "hh", "en", "Bevol", "alpha", "psi", "rho", "dustevol", "deltav")]
 
 
+class NdEvwrite(C.Structure):
+    """The columns of the reference's .ev line (src/evwrite_mhd.f90:296-320) plus the vector sums behind them."""
+    _fields_ = ([(n, C.c_double) for n in ("ekin", "etherm", "emag", "epot", "etot", "momtot", "angtot", "rhomax", "rhomean", "rhomin",
+                                            "emagp", "crosshel", "betamhdmin", "betamhdav", "divBav", "divBmax", "divBtot",
+                                            "omegamhdav", "omegamhdmax", "fracdivBok", "fluxtotmag",
+                                            "ekiny", "dmomtot", "totmassgas", "totmassdust")]
+                + [(n, C.c_double * 3) for n in ("mom", "dmom", "ang", "fluxtot")] + [("reserved", C.c_double * 8)])
+
+    def as_dict(self):
+        out = {}
+        for name, typ in self._fields_:
+            if name == "reserved":
+                continue
+            v = getattr(self, name)
+            out[name] = list(v) if hasattr(v, "__len__") else v
+        return out
+
+
 class NdScalars(C.Structure):
     _fields_ = [
         ("dtcourant", C.c_double), ("dtforce", C.c_double), ("dtav", C.c_double), ("dtdrag", C.c_double), ("dtvisc", C.c_double),

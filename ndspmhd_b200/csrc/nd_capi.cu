@@ -83,6 +83,7 @@ struct nd_ctx {
   int rate_chunks = 1; int *rlist = nullptr; size_t rlistcap = 0;
   std::function<int(int, int, int)> on_rates_chunk;
   std::vector<cudaEvent_t> chunk_events;   // (chunk, row0, row1) after the chunk's finalisation is enqueued
+  double *evpartial = nullptr, *h_ev = nullptr;        // evwrite reductions
   double *stepbuf = nullptr; size_t stepbufrows = 0;   // leapfrog `*in` copies (ndspmhd_b200_step), rows [0,npart)
   cudaEvent_t ev_pair[2] = {nullptr, nullptr};   // around the rates pair kernel alone (the roofline's kernel time)
   double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -771,6 +772,89 @@ __global__ void k_rates_zero_ghosts(ZeroArgs A) {                               
     if (A.dBevoldt) A.dBevoldt[(size_t)i * 3 + k] = 0.;
   }
   A.dudt[i] = 0.; A.dendt[i] = 0.; A.dpsidt[i] = 0.; A.divB[i] = 0.; A.del2u[i] = 0.; A.drhodt[i] = 0.; A.dhdt[i] = 0.;
+}
+
+// =====================================================================================================
+// per-step diagnostics: the particle loop of `evwrite`, src/evwrite_mhd.f90:124-266, as a two-stage
+// fixed-order reduction (EV_BLOCKS partial rows, then one block): deterministic run to run.
+// =====================================================================================================
+enum { EV_EKIN = 0, EV_ETHERM, EV_EMAG, EV_EMAGP, EV_MOM0, EV_MOM1, EV_MOM2, EV_DMOM0, EV_DMOM1, EV_DMOM2, EV_ANG0, EV_ANG1, EV_ANG2, EV_EKINY,
+       EV_MGAS, EV_MDUST, EV_BETAAV, EV_DIVBAV, EV_DIVBTOT, EV_OMEGAAV, EV_FRACOK, EV_FLUX0, EV_FLUX1, EV_FLUX2, EV_CROSSHEL, EV_RHOSUM, EV_NSUM,
+       EV_BETAMIN = EV_NSUM, EV_RHOMIN, EV_NMIN_END, EV_DIVBMAX = EV_NMIN_END, EV_OMEGAMAX, EV_RHOMAX, EV_NQ };
+constexpr int EV_BLOCKS = 592, EV_THREADS = 256;
+struct EvArgs {
+  const double *x, *vel, *pmass, *rho, *uu, *Bfield, *pr, *divB, *hh, *force, *dustfrac, *deltav;
+  int npart, ndim, imhd, onef;
+  double *partial;   // [EV_BLOCKS][EV_NQ]
+};
+__device__ __forceinline__ double ev_combine(int q, double a, double b) { return q < EV_NSUM ? a + b : (q < EV_NMIN_END ? fmin(a, b) : fmax(a, b)); }
+__device__ __forceinline__ double ev_identity(int q) { return q < EV_NSUM ? 0. : (q < EV_NMIN_END ? 1.7976931348623157e308 : 0.); }
+
+__global__ void __launch_bounds__(EV_THREADS) k_evwrite_partial(EvArgs A) {
+  double acc[EV_NQ];
+#pragma unroll
+  for (int q = 0; q < EV_NQ; q++) acc[q] = ev_identity(q);
+  for (int i = blockIdx.x * EV_THREADS + threadIdx.x; i < A.npart; i += EV_BLOCKS * EV_THREADS) {
+    const double m = A.pmass[i], rhoi = A.rho[i];
+    const double v0 = A.vel[(size_t)i * 3], v1 = A.vel[(size_t)i * 3 + 1], v2 = A.vel[(size_t)i * 3 + 2];
+    double xi[3] = {0., 0., 0.};
+    for (int d = 0; d < A.ndim; d++) xi[d] = A.x[(size_t)i * A.ndim + d];
+    acc[EV_MOM0] += m * v0; acc[EV_MOM1] += m * v1; acc[EV_MOM2] += m * v2;                                   // :129
+    acc[EV_DMOM0] += m * A.force[(size_t)i * 3]; acc[EV_DMOM1] += m * A.force[(size_t)i * 3 + 1]; acc[EV_DMOM2] += m * A.force[(size_t)i * 3 + 2];
+    if (A.ndim == 3) {                                                                                        // :131-136
+      acc[EV_ANG0] += m * (xi[1] * v2 - xi[2] * v1); acc[EV_ANG1] += m * (xi[2] * v0 - xi[0] * v2); acc[EV_ANG2] += m * (xi[0] * v1 - xi[1] * v0);
+    } else if (A.ndim == 2) acc[EV_ANG2] += m * (xi[0] * v1 - xi[1] * v0);
+    acc[EV_EKIN] += 0.5 * m * ((v0 * v0 + v1 * v1) + v2 * v2);                                                // :137
+    if (A.onef) {                                                                                             // :139-147
+      const double df = A.dustfrac[i], dterm = 1. - df;
+      const double d0 = A.deltav[(size_t)i * 3], d1 = A.deltav[(size_t)i * 3 + 1], d2 = A.deltav[(size_t)i * 3 + 2];
+      const double ekdv = 0.5 * m * df * dterm * ((d0 * d0 + d1 * d1) + d2 * d2);
+      acc[EV_EKIN] += ekdv; acc[EV_EKINY] += ekdv;
+      acc[EV_ETHERM] += m * A.uu[i] * dterm;
+      acc[EV_MGAS] += m * dterm; acc[EV_MDUST] += m * df;
+    } else {
+      if (A.ndim >= 2) acc[EV_EKINY] += 0.5 * m * v0 * v0;                                                    // :149 (sic: vel(1,i))
+      acc[EV_ETHERM] += m * A.uu[i];
+    }
+    acc[EV_RHOSUM] += rhoi; acc[EV_RHOMIN] = fmin(acc[EV_RHOMIN], rhoi); acc[EV_RHOMAX] = fmax(acc[EV_RHOMAX], rhoi);   // minmaxave, :269
+    if (A.imhd != 0) {                                                                                        // :172-263
+      const double b0 = A.Bfield[(size_t)i * 3], b1 = A.Bfield[(size_t)i * 3 + 1], b2 = A.Bfield[(size_t)i * 3 + 2];
+      const double B2 = (b0 * b0 + b1 * b1) + b2 * b2, Bmag = sqrt(B2), divBi = fabs(A.divB[i]);
+      acc[EV_EMAG] += 0.5 * m * B2 / rhoi;
+      acc[EV_EMAGP] += 0.5 * m * (b0 * b0 + b1 * b1) / rhoi;
+      const double beta = (B2 < 2.2250738585072014e-308) ? 0. : A.pr[i] / (0.5 * B2);
+      acc[EV_BETAAV] += beta; acc[EV_BETAMIN] = fmin(acc[EV_BETAMIN], beta);
+      acc[EV_DIVBMAX] = fmax(acc[EV_DIVBMAX], divBi); acc[EV_DIVBAV] += divBi; acc[EV_DIVBTOT] += m * divBi / rhoi;
+      const double omega = (Bmag < 1e-8) ? 0. : divBi * A.hh[i] / Bmag;                                       // :240-247
+      if (omega < 1.e-2) acc[EV_FRACOK] += 1.;
+      acc[EV_OMEGAMAX] = fmax(acc[EV_OMEGAMAX], omega); acc[EV_OMEGAAV] += omega;
+      const double br0 = b0 / rhoi, br1 = b1 / rhoi, br2 = b2 / rhoi;
+      acc[EV_FLUX0] += m * br0; acc[EV_FLUX1] += m * br1; acc[EV_FLUX2] += m * br2;                           // :255
+      acc[EV_CROSSHEL] += m * ((v0 * br0 + v1 * br1) + v2 * br2);                                             // :259
+    }
+  }
+  __shared__ double sh[EV_THREADS / 32][EV_NQ];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < EV_NQ; q++) {
+    double v = acc[q];
+    for (int o = 16; o; o >>= 1) v = ev_combine(q, v, __shfl_xor_sync(FULL, v, o));
+    if (lane == 0) sh[w][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < EV_NQ) {
+    double v = sh[0][threadIdx.x];
+    for (int k = 1; k < EV_THREADS / 32; k++) v = ev_combine(threadIdx.x, v, sh[k][threadIdx.x]);
+    A.partial[(size_t)blockIdx.x * EV_NQ + threadIdx.x] = v;
+  }
+}
+__global__ void k_evwrite_final(const double *partial, double *out_pinned) {
+  const int q = threadIdx.x;
+  if (q >= EV_NQ) return;
+  double v = partial[q];
+  for (int b = 1; b < EV_BLOCKS; b++) v = ev_combine(q, v, partial[(size_t)b * EV_NQ + q]);
+  out_pinned[q] = v;
+  __threadfence_system();
 }
 
 // =====================================================================================================
@@ -1725,6 +1809,8 @@ int ndspmhd_b200_destroy(nd_ctx *c) {
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->h_fmean) cudaFreeHost(c->h_fmean);
   if (c->stepbuf) cudaFree(c->stepbuf);
+  if (c->evpartial) cudaFree(c->evpartial);
+  if (c->h_ev) cudaFreeHost(c->h_ev);
   if (c->rlist) cudaFree(c->rlist);
   for (auto x : c->chunk_events) cudaEventDestroy(x);
   for (int k = 0; k < 8; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
@@ -2133,6 +2219,8 @@ int ndspmhd_b200_step(nd_ctx *c, const nd_step_opts *so, double *dt_inout, nd_sc
   const int planes = o.onef_dust ? STEP_NIN_DUST : STEP_NIN;
   if (c->stepbufrows < (size_t)np) {
     if (c->stepbuf) cudaFree(c->stepbuf);
+  if (c->evpartial) cudaFree(c->evpartial);
+  if (c->h_ev) cudaFreeHost(c->h_ev);
   if (c->rlist) cudaFree(c->rlist);
   for (auto x : c->chunk_events) cudaEventDestroy(x);
     c->stepbuf = nullptr; c->stepbufrows = 0;
@@ -2185,6 +2273,42 @@ int ndspmhd_b200_download_state(nd_ctx *c, const nd_state_out *st, int idim) {
   CU(dn(st->Bevol, c->Bevol, D * 3 * n)); CU(dn(st->alpha, c->alpha, D * 3 * n)); CU(dn(st->psi, c->psi, D * n)); CU(dn(st->rho, c->rho, D * n));
   if (c->o.onef_dust) { CU(dn(st->dustevol, c->dustevol, D * n)); CU(dn(st->deltav, c->deltav, D * 3 * n)); }
   CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int ndspmhd_b200_evwrite(nd_ctx *c, nd_evwrite *ev) {
+  if (!c || !ev) return ND_ERR_INVALID_ARG;
+  if (!c->uploaded || !c->rates_done) return set_err(c, ND_ERR_STATE, "evwrite needs the primitives and rates of a derivs / step");
+  CU(cudaSetDevice(c->device));
+  if (!c->evpartial) {
+    CU(cudaMalloc(&c->evpartial, sizeof(double) * EV_BLOCKS * EV_NQ));
+    CU(cudaMallocHost(&c->h_ev, sizeof(double) * 64));
+  }
+  EvArgs A;
+  A.x = c->x; A.vel = c->vel; A.pmass = c->pmass; A.rho = c->rho; A.uu = c->uu; A.Bfield = c->Bfield; A.pr = c->pr; A.divB = c->divB; A.hh = c->hh;
+  A.force = c->force; A.dustfrac = c->dustfrac; A.deltav = c->deltav; A.npart = c->npart; A.ndim = c->ndim; A.imhd = c->o.imhd; A.onef = c->o.onef_dust;
+  A.partial = c->evpartial;
+  LAUNCH(c, k_evwrite_partial, EV_BLOCKS, EV_THREADS, 0, A);
+  LAUNCH(c, k_evwrite_final, 1, 64, 0, c->evpartial, c->h_ev);
+  CU(cudaStreamSynchronize(c->stream));
+  const double *h = c->h_ev;
+  const double np = (double)c->npart;
+  memset(ev, 0, sizeof(*ev));
+  ev->ekin = h[EV_EKIN]; ev->etherm = h[EV_ETHERM]; ev->emag = h[EV_EMAG]; ev->emagp = h[EV_EMAGP]; ev->epot = 0.;
+  for (int k = 0; k < 3; k++) { ev->mom[k] = h[EV_MOM0 + k]; ev->dmom[k] = h[EV_DMOM0 + k]; ev->ang[k] = h[EV_ANG0 + k]; ev->fluxtot[k] = h[EV_FLUX0 + k]; }
+  ev->etot = ev->ekin + ev->emag + ev->epot;                                                        // :263
+  if (c->o.iprterm >= 0 || c->o.iprterm < -1) ev->etot = ev->etot + ev->etherm;
+  ev->momtot = std::sqrt((ev->mom[0] * ev->mom[0] + ev->mom[1] * ev->mom[1]) + ev->mom[2] * ev->mom[2]);
+  ev->dmomtot = std::sqrt((ev->dmom[0] * ev->dmom[0] + ev->dmom[1] * ev->dmom[1]) + ev->dmom[2] * ev->dmom[2]);
+  ev->angtot = std::sqrt((ev->ang[0] * ev->ang[0] + ev->ang[1] * ev->ang[1]) + ev->ang[2] * ev->ang[2]);
+  ev->rhomin = h[EV_RHOMIN]; ev->rhomax = h[EV_RHOMAX]; ev->rhomean = h[EV_RHOSUM] / np;           // minmaxave
+  ev->ekiny = h[EV_EKINY]; ev->totmassgas = h[EV_MGAS]; ev->totmassdust = h[EV_MDUST];
+  if (c->o.imhd != 0) {                                                                             // :277-284
+    ev->fluxtotmag = std::sqrt((ev->fluxtot[0] * ev->fluxtot[0] + ev->fluxtot[1] * ev->fluxtot[1]) + ev->fluxtot[2] * ev->fluxtot[2]);
+    ev->betamhdav = h[EV_BETAAV] / np; ev->betamhdmin = h[EV_BETAMIN];
+    ev->fracdivBok = 100. * h[EV_FRACOK] / np; ev->omegamhdav = h[EV_OMEGAAV] / np; ev->omegamhdmax = h[EV_OMEGAMAX];
+    ev->divBav = h[EV_DIVBAV] / np; ev->divBmax = h[EV_DIVBMAX]; ev->divBtot = h[EV_DIVBTOT]; ev->crosshel = h[EV_CROSSHEL];
+  }
   return 0;
 }
 

@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 from . import abi
-from .abi import NdArrays, NdOptions, NdScalars, NdStateOut, NdStepOpts, Particles
+from .abi import NdArrays, NdEvwrite, NdOptions, NdScalars, NdStateOut, NdStepOpts, Particles
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # NDSPMHD_B200_LIB: development override used by tools/ to time differently tuned builds of the same sources
@@ -33,7 +33,7 @@ EXPORTS = [
     "ndspmhd_b200_cons2prim", "ndspmhd_b200_get_rates", "ndspmhd_b200_derivs", "ndspmhd_b200_download",
     "ndspmhd_b200_host_alloc", "ndspmhd_b200_host_free", "ndspmhd_b200_last_timings", "ndspmhd_b200_launch_count",
     "ndspmhd_b200_stream", "ndspmhd_b200_rates_pairs", "ndspmhd_b200_rewind", "ndspmhd_b200_set_comm", "ndspmhd_b200_row_counts", "ndspmhd_b200_selftest_math", "ndspmhd_b200_derivs_host",
-    "ndspmhd_b200_step", "ndspmhd_b200_download_state",
+    "ndspmhd_b200_step", "ndspmhd_b200_download_state", "ndspmhd_b200_evwrite",
 ]
 
 
@@ -83,6 +83,7 @@ def load():
     L.ndspmhd_b200_rates_pairs.argtypes = [vp, _IP, _IP, C.c_longlong, C.POINTER(C.c_longlong)]
     L.ndspmhd_b200_step.argtypes = [vp, C.POINTER(NdStepOpts), _DP, C.POINTER(NdScalars)]
     L.ndspmhd_b200_download_state.argtypes = [vp, C.POINTER(NdStateOut), C.c_int]
+    L.ndspmhd_b200_evwrite.argtypes = [vp, C.POINTER(NdEvwrite)]
     _LIB = L
     return L
 
@@ -227,6 +228,12 @@ class Hotpath:
         for n in ("x", "vel", "hh", "en", "Bevol", "alpha", "psi", "rho", "dustevol", "deltav"):
             setattr(st, n, p.ptr(n))
         self._chk(self.L.ndspmhd_b200_download_state(self.ctx, C.byref(st), p.idim))
+
+    def evwrite(self) -> dict:
+        """The sums of `evwrite` (src/evwrite_mhd.f90:27) over the resident state, as device reductions."""
+        ev = NdEvwrite()
+        self._chk(self.L.ndspmhd_b200_evwrite(self.ctx, C.byref(ev)))
+        return ev.as_dict()
 
     def selftest_math(self, x: np.ndarray):
         """sqrt_nr / rsqrt_nr of the pair kernels evaluated on the device for the given arguments."""

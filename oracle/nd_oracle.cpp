@@ -1824,4 +1824,63 @@ int ndo_step(const nd_options *o, int ndim, ndo_arrays *a, int npart, int *ntota
   return 0;
 }
 
+/* the particle loop and totals of `evwrite` (src/evwrite_mhd.f90:124-284), serial, in the reference's order; fmag-based columns and
+ * epot are not produced (see include/ndspmhd_b200.h) */
+int ndo_evwrite(const nd_options *o, int ndim, const ndo_arrays *a, int npart, nd_evwrite *ev) {
+  memset(ev, 0, sizeof(*ev));
+  double ekin = 0., etherm = 0., emag = 0., emagp = 0., ekiny = 0., mgas = 0., mdust = 0.;
+  double mom[3] = {0, 0, 0}, dmom[3] = {0, 0, 0}, ang[3] = {0, 0, 0}, flux[3] = {0, 0, 0};
+  double betaav = 0., betamin = 1.7976931348623157e308, divBmax = 0., divBav = 0., divBtot = 0., omegaav = 0., omegamax = 0., fracok = 0., crosshel = 0.;
+  double rhomin = 1.7976931348623157e308, rhomax = 0., rhosum = 0.;
+  for (int i = 0; i < npart; i++) {
+    const double m = a->pmass[i], rhoi = a->rho[i];
+    const double *v = a->vel + (size_t)i * 3, *f = a->force + (size_t)i * 3;
+    double x[3] = {0, 0, 0};
+    for (int d = 0; d < ndim; d++) x[d] = a->x[(size_t)i * ndim + d];
+    for (int d = 0; d < 3; d++) { mom[d] += m * v[d]; dmom[d] += m * f[d]; }
+    if (ndim == 3) { ang[0] += m * (x[1] * v[2] - x[2] * v[1]); ang[1] += m * (x[2] * v[0] - x[0] * v[2]); ang[2] += m * (x[0] * v[1] - x[1] * v[0]); }
+    else if (ndim == 2) ang[2] += m * (x[0] * v[1] - x[1] * v[0]);
+    ekin += 0.5 * m * ((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+    if (o->onef_dust) {
+      const double df = a->dustfrac[i], dterm = 1. - df;
+      const double *dv = a->deltav + (size_t)i * 3;
+      const double ekdv = 0.5 * m * df * dterm * ((dv[0] * dv[0] + dv[1] * dv[1]) + dv[2] * dv[2]);
+      ekin += ekdv; ekiny += ekdv; etherm += m * a->uu[i] * dterm; mgas += m * dterm; mdust += m * df;
+    } else {
+      if (ndim >= 2) ekiny += 0.5 * m * v[0] * v[0];
+      etherm += m * a->uu[i];
+    }
+    rhosum += rhoi; rhomin = std::min(rhomin, rhoi); rhomax = std::max(rhomax, rhoi);
+    if (o->imhd != 0) {
+      const double *B = a->Bfield + (size_t)i * 3;
+      const double B2 = (B[0] * B[0] + B[1] * B[1]) + B[2] * B[2], Bmag = sqrt(B2), divBi = fabs(a->divB[i]);
+      emag += 0.5 * m * B2 / rhoi; emagp += 0.5 * m * (B[0] * B[0] + B[1] * B[1]) / rhoi;
+      const double beta = (B2 < 2.2250738585072014e-308) ? 0. : a->pr[i] / (0.5 * B2);
+      betaav += beta; if (beta < betamin) betamin = beta;
+      if (divBi > divBmax) divBmax = divBi;
+      divBav += divBi; divBtot += m * divBi / rhoi;
+      const double omega = (Bmag < 1e-8) ? 0. : divBi * a->hh[i] / Bmag;
+      if (omega < 1.e-2) fracok += 1.;
+      if (omega > omegamax) omegamax = omega;
+      omegaav += omega;
+      for (int d = 0; d < 3; d++) flux[d] += m * (B[d] / rhoi);
+      crosshel += m * ((v[0] * (B[0] / rhoi) + v[1] * (B[1] / rhoi)) + v[2] * (B[2] / rhoi));
+    }
+  }
+  ev->ekin = ekin; ev->etherm = etherm; ev->emag = emag; ev->emagp = emagp; ev->epot = 0.; ev->ekiny = ekiny; ev->totmassgas = mgas; ev->totmassdust = mdust;
+  for (int d = 0; d < 3; d++) { ev->mom[d] = mom[d]; ev->dmom[d] = dmom[d]; ev->ang[d] = ang[d]; ev->fluxtot[d] = flux[d]; }
+  ev->etot = ekin + emag + 0.;
+  if (o->iprterm >= 0 || o->iprterm < -1) ev->etot += etherm;
+  ev->momtot = sqrt((mom[0] * mom[0] + mom[1] * mom[1]) + mom[2] * mom[2]);
+  ev->dmomtot = sqrt((dmom[0] * dmom[0] + dmom[1] * dmom[1]) + dmom[2] * dmom[2]);
+  ev->angtot = sqrt((ang[0] * ang[0] + ang[1] * ang[1]) + ang[2] * ang[2]);
+  ev->rhomin = rhomin; ev->rhomax = rhomax; ev->rhomean = rhosum / npart;
+  if (o->imhd != 0) {
+    ev->fluxtotmag = sqrt((flux[0] * flux[0] + flux[1] * flux[1]) + flux[2] * flux[2]);
+    ev->betamhdav = betaav / npart; ev->betamhdmin = betamin; ev->fracdivBok = 100. * fracok / npart; ev->omegamhdav = omegaav / npart;
+    ev->omegamhdmax = omegamax; ev->divBav = divBav / npart; ev->divBmax = divBmax; ev->divBtot = divBtot; ev->crosshel = crosshel;
+  }
+  return 0;
+}
+
 }  // extern "C"

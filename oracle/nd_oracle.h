@@ -45,6 +45,9 @@ int ndo_derivs(const nd_options *o, int ndim, ndo_arrays *a, int npart, int *nto
 int ndo_step(const nd_options *o, int ndim, ndo_arrays *a, int npart, int *ntotal, int idim, double *dt_inout, double C_cour, double C_force,
              int dtfixed, nd_scalars *s);
 
+/* the sums of `evwrite` (src/evwrite_mhd.f90:124-284) over the host arrays, serial in the reference's order */
+int ndo_evwrite(const nd_options *o, int ndim, const ndo_arrays *a, int npart, nd_evwrite *ev);
+
 /* kernel tables as built by setkernels/setkerndrag (src/kernelND.f90:127-4289) */
 int ndo_kernel_tables(int ikernel, int ikerneldrag, int ndim, double *wij, double *grwij, double *grgrwij,
                       double *wijdrag, double *radkern2, double *dq2table);

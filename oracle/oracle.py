@@ -11,7 +11,7 @@ import subprocess
 
 import numpy as np
 
-from ndspmhd_b200.abi import NdOptions, NdScalars, Particles
+from ndspmhd_b200.abi import NdEvwrite, NdOptions, NdScalars, Particles
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -52,6 +52,8 @@ def lib():
         _LIB.ndo_step.restype = C.c_int
         _LIB.ndo_step.argtypes = [C.POINTER(NdOptions), C.c_int, C.POINTER(NdoArrays), C.c_int, _IP, C.c_int, _DP, C.c_double, C.c_double, C.c_int,
                                   C.POINTER(NdScalars)]
+        _LIB.ndo_evwrite.restype = C.c_int
+        _LIB.ndo_evwrite.argtypes = [C.POINTER(NdOptions), C.c_int, C.POINTER(NdoArrays), C.c_int, C.POINTER(NdEvwrite)]
         _LIB.ndo_kernel_tables.restype = C.c_int
         _LIB.ndo_kernel_tables.argtypes = [C.c_int, C.c_int, C.c_int, _DP, _DP, _DP, _DP, _DP, _DP]
         _LIB.ndo_interpolate.restype = C.c_int
@@ -107,6 +109,17 @@ def step(opts: NdOptions, p: Particles, dt: float, C_cour: float = 0.3, C_force:
     if e != 0:
         raise OracleError(e, L.ndo_last_error().decode())
     return d.value, s.as_dict()
+
+
+def evwrite(opts: NdOptions, p: Particles) -> dict:
+    """The sums of `evwrite` (src/evwrite_mhd.f90:124-284) over the host arrays of `p` (after a derivs or a step)."""
+    L = lib()
+    a = _arrays(p)
+    ev = NdEvwrite()
+    e = L.ndo_evwrite(C.byref(opts), p.ndim, C.byref(a), p.npart, C.byref(ev))
+    if e != 0:
+        raise OracleError(e, "evwrite")
+    return ev.as_dict()
 
 
 def kernel_tables(ikernel: int, ikerneldrag: int, ndim: int):

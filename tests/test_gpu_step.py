@@ -111,3 +111,50 @@ def test_step_zero_dt_is_identity():
         assert np.array_equal(getattr(before, f)[:n], getattr(after, f)[:n]), f
     # h is re-converged by the inner derivs from the same positions: same answer to the iteration tolerance's last bits
     assert np.max(np.abs(before.hh[:n] - after.hh[:n]) / before.hh[:n]) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["ot3d_glass", "ot2d_closepacked", "hydro3d", "briowu1d_fixed_ends", "onefluid_dust3d"])
+def test_evwrite_matches_oracle(name):
+    """ndspmhd_b200_evwrite: the sums of `evwrite` (src/evwrite_mhd.f90:124-284) as fixed-order device reductions, against the
+    oracle's serial loop on the same (bit-identical) inputs: 1e-12 of each sum's scale (sum of |terms|), extrema exact."""
+    o, p = CASES[name]()
+    o.device_ghosts = 1
+    o.want_aux = 0
+    po, pg = p.copy(), p.copy()
+    oracle.derivs(o, po)
+    evo = oracle.evwrite(o, po)
+    hot = lib.Hotpath(o, p.ndim, 0)
+    try:
+        hot.upload(pg)
+        hot.derivs()
+        ev1 = hot.evwrite()
+        ev2 = hot.evwrite()
+        pg.ntotal = po.ntotal
+        hot.download(pg, abi.DL_DENSITY | abi.DL_PRIM | abi.DL_RATES)
+    finally:
+        hot.close()
+    assert ev1 == ev2                                     # deterministic reduction order
+    # the oracle's sums over the GPU's own outputs isolate the reduction from the 1e-14 differences of the inputs
+    for f in ("pmass", "vel", "x", "dustfrac", "deltav"):
+        pg.arrays[f][...] = po.arrays[f]
+    evg_in = oracle.evwrite(o, pg)
+    n = p.npart
+    mtot = float(np.sum(p.pmass[:n]))
+    vmax = float(np.max(np.abs(po.vel[:n]))) + 1e-300
+    brho = mtot * float(np.max(np.abs(po.Bfield[:n]))) / float(np.min(po.rho[:n])) + 1e-300      # scale of sum m |B|/rho: the flux sums cancel
+    scale = {"mom": mtot * vmax, "dmom": mtot * (float(np.max(np.abs(po.force[:n]))) + 1e-300), "ang": mtot * vmax, "fluxtot": brho}
+    for k, v in evg_in.items():
+        g = ev1[k]
+        if isinstance(v, list):
+            s = scale[k]
+            assert np.max(np.abs(np.array(g) - np.array(v))) <= 1e-12 * s, (k, g, v)
+        elif k in ("rhomax", "rhomin", "divBmax"):
+            assert g == v, (k, g, v)                                  # extrema of stored values: exact
+        elif k in ("omegamhdmax", "betamhdmin"):
+            assert abs(g - v) <= 1e-15 * abs(v), (k, g, v)            # extrema of derived values: FMA contraction in |B|^2, a few ulp
+        elif k in ("momtot", "dmomtot", "angtot", "fluxtotmag"):
+            assert abs(g - v) <= 1e-12 * scale[{"momtot": "mom", "dmomtot": "dmom", "angtot": "ang", "fluxtotmag": "fluxtot"}[k]], (k, g, v)
+        elif k == "crosshel":
+            assert abs(g - v) <= 1e-12 * brho * vmax, (k, g, v)
+        else:
+            assert abs(g - v) <= 1e-12 * max(abs(v), 1e-300), (k, g, v)

@@ -66,3 +66,27 @@ def test_fixed_particles_keep_their_properties():
         dt, s = oracle.step(o, p, dt)
     for f, v in before.items():
         assert np.array_equal(getattr(p, f)[:n][fixed], v), f
+
+
+def test_evwrite_sums_against_numpy():
+    """ndo_evwrite (src/evwrite_mhd.f90:124-284) against the same sums written independently with numpy."""
+    o, p = setups.orszag_tang(ndim=3, nx=12, zfrac=0.5, perturb_amp=0.2, evolved=True)
+    oracle.derivs(o, p)
+    ev = oracle.evwrite(o, p)
+    n = p.npart
+    m, v, B, rho = p.pmass[:n], p.vel[:n], p.Bfield[:n], p.rho[:n]
+    ref = {
+        "ekin": 0.5 * np.sum(m * np.sum(v * v, 1)), "etherm": np.sum(m * p.uu[:n]), "emag": 0.5 * np.sum(m * np.sum(B * B, 1) / rho),
+        "emagp": 0.5 * np.sum(m * (B[:, 0] ** 2 + B[:, 1] ** 2) / rho), "rhomean": np.mean(rho), "rhomax": np.max(rho), "rhomin": np.min(rho),
+        "divBmax": np.max(np.abs(p.divB[:n])), "divBav": np.mean(np.abs(p.divB[:n])), "divBtot": np.sum(m * np.abs(p.divB[:n]) / rho),
+        "crosshel": np.sum(m * np.sum(v * B, 1) / rho), "ekiny": 0.5 * np.sum(m * v[:, 0] ** 2),
+        "betamhdav": np.mean(p.pr[:n] / (0.5 * np.sum(B * B, 1))),
+        "omegamhdmax": np.max(np.abs(p.divB[:n]) * p.hh[:n] / np.sqrt(np.sum(B * B, 1))),
+    }
+    for k, r in ref.items():
+        assert abs(ev[k] - r) <= 1e-12 * max(abs(r), 1e-300), (k, ev[k], r)
+    assert abs(ev["etot"] - (ev["ekin"] + ev["emag"] + ev["etherm"])) <= 1e-15
+    mom = np.sum(m[:, None] * v, 0)
+    assert np.allclose(ev["mom"], mom, rtol=0, atol=1e-14 * np.sum(m) * np.max(np.abs(v)))
+    ang = np.sum(m[:, None] * np.cross(p.x[:n], v), 0)
+    assert np.allclose(ev["ang"], ang, rtol=0, atol=1e-13 * np.sum(m))
