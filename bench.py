@@ -341,7 +341,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=512, help="particles along x (thin slab nx * nx * nx/8)")
-    ap.add_argument("--cpu-nx", type=int, default=160, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-nx", type=int, default=224, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--ref-nx", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
