@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
   double gpx = 0, gpy = 0, gpz = 0, gvx = 0, gvy = 0, gvz = 0, endiss = 0;
   // dtcourant = min over pairs of min(hi,hj)/vsigdtc = 1/max(max(1/hi,1/hj)*vsigdtc): track the denominator, divide once
 
+  bool any_coincident = false, vsig_det_bad = false;
   // ---- pair terms over the neighbour list (build_lists_kernel<LIST_RATES> applied src/ratesND_mhd.f90:401-415) ----
   auto body = [&](int k, const double4 &pj, const double4 &vj, const double4 &tj4, const double4 &gj, const double4 &bj) {
     const int tj = DRAG ? __ldg(G.typ + k) : 0;   // only the drag dispatch needs the neighbour's type on the fast path
@@ -200,13 +201,9 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
     const double rinv = rij2 > 4.930380657631324e-32 ? rsqrt_nr(rij2) : 0.;
     const double rij = rij2 * rinv;
     const double drx = dx * rinv, dry = dy * rinv, drz = dz * rinv;
-    if (rinv == 0.) {                                           // rare: bookkeeping of :417-427
-      if (__ldg(G.typ + k) == ti) {
-        const int origj = G.perm[k];
-        if (origj >= G.nown || orig > origj) nclumped++;
-        if (rij2 == 0. && ti != 2) atomicCAS(R.err, 0, 1 /*ND_ERR_INVALID_ARG: dx = 0*/);
-      }
-    }
+    // coincident pairs (:417-427) are only flagged here -- no branch in the pair body, which would end ptxas's scheduling
+    // block; their bookkeeping is redone from the list after the loop (rare)
+    any_coincident |= (rinv == 0.);
     const double pmassj = vj.w;
     const double dvx = vxi - vj.x, dvy = vyi - vj.y, dvz = vzi - vj.z;
     const double h1max = fmax(hi1, hj1);
@@ -264,7 +261,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
         const double vsig2j = spsoundj * spsoundj + valfven2j;
         const double vsigproji = vsig2i * vsig2i - 4. * ((spsoundi * projBi) * (spsoundi * projBi)) * rho1i;
         const double vsigprojj = vsig2j * vsig2j - 4. * ((spsoundj * projBj) * (spsoundj * projBj)) * rho1j;
-        if (vsigproji < 0. || vsigprojj < 0.) atomicCAS(R.err, 0, 6 /*ND_ERR_VSIG_DET*/);
+        vsig_det_bad |= (vsigproji < 0. || vsigprojj < 0.);   // ND_ERR_VSIG_DET, raised after the loop
         const double a4[4] = {vsigproji, vsigprojj, (dvx * dvx + dvy * dvy) + dvz * dvz /* norm2(dvel), :1433 */, pdiff};
         double r4[4];
         sqrt_n<4>(a4, r4);
@@ -281,10 +278,11 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
       double vsig = 0.5 * (fmax(vsigi + vsigj - O.beta * dvdotr, 0.0));          // :1452
       double vsigdtc = fmax(vsig, fmax(0.5 * (vsigi + vsigj + O.beta * fabs(dvdotr)), vsigB));   // :1465
       if (ONEF) vsigdtc = vsigdtc + sqrt(deltav2i + deltav2j);                                   // :1466-1468
-      if (ti == T_DUST) { vsig = 0.; vsigu = 0.; }                              // :1472-1474
-      else {                                                                    // :1476-1481
-        vsigmax = fmax(vsigmax, vsigdtc);
-        dtc_den = fmax(dtc_den, vsigdtc > zero ? h1max * vsigdtc : 0.);
+      {                                                                         // :1472-1481 as selects
+        const bool dust = (ti == T_DUST);
+        vsig = dust ? 0. : vsig; vsigu = dust ? 0. : vsigu;
+        vsigmax = fmax(vsigmax, dust ? 0. : vsigdtc);
+        dtc_den = fmax(dtc_den, (!dust && vsigdtc > zero) ? h1max * vsigdtc : 0.);
       }
       // ---- kernel gradients :1208-1241 (w = w[index] + dwdx*(q2 - index*dq2table), src/kernelND.f90:4443-4455) ----
       double grkerni = rowi.x + rowi.y * (q2i - __dmul_rn((double)idxi, G.dq2table));
@@ -544,13 +542,25 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
     if (ONEF) {   // the one-fluid dust instantiations have no registers to spare: direct loads
       walk_list(col, cnt, [&](int n, int k, int k1, int k2) { body(k, ld4(G.posh + k), ld4(G.vm + k), ld4(I.thermo + k), ld4(I.gal + k), MHD ? ld4(I.bpsi + k) : zero4); });
     } else {
+#if ND_RATES_STAGE == 5
+    // All five records of the next neighbour are in flight while this pair is evaluated.  The list column is read two entries
+    // ahead with plain rotation (k <- k1 <- k2 <- load): one coalesced load per pair and no branch in the loop besides its own.
+    const int last = cnt - 1;
+    int k = (int)__ldcs(col), k1 = (int)__ldcs(col + (size_t)min(1, last) * 32);
+    double4 pn = ld4(G.posh + k), vn = ld4(G.vm + k), tn = ld4(I.thermo + k), gn = ld4(I.gal + k), bn = MHD ? ld4(I.bpsi + k) : zero4;
+#pragma unroll 1
+    for (int n = 0; n < cnt; n++) {
+      const int k2 = (int)__ldcs(col + (size_t)min(n + 2, last) * 32);
+      const double4 pc = pn, vc = vn, tc = tn, gc = gn, bc = bn;
+      pn = ld4(G.posh + k1); vn = ld4(G.vm + k1); tn = ld4(I.thermo + k1); gn = ld4(I.gal + k1); bn = MHD ? ld4(I.bpsi + k1) : zero4;
+      body(k, pc, vc, tc, gc, bc);
+      k = k1; k1 = k2;
+    }
+#else
     const int kf = (int)col[0];
     double4 pn = ld4(G.posh + kf);
 #if ND_RATES_STAGE != 6
     double4 vn = ld4(G.vm + kf);
-#endif
-#if ND_RATES_STAGE == 5
-    double4 tn = ld4(I.thermo + kf), gn = ld4(I.gal + kf), bn = MHD ? ld4(I.bpsi + kf) : zero4;
 #endif
     walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
       const double4 pc = pn;
@@ -561,14 +571,9 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
 #else
       const double4 vc = ld4(G.vm + k);
 #endif
-#if ND_RATES_STAGE == 5
-      const double4 tc = tn, gc = gn, bc = bn;
-      tn = ld4(I.thermo + k1); gn = ld4(I.gal + k1); bn = MHD ? ld4(I.bpsi + k1) : zero4;
-      body(k, pc, vc, tc, gc, bc);
-#else
       body(k, pc, vc, ld4(I.thermo + k), ld4(I.gal + k), MHD ? ld4(I.bpsi + k) : zero4);
-#endif
     });
+#endif
     }
 #else
     walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
@@ -583,6 +588,20 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
 #endif
   }
 
+  if (vsig_det_bad) atomicCAS(R.err, 0, 6 /*ND_ERR_VSIG_DET*/);
+  if (any_coincident) {                                          // bookkeeping of :417-427 for the flagged targets
+    const unsigned *col = L.nbr + ((size_t)(tix >> 5) * L.lmax) * 32 + (tix & 31);
+    for (int n = 0; n < cnt; n++) {
+      const int k = (int)col[(size_t)n * 32];
+      const double4 pj = ld4(G.posh + k);
+      const double rij2 = dist2_exact(xi - pj.x, yi - pj.y, zi - pj.z);
+      if (!(rij2 > 4.930380657631324e-32) && __ldg(G.typ + k) == ti) {
+        const int origj = G.perm[k];
+        if (origj >= G.nown || orig > origj) nclumped++;
+        if (rij2 == 0. && ti != 2) atomicCAS(R.err, 0, 1 /*ND_ERR_INVALID_ARG: dx = 0*/);
+      }
+    }
+  }
   if (active) {
     st4(S.F + s, make_double4(fx, fy, fz, dudt));
     st4(S.dB + s, make_double4(dBx, dBy, dBz, divB));
