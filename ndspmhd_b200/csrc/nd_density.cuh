@@ -68,7 +68,6 @@ __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs 
   const double hfacwabi = powndim<NDIM>(hi1);
   double rho = 0, gradh = 0, drhodt = 0, densn = 0, gradhn = 0, gradgradh = 0, rhogas = 0, rhodust = 0;
   const bool onef = AUX && A.sdf != nullptr;
-  const bool bnd_first = FIRST && ti == T_BND;     // :273, :321 -- fixed particles keep rho, gradh
 
   // ---- pair sums over the neighbour list (built by build_lists_kernel with the reference's inclusion test) ----
   auto body = [&](int k, const double4 &pj, const double4 &vj) {
@@ -104,7 +103,8 @@ __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs 
     grkerni = grkerni * hfacwabi * hi1;
     const double dwdhi = -rij * grkerni * hi1 - NDIM * wabi * hi1;   // :260
     // self pair: the symmetric loop adds weight 1/2 twice (:204-208, :274, :286); the gather adds it once in full
-    if (!bnd_first) {
+    // (fixed particles keep rho and gradh in the first round, :273, :321: their sums are simply not used after the loop)
+    {
       rho += pmassj * wabi;
       gradh += pmassj * dwdhi;
       if (AUX) {
@@ -121,7 +121,7 @@ __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs 
         }
       }
     }
-    if (k != s) {                                  // :297-303
+    {                                              // :297-303 (j /= i: the self pair has dx = dv = 0 and adds an exact zero)
       const double dvdotr = ((vxi - vj.x) * (dx * rinve) + (vyi - vj.y) * (dy * rinve)) + (vzi - vj.z) * (dz * rinve);
       drhodt += pmassj * dvdotr * grkerni;
     }
@@ -129,13 +129,27 @@ __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs 
   if (cnt > 0) {
     const unsigned *col = L.nbr + ((size_t)(t >> 5) * L.lmax) * 32 + (t & 31);
 #if ND_DENS_PF == 4
-    // register pipeline: the next neighbour's two records load while this pair is evaluated
+    // register pipeline: the next neighbour's two records load while this pair is evaluated (list read in batches, walk_list)
     double4 pn = ld4(G.posh + (int)col[0]), vn = ld4(G.vm + (int)col[0]);
     walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
       const double4 pc = pn, vc = vn;
       pn = ld4(G.posh + k1); vn = ld4(G.vm + k1);
       body(k, pc, vc);
     });
+#elif ND_DENS_PF == 5
+    // register pipeline: the next neighbour's two records load while this pair is evaluated; the list column is read two entries
+    // ahead by plain rotation, so the loop holds no branch but its own
+    const int last = cnt - 1;
+    int k = (int)__ldcs(col), k1 = (int)__ldcs(col + (size_t)min(1, last) * 32);
+    double4 pn = ld4(G.posh + k), vn = ld4(G.vm + k);
+#pragma unroll 1
+    for (int n = 0; n < cnt; n++) {
+      const int k2 = (int)__ldcs(col + (size_t)min(n + 2, last) * 32);
+      const double4 pc = pn, vc = vn;
+      pn = ld4(G.posh + k1); vn = ld4(G.vm + k1);
+      body(k, pc, vc);
+      k = k1; k1 = k2;
+    }
 #elif ND_DENS_PF == 3
     // two neighbours per trip: their four record loads are issued together and overlap the other's arithmetic
     walk_list2(col, cnt, [&](int ka, int kb, bool twob) {

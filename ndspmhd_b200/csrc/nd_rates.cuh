@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
   mbar_wait(mbar, 0);
 #endif
   const int iav = FAST ? 2 : O.iav, iener = FAST ? (O.iener != 0 ? 2 : 0) : O.iener, ikernav = FAST ? 3 : O.ikernav, iresist = FAST ? 0 : O.iresist;
-  const int iavlim0 = O.iavlim0, iavlim1 = O.iavlim1, iavlim2 = O.iavlim2;
+  // FAST excludes iavlim(1) = 3 and iavlim(3) = 2 at compile time; the remaining run-time options of the fast tuple enter the pair
+  // body as 0/1 multipliers instead of (uniform) branches, which would split the scheduling block
+  const int iavlim0 = FAST ? 0 : O.iavlim0, iavlim1 = O.iavlim1, iavlim2 = FAST ? 0 : O.iavlim2;
+  const double sel_del2u = (O.iavlim1 > 0) ? 1. : 0., sel_gradpsi = (O.idivbzero >= 2) ? 1. : 0.;
   const double zero = 1.e-10;
   const double eps = 2.220446049250313e-16;
   // block-wide reductions are carried across the chunks of a persistent block and flushed once
@@ -436,9 +439,9 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
           dBx -= c * (f * dBxx); dBy -= c * (f * dByy); dBz -= c * (f * dBzz);
           if (iener > 0) dudt += pmassj * (-etaij * rho1i * rho1j * ((dBxx * dBxx + dByy * dByy) + dBzz * dBzz) * grkern / rij);
         }
-        if (O.idivbzero >= 2) {                                  // :2712-2716
+        if (FAST || O.idivbzero >= 2) {                          // :2712-2716
           const double gradpsiterm = psii * rho21i * grkerni + psij * rho21j * grkernj;
-          const double c = pmassj * gradpsiterm;
+          const double c = (FAST ? sel_gradpsi : 1.) * (pmassj * gradpsiterm);
           gpx -= c * drx; gpy -= c * dry; gpz -= c * drz;
         }
       }
@@ -455,7 +458,8 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
       }
       fx += fix; fy += fiy; fz += fiz;
       if (iav > 0) {                                             // :1639-1656 switch sources
-        if (iavlim1 > 0) del2u += pmassj * rho1j * ((uui - uuj) * rinv) * grkerni;
+        if (FAST) del2u += sel_del2u * (pmassj * rho1j * ((uui - uuj) * rinv) * grkerni);
+        else if (iavlim1 > 0) del2u += pmassj * rho1j * ((uui - uuj) * rinv) * grkerni;
         if (iavlim0 == 3) {
           const double c = pmassj * rho1j * rinv * dvdotr * grkerni;
           gvx += c * drx; gvy += c * dry; gvz += c * drz;
