@@ -1500,7 +1500,7 @@ RatesOpts make_rates_opts(const nd_ctx *c) {
 
 enum { RED_DTC = 0, RED_VSIG = 1, RED_DTAV = 2, RED_TS = 3, RED_HCS = 4, RED_FH = 5, RED_DTF = 6, RED_STRESS = 7 };
 
-template <int NDIM, bool MHD, bool DRAG, bool FAST, bool ONEF> int launch_rates_pair(nd_ctx *c, const RatesIn &I, const RatesOpts &O, const RatesSums &S, const RatesRed &R, int *pi, int *pj,
+template <int NDIM, bool MHD, bool DRAG, int FAST, bool ONEF> int launch_rates_pair(nd_ctx *c, const RatesIn &I, const RatesOpts &O, const RatesSums &S, const RatesRed &R, int *pi, int *pj,
                                                                           unsigned long long *pc, long long cap, const int *targets, int ntargets) {
   Grid G = make_grid(c);
   const int n = targets ? ntargets : c->ntotal;
@@ -1575,14 +1575,16 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   // first-class tuple without run-time option tests (and without the dead graddivv "curl v" sums: want_aux = 0)
   const bool fast = !drag && o.idust != 1 && !o.want_aux && o.iav == 2 && (o.iener == 0 || o.iener == 2) && o.ikernav == 3 && o.iresist == 0 && o.iavlim[0] != 3 && o.iavlim[2] != 2;
   auto pair = [&](const int *targets, int ntargets) -> int {
-    if (o.idust == 1 && mhd) return launch_rates_pair<NDIM, true, false, false, true>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
-    if (o.idust == 1) return launch_rates_pair<NDIM, false, false, false, true>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
-    if (mhd && fast) return launch_rates_pair<NDIM, true, false, true, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
-    if (!mhd && fast) return launch_rates_pair<NDIM, false, false, true, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
-    if (mhd && !drag) return launch_rates_pair<NDIM, true, false, false, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
-    if (!mhd && !drag) return launch_rates_pair<NDIM, false, false, false, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
-    if (!mhd && drag) return launch_rates_pair<NDIM, false, true, false, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
-    return launch_rates_pair<NDIM, true, true, false, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (o.idust == 1 && mhd) return launch_rates_pair<NDIM, true, false, 0, true>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (o.idust == 1) return launch_rates_pair<NDIM, false, false, 0, true>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (mhd && fast && o.iener != 0) return launch_rates_pair<NDIM, true, false, 2, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (mhd && fast) return launch_rates_pair<NDIM, true, false, 1, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (!mhd && fast && o.iener != 0) return launch_rates_pair<NDIM, false, false, 2, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (!mhd && fast) return launch_rates_pair<NDIM, false, false, 1, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (mhd && !drag) return launch_rates_pair<NDIM, true, false, 0, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (!mhd && !drag) return launch_rates_pair<NDIM, false, false, 0, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (!mhd && drag) return launch_rates_pair<NDIM, false, true, 0, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    return launch_rates_pair<NDIM, true, true, 0, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
   };
   FinalArgs FA;
   FA.perm = c->perm; FA.typ = c->typ; FA.posh = c->posh; FA.vm = c->vm; FA.bpsi = c->bpsi; FA.thermo = c->thermo; FA.gal = c->gal; FA.S = S; FA.O = O;

@@ -89,10 +89,10 @@ __device__ __forceinline__ double get_tstop(int idrag_nature, double rhogas, dou
   return 1.7976931348623157e308;
 }
 
-// FAST = the first-class option tuple compiled without run-time option tests: iav=2, iener in {0,2}, ikernav=3, iresist=0,
+// FAST (1: iener=0, 2: iener=2) = the first-class option tuple compiled without run-time option tests: iav=2, ikernav=3, iresist=0,
 // iavlim(1) /= 3, iavlim(3) /= 2, pext folded into thermo.  Everything else runs the generic instantiation.
 // ONEF = one-fluid dust (idust=1): dust_derivs (:2726-2807) and artificial_dissipation_dust (:1969-2148) on the generic path.
-template <int NDIM, bool MHD, bool DRAG, bool FAST, bool ONEF>
+template <int NDIM, bool MHD, bool DRAG, int FAST, bool ONEF>
 __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(Grid G, RatesIn I, RatesOpts O, RatesSums S, RatesRed R, NbrLists L,
                                                                                  int s0, int ntargets, const int *targets) {
   // dynamic shared memory: [0,16) mbarrier, then the {grad W, slope} rows of the kernel table (64 KB; every pair does two
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
   __syncthreads();
   mbar_wait(mbar, 0);
 #endif
-  const int iav = FAST ? 2 : O.iav, iener = FAST ? (O.iener != 0 ? 2 : 0) : O.iener, ikernav = FAST ? 3 : O.ikernav, iresist = FAST ? 0 : O.iresist;
+  const int iav = FAST ? 2 : O.iav, iener = FAST == 2 ? 2 : (FAST == 1 ? 0 : O.iener), ikernav = FAST ? 3 : O.ikernav, iresist = FAST ? 0 : O.iresist;
   // FAST excludes iavlim(1) = 3 and iavlim(3) = 2 at compile time; the remaining run-time options of the fast tuple enter the pair
   // body as 0/1 multipliers instead of (uniform) branches, which would split the scheduling block
   const int iavlim0 = FAST ? 0 : O.iavlim0, iavlim1 = O.iavlim1, iavlim2 = FAST ? 0 : O.iavlim2;
