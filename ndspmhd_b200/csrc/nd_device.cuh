@@ -333,36 +333,61 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
   const float4 pf = G.p32[s];
   const float Ti = (MODE == LIST_RATES) ? pf.w : screen_h2(hcur, G.hhmax1);
   const float marg = G.screen_margin;
-  auto visit = [&](int k, const float4 &qj) {
-    const float ddx = pf.x - qj.x, ddy = pf.y - qj.y, ddz = pf.z - qj.z;
-    const float r2 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
-    const float a = r2 - Ti, b = (MODE == LIST_DENS_PARTIAL) ? a : r2 - qj.w;
-    bool counts = fminf(a, b) < 0.f;                              // :189-190 / :528 / ratesND_mhd.f90:415
-    bool store = (MODE == LIST_DENS_FIRST) ? (a < 0.f) : counts;
-    if (fminf(fabsf(a), fabsf(b)) <= marg) exact(k, counts, store);
+  // A row is scanned in groups of up to 32 consecutive slots.  The per-candidate work is branch-free: the FP32 verdicts go into
+  // bit masks (listed / counted as a neighbour / inside the ambiguity band); the rare exact decisions, the type rules and the
+  // stores of the accepted slots happen once per group.  (Per-candidate branches and stores cost 27 instructions a candidate
+  // and kept ptxas from overlapping the loads of one candidate with the arithmetic of the next.)
+  auto scan_group = [&](int g0, int gn) {
+    unsigned mstore = 0u, mcount = 0u, mamb = 0u, bit = 1u;
+#pragma unroll 4
+    for (int u = 0; u < gn; u++) {
+      const float4 qj = __ldg(G.p32 + g0 + u);
+      const float ddx = pf.x - qj.x, ddy = pf.y - qj.y, ddz = pf.z - qj.z;
+      const float r2 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
+      const float a = r2 - Ti, b = (MODE == LIST_DENS_PARTIAL) ? a : r2 - qj.w;
+      if (fminf(a, b) < 0.f) mcount |= bit;                       // :189-190 / :528 / ratesND_mhd.f90:415
+      if (MODE == LIST_DENS_FIRST && a < 0.f) mstore |= bit;
+      if (fminf(fabsf(a), fabsf(b)) <= marg) mamb |= bit;
+      bit <<= 1;
+    }
+    if (MODE != LIST_DENS_FIRST) mstore = mcount;
+    while (mamb) {                                                // exact FP64 decision inside the band (1e-4 of the candidates)
+      const int u = __ffs(mamb) - 1;
+      mamb &= mamb - 1u;
+      bool counts, store;
+      exact(g0 + u, counts, store);
+      mcount = counts ? (mcount | (1u << u)) : (mcount & ~(1u << u));
+      mstore = store ? (mstore | (1u << u)) : (mstore & ~(1u << u));
+    }
     if (MODE == LIST_RATES) {
-      if (k == s) counts = store = false;                         // j /= i (both-ghost pairs cannot occur: the target is real)
-      if (hook && store) {                                        // parity-test hook: the accepted pair before the type dispatch
-        unsigned long long n = atomicAdd(A.pair_count, 1ull);
-        if ((long long)n < A.pair_cap) { A.pair_out_i[n] = orig + 1; A.pair_out_j[n] = G.perm[k] + 1; }
+      if (s >= g0 && s < g0 + gn) { mcount &= ~(1u << (s - g0)); mstore &= ~(1u << (s - g0)); }   // j /= i (the target is real: no ghost-ghost pair)
+      if (hook) {                                                 // parity-test hook: the accepted pairs before the type dispatch
+        for (unsigned m = mstore; m; m &= m - 1u) {
+          const int k = g0 + __ffs(m) - 1;
+          unsigned long long n = atomicAdd(A.pair_count, 1ull);
+          if ((long long)n < A.pair_cap) { A.pair_out_i[n] = orig + 1; A.pair_out_j[n] = G.perm[k] + 1; }
+        }
       }
     }
-    if (TYPES && counts) {
-      const int tj = __ldg(G.typ + k);
-      bool ok;
-      if (MODE == LIST_DENS_FIRST) ok = types_interact(ti, tj);   // density_sums.f90:169-174
-      else if (MODE == LIST_DENS_PARTIAL) ok = (tj == ti) || (tj == T_BND);   // :517
-      else ok = A.drag || types_interact(ti, tj);                 // ratesND_mhd.f90:436-446
-      counts = counts && ok; store = store && ok;
+    if (TYPES) {
+      for (unsigned m = mcount; m; m &= m - 1u) {
+        const int u = __ffs(m) - 1;
+        const int tj = __ldg(G.typ + g0 + u);
+        bool ok;
+        if (MODE == LIST_DENS_FIRST) ok = types_interact(ti, tj);   // density_sums.f90:169-174
+        else if (MODE == LIST_DENS_PARTIAL) ok = (tj == ti) || (tj == T_BND);   // :517
+        else ok = A.drag || types_interact(ti, tj);                 // ratesND_mhd.f90:436-446
+        if (!ok) { mcount &= ~(1u << u); mstore &= ~(1u << u); }
+      }
     }
-    nneigh += counts ? 1 : 0;                                     // :196-197 / :532
-    if (store) {
-      if (cnt < L.lmax) col[(size_t)cnt * 32] = (unsigned)k;
+    nneigh += __popc(mcount);                                     // :196-197 / :532
+    for (unsigned m = mstore; m; m &= m - 1u) {
+      if (cnt < L.lmax) col[(size_t)cnt * 32] = (unsigned)(g0 + __ffs(m) - 1);
       cnt++;
     }
   };
 
-  constexpr int NY = (NDIM >= 2) ? 3 : 1, NZ = (NDIM >= 3) ? 3 : 1, UNROLL = 4;
+  constexpr int NY = (NDIM >= 2) ? 3 : 1, NZ = (NDIM >= 3) ? 3 : 1;
   // Chord clipping.  In cell units (dxcell = radkern*hhmax) no accepted or counted pair is farther than Rc: 1 when the
   // neighbour's h can decide (h_j <= hhmax), (h_i/hhmax) when only the target's does.  A stencil row at transverse distance d
   // from the target can only hold such pairs within |dx| <= sqrt(Rc^2 - d^2): the scan covers just the fine bins that
@@ -391,15 +416,7 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
       int k = __ldg(G.fineStart + (size_t)c0 * CELL_FX + blo);
       const int e = __ldg(G.fineStart + (size_t)c0 * CELL_FX + bhi + 1);
 #pragma unroll 1
-      for (; k + UNROLL <= e; k += UNROLL) {
-        float4 qj[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) qj[u] = __ldg(G.p32 + k + u);
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) visit(k + u, qj[u]);
-      }
-#pragma unroll 1
-      for (; k < e; k++) visit(k, __ldg(G.p32 + k));
+      for (; k < e; k += 32) scan_group(k, min(32, e - k));
     }
   }
   if (cnt > L.lmax) { atomicMax(L.overflow, cnt); cnt = L.lmax; }
