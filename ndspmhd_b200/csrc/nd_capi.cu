@@ -81,8 +81,8 @@ struct nd_ctx {
   // rates in row chunks (ndspmhd_b200_derivs_host): chunk q = original rows [q*rows, (q+1)*rows) so that its results can be
   // downloaded while the next chunk's pair kernel runs
   int rate_chunks = 1; int *rlist = nullptr; size_t rlistcap = 0;
-  std::function<int(int, int, int)> on_rates_chunk;
-  std::vector<cudaEvent_t> chunk_events;   // (chunk, row0, row1) after the chunk's finalisation is enqueued
+  std::function<int(int, int, int)> on_rates_chunk;   // (chunk, row0, row1) after the chunk's finalisation is enqueued
+  std::vector<cudaEvent_t> chunk_events;
   double *evpartial = nullptr, *h_ev = nullptr;        // evwrite reductions
   double *stepbuf = nullptr; size_t stepbufrows = 0;   // leapfrog `*in` copies (ndspmhd_b200_step), rows [0,npart)
   cudaEvent_t ev_pair[2] = {nullptr, nullptr};   // around the rates pair kernel alone (the roofline's kernel time)
@@ -2221,10 +2221,6 @@ int ndspmhd_b200_step(nd_ctx *c, const nd_step_opts *so, double *dt_inout, nd_sc
   const int planes = o.onef_dust ? STEP_NIN_DUST : STEP_NIN;
   if (c->stepbufrows < (size_t)np) {
     if (c->stepbuf) cudaFree(c->stepbuf);
-  if (c->evpartial) cudaFree(c->evpartial);
-  if (c->h_ev) cudaFreeHost(c->h_ev);
-  if (c->rlist) cudaFree(c->rlist);
-  for (auto x : c->chunk_events) cudaEventDestroy(x);
     c->stepbuf = nullptr; c->stepbufrows = 0;
     CU(cudaMalloc(&c->stepbuf, sizeof(double) * (size_t)STEP_NIN_DUST * (size_t)np));
     c->stepbufrows = (size_t)np;

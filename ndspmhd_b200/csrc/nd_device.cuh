@@ -269,6 +269,10 @@ template <class F> __device__ __forceinline__ void walk_list2(const unsigned *co
 }
 
 enum { LIST_DENS_FIRST = 0, LIST_DENS_PARTIAL = 1, LIST_RATES = 2 };
+#ifndef ND_LIST_UNROLL
+#define ND_LIST_UNROLL 4
+#endif
+constexpr int LIST_UNROLL = ND_LIST_UNROLL;   // candidate records in flight per thread in the list builder
 
 struct ListArgs {
   const double *hh;        // original-order current smoothing lengths (density modes)
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
   // and kept ptxas from overlapping the loads of one candidate with the arithmetic of the next.)
   auto scan_group = [&](int g0, int gn) {
     unsigned mstore = 0u, mcount = 0u, mamb = 0u, bit = 1u;
-#pragma unroll 4
+#pragma unroll LIST_UNROLL
     for (int u = 0; u < gn; u++) {
       const float4 qj = __ldg(G.p32 + g0 + u);
       const float ddx = pf.x - qj.x, ddy = pf.y - qj.y, ddz = pf.z - qj.z;

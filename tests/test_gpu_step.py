@@ -5,6 +5,8 @@ Both sides start from the same upload + derivs and take the same number of steps
 The evolved state must agree within RTOL = 1e-12 of each field's magnitude (the rates agree to ~1e-14 per derivs and enter the
 state multiplied by dt); integer outputs of the inner derivs are not compared here because the two states differ in the last
 bits after the first step (tests/test_gpu_parity.py pins them on bit-identical inputs)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -158,3 +160,32 @@ def test_evwrite_matches_oracle(name):
             assert abs(g - v) <= 1e-12 * brho * vmax, (k, g, v)
         else:
             assert abs(g - v) <= 1e-12 * max(abs(v), 1e-300), (k, g, v)
+
+
+def test_context_teardown_after_every_api_mix():
+    """Create / use / destroy contexts through every mix of entry points (pipelined host call with and without row chunks, resident
+    derivs, steps, diagnostics): a regression test for a double free in the teardown that only showed after derivs_host + step."""
+    o, p0 = setups.orszag_tang(ndim=3, nx=16, zfrac=0.5, perturb_amp=0.2, evolved=True)
+    o.device_ghosts = 1
+    o.want_aux = 0
+    mask = abi.DL_DENSITY | abi.DL_PRIM | abi.DL_RATES
+    for rep in range(6):
+        p = p0.copy()
+        hot = lib.Hotpath(o, 3, 0)
+        try:
+            hot.derivs_host(p, mask)
+            os.environ["NDSPMHD_B200_RATE_CHUNKS"] = "3"
+            try:
+                hot.derivs_host(p, mask)
+            finally:
+                os.environ.pop("NDSPMHD_B200_RATE_CHUNKS")
+            p.ntotal = p.npart
+            hot.upload(p)
+            s = hot.derivs()
+            dt = min(0.25 * s["dtforce"], 0.3 * s["dtcourant"])
+            for _ in range(2):
+                dt, s = hot.step(dt)
+            ev = hot.evwrite()
+            assert np.isfinite(ev["etot"]) and ev["etot"] > 0
+        finally:
+            hot.close()
