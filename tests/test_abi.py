@@ -35,6 +35,9 @@ def test_header_is_plain_c_and_struct_layout_matches_ctypes():
         "nd_options": ["iener", "iavlim", "ibound", "device_ghosts", "idustevol", "hfact", "gamma", "xmin", "Bconst", "hhmax", "reserved_d"],
         "nd_arrays": ["x", "rho_in", "hh", "dens", "force", "del2u", "x_out", "dustevol", "dustfrac_in", "dustfrac", "ddeltavdt"],
         "nd_scalars": ["dtcourant", "fmean", "itsdensity", "ncellsx", "nrelink", "ncalctotal", "reserved_i"],
+        "nd_step_opts": ["C_cour", "C_force", "dtfixed", "reserved"],
+        "nd_state_out": ["x", "rho", "dustevol", "deltav"],
+        "nd_evwrite": ["ekin", "rhomin", "emagp", "divBtot", "fluxtotmag", "ekiny", "totmassdust", "mom", "fluxtot", "reserved"],
     }
     prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for st, fl in fields.items():
@@ -49,7 +52,8 @@ def test_header_is_plain_c_and_struct_layout_matches_ctypes():
         subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-o", exe, cfile])
         out = subprocess.check_output([exe]).decode().split("\n")
     got = dict(l.split() for l in out if l.strip())
-    mirror = {"nd_options": abi.NdOptions, "nd_arrays": abi.NdArrays, "nd_scalars": abi.NdScalars}
+    mirror = {"nd_options": abi.NdOptions, "nd_arrays": abi.NdArrays, "nd_scalars": abi.NdScalars, "nd_step_opts": abi.NdStepOpts,
+              "nd_state_out": abi.NdStateOut, "nd_evwrite": abi.NdEvwrite}
     for st, cls in mirror.items():
         assert int(got[st]) == C.sizeof(cls), st
         for f in fields[st]:
