@@ -47,7 +47,8 @@ struct nd_ctx {
   double *force = nullptr, *dudt = nullptr, *dendt = nullptr, *dBevoldt = nullptr, *daldt = nullptr, *dpsidt = nullptr, *gradpsi = nullptr, *divB = nullptr,
          *curlB = nullptr, *graddivv = nullptr, *del2u = nullptr;
   // ---- sorted-order arrays ----
-  double4 *posh = nullptr, *vm = nullptr, *bpsi = nullptr, *thermo = nullptr, *gal = nullptr;
+  double4 *posh = nullptr, *vm = nullptr, *posm = nullptr, *bpsi = nullptr, *thermo = nullptr, *gal = nullptr;
+  bool dens_light = false;   // set by the fused entry points: the rates kernel of the same derivs makes drho/dt (fast tuple)
   float4 *p32 = nullptr;   // FP32 screening records of the list builder (nd_device.cuh)
   double *srho = nullptr;
   // ---- one-fluid dust (idust=1; allocated only then) ----
@@ -417,7 +418,7 @@ __global__ void k_cell_order(const int *fineStart, int ncells, const int *permtm
 
 struct GatherArgs {
   const int *perm, *cellOfOrig, *itype, *ireal; const double *x, *vel, *pmass, *hh;
-  double4 *posh, *vm; float4 *p32; int *typ, *cellOf, *inv, *mixed; int npart, ntotal;
+  double4 *posh, *vm, *posm; float4 *p32; int *typ, *cellOf, *inv, *mixed; int npart, ntotal;
   const double *dustfrac; double *sdf;   // one-fluid dust (NULL otherwise)
   double xminpart[3], dxcell1, hhmax1;
 };
@@ -433,6 +434,7 @@ template <int NDIM> __global__ void k_gather_sorted(GatherArgs A) {
   for (int d = 0; d < NDIM; d++) q[d] = (float)((p[d] - A.xminpart[d]) * A.dxcell1);
   A.p32[s] = make_float4(q[0], q[1], q[2], screen_h2(A.hh[st], A.hhmax1));
   A.vm[s] = make_double4(A.vel[(size_t)r * 3], A.vel[(size_t)r * 3 + 1], A.vel[(size_t)r * 3 + 2], A.pmass[st]);
+  A.posm[s] = make_double4(p[0], p[1], p[2], A.pmass[st]);
   A.typ[s] = A.itype[r];
   if (A.sdf) A.sdf[s] = A.dustfrac[st];
   if (A.itype[r] != A.itype[0]) *A.mixed = 1;
@@ -606,6 +608,7 @@ struct FinalArgs {
   const double *drhodt_in, *Bevol, *dens, *hh, *rho, *pr; const unsigned long long *vsigmax_key;
   double *force, *dudt, *dendt, *dBevoldt, *daldt, *dpsidt, *gradpsi, *divB, *curlB, *graddivv, *del2u, *drhodt, *dhdt;
   RatesRed R; int npart, ntotal;
+  int drho_from_pairs, ndim;          // fast tuple: drho/dt comes from the pair kernel's sum (S.V.w), dh/dt is made here
   const int *targets; int ntargets;   // row-chunked finalisation: the chunk's target slots (NULL: every slot)
   // one-fluid dust (dusta NULL otherwise)
   const double4 *dusta; const double2 *dustb; const int *fineStart, *cellOf; double *ddustevoldt, *ddeltavdt;
@@ -639,7 +642,10 @@ __global__ void k_rates_final(FinalArgs A) {
       double valfven2i = 0.;
       if (O.imhd != 0) valfven2i = ((bx * bx + by * by) + bz * bz) / A.dens[i];                      // :690
       const double vsig = sqrt(th.z * th.z + valfven2i);                                             // :695-696
-      const double drhodti = A.drhodt_in[i];
+      // drho/dt: the density iteration's (iterate_density.f90:272), or -- fast tuple -- the pair kernel's sum over the same pairs with the
+      // same grad W (already times gradh); dh/dt = dhdrho * drho/dt (:273) is then made here
+      const double drhodti = A.drho_from_pairs ? V.w : A.drhodt_in[i];
+      if (A.drho_from_pairs) { A.drhodt[i] = drhodti; A.dhdt[i] = (-hi / (A.ndim * rhoi)) * drhodti; }
       double dbx = dB4.x, dby = dB4.y, dbz = dB4.z, gpx = P.x, gpy = P.y, gpz = P.z;
       if (O.imhd >= 11) {                                                                            // :722-730
         const double *Be = A.Bevol + (size_t)i * 3;
@@ -996,7 +1002,7 @@ void register_rows(nd_ctx *c) {
   R1(dens); R1(uu); R1(pr); R1(spsound); R3(Bfield);
   R3(force); R1(dudt); R1(dendt); R3(dBevoldt); R3(daldt); R1(dpsidt); R3(gradpsi); R1(divB); R3(curlB); R3(graddivv); R1(del2u);
   v.push_back({(void **)&c->p32, sizeof(float4)});
-  R1(srho); R4(posh); R4(vm); R4(bpsi); R4(thermo); R4(gal); R4(sF); R4(sdB); R4(sC); R4(sP); R4(sV);
+  R1(srho); R4(posh); R4(vm); R4(posm); R4(bpsi); R4(thermo); R4(gal); R4(sF); R4(sdB); R4(sC); R4(sP); R4(sV);
   RI(typ); RI(perm); RI(permtmp); RI(inv); RI(cellOf); RI(cellOfOrig); RI(redo); RI(list); RI(ghostcount);
   if (c->o.onef_dust) {
     R1(dustevol); R1(dustfrac); R3(deltav); R1(rhogas); R1(rhodust); R1(ddustevoldt); R3(ddeltavdt); R1(sdf); R4(dusta); R4(sD);
@@ -1065,7 +1071,7 @@ int check_options(nd_ctx *c, const nd_options &o, int ndim) {
 
 Grid make_grid(nd_ctx *c) {
   Grid G;
-  G.fineStart = c->cellStart; G.cellOf = c->cellOf; G.perm = c->perm; G.posh = c->posh; G.vm = c->vm; G.typ = c->typ; G.p32 = c->p32;
+  G.fineStart = c->cellStart; G.cellOf = c->cellOf; G.perm = c->perm; G.posh = c->posh; G.vm = c->vm; G.posm = c->posm; G.typ = c->typ; G.p32 = c->p32;
   G.hhmax1 = 1.0 / c->hhmax;
   // FP32 screening band (scaled units, cell = 1): 4 * 2^-23 * largest scaled coordinate + rounding of the thresholds
   G.screen_margin = 4.f * 1.1920929e-7f * (float)std::max(c->ncellsx[0], std::max(c->ncellsx[1], c->ncellsx[2])) + 2.e-6f;
@@ -1300,7 +1306,7 @@ template <int NDIM> int build_cells(nd_ctx *c) {
   LAUNCH(c, k_cell_order, nblocks((long long)c->ncells * 32, 256), 256, 0, c->cellStart, c->ncells, c->permtmp, c->perm);
   GatherArgs GA;
   GA.perm = c->perm; GA.cellOfOrig = c->cellOfOrig; GA.itype = c->itype; GA.ireal = c->ireal; GA.x = c->x; GA.vel = c->vel; GA.pmass = c->pmass; GA.hh = c->hh;
-  GA.posh = c->posh; GA.vm = c->vm; GA.p32 = c->p32; GA.typ = c->typ; GA.cellOf = c->cellOf; GA.inv = c->inv; GA.npart = c->npart; GA.ntotal = nt;
+  GA.posh = c->posh; GA.vm = c->vm; GA.posm = c->posm; GA.p32 = c->p32; GA.typ = c->typ; GA.cellOf = c->cellOf; GA.inv = c->inv; GA.npart = c->npart; GA.ntotal = nt;
   for (int d = 0; d < 3; d++) GA.xminpart[d] = c->xminpart[d];
   GA.dxcell1 = 1.0 / c->dxcell; GA.hhmax1 = 1.0 / c->hhmax; GA.mixed = c->flags + 6;
   GA.dustfrac = c->dustfrac; GA.sdf = c->o.onef_dust ? c->sdf : nullptr;
@@ -1368,6 +1374,13 @@ template <int NDIM, int MODE> int build_lists(nd_ctx *c, const Grid &G, ListArgs
   return set_err(c, ND_ERR_NEIGHBOUR_OVERFLOW, "neighbour list overflow");
 }
 
+// the first-class option tuple (FAST instantiations of the rates pair kernel): no run-time option tests, and the kernel also
+// makes drho/dt (so the density rounds of a fused derivs can run LIGHT)
+static bool fast_tuple(const nd_options &o) {
+  return o.idust != 2 && o.idust != 1 && !o.want_aux && o.iav == 2 && (o.iener == 0 || o.iener == 2) && o.ikernav == 3 && o.iresist == 0 && o.iavlim[0] != 3 &&
+         o.iavlim[2] != 2;
+}
+
 template <int NDIM, bool FIRST> int launch_density_round(nd_ctx *c, DensityArgs A, int n) {
   Grid G = make_grid(c);
   for (int c0 = 0; c0 < n; c0 += LIST_CHUNK) {
@@ -1382,17 +1395,21 @@ template <int NDIM, bool FIRST> int launch_density_round(nd_ctx *c, DensityArgs 
     const bool aux = c->o.want_aux || c->o.onef_dust;
 #if ND_DENS_TABSMEM
     // persistent blocks, one per SM (128 KB of shared-memory tables each); warps draw 32-target units from flags[9]
-    auto kaux = density_round_kernel<NDIM, FIRST, true>;
-    auto kfast = density_round_kernel<NDIM, FIRST, false>;
+    auto kaux = density_round_kernel<NDIM, FIRST, true, false>;
+    auto kfast = density_round_kernel<NDIM, FIRST, false, false>;
+    auto klight = density_round_kernel<NDIM, FIRST, false, true>;
     CU(cudaFuncSetAttribute(kaux, cudaFuncAttributeMaxDynamicSharedMemorySize, DENS_SMEM_BYTES));
     CU(cudaFuncSetAttribute(kfast, cudaFuncAttributeMaxDynamicSharedMemorySize, DENS_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(klight, cudaFuncAttributeMaxDynamicSharedMemorySize, DENS_SMEM_BYTES));
     CU(cudaMemsetAsync(c->flags + 9, 0, sizeof(int), c->stream));
     const int grid = std::min(nblocks(m, DENS_BLOCK), c->num_sms);
     if (aux) LAUNCH(c, kaux, grid, DENS_BLOCK, DENS_SMEM_BYTES, G, A, L);
+    else if (c->dens_light) LAUNCH(c, klight, std::min(nblocks(m, DENS_BLOCK_LIGHT), c->num_sms), DENS_BLOCK_LIGHT, DENS_SMEM_BYTES, G, A, L);
     else LAUNCH(c, kfast, grid, DENS_BLOCK, DENS_SMEM_BYTES, G, A, L);
 #else
-    if (aux) LAUNCH(c, (density_round_kernel<NDIM, FIRST, true>), nblocks(m, DENS_BLOCK), DENS_BLOCK, 0, G, A, L);
-    else LAUNCH(c, (density_round_kernel<NDIM, FIRST, false>), nblocks(m, DENS_BLOCK), DENS_BLOCK, 0, G, A, L);
+    if (aux) LAUNCH(c, (density_round_kernel<NDIM, FIRST, true, false>), nblocks(m, DENS_BLOCK), DENS_BLOCK, 0, G, A, L);
+    else if (c->dens_light) LAUNCH(c, (density_round_kernel<NDIM, FIRST, false, true>), nblocks(m, DENS_BLOCK_LIGHT), DENS_BLOCK_LIGHT, 0, G, A, L);
+    else LAUNCH(c, (density_round_kernel<NDIM, FIRST, false, false>), nblocks(m, DENS_BLOCK), DENS_BLOCK, 0, G, A, L);
 #endif
   }
   return 0;
@@ -1573,7 +1590,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   CU(cudaEventRecord(c->ev[3], c->stream));
   const bool mhd = o.imhd != 0, drag = (o.idust == 2);
   // first-class tuple without run-time option tests (and without the dead graddivv "curl v" sums: want_aux = 0)
-  const bool fast = !drag && o.idust != 1 && !o.want_aux && o.iav == 2 && (o.iener == 0 || o.iener == 2) && o.ikernav == 3 && o.iresist == 0 && o.iavlim[0] != 3 && o.iavlim[2] != 2;
+  const bool fast = fast_tuple(o);
   auto pair = [&](const int *targets, int ntargets) -> int {
     if (o.idust == 1 && mhd) return launch_rates_pair<NDIM, true, false, 0, true>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
     if (o.idust == 1) return launch_rates_pair<NDIM, false, false, 0, true>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
@@ -1591,7 +1608,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   FA.drhodt_in = c->drhodt; FA.Bevol = c->Bevol; FA.dens = c->dens; FA.hh = c->hh; FA.rho = c->rho; FA.pr = c->pr; FA.vsigmax_key = c->red + RED_VSIG;
   FA.force = c->force; FA.dudt = c->dudt; FA.dendt = c->dendt; FA.dBevoldt = c->dBevoldt; FA.daldt = c->daldt; FA.dpsidt = c->dpsidt; FA.gradpsi = c->gradpsi;
   FA.divB = c->divB; FA.curlB = c->curlB; FA.graddivv = c->graddivv; FA.del2u = c->del2u; FA.drhodt = c->drhodt; FA.dhdt = c->dhdt;
-  FA.R = R; FA.npart = np; FA.ntotal = nt; FA.targets = nullptr; FA.ntargets = 0;
+  FA.R = R; FA.npart = np; FA.ntotal = nt; FA.targets = nullptr; FA.ntargets = 0; FA.drho_from_pairs = (ND_DENS_LIGHT && fast) ? 1 : 0; FA.ndim = NDIM;
   FA.dusta = o.onef_dust ? c->dusta : nullptr; FA.dustb = c->dustb; FA.fineStart = c->cellStart; FA.cellOf = c->cellOf;
   FA.ddustevoldt = c->ddustevoldt; FA.ddeltavdt = c->ddeltavdt;
   const int nchunk = (c->rate_chunks > 1 && !c->has_comm && !pi) ? c->rate_chunks : 1;
@@ -2010,7 +2027,9 @@ int ndspmhd_b200_derivs(nd_ctx *c, nd_scalars *s) {
   int e = DISPATCH_NDIM(c, do_link<1>(c), do_link<2>(c), do_link<3>(c));
   if (e) return e;
   CU(cudaEventRecord(c->ev[1], c->stream));
+  c->dens_light = ND_DENS_LIGHT && fast_tuple(c->o) && !c->has_comm;   // get_rates follows in this call and makes drho/dt itself
   e = DISPATCH_NDIM(c, do_iterate_density<1>(c, 0), do_iterate_density<2>(c, 0), do_iterate_density<3>(c, 0));
+  c->dens_light = false;
   if (e) return e;
   CU(cudaEventRecord(c->ev[2], c->stream));
   e = do_cons2prim(c);
@@ -2068,7 +2087,12 @@ int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int
   CU(cudaStreamWaitEvent(c->stream, c->ev_in[0], 0));
   CU(cudaEventRecord(c->ev[0], c->stream));
   int e = DISPATCH_NDIM(c, do_link<1>(c), do_link<2>(c), do_link<3>(c));
-  if (!e) { CU(cudaEventRecord(c->ev[1], c->stream)); e = DISPATCH_NDIM(c, do_iterate_density<1>(c, 0), do_iterate_density<2>(c, 0), do_iterate_density<3>(c, 0)); }
+  if (!e) {
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    c->dens_light = ND_DENS_LIGHT && fast_tuple(c->o) && !c->has_comm && (mask & ND_DL_RATES);   // the rates of this call make drho/dt
+    e = DISPATCH_NDIM(c, do_iterate_density<1>(c, 0), do_iterate_density<2>(c, 0), do_iterate_density<3>(c, 0));
+    c->dens_light = false;
+  }
   if (e) { cudaStreamSynchronize(c->stream_h2d); return e; }
   if (idim < c->ntotal) { cudaStreamSynchronize(c->stream_h2d); return set_err(c, ND_ERR_INVALID_ARG, "derivs_host: idim < ntotal after ghost generation"); }
   const size_t nout = (size_t)(c->has_comm ? c->nown : c->ntotal);

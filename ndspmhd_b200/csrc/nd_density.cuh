@@ -31,21 +31,31 @@ struct DensityArgs {
 #ifndef ND_DENS_PF
 #define ND_DENS_PF 4   // neighbour records: 0 direct loads, 1/2 + L1 prefetch 1/2 pairs ahead, 3 two pairs per trip, 4 register pipeline one pair ahead
 #endif
+#ifndef ND_DENS_LIGHT
+#define ND_DENS_LIGHT 1   // 1: in a fused derivs of the fast option tuple the density rounds run LIGHT (no drho/dt sum, one gather a pair) and the rates pair kernel makes drho/dt
+#endif
 #ifndef ND_DENS_TABSMEM
 #define ND_DENS_TABSMEM 1   // {W, slope} and {grad W, slope} rows in shared memory (two TMA bulk copies per persistent block)
 #endif
 #ifndef ND_DENS_BLOCK
 #define ND_DENS_BLOCK (ND_DENS_TABSMEM ? 512 : 128)
 #endif
+#ifndef ND_DENS_BLOCK_LIGHT
+#define ND_DENS_BLOCK_LIGHT (ND_DENS_TABSMEM ? 1024 : ND_DENS_BLOCK)   // LIGHT instantiations: 64 registers without spills, 32 warps on an SM instead of 16
+#endif
 #ifndef ND_DENS_MINB
 #define ND_DENS_MINB (ND_DENS_TABSMEM ? 1 : 4)
 #endif
 constexpr int DENS_BLOCK = ND_DENS_BLOCK;
+constexpr int DENS_BLOCK_LIGHT = ND_DENS_BLOCK_LIGHT;
 constexpr int DENS_TAB_BYTES = (IKERN + 1) * 16;                         // one {value, slope} table, 64016 B
 constexpr int DENS_TAB_STRIDE = ((DENS_TAB_BYTES + 127) / 128) * 128;
 constexpr int DENS_SMEM_BYTES = ND_DENS_TABSMEM ? 128 + 2 * DENS_TAB_STRIDE : 0;
 
-template <int NDIM, bool FIRST, bool AUX>
+// LIGHT: the round makes rho, gradh and the Newton-Raphson update only.  drho/dt is left to the rates pair kernel of the same derivs
+// (fast option tuple), which visits the same pairs with the same grad W anyway: a neighbour then costs ONE 32-byte gather
+// ({x,y,z,m}) instead of two (position + velocity records), and the L1 gather path is what bounds this kernel.
+template <int NDIM, bool FIRST, bool AUX, bool LIGHT>
 __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs &A, const NbrLists &L, int t, const double2 *tabw, const double2 *tabg) {
   const int s = FIRST ? A.s0 + t : A.list[t];
   const int orig = G.perm[s];
@@ -84,7 +94,7 @@ __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs 
     const double rinv = rsqrt_nr(rij2);          // 0 for the self pair
     const double rij = rij2 * rinv;
     const double rinve = rinv - 2.220446049250313e-16 * rinv * rinv;
-    const double pmassj = vj.w;
+    const double pmassj = LIGHT ? pj.w : vj.w;
     double wabi, grkerni, grgrkerni = 0.;
 #if ND_DENS_TABSMEM
     {
@@ -121,7 +131,7 @@ __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs 
         }
       }
     }
-    {                                              // :297-303 (j /= i: the self pair has dx = dv = 0 and adds an exact zero)
+    if (!LIGHT) {                                  // :297-303 (j /= i: the self pair has dx = dv = 0 and adds an exact zero)
       const double dvdotr = ((vxi - vj.x) * (dx * rinve) + (vyi - vj.y) * (dy * rinve)) + (vzi - vj.z) * (dz * rinve);
       drhodt += pmassj * dvdotr * grkerni;
     }
@@ -130,12 +140,21 @@ __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs 
     const unsigned *col = L.nbr + ((size_t)(t >> 5) * L.lmax) * 32 + (t & 31);
 #if ND_DENS_PF == 4
     // register pipeline: the next neighbour's two records load while this pair is evaluated (list read in batches, walk_list)
-    double4 pn = ld4(G.posh + (int)col[0]), vn = ld4(G.vm + (int)col[0]);
-    walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
-      const double4 pc = pn, vc = vn;
-      pn = ld4(G.posh + k1); vn = ld4(G.vm + k1);
-      body(k, pc, vc);
-    });
+    if (LIGHT) {
+      double4 pn = ld4(G.posm + (int)col[0]);
+      walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
+        const double4 pc = pn;
+        pn = ld4(G.posm + k1);
+        body(k, pc, pc);
+      });
+    } else {
+      double4 pn = ld4(G.posh + (int)col[0]), vn = ld4(G.vm + (int)col[0]);
+      walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
+        const double4 pc = pn, vc = vn;
+        pn = ld4(G.posh + k1); vn = ld4(G.vm + k1);
+        body(k, pc, vc);
+      });
+    }
 #elif ND_DENS_PF == 5
     // register pipeline: the next neighbour's two records load while this pair is evaluated; the list column is read two entries
     // ahead by plain rotation, so the loop holds no branch but its own
@@ -212,21 +231,21 @@ __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs 
       redo = 1;
       if (A.itsdensity <= A.itsdensitymax) A.hh[orig] = hnew;         // :253-255
       if (hnew > A.hhmax) relink = true;                              // :260-262
-      A.drhodt[orig] = drhodt;
-    } else {
+      if (!LIGHT) A.drhodt[orig] = drhodt;
+    } else if (!LIGHT) {
       const double d = drhodt * gradh_out;                            // :272-273
       A.drhodt[orig] = d;
       A.dhdt[orig] = dhdrhoi * d;
     }
     if (relink) A.flags[0] = 1;
-  } else {
+  } else if (!LIGHT) {
     A.drhodt[orig] = drhodt;                                          // density_sums.f90:300 runs for fixed particles too
   }
   A.redo[s] = redo;
 }
 
-template <int NDIM, bool FIRST, bool AUX>
-__global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel(Grid G, DensityArgs A, NbrLists L) {
+template <int NDIM, bool FIRST, bool AUX, bool LIGHT>
+__global__ void __launch_bounds__(LIGHT ? DENS_BLOCK_LIGHT : DENS_BLOCK, ND_DENS_MINB) density_round_kernel(Grid G, DensityArgs A, NbrLists L) {
 #if ND_DENS_TABSMEM
   // One persistent block per SM: the two interpolation tables (128 KB) arrive by TMA bulk copies, then every warp draws
   // 32-target units from a global counter until the work is gone.
@@ -251,11 +270,11 @@ __global__ void __launch_bounds__(DENS_BLOCK, ND_DENS_MINB) density_round_kernel
     unit = __shfl_sync(FULL, unit, 0);
     if (unit >= nunits) break;
     const int t = unit * 32 + (threadIdx.x & 31);
-    if (t < A.nlist) density_target<NDIM, FIRST, AUX>(G, A, L, t, tabw, tabg);
+    if (t < A.nlist) density_target<NDIM, FIRST, AUX, LIGHT>(G, A, L, t, tabw, tabg);
   }
 #else
-  const int t = blockIdx.x * DENS_BLOCK + threadIdx.x;
-  if (t < A.nlist) density_target<NDIM, FIRST, AUX>(G, A, L, t, nullptr, nullptr);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < A.nlist) density_target<NDIM, FIRST, AUX, LIGHT>(G, A, L, t, nullptr, nullptr);
 #endif
 }
 

@@ -27,6 +27,7 @@ struct Grid {
   const int *perm;          // [ntotal]   sorted slot -> original row
   const double4 *posh;      // [ntotal]   {x,y,z,1/h}  (1/h correctly rounded: h1(i) = 1./hh(i), density_sums.f90:130)
   const double4 *vm;        // [ntotal]   {vx,vy,vz,m}
+  const double4 *posm;      // [ntotal]   {x,y,z,m}: all the LIGHT density round needs of a neighbour (one 32-byte gather a pair)
   const int *typ;           // [ntotal]
   const float4 *p32;        // [ntotal]   FP32 screening record {(x - xminpart)/dxcell, (h/hhmax)^2}: |dX|^2 < (h/hhmax)^2  <=>  rij2/h^2 < radkern2
   double hhmax1; float screen_margin, cull_margin;

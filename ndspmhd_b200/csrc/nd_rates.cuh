@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
   // accumulators
   double fx = 0, fy = 0, fz = 0, dudt = 0, dBx = 0, dBy = 0, dBz = 0, divB = 0, cBx = 0, cBy = 0, cBz = 0, del2u = 0;
   double gpx = 0, gpy = 0, gpz = 0, gvx = 0, gvy = 0, gvz = 0, endiss = 0;
+  double drho = 0;   // FAST: drho/dt of the density sums (density_sums.f90:297-303 with dr = dx/(rij + epsilon)), times gradh through grkerni
   // dtcourant = min over pairs of min(hi,hj)/vsigdtc = 1/max(max(1/hi,1/hj)*vsigdtc): track the denominator, divide once
 
   bool any_coincident = false, vsig_det_bad = false;
@@ -410,6 +411,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
         dudt += dudti + pmassj * diffu;
       }
       dtav_den = fmax(dtav_den, vsigav > zero ? h1max * vsigav : 0.);              // :1500
+      if (FAST && ND_DENS_LIGHT) drho += pmassj * (dvdotr * (1. - eps * rinv)) * grkerni;   // sum m_j (dv.dr) grad W_i: the density loop's drhodt (LIGHT rounds skip it)
       {                                                          // pressure, :1538-1567 (phi = 1, sqrtg = 1)
         const double prterm = Prho2i * grkerni + Prho2j * grkernj;
         const double c = pmassj * prterm;
@@ -611,7 +613,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
     st4(S.dB + s, make_double4(dBx, dBy, dBz, divB));
     st4(S.C + s, make_double4(cBx, cBy, cBz, del2u));
     st4(S.P + s, make_double4(gpx, gpy, gpz, endiss));
-    st4(S.V + s, make_double4(gvx, gvy, gvz, 0.));
+    st4(S.V + s, make_double4(gvx, gvy, gvz, drho));
     if (ONEF) {                                                  // ddeltavdt(:,i) - rhoi/rhogasi*forcei(:), :460
       const double c = rhoi / rhogasi;
       st4(S.D + s, make_double4(ddvx - c * fgx, ddvy - c * fgy, ddvz - c * fgz, ddust));
