@@ -49,6 +49,7 @@ struct nd_ctx {
   // ---- sorted-order arrays ----
   double4 *posh = nullptr, *vm = nullptr, *posm = nullptr, *bpsi = nullptr, *thermo = nullptr, *gal = nullptr;
   bool dens_light = false;   // set by the fused entry points: the rates kernel of the same derivs makes drho/dt (fast tuple)
+  bool drho_pairs = false;   // the density rounds of this derivs ran LIGHT: k_rates_final takes drho/dt from the pair sums and makes dh/dt
   float4 *p32 = nullptr;   // FP32 screening records of the list builder (nd_device.cuh)
   double *srho = nullptr;
   // ---- one-fluid dust (idust=1; allocated only then) ----
@@ -1608,7 +1609,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   FA.drhodt_in = c->drhodt; FA.Bevol = c->Bevol; FA.dens = c->dens; FA.hh = c->hh; FA.rho = c->rho; FA.pr = c->pr; FA.vsigmax_key = c->red + RED_VSIG;
   FA.force = c->force; FA.dudt = c->dudt; FA.dendt = c->dendt; FA.dBevoldt = c->dBevoldt; FA.daldt = c->daldt; FA.dpsidt = c->dpsidt; FA.gradpsi = c->gradpsi;
   FA.divB = c->divB; FA.curlB = c->curlB; FA.graddivv = c->graddivv; FA.del2u = c->del2u; FA.drhodt = c->drhodt; FA.dhdt = c->dhdt;
-  FA.R = R; FA.npart = np; FA.ntotal = nt; FA.targets = nullptr; FA.ntargets = 0; FA.drho_from_pairs = (ND_DENS_LIGHT && fast) ? 1 : 0; FA.ndim = NDIM;
+  FA.R = R; FA.npart = np; FA.ntotal = nt; FA.targets = nullptr; FA.ntargets = 0; FA.drho_from_pairs = (c->drho_pairs && fast) ? 1 : 0; FA.ndim = NDIM;
   FA.dusta = o.onef_dust ? c->dusta : nullptr; FA.dustb = c->dustb; FA.fineStart = c->cellStart; FA.cellOf = c->cellOf;
   FA.ddustevoldt = c->ddustevoldt; FA.ddeltavdt = c->ddeltavdt;
   const int nchunk = (c->rate_chunks > 1 && !c->has_comm && !pi) ? c->rate_chunks : 1;
@@ -2028,13 +2029,16 @@ int ndspmhd_b200_derivs(nd_ctx *c, nd_scalars *s) {
   if (e) return e;
   CU(cudaEventRecord(c->ev[1], c->stream));
   c->dens_light = ND_DENS_LIGHT && fast_tuple(c->o) && !c->has_comm;   // get_rates follows in this call and makes drho/dt itself
+  const bool light = c->dens_light;
   e = DISPATCH_NDIM(c, do_iterate_density<1>(c, 0), do_iterate_density<2>(c, 0), do_iterate_density<3>(c, 0));
   c->dens_light = false;
   if (e) return e;
   CU(cudaEventRecord(c->ev[2], c->stream));
   e = do_cons2prim(c);
   if (e) return e;
+  c->drho_pairs = light;
   e = DISPATCH_NDIM(c, do_get_rates<1>(c, nullptr, nullptr, nullptr, 0), do_get_rates<2>(c, nullptr, nullptr, nullptr, 0), do_get_rates<3>(c, nullptr, nullptr, nullptr, 0));
+  c->drho_pairs = false;
   if (e) return e;
   if (int e2 = fill_density_scalars(c)) return e2;
   CU(cudaEventSynchronize(c->ev[5]));
@@ -2087,9 +2091,11 @@ int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int
   CU(cudaStreamWaitEvent(c->stream, c->ev_in[0], 0));
   CU(cudaEventRecord(c->ev[0], c->stream));
   int e = DISPATCH_NDIM(c, do_link<1>(c), do_link<2>(c), do_link<3>(c));
+  bool light = false;
   if (!e) {
     CU(cudaEventRecord(c->ev[1], c->stream));
     c->dens_light = ND_DENS_LIGHT && fast_tuple(c->o) && !c->has_comm && (mask & ND_DL_RATES);   // the rates of this call make drho/dt
+    light = c->dens_light;
     e = DISPATCH_NDIM(c, do_iterate_density<1>(c, 0), do_iterate_density<2>(c, 0), do_iterate_density<3>(c, 0));
     c->dens_light = false;
   }
@@ -2121,7 +2127,9 @@ int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int
     if (cudaEventRecord(cev[q], c->stream) != cudaSuccess || cudaStreamWaitEvent(c->stream_d2h, cev[q], 0) != cudaSuccess) { cb_err = 1; return set_err(c, ND_ERR_CUDA, "derivs_host: chunk event"); }
     return download_rates_rows(c, a, (size_t)r0, (size_t)r1, mask, c->stream_d2h, false);
   };
+  c->drho_pairs = light;
   e = DISPATCH_NDIM(c, do_get_rates<1>(c, nullptr, nullptr, nullptr, 0), do_get_rates<2>(c, nullptr, nullptr, nullptr, 0), do_get_rates<3>(c, nullptr, nullptr, nullptr, 0));
+  c->drho_pairs = false;
   c->rate_chunks = 1; c->on_rates_chunk = nullptr;
   if (e || cb_err) { cudaStreamSynchronize(c->stream_h2d); cudaStreamSynchronize(c->stream_d2h); return e ? e : ND_ERR_CUDA; }
   if (nchunk == 1) {
