@@ -246,14 +246,15 @@ def test_pipelined_derivs_host_equals_upload_derivs_download(aux):
         assert sa[k] == sb[k]
 
 
-@pytest.mark.parametrize("name,chunks", [("ot3d_glass", 3), ("briowu1d", 4), ("dustybox3d", 2), ("onefluid_dust3d_mhd", 5), ("ot2d_closepacked", 7)])
+@pytest.mark.parametrize("name,chunks", [("ot3d_glass", 3), ("briowu1d", 4), ("dustybox3d", 2), ("onefluid_dust3d_mhd", 5), ("ot2d_closepacked", 7),
+                                         ("ot3d_glass_noaux", 3), ("briowu1d_noaux", 4)])   # the last two: fast tuple, LIGHT density rounds
 def test_row_chunked_rates_equal_the_single_launch(name, chunks, monkeypatch):
     """ndspmhd_b200_derivs_host runs the rates in chunks of original rows so that a chunk's results download while the next
     chunk's pair kernel runs (4 chunks above 1 Mi particles; forced here).  Every target's sums are its own and dpsidt is made
     from the global vsigmax after the last chunk, so the outputs must equal the single launch bit for bit."""
     o, p = CASES[name][0]()
     o.device_ghosts = 1
-    o.want_aux = 1
+    o.want_aux = CASES[name][1]
     a, b = p.copy(), p.copy()
     hot = lib.Hotpath(o, p.ndim)
     try:
