@@ -4,7 +4,8 @@ multi/multi_shock.f90:65-87 and src/setup_shockND.f90:108-123), must land on ans
 
 * Sod tube (gamma = 5/3): the exact Riemann solution (iterative pressure solve, Toro ch. 4) -- both plateaus, the contact speed, the shock
   position and the velocity profile of the rarefaction fan;
-* Brio-Wu MHD tube (gamma = 2): a first-order HLL finite-volume solution of 1-D ideal MHD on 3000 cells, written here in numpy.
+* Brio-Wu MHD tube (gamma = 2): a first-order HLL finite-volume solution of 1-D ideal MHD on 3000 cells, written here in numpy;
+* DUSTYBOX (two-fluid drag, src/setup_dustybox.f90): the analytic exponential relaxation of the differential velocity.
 
 The reference ships no expected outputs; these are the published test problems its documentation shows it on.  Tolerances are those of
 SPH at this resolution (AV-broadened shocks, ~500-1100 particles), not round-off: what they exclude is a wrong term, sign or factor in
@@ -142,3 +143,33 @@ def test_brio_wu_tube_lands_on_an_independent_finite_volume_solution():
         for f in ("vx", "vy"):                       # velocities against the largest speed of the problem (some plateaus are near rest)
             a, b = np.median(sph[f][ms]), np.median(fv[f][mf])
             assert abs(a - b) < tol * 1.6, (name, f, a, b)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("ndim,nx", [(2, 16), (3, 8)])
+def test_dustybox_relaxes_at_the_analytic_rate(ndim, nx):
+    """DUSTYBOX (Laibe & Price 2011, MNRAS 418, 1491; the reference's src/setup_dustybox.f90): uniform gas streaming through uniform dust with
+    a constant drag coefficient K.  The differential velocity decays as exp(-K (1/rho_g + 1/rho_d) t), the barycentre keeps its velocity
+    and the lost kinetic energy heats the gas (src/ratesND_mhd.f90:1074-1169 + the leapfrog)."""
+    K = 1.0
+    o, p = setups.dustybox(ndim=ndim, nx=nx, perturb_amp=0.0, Kdrag=K)
+    n = p.npart
+    gas = p.itype[:n] == 0
+    dust = ~gas
+    p.vel[:n] = 0.0
+    p.vel[:n, 0][gas] = 1.0
+    m = p.pmass[:n]
+    e0 = float(np.sum(m * (0.5 * (p.vel[:n] ** 2).sum(axis=1) + p.en[:n])))
+    tmax = 0.5
+    _evolve(o, p, tmax)
+    vg, vd = p.vel[:n, 0][gas], p.vel[:n, 0][dust]
+    rg, rd = float(p.rho[:n][gas].mean()), float(p.rho[:n][dust].mean())
+    assert np.ptp(vg) < 1e-12 and np.ptp(vd) < 1e-12                       # the uniform state stays uniform
+    assert abs((vg.mean() - vd.mean()) / np.exp(-K * (1.0 / rg + 1.0 / rd) * tmax) - 1.0) < 0.01
+    assert abs(0.5 * (vg.mean() + vd.mean()) - 0.5) < 1e-12                # equal masses: barycentre velocity 1/2
+    assert np.max(np.abs(p.vel[:n, 1:])) < 1e-4                             # pairwise drag acts along r^: transverse parts cancel to lattice order
+    e1 = float(np.sum(m * (0.5 * (p.vel[:n] ** 2).sum(axis=1) + p.en[:n])))
+    assert abs(e1 / e0 - 1.0) < 2e-3                                       # drag heating = kinetic energy lost (second-order in dt)
+    assert np.all(p.en[:n][gas] > 1.2) and np.all(p.en[:n][dust] == 0.0)   # the heat goes to the gas only
