@@ -173,3 +173,52 @@ def test_dustybox_relaxes_at_the_analytic_rate(ndim, nx):
     e1 = float(np.sum(m * (0.5 * (p.vel[:n] ** 2).sum(axis=1) + p.en[:n])))
     assert abs(e1 / e0 - 1.0) < 2e-3                                       # drag heating = kinetic energy lost (second-order in dt)
     assert np.all(p.en[:n][gas] > 1.2) and np.all(p.en[:n][dust] == 0.0)   # the heat goes to the gas only
+
+
+def _wave1d(nx, kind, amp):
+    """1-D periodic box [0,1], rho = 1 (the geometry of src/setup_wave_x_ND.f90).  `sound`: linear acoustic wave, c_s = 1;
+    `alfven`: circularly polarised Alfven wave on Bx = 1 -- an exact nonlinear solution of ideal MHD travelling at v_A = 1."""
+    from ndspmhd_b200.setups import _alloc, _finish, cubic_lattice, default_options
+    o = default_options(1)
+    o.ibound[0] = 3
+    o.xmin[0], o.xmax[0] = 0.0, 1.0
+    o.psep = 1.0 / nx
+    o.imhd = 1 if kind == "alfven" else 0
+    o.iener = 2
+    x, _ = cubic_lattice([0.0], [1.0], o.psep)
+    n = x.shape[0]
+    p = _alloc(1, x, o, o.hfact * o.psep)
+    p.pmass[:n] = 1.0 / n
+    k, g = 2.0 * np.pi, o.gamma
+    xx = x[:, 0]
+    if kind == "sound":
+        xx = xx + amp / k * np.cos(k * xx)        # displaced lattice: the SPH density itself carries rho0 (1 + amp sin kx)
+        p.x[:n, 0] = xx
+        p.vel[:n, 0] = amp * np.sin(k * xx)
+        dens, uu, B = 1.0 + amp * np.sin(k * xx), (1.0 + (g - 1.0) * amp * np.sin(k * xx)) / (g * (g - 1.0)), None
+    else:
+        dens, uu = np.ones(n), np.full(n, 0.15)
+        B = np.stack([np.ones(n), amp * np.sin(k * xx), amp * np.cos(k * xx)], axis=1)
+        p.vel[:n, 1], p.vel[:n, 2] = -amp * np.sin(k * xx), -amp * np.cos(k * xx)   # right-going: v_perp = -B_perp / sqrt(rho)
+    _finish(p, o, dens, uu, B)
+    return o, p
+
+
+def _fourier(x, f):
+    c, s = np.sum(f * np.cos(2.0 * np.pi * x)), np.sum(f * np.sin(2.0 * np.pi * x))
+    return np.arctan2(c, s), 2.0 * np.hypot(c, s) / len(x)       # f = A sin(2 pi x + phase)
+
+
+@pytest.mark.parametrize("kind,nx,amp,tol", [("sound", 64, 1e-3, 0.01), ("alfven", 64, 0.1, 0.003), ("alfven", 128, 0.1, 0.001)])
+def test_waves_travel_at_the_sound_and_alfven_speeds(kind, nx, amp, tol):
+    o, p = _wave1d(nx, kind, amp)
+    n = p.npart
+    field = (lambda q: q.vel[:n, 0]) if kind == "sound" else (lambda q: q.Bevol[:n, 1] * q.rho[:n])   # imhd = 1 evolves B/rho
+    oracle.derivs(o, p)
+    ph0, a0 = _fourier(p.x[:n, 0], field(p))
+    tmax = 0.5
+    _evolve(o, p, tmax)
+    ph1, a1 = _fourier(p.x[:n, 0], field(p))
+    speed = ((ph0 - ph1) % (2.0 * np.pi)) / (2.0 * np.pi * tmax)
+    assert abs(speed - 1.0) < tol, speed
+    assert 0.98 < a1 / a0 < 1.001
