@@ -2,7 +2,8 @@
 oracle frozen at the time they were made.  They are not NDSPMHD outputs (the reference cannot be built here).
 
 * CPU: the oracle of today must reproduce them (a drift alarm for the checker itself), and the generators must still produce the inputs.
-* GPU: the CUDA path through the C-ABI is compared with the frozen outputs, without executing anything under oracle/.
+* GPU (tests/test_gpu_vectors.py): the CUDA path through the C-ABI is compared with the frozen outputs, without executing anything
+  under oracle/.
 """
 import glob
 import json
@@ -64,14 +65,3 @@ def test_generators_still_make_the_golden_inputs():
         assert p2.npart == pin.npart
         for k in pin.arrays:
             assert np.array_equal(p2.arrays[k][: pin.npart], pin.arrays[k][: pin.npart]), (name, k)
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", NAMES)
-def test_cuda_path_matches_the_golden_outputs(name):
-    from ndspmhd_b200 import lib
-    o, pin, pout, scal, aux = load_case(name)
-    pg = pin.copy()
-    sg = lib.derivs_host(o, pg)
-    errs = parity.assert_parity(pg, pout, sg, scal, o, aux=bool(aux))
-    assert max(errs.values()) <= parity.RTOL

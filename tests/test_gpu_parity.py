@@ -190,38 +190,6 @@ def test_phase_by_phase_calls_equal_fused_derivs():
         assert s1[k] == s2[k]
 
 
-def test_fast_tuple_fused_derivs_agree_with_phase_by_phase_calls():
-    """Fast option tuple (want_aux=0): a fused derivs runs the density rounds LIGHT and takes drho/dt from the pair sums of
-    get_rates; the phase-by-phase calls keep drho/dt in the density sums (src/density_sums.f90:297-303).  Same pairs, same
-    grad W, different order of summation: everything made before the rates is bit-equal, drho/dt and what is built on it
-    agree to the parity tolerance."""
-    o, p = setups.orszag_tang(ndim=3, nx=16, zfrac=0.5, perturb_amp=0.2, evolved=True)
-    o.device_ghosts = 1
-    o.want_aux = 0
-    p1, p2 = p.copy(), p.copy()
-    s1 = lib.derivs_host(o, p1)
-    hot = lib.Hotpath(o, 3)
-    try:
-        hot.upload(p2)
-        hot.set_linklist()
-        sd = hot.iterate_density()
-        hot.conservative2primitive()
-        s2 = hot.get_rates()
-        p2.ntotal = sd["ntotal"]
-        hot.download(p2)
-    finally:
-        hot.close()
-    n = p.npart
-    for f in ["hh", "rho", "gradh"] + parity.PRIM_FIELDS + ["force", "gradpsi", "divB", "curlB"]:
-        assert np.array_equal(getattr(p1, f)[:n], getattr(p2, f)[:n]), f
-    scales = parity.natural_scales(p2, n)
-    for f in ["drhodt", "dhdt", "dudt", "dendt", "dBevoldt", "daldt", "dpsidt"]:
-        err = parity.field_error(getattr(p1, f)[:n], getattr(p2, f)[:n], scales[f])
-        assert err <= parity.RTOL, (f, err)
-    for k in ("dtcourant", "dtforce", "vsigmax", "itsdensity", "ntotal"):
-        assert s1[k] == s2[k]
-
-
 @pytest.mark.parametrize("aux", [0, 1])
 def test_pipelined_derivs_host_equals_upload_derivs_download(aux):
     """ndspmhd_b200_derivs_host overlaps the copies with the kernels on separate streams; same bits as the serial calls."""
@@ -246,8 +214,7 @@ def test_pipelined_derivs_host_equals_upload_derivs_download(aux):
         assert sa[k] == sb[k]
 
 
-@pytest.mark.parametrize("name,chunks", [("ot3d_glass", 3), ("briowu1d", 4), ("dustybox3d", 2), ("onefluid_dust3d_mhd", 5), ("ot2d_closepacked", 7),
-                                         ("ot3d_glass_noaux", 3), ("briowu1d_noaux", 4)])   # the last two: fast tuple, LIGHT density rounds
+@pytest.mark.parametrize("name,chunks", [("ot3d_glass", 3), ("briowu1d", 4), ("dustybox3d", 2), ("onefluid_dust3d_mhd", 5), ("ot2d_closepacked", 7)])
 def test_row_chunked_rates_equal_the_single_launch(name, chunks, monkeypatch):
     """ndspmhd_b200_derivs_host runs the rates in chunks of original rows so that a chunk's results download while the next
     chunk's pair kernel runs (4 chunks above 1 Mi particles; forced here).  Every target's sums are its own and dpsidt is made
