@@ -25,11 +25,11 @@ CASES = {
     # BASELINE.json configs[0]: 1-D Brio-Wu tube with fixed ends
     "briowu1d": (lambda: setups.shock1d(nright=40), 1),
     # configs[1]: 2-D Orszag-Tang on the close-packed lattice
-    "ot2d_closepacked": (lambda: setups.orszag_tang(ndim=2, nx=20, lattice="cp", perturb_amp=0.2, evolved=True), 1),
+    "ot2d_closepacked": (lambda: setups.orszag_tang(ndim=2, nx=32, lattice="cp", perturb_amp=0.2, evolved=True), 1),
     # configs[2]/[4]: 3-D MHD Orszag-Tang slab, the first-class option tuple (want_aux = 0: the FAST kernels, LIGHT density rounds)
-    "ot3d_glass_fast": (lambda: setups.orszag_tang(ndim=3, nx=10, zfrac=0.5, perturb_amp=0.2, evolved=True), 0),
+    "ot3d_glass_fast": (lambda: setups.orszag_tang(ndim=3, nx=12, zfrac=0.5, perturb_amp=0.25, evolved=True), 0),
     # configs[3]: two-fluid dust + gas
-    "dustybox3d": (lambda: setups.dustybox(ndim=3, nx=6), 1),
+    "dustybox3d": (lambda: setups.dustybox(ndim=3, nx=10), 1),
 }
 
 
