@@ -49,6 +49,7 @@ struct nd_ctx {
   // ---- sorted-order arrays ----
   double4 *posh = nullptr, *vm = nullptr, *posm = nullptr, *bpsi = nullptr, *thermo = nullptr, *gal = nullptr;
   bool dens_light = false;   // set by the fused entry points: the rates kernel of the same derivs makes drho/dt (fast tuple)
+  bool slab_light = false;   // NDSPMHD_B200_SLAB_LIGHT=1: LIGHT rounds in slab-decomposed contexts too (off until it has run on >= 2 GPUs)
   bool drho_pairs = false;   // the density rounds of this derivs ran LIGHT: k_rates_final takes drho/dt from the pair sums and makes dh/dt
   float4 *p32 = nullptr;   // FP32 screening records of the list builder (nd_device.cuh)
   double *srho = nullptr;
@@ -1767,6 +1768,7 @@ int ndspmhd_b200_create(const nd_options *o, int ndim, int device, nd_ctx **out)
   if (device < 0 || device >= ndev) return set_err(c, ND_ERR_INVALID_ARG, "bad device ordinal");
   CU(cudaSetDevice(device));
   CU(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
+  if (const char *ev = getenv("NDSPMHD_B200_SLAB_LIGHT")) c->slab_light = atoi(ev) != 0;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (int k = 0; k < 8; k++) CU(cudaEventCreate(&c->ev[k]));
   for (int k = 0; k < 2; k++) CU(cudaEventCreate(&c->ev_pair[k]));
@@ -2028,7 +2030,7 @@ int ndspmhd_b200_derivs(nd_ctx *c, nd_scalars *s) {
   int e = DISPATCH_NDIM(c, do_link<1>(c), do_link<2>(c), do_link<3>(c));
   if (e) return e;
   CU(cudaEventRecord(c->ev[1], c->stream));
-  c->dens_light = ND_DENS_LIGHT && fast_tuple(c->o) && !c->has_comm;   // get_rates follows in this call and makes drho/dt itself
+  c->dens_light = ND_DENS_LIGHT && fast_tuple(c->o) && (!c->has_comm || c->slab_light);   // get_rates follows in this call and makes drho/dt itself
   const bool light = c->dens_light;
   e = DISPATCH_NDIM(c, do_iterate_density<1>(c, 0), do_iterate_density<2>(c, 0), do_iterate_density<3>(c, 0));
   c->dens_light = false;
@@ -2094,7 +2096,7 @@ int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int
   bool light = false;
   if (!e) {
     CU(cudaEventRecord(c->ev[1], c->stream));
-    c->dens_light = ND_DENS_LIGHT && fast_tuple(c->o) && !c->has_comm && (mask & ND_DL_RATES);   // the rates of this call make drho/dt
+    c->dens_light = ND_DENS_LIGHT && fast_tuple(c->o) && (!c->has_comm || c->slab_light) && (mask & ND_DL_RATES);   // the rates of this call make drho/dt
     light = c->dens_light;
     e = DISPATCH_NDIM(c, do_iterate_density<1>(c, 0), do_iterate_density<2>(c, 0), do_iterate_density<3>(c, 0));
     c->dens_light = false;
