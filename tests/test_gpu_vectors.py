@@ -12,7 +12,8 @@ from test_golden import NAMES, load_case
 from test_gpu_parity import CASES, run_both
 from test_gpu_step import _dt0
 
-pytestmark = pytest.mark.gpu
+# none of these has run on a GPU yet: a stuck kernel must end the pytest process (and free the device), not hold the box
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
 
 
 @pytest.mark.parametrize("name", NAMES)
