@@ -59,13 +59,21 @@ __device__ __forceinline__ void st4(double4 *p, const double4 &v) {
 // (5 FP64 instructions, <= 1 ulp), one coupled Goldschmidt step + residual correction for sqrt (7 instructions, <= 0.5 ulp
 // measured).  CUDA's sqrt()/rsqrt() carry a slow-path branch per call, which stops ptxas from interleaving the six
 // independent square roots of a rates pair; these do not.  Arguments <= 1e-300 give 0.
+#ifndef ND_SQRT_INTGUARD
+#define ND_SQRT_INTGUARD 0   // 1: the x > 1e-300 guards as integer compares on the high word (DSETP issues on the half-rate FP64 pipe); untried on a GPU
+#endif
+#if ND_SQRT_INTGUARD
+#define ND_SQRT_ARG_OK(x) (__double2hiint(x) > 0x01A56E1F)   // high word of 1e-300; the arguments are non-negative or fail the test as negatives do
+#else
+#define ND_SQRT_ARG_OK(x) ((x) > 1.e-300)
+#endif
 __device__ __forceinline__ double rsqrt_nr(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   const double t = x * y, e = fma(-t, y, 1.0);          // e = 1 - x y^2
   const double q = fma(0.375, e, 0.5) * e;              // y (1 + e/2 + 3 e^2/8)
   y = fma(y, q, y);
-  return x > 1.e-300 ? y : 0.;
+  return ND_SQRT_ARG_OK(x) ? y : 0.;
 }
 __device__ __forceinline__ double sqrt_nr(double x) {
   double y;
@@ -75,7 +83,7 @@ __device__ __forceinline__ double sqrt_nr(double x) {
   const double s1 = fma(s0, r, s0), h1 = fma(h0, r, h0);
   const double d = fma(-s1, s1, x);
   const double s = fma(d, h1, s1);
-  return x > 1.e-300 ? s : 0.;
+  return ND_SQRT_ARG_OK(x) ? s : 0.;
 }
 // N independent square roots advanced in lockstep: the source order interleaves the (serial, ~9-cycle per step) chains so
 // that ptxas, which keeps close to source order under register pressure, issues them back to back instead of one after another.
@@ -92,7 +100,7 @@ template <int N> __device__ __forceinline__ void sqrt_n(const double (&x)[N], do
 #pragma unroll
   for (int i = 0; i < N; i++) d[i] = fma(-s1[i], s1[i], x[i]);
 #pragma unroll
-  for (int i = 0; i < N; i++) out[i] = x[i] > 1.e-300 ? fma(d[i], h1[i], s1[i]) : 0.;
+  for (int i = 0; i < N; i++) out[i] = ND_SQRT_ARG_OK(x[i]) ? fma(d[i], h1[i], s1[i]) : 0.;
 }
 
 __global__ void k_selftest_math(const double *in, double *out_sqrt, double *out_rsqrt, int n) {
