@@ -47,6 +47,16 @@ struct RatesRed {
   int *sched;              // work counter of the persistent warps (zeroed before each launch)
 };
 
+#ifndef ND_FMAX_INT
+#define ND_FMAX_INT 0   // 1: the maxima of the pair body as signed 64-bit integer compares (DSETP.MAX issues on the half-rate FP64 pipe); untried on a GPU
+#endif
+#if ND_FMAX_INT
+// max(a, b) for finite a of either sign and b >= +0: IEEE doubles of equal sign order like their bit patterns, a negative a is a negative integer
+__device__ __forceinline__ double fmax_nonneg(double a, double b) { return __double_as_longlong(a) > __double_as_longlong(b) ? a : b; }
+#define ND_FMAX(a, b) fmax_nonneg(a, b)
+#else
+#define ND_FMAX(a, b) fmax(a, b)
+#endif
 #ifndef ND_RATES_MINB
 #define ND_RATES_MINB 2
 #endif
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
     any_coincident |= (rinv == 0.);
     const double pmassj = vj.w;
     const double dvx = vxi - vj.x, dvy = vyi - vj.y, dvz = vzi - vj.z;
-    const double h1max = fmax(hi1, hj1);
+    const double h1max = ND_FMAX(hi1, hj1);
     if (!DRAG || types_interact(ti, tj)) {
       // =============================== rates_core ===============================
       // kernel gradient table rows for q2i, q2j: the loads are issued here, the interpolation (their first use) comes after the
@@ -279,14 +289,14 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
         vsigi = spsoundi; vsigj = spsoundj; vsigB = 0.;
         vsigu = sqrt_nr(pdiff);
       }
-      double vsig = 0.5 * (fmax(vsigi + vsigj - O.beta * dvdotr, 0.0));          // :1452
-      double vsigdtc = fmax(vsig, fmax(0.5 * (vsigi + vsigj + O.beta * fabs(dvdotr)), vsigB));   // :1465
+      double vsig = 0.5 * (ND_FMAX(vsigi + vsigj - O.beta * dvdotr, 0.0));          // :1452
+      double vsigdtc = ND_FMAX(vsig, ND_FMAX(0.5 * (vsigi + vsigj + O.beta * fabs(dvdotr)), vsigB));   // :1465
       if (ONEF) vsigdtc = vsigdtc + sqrt(deltav2i + deltav2j);                                   // :1466-1468
       {                                                                         // :1472-1481 as selects
         const bool dust = (ti == T_DUST);
         vsig = dust ? 0. : vsig; vsigu = dust ? 0. : vsigu;
-        vsigmax = fmax(vsigmax, dust ? 0. : vsigdtc);
-        dtc_den = fmax(dtc_den, (!dust && vsigdtc > zero) ? h1max * vsigdtc : 0.);
+        vsigmax = ND_FMAX(vsigmax, dust ? 0. : vsigdtc);
+        dtc_den = ND_FMAX(dtc_den, (!dust && vsigdtc > zero) ? h1max * vsigdtc : 0.);
       }
       // ---- kernel gradients :1208-1241 (w = w[index] + dwdx*(q2 - index*dq2table), src/kernelND.f90:4443-4455) ----
       double grkerni = rowi.x + rowi.y * (q2i - __dmul_rn((double)idxi, G.dq2table));
@@ -308,7 +318,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
       if (ONEF && iav > 0) {
         // =============================== artificial_dissipation_dust (iav = 1, 2, 3) ===============================
         const double alphaav = 0.5 * (alphai + gj.y), alphau = 0.5 * (alphaui + gj.z), alphaB = 0.5 * (alphaBi + gj.w);
-        vsigav = fmax(alphaav, alphau) * vsig;                   // :1984
+        vsigav = ND_FMAX(alphaav, alphau) * vsig;                   // :1984
         const double dustfracav = 0.5 * (dustfraci + dustfracj);
         const double projdvgasav = dvdotr - dustfracav * (projdeltavi - projdeltavj);
         const double ddx_ = dvix - dvjx, ddy_ = dviy - dvjy, ddz_ = dviz - dvjz;
@@ -350,7 +360,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
       } else if (iav > 0 && iav != 3) {
         // =============================== artificial_dissipation ===============================
         const double alphaav = 0.5 * (alphai + gj.y), alphau = 0.5 * (alphaui + gj.z), alphaB = 0.5 * (alphaBi + gj.w);   // :1712-1714
-        vsigav = fmax(alphaav, fmax(alphau, alphaB)) * vsig;
+        vsigav = ND_FMAX(alphaav, ND_FMAX(alphau, alphaB)) * vsig;
         const double rg = rhoav1 * grkern;
         const double term = vsig * rg;                           // :1723
         const double termu = vsigu * rg;                         // :1727
@@ -397,8 +407,8 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
         const double rhoj = __ldg(I.srho + k);
         double dudti = 0.;
         if (dvdotr < 0.) {
-          const double vsi = fmax(alphai * spsoundi - O.beta * dvdotr, 0.);
-          const double vsj = fmax(gj.y * spsoundj - O.beta * dvdotr, 0.);
+          const double vsi = ND_FMAX(alphai * spsoundi - O.beta * dvdotr, 0.);
+          const double vsj = ND_FMAX(gj.y * spsoundj - O.beta * dvdotr, 0.);
           const double qi = -0.5 * rhoi * vsi * dvdotr, qj = -0.5 * rhoj * vsj * dvdotr;
           const double visc = (qi * rho21i * grkerni + qj * rho21j * grkernj);
           const double c = pmassj * visc;
@@ -410,7 +420,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
         const double diffu = cfaci * grkerni * (rho1i * rho1i) + cfacj * grkernj * (rho1j * rho1j);
         dudt += dudti + pmassj * diffu;
       }
-      dtav_den = fmax(dtav_den, vsigav > zero ? h1max * vsigav : 0.);              // :1500
+      dtav_den = ND_FMAX(dtav_den, vsigav > zero ? h1max * vsigav : 0.);              // :1500
       if (FAST && ND_DENS_LIGHT) drho += pmassj * (dvdotr * (1. - eps * rinv)) * grkerni;   // sum m_j (dv.dr) grad W_i: the density loop's drhodt (LIGHT rounds skip it)
       {                                                          // pressure, :1538-1567 (phi = 1, sqrtg = 1)
         const double prterm = Prho2i * grkerni + Prho2j * grkernj;
