@@ -167,7 +167,11 @@ enum {
   ND_DL_PRIM    = 2u,   /* dens uu pr spsound Bfield (+dustfrac) */
   ND_DL_RATES   = 4u,   /* force dudt dendt dBevoldt daldt dpsidt gradpsi divB curlB graddivv del2u (+ddustevoldt ddeltavdt) */
   ND_DL_GHOSTS  = 8u,   /* x_out vel_out ireal_out itype_out rows [npart,ntotal) */
-  ND_DL_ALL     = 15u
+  ND_DL_ALL     = 15u,
+  /* modifier: the groups above come down for rows [0,npart) only.  The ghost rows of those arrays are copies of their parents
+     (src/iterate_density.f90:330-344, src/conservative2primitive.f90:441-467) or zeros (src/ratesND_mhd.f90:949-965) and are rebuilt by
+     the next set_ghost_particles; leave the bit clear when the caller reads them (e.g. a dump of ghost rows). */
+  ND_DL_REAL_ROWS = 16u
 };
 
 /* scalars returned by the path: module timestep (src/variablesND.f90:255-273), hterms:itsdensity, bound:hhmax */

@@ -29,6 +29,7 @@ ND_NEED_RELINK = 100
 ITYPE_GAS, ITYPE_BND, ITYPE_DUST, ITYPE_GAS1, ITYPE_GAS2, ITYPE_BND2, ITYPE_BNDDUST = 0, 1, 2, 3, 4, 11, 12
 
 DL_DENSITY, DL_PRIM, DL_RATES, DL_GHOSTS, DL_ALL = 1, 2, 4, 8, 15
+DL_REAL_ROWS = 16   # modifier: rows [0,npart) only
 
 
 class NdOptions(C.Structure):

@@ -2056,10 +2056,10 @@ int ndspmhd_b200_download(nd_ctx *c, nd_arrays *a, unsigned mask, int idim) {
   if (!c->uploaded) return set_err(c, ND_ERR_STATE, "download before upload");
   if (idim < c->ntotal) return set_err(c, ND_ERR_INVALID_ARG, "download: idim < ntotal (re-allocate the host arrays, src/ghostND_mhd.f90:383-386)");
   CU(cudaSetDevice(c->device));
-  const size_t n = (size_t)(c->has_comm ? c->nown : c->ntotal);   // with slabs only this rank's own rows go back
+  const size_t n = (size_t)(c->has_comm ? c->nown : ((mask & ND_DL_REAL_ROWS) ? c->npart : c->ntotal));   // with slabs only this rank's own rows go back
   for (int g = 1; g <= 3; g++) if (int e = download_group(c, a, n, g, mask, c->stream)) return e;
   if ((mask & ND_DL_GHOSTS) && !c->has_comm) {
-    const size_t g0 = (size_t)c->npart, ng = n - g0, D = sizeof(double);
+    const size_t g0 = (size_t)c->npart, ng = (size_t)c->ntotal - g0, D = sizeof(double);
     auto dn = [&](void *dst, const void *src, size_t bytes) -> cudaError_t { return (dst && src) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess; };
     if (ng > 0) {
       if (a->x_out) CU(dn(a->x_out + g0 * c->ndim, c->x + g0 * c->ndim, D * c->ndim * ng));
@@ -2103,7 +2103,7 @@ int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int
   }
   if (e) { cudaStreamSynchronize(c->stream_h2d); return e; }
   if (idim < c->ntotal) { cudaStreamSynchronize(c->stream_h2d); return set_err(c, ND_ERR_INVALID_ARG, "derivs_host: idim < ntotal after ghost generation"); }
-  const size_t nout = (size_t)(c->has_comm ? c->nown : c->ntotal);
+  const size_t nout = (size_t)(c->has_comm ? c->nown : ((mask & ND_DL_REAL_ROWS) ? c->npart : c->ntotal));
   CU(cudaEventRecord(c->ev_out[0], c->stream));
   CU(cudaStreamWaitEvent(c->stream_d2h, c->ev_out[0], 0));
   if (int e2 = download_group(c, a, nout, 1, mask, c->stream_d2h)) return e2;

@@ -159,3 +159,37 @@ def test_dustybox_on_the_device_relaxes_at_the_analytic_rate():
     rg, rd = float(p.rho[:n][gas].mean()), float(p.rho[:n][~gas].mean())
     assert abs((vg.mean() - vd.mean()) / np.exp(-K * (1.0 / rg + 1.0 / rd) * tmax) - 1.0) < 0.01
     assert abs(0.5 * (vg.mean() + vd.mean()) - 0.5) < 1e-12
+
+
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_real_rows_modifier_leaves_ghost_rows_of_the_outputs_alone(pipelined):
+    """ND_DL_REAL_ROWS: rows [0,npart) of the output arrays equal the full download bit for bit; rows [npart,ntotal) are not written."""
+    o, p = setups.orszag_tang(ndim=3, nx=16, zfrac=0.5, perturb_amp=0.2, evolved=True)
+    o.device_ghosts = 1
+    o.want_aux = 0
+    mask = abi.DL_DENSITY | abi.DL_PRIM | abi.DL_RATES
+    a, b = p.copy(), p.copy()
+    sentinel = -7.25
+    for f in ("rho", "pr", "force", "divB", "drhodt"):
+        getattr(b, f)[p.npart:] = sentinel
+    hot = lib.Hotpath(o, 3)
+    try:
+        if pipelined:
+            sa = hot.derivs_host(a, mask)
+            sb = hot.derivs_host(b, mask | abi.DL_REAL_ROWS)
+        else:
+            hot.upload(a)
+            sa = hot.derivs()
+            a.ntotal = sa["ntotal"]
+            hot.download(a, mask)
+            b.ntotal = sa["ntotal"]
+            hot.download(b, mask | abi.DL_REAL_ROWS)
+            sb = sa
+    finally:
+        hot.close()
+    n, nt = p.npart, sa["ntotal"]
+    assert nt > n and sb["ntotal"] == nt
+    for f in parity.DENSITY_FIELDS + parity.PRIM_FIELDS + [x for x in parity.RATES_FIELDS if x not in ("graddivv", "del2u")]:
+        assert np.array_equal(getattr(a, f)[:n], getattr(b, f)[:n]), f
+    for f in ("rho", "pr", "force", "divB", "drhodt"):
+        assert np.all(getattr(b, f)[n:nt] == sentinel), f
