@@ -183,7 +183,7 @@ def _wave1d(nx, kind, amp):
     o.ibound[0] = 3
     o.xmin[0], o.xmax[0] = 0.0, 1.0
     o.psep = 1.0 / nx
-    o.imhd = 1 if kind == "alfven" else 0
+    o.imhd = 0 if kind == "sound" else 1
     o.iener = 2
     x, _ = cubic_lattice([0.0], [1.0], o.psep)
     n = x.shape[0]
@@ -196,6 +196,13 @@ def _wave1d(nx, kind, amp):
         p.x[:n, 0] = xx
         p.vel[:n, 0] = amp * np.sin(k * xx)
         dens, uu, B = 1.0 + amp * np.sin(k * xx), (1.0 + (g - 1.0) * amp * np.sin(k * xx)) / (g * (g - 1.0)), None
+    elif kind == "fast":
+        # fast magnetosonic wave across B = (0, 0.75, 0): v_f^2 = c_s^2 + v_A^2 = 1 + 0.5625; d rho/rho = dBy/By = dvx/v_f = amp sin kx
+        xx = xx + amp / k * np.cos(k * xx)
+        p.x[:n, 0] = xx
+        p.vel[:n, 0] = 1.25 * amp * np.sin(k * xx)
+        dens, uu = 1.0 + amp * np.sin(k * xx), (1.0 + (g - 1.0) * amp * np.sin(k * xx)) / (g * (g - 1.0))
+        B = np.stack([np.zeros(n), 0.75 * (1.0 + amp * np.sin(k * xx)), np.zeros(n)], axis=1)
     else:
         dens, uu = np.ones(n), np.full(n, 0.15)
         B = np.stack([np.ones(n), amp * np.sin(k * xx), amp * np.cos(k * xx)], axis=1)
@@ -209,16 +216,17 @@ def _fourier(x, f):
     return np.arctan2(c, s), 2.0 * np.hypot(c, s) / len(x)       # f = A sin(2 pi x + phase)
 
 
-@pytest.mark.parametrize("kind,nx,amp,tol", [("sound", 64, 1e-3, 0.01), ("alfven", 64, 0.1, 0.003), ("alfven", 128, 0.1, 0.001)])
-def test_waves_travel_at_the_sound_and_alfven_speeds(kind, nx, amp, tol):
+@pytest.mark.parametrize("kind,nx,amp,tol,speed_exact", [("sound", 64, 1e-3, 0.01, 1.0), ("alfven", 64, 0.1, 0.003, 1.0), ("alfven", 128, 0.1, 0.001, 1.0),
+                                                         ("fast", 64, 1e-3, 0.01, 1.25)])
+def test_waves_travel_at_the_sound_alfven_and_fast_speeds(kind, nx, amp, tol, speed_exact):
     o, p = _wave1d(nx, kind, amp)
     n = p.npart
-    field = (lambda q: q.vel[:n, 0]) if kind == "sound" else (lambda q: q.Bevol[:n, 1] * q.rho[:n])   # imhd = 1 evolves B/rho
+    field = (lambda q: q.vel[:n, 0]) if kind != "alfven" else (lambda q: q.Bevol[:n, 1] * q.rho[:n])   # imhd = 1 evolves B/rho
     oracle.derivs(o, p)
     ph0, a0 = _fourier(p.x[:n, 0], field(p))
-    tmax = 0.5
+    tmax = 0.5 / speed_exact
     _evolve(o, p, tmax)
     ph1, a1 = _fourier(p.x[:n, 0], field(p))
     speed = ((ph0 - ph1) % (2.0 * np.pi)) / (2.0 * np.pi * tmax)
-    assert abs(speed - 1.0) < tol, speed
+    assert abs(speed / speed_exact - 1.0) < tol, speed
     assert 0.98 < a1 / a0 < 1.001
