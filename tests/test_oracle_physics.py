@@ -230,3 +230,33 @@ def test_waves_travel_at_the_sound_alfven_and_fast_speeds(kind, nx, amp, tol, sp
     speed = ((ph0 - ph1) % (2.0 * np.pi)) / (2.0 * np.pi * tmax)
     assert abs(speed / speed_exact - 1.0) < tol, speed
     assert 0.98 < a1 / a0 < 1.001
+
+
+@pytest.mark.parametrize("ndim,nx,tol", [(2, 16, 0.015), (3, 8, 0.04)])
+def test_onefluid_dustybox_relaxes_at_the_analytic_rate(ndim, nx, tol):
+    """The same relaxation in the one-fluid formulation (idust = 1; Laibe & Price 2014; src/ratesND_mhd.f90:548-582, :2726-2807): a uniform
+    mixture with dust fraction 1/2 and differential velocity 1 obeys d(dv)/dt = -dv/t_s, t_s = rho_g rho_d / (K rho), the barycentre stays
+    at rest and E = sum m [v^2/2 + eps (1 - eps) dv^2/2 + (1 - eps) u] is conserved."""
+    K, tmax = 1.0, 0.15
+    o, p = setups.dustywave_onefluid(ndim=ndim, nx=nx, perturb_amp=0.0, Kdrag=K)
+    n = p.npart
+    p.vel[:n] = 0.0
+    p.dustfrac[:n] = p.dustevol[:n] = 0.5
+    p.deltav[:n] = 0.0
+    p.deltav[:n, 0] = 1.0
+    p.en[:n] = 0.9
+    p.alpha[:n] = [o.alphamin, o.alphaumin, o.alphaBmin]
+
+    def energy(q):
+        eps = q.dustfrac[:n]
+        return float(np.sum(q.pmass[:n] * (0.5 * (q.vel[:n] ** 2).sum(axis=1) + 0.5 * eps * (1 - eps) * (q.deltav[:n] ** 2).sum(axis=1) + (1 - eps) * q.en[:n])))
+
+    e0 = energy(p)
+    _evolve(o, p, tmax)
+    rho = float(p.rho[:n].mean())
+    eps = float(p.dustfrac[:n].mean())
+    assert abs(eps - 0.5) < 1e-12 and np.ptp(p.deltav[:n, 0]) < 1e-12            # uniform stays uniform, no dust-fraction evolution
+    rate = -np.log(p.deltav[:n, 0].mean()) / tmax
+    assert abs(rate / (K / (rho * eps * (1 - eps))) - 1.0) < tol, rate
+    assert np.max(np.abs(p.vel[:n])) < 1e-12 and np.max(np.abs(p.deltav[:n, 1:])) < 1e-12
+    assert abs(energy(p) / e0 - 1.0) < 2e-3
