@@ -260,3 +260,30 @@ def test_onefluid_dustybox_relaxes_at_the_analytic_rate(ndim, nx, tol):
     assert abs(rate / (K / (rho * eps * (1 - eps))) - 1.0) < tol, rate
     assert np.max(np.abs(p.vel[:n])) < 1e-12 and np.max(np.abs(p.deltav[:n, 1:])) < 1e-12
     assert abs(energy(p) / e0 - 1.0) < 2e-3
+
+
+def test_hyperbolic_cleaning_carries_a_divergence_blob_away():
+    """Dedner's static divergence-advection test in the Tricco & Price (2012) form: B_x = [(r/r0)^8 - 2 (r/r0)^4 + 1]/sqrt(4 pi) inside
+    r0 = 1/sqrt(8) of a fluid at rest.  Without cleaning (idivbzero = 0) the divergence error sits there; with the psi terms (idivbzero = 2:
+    gradpsi in dB/dt, dpsi/dt = -c_h^2 div B - psi/tau; src/ratesND_mhd.f90:2712-2717, :902) it is radiated away and damped -- a wrong sign in
+    either term makes it grow instead."""
+    def run(idivbzero):
+        o, p = setups.orszag_tang(ndim=2, nx=32, lattice="cubic", perturb_amp=0.0, evolved=False, imhd=11, idivbzero=idivbzero)
+        n = p.npart
+        r = np.sqrt((p.x[:n] ** 2).sum(axis=1)) * np.sqrt(8.0)
+        B = np.zeros((n, 3))
+        B[:, 0] = np.where(r < 1.0, (r**8 - 2.0 * r**4 + 1.0) / np.sqrt(4.0 * np.pi), 0.0)
+        B[:, 2] = 1.0 / np.sqrt(4.0 * np.pi)
+        p.vel[:n] = 0.0
+        p.Bfield[:n] = p.Bevol[:n] = B
+        p.psi[:n] = 0.0
+        oracle.derivs(o, p)
+        before = np.abs(p.divB[:n]).copy()
+        _evolve(o, p, 0.3)
+        return before, np.abs(p.divB[:n])
+
+    b0, b1 = run(0)
+    assert abs(b1.max() / b0.max() - 1.0) < 0.05 and abs(b1.mean() / b0.mean() - 1.0) < 0.05
+    c0, c1 = run(2)
+    assert np.array_equal(b0, c0)
+    assert c1.max() < 0.6 * c0.max() and c1.mean() < 0.8 * c0.mean()
