@@ -15,7 +15,7 @@ module ndspmhd_b200
 
  integer(c_int), parameter :: ND_OK = 0, ND_ERR_UNSUPPORTED_OPTION = 2, ND_NEED_RELINK = 100
  integer(c_int), parameter :: ND_DL_DENSITY = 1, ND_DL_PRIM = 2, ND_DL_RATES = 4, ND_DL_GHOSTS = 8, ND_DL_ALL = 15
- integer(c_int), parameter :: ND_DL_REAL_ROWS = 16   ! modifier: rows 1..npart of the output arrays only (ghost rows are rebuilt by set_ghost_particles)
+ integer(c_int), parameter :: ND_DL_REAL_ROWS = 16   ! modifier: rows 1..npart of the output arrays only
 
  type, bind(C) :: nd_options
     integer(c_int) :: iener,icty,iav,ikernav,ihvar,iprterm
