@@ -47,7 +47,8 @@ subroutine set_linklist
     call b200_check(ierr,'set_options')
  endif
  call b200_fill_arrays(a)
- call b200_check(ndspmhd_b200_upload(b200_ctx,a,int(npart,c_int),int(ntotal,c_int),int(size(pmass),c_int)),'upload')   ! size(pmass) = idim, the allocated length (src/allocateND.f90:313)
+ ! size(pmass) = idim, the allocated length (src/allocateND.f90:313)
+ call b200_check(ndspmhd_b200_upload(b200_ctx,a,int(npart,c_int),int(ntotal,c_int),int(size(pmass),c_int)),'upload')
  call b200_check(ndspmhd_b200_link(b200_ctx),'set_linklist')
  b200_resident = .true.
 end subroutine set_linklist

@@ -91,7 +91,8 @@ module ndspmhd_b200
      import; type(c_ptr), value :: ctx; type(nd_arrays), intent(in) :: a; integer(c_int), value :: npart,ntotal,idim
     end function
     integer(c_int) function ndspmhd_b200_update_ghosts(ctx,a,ntotal,idim,hhmax) bind(C,name='ndspmhd_b200_update_ghosts')
-     import; type(c_ptr), value :: ctx; type(nd_arrays), intent(in) :: a; integer(c_int), value :: ntotal,idim; real(c_double), value :: hhmax
+     import; type(c_ptr), value :: ctx; type(nd_arrays), intent(in) :: a; &
+       integer(c_int), value :: ntotal,idim; real(c_double), value :: hhmax
     end function
     integer(c_int) function ndspmhd_b200_link(ctx) bind(C,name='ndspmhd_b200_link')
      import; type(c_ptr), value :: ctx
@@ -112,7 +113,8 @@ module ndspmhd_b200
      import; type(c_ptr), value :: ctx; type(nd_arrays), intent(in) :: a; integer(c_int), value :: mask,idim
     end function
     integer(c_int) function ndspmhd_b200_step(ctx,so,dt,s) bind(C,name='ndspmhd_b200_step')
-     import; type(c_ptr), value :: ctx; type(nd_step_opts), intent(in) :: so; real(c_double), intent(inout) :: dt; type(nd_scalars), intent(out) :: s
+     import; type(c_ptr), value :: ctx; type(nd_step_opts), intent(in) :: so; &
+       real(c_double), intent(inout) :: dt; type(nd_scalars), intent(out) :: s
     end function
     integer(c_int) function ndspmhd_b200_download_state(ctx,st,idim) bind(C,name='ndspmhd_b200_download_state')
      import; type(c_ptr), value :: ctx; type(nd_state_out), intent(in) :: st; integer(c_int), value :: idim
