@@ -109,3 +109,69 @@ def test_product_never_touches_the_oracle():
                 assert "nd_oracle" not in txt and "import oracle" not in txt and "from oracle" not in txt, os.path.join(base, f)
     out = subprocess.check_output(["ldd", lib.LIB_PATH]).decode()
     assert "oracle" not in out
+
+
+def test_fortran_module_types_match_the_c_abi():
+    """ndspmhd_b200/fortran/ndspmhd_b200_mod.f90 cannot be compiled here (no Fortran compiler in the image): its `type, bind(C)` blocks are
+    parsed with numpy.f2py's crackfortran instead and compared with the ctypes mirror of include/ndspmhd_b200.h -- member names, order,
+    base type and array extents -- and no source line of the shims may pass column 132 (the reference builds with -std=f2008)."""
+    import contextlib
+    import ctypes as C
+    import glob
+    import io
+
+    from numpy.f2py import crackfortran
+
+    fdir = os.path.join(ROOT, "ndspmhd_b200", "fortran")
+    for f in glob.glob(os.path.join(fdir, "*.f90")):
+        for i, line in enumerate(open(f), 1):
+            assert len(line.rstrip("\n")) <= 132, (os.path.basename(f), i)
+    src = os.path.join(fdir, "ndspmhd_b200_mod.f90")
+    crackfortran.verbose = 0
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        blocks = crackfortran.crackfortran([src])
+    types = {b["name"]: b for b in blocks[0]["body"] if b["block"] == "type"}
+    text = open(src).read().lower()
+    pairs = {"nd_options": abi.NdOptions, "nd_arrays": abi.NdArrays, "nd_scalars": abi.NdScalars, "nd_step_opts": abi.NdStepOpts,
+             "nd_state_out": abi.NdStateOut}
+    kinds = {"c_double": ("real", "c_double"), "c_int": ("integer", "c_int"), "c_longlong": ("integer", "c_long_long"),
+             "c_long": ("integer", "c_long_long")}   # ctypes aliases c_longlong to c_long on LP64
+    for fname, ct in pairs.items():
+        t = types[fname]
+        forder = [v.lower() for v in (t.get("sortvars") or list(t["vars"]))]
+        assert forder == [n.lower() for n, _ in ct._fields_], fname
+        for n, ctyp in ct._fields_:
+            v = t["vars"][n] if n in t["vars"] else t["vars"][n.lower()]
+            base, length = ctyp, 1
+            while hasattr(base, "_length_"):
+                length *= base._length_
+                base = base._type_
+            if base.__name__ in kinds:
+                ftype, fkind = kinds[base.__name__]
+                kind = (v.get("kindselector") or {}).get("kind")
+                assert v.get("typespec") == ftype, (fname, n)
+                assert str(kind) == fkind or f"{ftype}({fkind}) :: {n.lower()}" in text, (fname, n, kind)
+                flen = 1
+                for d in v.get("dimension") or []:
+                    flen *= int(d)
+                assert flen == length, (fname, n, flen, length)
+            else:                                   # pointers travel as type(c_ptr)
+                assert v.get("typespec") == "type" and "c_ptr" in str(v.get("typename", "")).lower(), (fname, n)
+    # the interface block: every bound function exists in the header with the same number of arguments; a C pointer argument is either a
+    # by-reference dummy or a type(c_ptr) passed by value, every other C argument is a `value` dummy
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ndspmhd_b200.h")).read(), flags=re.S)
+    protos = {m.group(2): [a.strip() for a in m.group(3).split(",")]
+              for m in re.finditer(r"\b(int|void|const char \*|void \*)\s*(ndspmhd_b200_\w+)\s*\(([^)]*)\)\s*;", hdr)}
+    iface = [b for b in blocks[0]["body"] if b["block"] == "interface"][0]
+    assert len(iface["body"]) >= 15
+    for f in iface["body"]:
+        cargs = protos[f["name"]]
+        assert len(cargs) == len(f["args"]), f["name"]
+        for fa, ca in zip(f["args"], cargs):
+            v = f["vars"][fa]
+            byval = "value" in (v.get("attrspec") or [])
+            is_cptr = v.get("typespec") == "type" and "c_ptr" in str(v.get("typename", "")).lower()
+            if "*" in ca:
+                assert (not byval) or is_cptr, (f["name"], fa, ca)
+            else:
+                assert byval and not is_cptr, (f["name"], fa, ca)
