@@ -47,6 +47,10 @@ struct RatesRed {
   int *sched;              // work counter of the persistent warps (zeroed before each launch)
 };
 
+#ifndef ND_RATES_FUSEDR
+#define ND_RATES_FUSEDR 0   // 1: the scalar coefficients of dr in the force (AV, pressure, isotropic magnetic part) are summed before they
+                            //    meet dr: 7 fewer FP64 instructions a pair, same terms in another order of rounding; untried on a GPU
+#endif
 #ifndef ND_FMAX_INT
 #define ND_FMAX_INT 0   // 1: the maxima of the pair body as signed 64-bit integer compares (DSETP.MAX issues on the half-rate FP64 pipe); untried on a GPU
 #endif
@@ -301,10 +305,17 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
       // ---- kernel gradients :1208-1241 (w = w[index] + dwdx*(q2 - index*dq2table), src/kernelND.f90:4443-4455) ----
       double grkerni = rowi.x + rowi.y * (q2i - __dmul_rn((double)idxi, G.dq2table));
       double grkernj = rowj.x + rowj.y * (q2j - __dmul_rn((double)idxj, G.dq2table));
+      double grkern;
+      if (ND_RATES_FUSEDR && ikernav == 3) {
+        // h^-(ndim+1) * gradh as one factor per side: the target's is loop-invariant, the neighbour's reuses hj21 = (1/h_j)^2
+        const double hgj = (NDIM == 3 ? hj21 * hj21 : NDIM == 2 ? hj21 * hj1 : hj21) * gj.x;
+        grkerni = grkerni * (hfacgrkerni * gradhi);
+        grkernj = grkernj * hgj;
+        grkern = 0.5 * (grkerni + grkernj);
+      } else {
       grkerni = grkerni * hfacgrkerni;
       const double hfacwabj = powndim<NDIM>(hj1), hfacgrkernj = hfacwabj * hj1;   // :1215-1216
       grkernj = grkernj * hfacgrkernj;
-      double grkern;
       if (ikernav == 3) {                                       // :1227-1237
         grkerni = grkerni * gradhi;
         grkernj = grkernj * gj.x;
@@ -313,7 +324,10 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
         grkern = 0.5 * (grkerni + grkernj);
         grkerni = grkern; grkernj = grkern;
       }
+      }
       double fix = 0, fiy = 0, fiz = 0;   // forcei contribution of this pair
+      constexpr bool FUSEDR = ND_RATES_FUSEDR && !ONEF;
+      double cdr = 0.;                    // FUSEDR: forcei = pmassj * ((fix, fiy, fiz) - cdr * dr)
       double vsigav = 0.;
       if (ONEF && iav > 0) {
         // =============================== artificial_dissipation_dust (iav = 1, 2, 3) ===============================
@@ -368,8 +382,11 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
         const double approaching = dvdotr < 0. ? 1. : 0.;        // :1745-1748 as a select: no divergent branch in the pair body
         {
           const double visc = alphaav * term * (-dvdotr);
+          if (FUSEDR) cdr += visc * approaching;
+          else {
           const double c = pmassj * visc * approaching;
           fix -= c * drx; fiy -= c * dry; fiz -= c * drz;
+          }
         }
         if (MHD) {                                               // :1762-1774
           double bvx, bvy, bvz;
@@ -411,8 +428,11 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
           const double vsj = ND_FMAX(gj.y * spsoundj - O.beta * dvdotr, 0.);
           const double qi = -0.5 * rhoi * vsi * dvdotr, qj = -0.5 * rhoj * vsj * dvdotr;
           const double visc = (qi * rho21i * grkerni + qj * rho21j * grkernj);
+          if (FUSEDR) cdr += visc;
+          else {
           const double c = pmassj * visc;
           fix -= c * drx; fiy -= c * dry; fiz -= c * drz;
+          }
           dudti = qi * rho21i * pmassj * dvdotr * grkerni;
         }
         const double du = uui - uuj;
@@ -424,8 +444,11 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
       if (FAST && ND_DENS_LIGHT) drho += pmassj * (dvdotr * (1. - eps * rinv)) * grkerni;   // sum m_j (dv.dr) grad W_i: the density loop's drhodt (LIGHT rounds skip it)
       {                                                          // pressure, :1538-1567 (phi = 1, sqrtg = 1)
         const double prterm = Prho2i * grkerni + Prho2j * grkernj;
+        if (FUSEDR) cdr += prterm;
+        else {
         const double c = pmassj * prterm;
         fix -= c * drx; fiy -= c * dry; fiz -= c * drz;
+        }
       }
       if (MHD) {
         // =============================== mhd_terms ===============================
@@ -434,9 +457,12 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
         // faniso = (Brho_i (Brho_i.dr) - stressmax dr/rho_i^2) grkern_i + (same for j), :2534-2537; the force is faniso - fiso dr
         const double ai = projBrhoi * grkerni, aj = projBrhoj * grkernj;
         const double sdr = sm * (rho21i * grkerni + rho21j * grkernj) + fiso;
+        if (FUSEDR) { cdr += sdr; fix = Brhoxi * ai + Brhoxj * aj; fiy = Brhoyi * ai + Brhoyj * aj; fiz = Brhozi * ai + Brhozj * aj; }
+        else {
         fix += pmassj * ((Brhoxi * ai + Brhoxj * aj) - sdr * drx);               // :2541, :2629
         fiy += pmassj * ((Brhoyi * ai + Brhoyj * aj) - sdr * dry);
         fiz += pmassj * ((Brhozi * ai + Brhozj * aj) - sdr * drz);
+        }
         const double mg = pmassj * grkern;
         divB -= mg * projdB;                                     // :2552
         cBx += (dByy * drz - dBzz * dry) * mg;                   // :2601-2602 curlB += pmassj*(dB x dr)*grkern
@@ -468,7 +494,13 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
         if (iener > 0) dudt += pmassj * (pri * rho1i / rhogasi * projdvgas - rhodusti * rho21i * (uui - uuj) * projdeltavi) * grkerni;   // :2801-2803
         fgx += fix; fgy += fiy; fgz += fiz;
       }
+      if (FUSEDR) {
+        const double cm = pmassj * cdr;
+        if (MHD) { fx = fma(pmassj, fix, fx); fy = fma(pmassj, fiy, fy); fz = fma(pmassj, fiz, fz); }
+        fx = fma(-cm, drx, fx); fy = fma(-cm, dry, fy); fz = fma(-cm, drz, fz);
+      } else {
       fx += fix; fy += fiy; fz += fiz;
+      }
       if (iav > 0) {                                             // :1639-1656 switch sources
         if (FAST) del2u += sel_del2u * (pmassj * rho1j * ((uui - uuj) * rinv) * grkerni);
         else if (iavlim1 > 0) del2u += pmassj * rho1j * ((uui - uuj) * rinv) * grkerni;
