@@ -6,11 +6,11 @@
 # 1. the whole GPU suite (tests/test_gpu_vectors.py has never run on a GPU), 2. the integer-compare variant of the pair kernel against the
 # default at nx=256, 3. the end-to-end number with ND_DL_REAL_ROWS, 4. (needs --gpus 2) LIGHT density rounds in slab contexts.
 TAG=${1:-next}; OUT=gpurun_out/$TAG; mkdir -p $OUT
+shopt -s nullglob
 timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -15 | tee $OUT/pytest_gpu.txt
 for so in ndspmhd_b200/variants/*.so; do   # parity of every variant build before its timing counts
   NDSPMHD_B200_LIB=$PWD/$so timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_step.py -q -m gpu 2>&1 | tail -3 | tee $OUT/pytest_$(basename $so .so).txt
 done
-shopt -s nullglob
 for so in ndspmhd_b200/libndspmhd_b200.so ndspmhd_b200/variants/*.so; do
   NDSPMHD_B200_LIB=$PWD/$so timeout 300 python bench.py --nx 256 --steps 5 --warmup 3 --no-cpu 2>&1 | tail -1 > $OUT/bench256_$(basename $so .so).json
 done
