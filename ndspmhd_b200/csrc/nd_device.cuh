@@ -144,11 +144,20 @@ __device__ __forceinline__ double dist2_exact(double dx, double dy, double dz) {
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
+#ifndef ND_TABIDX_SAT
+#define ND_TABIDX_SAT 0   // 1: range clamp of the table index by the saturating conversion + an integer minimum; untried on a GPU
+#endif
 // index = int(q2*ddq2table), clamped (src/kernelND.f90:4435-4438)
 __device__ __forceinline__ int tab_index(double q2, double ddq2table) {
   double t = __dmul_rn(q2, ddq2table);
+#if ND_TABIDX_SAT
+  // cvt.rzi.s32.f64 saturates (large -> INT_MAX, negative -> INT_MIN, NaN -> 0); an unsigned minimum then clamps both ends to IKERN
+  // without the two DSETP of the range test (they issue on the half-rate FP64 pipe)
+  return (int)min((unsigned)__double2int_rz(t), (unsigned)IKERN);
+#else
   int idx = (t < 2147483000.0 && t >= 0.0) ? __double2int_rz(t) : IKERN;
   return idx > IKERN ? IKERN : idx;
+#endif
 }
 
 // w = w[index] + dwdx*(q2 - index*dq2table)   (src/kernelND.f90:4443-4455)
