@@ -43,11 +43,15 @@ struct DensityArgs {
 #ifndef ND_DENS_BLOCK_LIGHT
 #define ND_DENS_BLOCK_LIGHT (ND_DENS_TABSMEM ? 1024 : ND_DENS_BLOCK)   // LIGHT instantiations: 64 registers without spills, 32 warps on an SM instead of 16
 #endif
+#ifndef ND_DENS_BLOCK_FAST
+#define ND_DENS_BLOCK_FAST ND_DENS_BLOCK   // block size of the two-gather rounds without the aux sums (768: 78 registers, no spills; untried on a GPU)
+#endif
 #ifndef ND_DENS_MINB
 #define ND_DENS_MINB (ND_DENS_TABSMEM ? 1 : 4)
 #endif
 constexpr int DENS_BLOCK = ND_DENS_BLOCK;
 constexpr int DENS_BLOCK_LIGHT = ND_DENS_BLOCK_LIGHT;
+constexpr int DENS_BLOCK_FAST = ND_DENS_BLOCK_FAST;
 constexpr int DENS_TAB_BYTES = (IKERN + 1) * 16;                         // one {value, slope} table, 64016 B
 constexpr int DENS_TAB_STRIDE = ((DENS_TAB_BYTES + 127) / 128) * 128;
 constexpr int DENS_SMEM_BYTES = ND_DENS_TABSMEM ? 128 + 2 * DENS_TAB_STRIDE : 0;
@@ -245,7 +249,7 @@ __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs 
 }
 
 template <int NDIM, bool FIRST, bool AUX, bool LIGHT>
-__global__ void __launch_bounds__(LIGHT ? DENS_BLOCK_LIGHT : DENS_BLOCK, ND_DENS_MINB) density_round_kernel(Grid G, DensityArgs A, NbrLists L) {
+__global__ void __launch_bounds__(LIGHT ? DENS_BLOCK_LIGHT : AUX ? DENS_BLOCK : DENS_BLOCK_FAST, ND_DENS_MINB) density_round_kernel(Grid G, DensityArgs A, NbrLists L) {
 #if ND_DENS_TABSMEM
   // One persistent block per SM: the two interpolation tables (128 KB) arrive by TMA bulk copies, then every warp draws
   // 32-target units from a global counter until the work is gone.

@@ -430,11 +430,11 @@ template <int NDIM, bool FIRST> int launch_density_round(nd_ctx *c, DensityArgs 
     const int grid = std::min(nblocks(m, DENS_BLOCK), c->num_sms);
     if (aux) LAUNCH(c, kaux, grid, DENS_BLOCK, DENS_SMEM_BYTES, G, A, L);
     else if (c->dens_light) LAUNCH(c, klight, std::min(nblocks(m, DENS_BLOCK_LIGHT), c->num_sms), DENS_BLOCK_LIGHT, DENS_SMEM_BYTES, G, A, L);
-    else LAUNCH(c, kfast, grid, DENS_BLOCK, DENS_SMEM_BYTES, G, A, L);
+    else LAUNCH(c, kfast, std::min(nblocks(m, DENS_BLOCK_FAST), c->num_sms), DENS_BLOCK_FAST, DENS_SMEM_BYTES, G, A, L);
 #else
     if (aux) LAUNCH(c, (density_round_kernel<NDIM, FIRST, true, false>), nblocks(m, DENS_BLOCK), DENS_BLOCK, 0, G, A, L);
     else if (c->dens_light) LAUNCH(c, (density_round_kernel<NDIM, FIRST, false, true>), nblocks(m, DENS_BLOCK_LIGHT), DENS_BLOCK_LIGHT, 0, G, A, L);
-    else LAUNCH(c, (density_round_kernel<NDIM, FIRST, false, false>), nblocks(m, DENS_BLOCK), DENS_BLOCK, 0, G, A, L);
+    else LAUNCH(c, (density_round_kernel<NDIM, FIRST, false, false>), nblocks(m, DENS_BLOCK_FAST), DENS_BLOCK_FAST, 0, G, A, L);
 #endif
   }
   return 0;

@@ -1,6 +1,7 @@
 #!/bin/bash
 # First GPU session after round 1 (everything below was prepared without a GPU; see DESIGN.md "what the v5 profiles say to do next"):
 #   here:   make -C ndspmhd_b200/csrc variant TAG=intcmp DEFS="-DND_SQRT_INTGUARD=1 -DND_FMAX_INT=1"
+#           make -C ndspmhd_b200/csrc variant TAG=dens768 DEFS="-DND_DENS_BLOCK_FAST=768"   (two-gather rounds: slab contexts, phase-by-phase calls)
 #           make -C ndspmhd_b200/csrc variant TAG=fp64lean DEFS="-DND_SQRT_INTGUARD=1 -DND_FMAX_INT=1 -DND_RATES_FUSEDR=1 -DND_TABIDX_SAT=1"
 #   gpurun --timeout 900 -- 'bash tools/gpu_next_session.sh r02a'
 # 1. the whole GPU suite (tests/test_gpu_vectors.py has never run on a GPU), 2. the integer-compare variant of the pair kernel against the
