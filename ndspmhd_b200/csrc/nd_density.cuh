@@ -28,33 +28,21 @@ struct DensityArgs {
   int *sched;            // work counter of the persistent warps (zeroed before each launch)
 };
 
-#ifndef ND_DENS_PF
-#define ND_DENS_PF 4   // neighbour records: 0 direct loads, 1/2 + L1 prefetch 1/2 pairs ahead, 3 two pairs per trip, 4 register pipeline one pair ahead
-#endif
 #ifndef ND_DENS_LIGHT
 #define ND_DENS_LIGHT 1   // 1: in a fused derivs of the fast option tuple the density rounds run LIGHT (no drho/dt sum, one gather a pair) and the rates pair kernel makes drho/dt
 #endif
-#ifndef ND_DENS_TABSMEM
-#define ND_DENS_TABSMEM 1   // {W, slope} and {grad W, slope} rows in shared memory (two TMA bulk copies per persistent block)
-#endif
+// The {W, slope} and {grad W, slope} rows live in shared memory (two TMA bulk copies per persistent block, one block per SM).
 #ifndef ND_DENS_BLOCK
-#define ND_DENS_BLOCK (ND_DENS_TABSMEM ? 512 : 128)
+#define ND_DENS_BLOCK 512
 #endif
 #ifndef ND_DENS_BLOCK_LIGHT
-#define ND_DENS_BLOCK_LIGHT (ND_DENS_TABSMEM ? 1024 : ND_DENS_BLOCK)   // LIGHT instantiations: 64 registers without spills, 32 warps on an SM instead of 16
-#endif
-#ifndef ND_DENS_BLOCK_FAST
-#define ND_DENS_BLOCK_FAST ND_DENS_BLOCK   // block size of the two-gather rounds without the aux sums (768: 78 registers, no spills; untried on a GPU)
-#endif
-#ifndef ND_DENS_MINB
-#define ND_DENS_MINB (ND_DENS_TABSMEM ? 1 : 4)
+#define ND_DENS_BLOCK_LIGHT 1024   // LIGHT instantiations: 64 registers without spills, 32 warps on an SM instead of 16
 #endif
 constexpr int DENS_BLOCK = ND_DENS_BLOCK;
 constexpr int DENS_BLOCK_LIGHT = ND_DENS_BLOCK_LIGHT;
-constexpr int DENS_BLOCK_FAST = ND_DENS_BLOCK_FAST;
 constexpr int DENS_TAB_BYTES = (IKERN + 1) * 16;                         // one {value, slope} table, 64016 B
 constexpr int DENS_TAB_STRIDE = ((DENS_TAB_BYTES + 127) / 128) * 128;
-constexpr int DENS_SMEM_BYTES = ND_DENS_TABSMEM ? 128 + 2 * DENS_TAB_STRIDE : 0;
+constexpr int DENS_SMEM_BYTES = 128 + 2 * DENS_TAB_STRIDE;
 
 // LIGHT: the round makes rho, gradh and the Newton-Raphson update only.  drho/dt is left to the rates pair kernel of the same derivs
 // (fast option tuple), which visits the same pairs with the same grad W anyway: a neighbour then costs ONE 32-byte gather
@@ -100,7 +88,6 @@ __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs 
     const double rinve = rinv - 2.220446049250313e-16 * rinv * rinv;
     const double pmassj = LIGHT ? pj.w : vj.w;
     double wabi, grkerni, grgrkerni = 0.;
-#if ND_DENS_TABSMEM
     {
       const int idx = tab_index(q2i, G.ddq2table);
       const double2 rw = tabw[idx], rg = tabg[idx];
@@ -109,10 +96,6 @@ __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs 
       grkerni = rg.x + rg.y * dxx;
       if (AUX) { const double2 r2 = __ldg(reinterpret_cast<const double2 *>(G.tab2 + idx)); grgrkerni = r2.x + r2.y * dxx; }
     }
-#else
-    if (AUX) interp_wggg(G, q2i, wabi, grkerni, grgrkerni);
-    else interp_wg(G, q2i, wabi, grkerni);
-#endif
     wabi = wabi * hfacwabi;                        // :237-241 / :549-553
     grkerni = grkerni * hfacwabi * hi1;
     const double dwdhi = -rij * grkerni * hi1 - NDIM * wabi * hi1;   // :260
@@ -142,8 +125,7 @@ __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs 
   };
   if (cnt > 0) {
     const unsigned *col = L.nbr + ((size_t)(t >> 5) * L.lmax) * 32 + (t & 31);
-#if ND_DENS_PF == 4
-    // register pipeline: the next neighbour's two records load while this pair is evaluated (list read in batches, walk_list)
+    // register pipeline: the next neighbour's records load while this pair is evaluated (list read in batches, walk_list)
     if (LIGHT) {
       double4 pn = ld4(G.posm + (int)col[0]);
       walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
@@ -159,37 +141,6 @@ __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs 
         body(k, pc, vc);
       });
     }
-#elif ND_DENS_PF == 5
-    // register pipeline: the next neighbour's two records load while this pair is evaluated; the list column is read two entries
-    // ahead by plain rotation, so the loop holds no branch but its own
-    const int last = cnt - 1;
-    int k = (int)__ldcs(col), k1 = (int)__ldcs(col + (size_t)min(1, last) * 32);
-    double4 pn = ld4(G.posh + k), vn = ld4(G.vm + k);
-#pragma unroll 1
-    for (int n = 0; n < cnt; n++) {
-      const int k2 = (int)__ldcs(col + (size_t)min(n + 2, last) * 32);
-      const double4 pc = pn, vc = vn;
-      pn = ld4(G.posh + k1); vn = ld4(G.vm + k1);
-      body(k, pc, vc);
-      k = k1; k1 = k2;
-    }
-#elif ND_DENS_PF == 3
-    // two neighbours per trip: their four record loads are issued together and overlap the other's arithmetic
-    walk_list2(col, cnt, [&](int ka, int kb, bool twob) {
-      const double4 pa = ld4(G.posh + ka), va = ld4(G.vm + ka), pb = ld4(G.posh + kb), vb = ld4(G.vm + kb);
-      body(ka, pa, va);
-      if (twob) body(kb, pb, vb);
-    });
-#else
-    walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
-#if ND_DENS_PF == 2
-      prefetch_l1(G.posh + k2); prefetch_l1(G.vm + k2);          // records two pairs ahead into L1, no registers held
-#elif ND_DENS_PF == 1
-      prefetch_l1(G.posh + k1); prefetch_l1(G.vm + k1);
-#endif
-      body(k, ld4(G.posh + k), ld4(G.vm + k));
-    });
-#endif
   }
   const int nneigh = active ? A.numneigh[orig] : 0;   // counted by build_lists_kernel (:196-197 / :532)
 
@@ -249,8 +200,7 @@ __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs 
 }
 
 template <int NDIM, bool FIRST, bool AUX, bool LIGHT>
-__global__ void __launch_bounds__(LIGHT ? DENS_BLOCK_LIGHT : AUX ? DENS_BLOCK : DENS_BLOCK_FAST, ND_DENS_MINB) density_round_kernel(Grid G, DensityArgs A, NbrLists L) {
-#if ND_DENS_TABSMEM
+__global__ void __launch_bounds__(LIGHT ? DENS_BLOCK_LIGHT : DENS_BLOCK, 1) density_round_kernel(Grid G, DensityArgs A, NbrLists L) {
   // One persistent block per SM: the two interpolation tables (128 KB) arrive by TMA bulk copies, then every warp draws
   // 32-target units from a global counter until the work is gone.
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -276,10 +226,6 @@ __global__ void __launch_bounds__(LIGHT ? DENS_BLOCK_LIGHT : AUX ? DENS_BLOCK : 
     const int t = unit * 32 + (threadIdx.x & 31);
     if (t < A.nlist) density_target<NDIM, FIRST, AUX, LIGHT>(G, A, L, t, tabw, tabg);
   }
-#else
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < A.nlist) density_target<NDIM, FIRST, AUX, LIGHT>(G, A, L, t, nullptr, nullptr);
-#endif
 }
 
 }  // namespace ndk

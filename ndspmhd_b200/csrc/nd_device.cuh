@@ -59,14 +59,9 @@ __device__ __forceinline__ void st4(double4 *p, const double4 &v) {
 // (5 FP64 instructions, <= 1 ulp), one coupled Goldschmidt step + residual correction for sqrt (7 instructions, <= 0.5 ulp
 // measured).  CUDA's sqrt()/rsqrt() carry a slow-path branch per call, which stops ptxas from interleaving the six
 // independent square roots of a rates pair; these do not.  Arguments <= 1e-300 give 0.
-#ifndef ND_SQRT_INTGUARD
-#define ND_SQRT_INTGUARD 0   // 1: the x > 1e-300 guards as integer compares on the high word (DSETP issues on the half-rate FP64 pipe); untried on a GPU
-#endif
-#if ND_SQRT_INTGUARD
-#define ND_SQRT_ARG_OK(x) (__double2hiint(x) > 0x01A56E1F)   // high word of 1e-300; the arguments are non-negative or fail the test as negatives do
-#else
-#define ND_SQRT_ARG_OK(x) ((x) > 1.e-300)
-#endif
+// The x > 1e-300 guard is an integer compare on the high word (a DSETP would issue on the half-rate FP64 pipe): 0x01A56E1F is the
+// high word of 1e-300; the arguments are non-negative or fail the test as negatives do.
+#define ND_SQRT_ARG_OK(x) (__double2hiint(x) > 0x01A56E1F)
 __device__ __forceinline__ double rsqrt_nr(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -144,20 +139,12 @@ __device__ __forceinline__ double dist2_exact(double dx, double dy, double dz) {
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-#ifndef ND_TABIDX_SAT
-#define ND_TABIDX_SAT 0   // 1: range clamp of the table index by the saturating conversion + an integer minimum; untried on a GPU
-#endif
 // index = int(q2*ddq2table), clamped (src/kernelND.f90:4435-4438)
 __device__ __forceinline__ int tab_index(double q2, double ddq2table) {
-  double t = __dmul_rn(q2, ddq2table);
-#if ND_TABIDX_SAT
+  const double t = __dmul_rn(q2, ddq2table);
   // cvt.rzi.s32.f64 saturates (large -> INT_MAX, negative -> INT_MIN, NaN -> 0); an unsigned minimum then clamps both ends to IKERN
-  // without the two DSETP of the range test (they issue on the half-rate FP64 pipe)
+  // without the two DSETP of a range test (they would issue on the half-rate FP64 pipe)
   return (int)min((unsigned)__double2int_rz(t), (unsigned)IKERN);
-#else
-  int idx = (t < 2147483000.0 && t >= 0.0) ? __double2int_rz(t) : IKERN;
-  return idx > IKERN ? IKERN : idx;
-#endif
 }
 
 // w = w[index] + dwdx*(q2 - index*dq2table)   (src/kernelND.f90:4443-4455)
@@ -261,25 +248,6 @@ template <class F> __device__ __forceinline__ void walk_list(const unsigned *col
       const int k1 = u == 0 ? c1 : u == 1 ? c2 : u == 2 ? c3 : n0;
       const int k2 = u == 0 ? c2 : u == 1 ? c3 : u == 2 ? n0 : n1;
       f(nb + u, k, k1, k2);
-    }
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    n0 = m0; n1 = m1; n2 = m2; n3 = m3;
-  }
-}
-
-// Same batching, two entries per trip: f(ka, kb, has_b).
-template <class F> __device__ __forceinline__ void walk_list2(const unsigned *col, int cnt, F &&f) {
-  const int last = cnt - 1;
-  auto ld = [&](int n) { return (int)__ldcs(col + (size_t)min(n, last) * 32); };
-  int c0 = ld(0), c1 = ld(1), c2 = ld(2), c3 = ld(3);
-  int n0 = ld(4), n1 = ld(5), n2 = ld(6), n3 = ld(7);
-#pragma unroll 1
-  for (int nb = 0; nb < cnt; nb += 4) {
-    const int m0 = ld(nb + 8), m1 = ld(nb + 9), m2 = ld(nb + 10), m3 = ld(nb + 11);
-#pragma unroll 1
-    for (int u = 0; u < 4; u += 2) {
-      if (nb + u >= cnt) break;
-      f(u == 0 ? c0 : c2, u == 0 ? c1 : c3, nb + u + 1 < cnt);
     }
     c0 = n0; c1 = n1; c2 = n2; c3 = n3;
     n0 = m0; n1 = m1; n2 = m2; n3 = m3;

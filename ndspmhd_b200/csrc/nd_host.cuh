@@ -418,7 +418,6 @@ template <int NDIM, bool FIRST> int launch_density_round(nd_ctx *c, DensityArgs 
     A.list = FIRST ? nullptr : c->list + c0; A.nlist = m; A.s0 = c0;
     A.sched = c->flags + 9;
     const bool aux = c->o.want_aux || c->o.onef_dust;
-#if ND_DENS_TABSMEM
     // persistent blocks, one per SM (128 KB of shared-memory tables each); warps draw 32-target units from flags[9]
     auto kaux = density_round_kernel<NDIM, FIRST, true, false>;
     auto kfast = density_round_kernel<NDIM, FIRST, false, false>;
@@ -430,12 +429,7 @@ template <int NDIM, bool FIRST> int launch_density_round(nd_ctx *c, DensityArgs 
     const int grid = std::min(nblocks(m, DENS_BLOCK), c->num_sms);
     if (aux) LAUNCH(c, kaux, grid, DENS_BLOCK, DENS_SMEM_BYTES, G, A, L);
     else if (c->dens_light) LAUNCH(c, klight, std::min(nblocks(m, DENS_BLOCK_LIGHT), c->num_sms), DENS_BLOCK_LIGHT, DENS_SMEM_BYTES, G, A, L);
-    else LAUNCH(c, kfast, std::min(nblocks(m, DENS_BLOCK_FAST), c->num_sms), DENS_BLOCK_FAST, DENS_SMEM_BYTES, G, A, L);
-#else
-    if (aux) LAUNCH(c, (density_round_kernel<NDIM, FIRST, true, false>), nblocks(m, DENS_BLOCK), DENS_BLOCK, 0, G, A, L);
-    else if (c->dens_light) LAUNCH(c, (density_round_kernel<NDIM, FIRST, false, true>), nblocks(m, DENS_BLOCK_LIGHT), DENS_BLOCK_LIGHT, 0, G, A, L);
-    else LAUNCH(c, (density_round_kernel<NDIM, FIRST, false, false>), nblocks(m, DENS_BLOCK_FAST), DENS_BLOCK_FAST, 0, G, A, L);
-#endif
+    else LAUNCH(c, kfast, grid, DENS_BLOCK, DENS_SMEM_BYTES, G, A, L);
   }
   return 0;
 }
@@ -570,7 +564,7 @@ template <int NDIM, bool MHD, bool DRAG, int FAST, bool ONEF> int launch_rates_p
     CU(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
     CU(cudaMemsetAsync(c->flags + 8, 0, sizeof(int), c->stream));
     if (c0 == 0) CU(cudaEventRecord(c->ev_pair[0], c->stream));   // the first chunk's launch is the one timed (the only one below 32 Mi rows)
-    LAUNCH(c, (rates_pair_kernel<NDIM, MHD, DRAG, FAST, ONEF>), ND_RATES_PERSIST ? std::min(nblocks(m, RATES_BLOCK), resident) : nblocks(m, RATES_BLOCK), RATES_BLOCK, RATES_SMEM_BYTES, G, I, O, S, R, L, c0, m, targets ? targets + c0 : nullptr);
+    LAUNCH(c, (rates_pair_kernel<NDIM, MHD, DRAG, FAST, ONEF>), std::min(nblocks(m, RATES_BLOCK), resident), RATES_BLOCK, RATES_SMEM_BYTES, G, I, O, S, R, L, c0, m, targets ? targets + c0 : nullptr);
     if (c0 == 0) CU(cudaEventRecord(c->ev_pair[1], c->stream));
   }
   return 0;

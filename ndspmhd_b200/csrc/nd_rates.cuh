@@ -47,53 +47,19 @@ struct RatesRed {
   int *sched;              // work counter of the persistent warps (zeroed before each launch)
 };
 
-#ifndef ND_RATES_FUSEDR
-#define ND_RATES_FUSEDR 0   // 1: the scalar coefficients of dr in the force (AV, pressure, isotropic magnetic part) are summed before they
-                            //    meet dr: 7 fewer FP64 instructions a pair, same terms in another order of rounding; untried on a GPU
-#endif
-#ifndef ND_FMAX_INT
-#define ND_FMAX_INT 0   // 1: the maxima of the pair body as signed 64-bit integer compares (DSETP.MAX issues on the half-rate FP64 pipe); untried on a GPU
-#endif
-#if ND_FMAX_INT
-// max(a, b) for finite a of either sign and b >= +0: IEEE doubles of equal sign order like their bit patterns, a negative a is a negative integer
+// max(a, b) for finite a of either sign and b >= +0 as a signed 64-bit integer compare: IEEE doubles of equal sign order like their bit
+// patterns and a negative a is a negative integer (DSETP/DMNMX issue on the half-rate FP64 pipe, the integer compare does not)
 __device__ __forceinline__ double fmax_nonneg(double a, double b) { return __double_as_longlong(a) > __double_as_longlong(b) ? a : b; }
 #define ND_FMAX(a, b) fmax_nonneg(a, b)
-#else
-#define ND_FMAX(a, b) fmax(a, b)
-#endif
 #ifndef ND_RATES_MINB
 #define ND_RATES_MINB 2
 #endif
 #ifndef ND_RATES_BLOCK
 #define ND_RATES_BLOCK 128
 #endif
-#ifndef ND_RATES_STAGE
-#define ND_RATES_STAGE 5   // how neighbour records reach the pair body: 0 direct 256-bit loads, 1/2 + L1 prefetch 1/2 pairs ahead, 3 cp.async to shared, 4/5/6 register pipeline
-#endif
 constexpr int RATES_BLOCK = ND_RATES_BLOCK;
-constexpr int RATES_NREC = 5;    // staged records per neighbour: posh, vm, thermo, gal, bpsi
-#ifndef ND_RATES_TABSMEM
-#define ND_RATES_TABSMEM 1   // kernel-gradient table rows in shared memory (TMA bulk copy per block) instead of global loads
-#endif
-#ifndef ND_RATES_PERSIST
-#define ND_RATES_PERSIST 1   // persistent blocks (one table load per block); every warp draws 32-target units from a global counter
-#endif
 constexpr int RATES_TABG_BYTES = (IKERN + 1) * 16;                       // {grad W, slope} rows, 64016 B
-constexpr int RATES_TAB_BYTES = ND_RATES_TABSMEM ? ((16 + RATES_TABG_BYTES + 127) / 128) * 128 : 0;
-constexpr int RATES_SMEM_BYTES = RATES_TAB_BYTES + (ND_RATES_STAGE == 3 ? 2 * RATES_NREC * 2 * RATES_BLOCK * 16 : 0);
-
-// per-thread staging slots in shared memory: plane (stage, record, half) holds one 16-byte half-record per thread, so the
-// 128-bit reads of a warp are conflict-free
-__device__ __forceinline__ void stage_put(double2 *stg, int st, int rec, const double4 *src) {
-  double2 *d = stg + ((st * RATES_NREC + rec) * 2) * RATES_BLOCK + threadIdx.x;
-  cp_async16(d, src);
-  cp_async16(d + RATES_BLOCK, reinterpret_cast<const double2 *>(src) + 1);
-}
-__device__ __forceinline__ double4 stage_get(const double2 *stg, int st, int rec) {
-  const double2 *d = stg + ((st * RATES_NREC + rec) * 2) * RATES_BLOCK + threadIdx.x;
-  const double2 a = d[0], b = d[RATES_BLOCK];
-  return make_double4(a.x, a.y, b.x, b.y);
-}
+constexpr int RATES_SMEM_BYTES = ((16 + RATES_TABG_BYTES + 127) / 128) * 128;
 
 __device__ __forceinline__ double get_tstop(int idrag_nature, double rhogas, double rhodust, double Kdrag) {
   // src/dust.f90:77-102
@@ -110,16 +76,12 @@ template <int NDIM, bool MHD, bool DRAG, int FAST, bool ONEF>
 __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(Grid G, RatesIn I, RatesOpts O, RatesSums S, RatesRed R, NbrLists L,
                                                                                  int s0, int ntargets, const int *targets) {
   // dynamic shared memory: [0,16) mbarrier, then the {grad W, slope} rows of the kernel table (64 KB; every pair does two
-  // random lookups, which as global loads cost ~30 L1 wavefronts each and were the largest long-scoreboard stall), then the
-  // cp.async staging slots.  The table arrives by one TMA bulk copy per block; blocks are persistent (grid = resident blocks)
-  // so it is loaded once per SM slot, not once per 128 targets.
+  // random lookups, which as global loads cost ~30 L1 wavefronts each and were the largest long-scoreboard stall).
+  // The table arrives by one TMA bulk copy per block; blocks are persistent (grid = resident blocks) so it is loaded once
+  // per SM slot, not once per 128 targets.
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
   const double2 *tabs = reinterpret_cast<const double2 *>(smem_raw + 16);
-#if ND_RATES_STAGE == 3
-  double2 *stg = reinterpret_cast<double2 *>(smem_raw + RATES_TAB_BYTES);   // [stage][record][half][thread], 40 KB
-#endif
-#if ND_RATES_TABSMEM
   if (threadIdx.x == 0) {
     mbar_init(mbar, 1);
     fence_mbar_init();
@@ -128,8 +90,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
   }
   __syncthreads();
   mbar_wait(mbar, 0);
-#endif
-  const int iav = FAST ? 2 : O.iav, iener = FAST == 2 ? 2 : (FAST == 1 ? 0 : O.iener), ikernav = FAST ? 3 : O.ikernav, iresist = FAST ? 0 : O.iresist;
+  const int iav = FAST ? 2 : O.iav, iener = FAST == 2 ? 2 : (FAST == 1 ? 0 : O.iener), iresist = FAST ? 0 : O.iresist;
   // FAST excludes iavlim(1) = 3 and iavlim(3) = 2 at compile time; the remaining run-time options of the fast tuple enter the pair
   // body as 0/1 multipliers instead of (uniform) branches, which would split the scheduling block
   const int iavlim0 = FAST ? 0 : O.iavlim0, iavlim1 = O.iavlim1, iavlim2 = FAST ? 0 : O.iavlim2;
@@ -147,15 +108,9 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
   const int lane = threadIdx.x & 31;
 #pragma unroll 1
   for (int trip = 0;; trip++) {
-    int unit;
-#if ND_RATES_PERSIST
-    unit = 0;
+    int unit = 0;
     if (lane == 0) unit = atomicAdd(R.sched, 1);
     unit = __shfl_sync(FULL, unit, 0);
-#else
-    unit = (blockIdx.x * RATES_BLOCK + threadIdx.x) >> 5;
-    if (trip > 0) break;
-#endif
     if (unit >= nunits) break;
   const int tix = unit * 32 + lane;   // target index within this launch
   int s = s0 + tix;                                  // target slot: a contiguous range, or the entries of a target list
@@ -230,11 +185,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
       // kernel gradient table rows for q2i, q2j: the loads are issued here, the interpolation (their first use) comes after the
       // signal-velocity block so that ~250 independent FP64 instructions cover the lookup latency
       const int idxi = tab_index(q2i, G.ddq2table), idxj = tab_index(q2j, G.ddq2table);
-      #if ND_RATES_TABSMEM
       const double2 rowi = tabs[idxi], rowj = tabs[idxj];
-#else
-      const double2 rowi = __ldg(G.tabg + idxi), rowj = __ldg(G.tabg + idxj);
-#endif
       const double dvdotr = (dvx * drx + dvy * dry) + dvz * drz;   // :1250
       const double rho1j = tj4.x, rho21j = rho1j * rho1j;          // :1256-1258
       const double rhoav1 = 0.5 * (rho1i + rho1j);                 // :1261
@@ -305,29 +256,17 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
       // ---- kernel gradients :1208-1241 (w = w[index] + dwdx*(q2 - index*dq2table), src/kernelND.f90:4443-4455) ----
       double grkerni = rowi.x + rowi.y * (q2i - __dmul_rn((double)idxi, G.dq2table));
       double grkernj = rowj.x + rowj.y * (q2j - __dmul_rn((double)idxj, G.dq2table));
-      double grkern;
-      if (ND_RATES_FUSEDR && ikernav == 3) {
-        // h^-(ndim+1) * gradh as one factor per side: the target's is loop-invariant, the neighbour's reuses hj21 = (1/h_j)^2
-        const double hgj = (NDIM == 3 ? hj21 * hj21 : NDIM == 2 ? hj21 * hj1 : hj21) * gj.x;
-        grkerni = grkerni * (hfacgrkerni * gradhi);
-        grkernj = grkernj * hgj;
-        grkern = 0.5 * (grkerni + grkernj);
-      } else {
-      grkerni = grkerni * hfacgrkerni;
-      const double hfacwabj = powndim<NDIM>(hj1), hfacgrkernj = hfacwabj * hj1;   // :1215-1216
-      grkernj = grkernj * hfacgrkernj;
-      if (ikernav == 3) {                                       // :1227-1237
-        grkerni = grkerni * gradhi;
-        grkernj = grkernj * gj.x;
-        grkern = 0.5 * (grkerni + grkernj);
-      } else {                                                  // :1239-1241
-        grkern = 0.5 * (grkerni + grkernj);
-        grkerni = grkern; grkernj = grkern;
-      }
-      }
+      // :1215-1237 with ikernav = 3 (the only supported value, check_options): h^-(ndim+1) * gradh as one factor per side -- the
+      // target's is loop-invariant, the neighbour's reuses hj21 = (1/h_j)^2
+      const double hgj = (NDIM == 3 ? hj21 * hj21 : NDIM == 2 ? hj21 * hj1 : hj21) * gj.x;
+      grkerni = grkerni * (hfacgrkerni * gradhi);
+      grkernj = grkernj * hgj;
+      const double grkern = 0.5 * (grkerni + grkernj);
       double fix = 0, fiy = 0, fiz = 0;   // forcei contribution of this pair
-      constexpr bool FUSEDR = ND_RATES_FUSEDR && !ONEF;
-      double cdr = 0.;                    // FUSEDR: forcei = pmassj * ((fix, fiy, fiz) - cdr * dr)
+      // FUSEDR (every instantiation but one-fluid dust, which needs forcei on its own): the scalar coefficients of dr in the force
+      // (AV, pressure, isotropic magnetic part) are summed before they meet dr -- forcei = pmassj * ((fix, fiy, fiz) - cdr * dr)
+      constexpr bool FUSEDR = !ONEF;
+      double cdr = 0.;
       double vsigav = 0.;
       if (ONEF && iav > 0) {
         // =============================== artificial_dissipation_dust (iav = 1, 2, 3) ===============================
@@ -541,99 +480,24 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
   if (cnt > 0) {
     const unsigned *col = L.nbr + ((size_t)(tix >> 5) * L.lmax) * 32 + (tix & 31);
     const double4 zero4 = make_double4(0., 0., 0., 0.);
-#if ND_RATES_STAGE == 3
-    // The five 32-byte records of the NEXT neighbour are copied global -> shared by cp.async while the current pair is
-    // evaluated (double buffer, no registers held across the copy); a thread only reads the slots it filled itself.
-    auto fetch = [&](int k, int st) {
-      stage_put(stg, st, 0, G.posh + k); stage_put(stg, st, 1, G.vm + k); stage_put(stg, st, 2, I.thermo + k); stage_put(stg, st, 3, I.gal + k);
-      if (MHD) stage_put(stg, st, 4, I.bpsi + k);
-      cp_async_commit();
-    };
-    fetch((int)col[0], 0);
-    walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
-      fetch(k1, (n + 1) & 1);                                   // for the last entry this refetches it; harmless
-      cp_async_wait<1>();
-      const int st = n & 1;
-      body(k, stage_get(stg, st, 0), stage_get(stg, st, 1), stage_get(stg, st, 2), stage_get(stg, st, 3), MHD ? stage_get(stg, st, 4) : zero4);
-    });
-    cp_async_wait<0>();
-#elif ND_RATES_STAGE == 7
-    // Register software pipeline, all five records one pair ahead in two alternating register sets (A, B): the body is
-    // instantiated twice per trip so no set is ever copied (the rotating single-set form costs 40 register moves a pair).
-    struct Rec5 { double4 p, v, t, g, b; };
-    auto load5 = [&](int k) { Rec5 r; r.p = ld4(G.posh + k); r.v = ld4(G.vm + k); r.t = ld4(I.thermo + k); r.g = ld4(I.gal + k); r.b = MHD ? ld4(I.bpsi + k) : zero4; return r; };
-    {
-      const int last = cnt - 1;
-      auto ld = [&](int n) { return (int)__ldcs(col + (size_t)min(n, last) * 32); };
-      // list entries are read one batch of four (thousands of cycles) ahead
-      int c0 = ld(0), c1 = ld(1), c2 = ld(2), c3 = ld(3);
-      Rec5 A = load5(c0), B;
-#pragma unroll 1
-      for (int nb = 0; nb < cnt; nb += 4) {
-        const int n0 = ld(nb + 4), n1 = ld(nb + 5), n2 = ld(nb + 6), n3 = ld(nb + 7);
-#pragma unroll 1
-        for (int v = 0; v < 2; v++) {
-          const int n = nb + 2 * v;
-          if (n >= cnt) break;
-          const int ka = v ? c2 : c0, kb = v ? c3 : c1, kn = v ? n0 : c2;
-          B = load5(kb);
-          body(ka, A.p, A.v, A.t, A.g, A.b);
-          A = load5(kn);                                        // past the end these reload the last entry; harmless
-          if (n + 1 < cnt) body(kb, B.p, B.v, B.t, B.g, B.b);
-        }
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-      }
-    }
-#elif ND_RATES_STAGE >= 4
-    // Register software pipeline: the records the body touches first are loaded one pair ahead (4: posh + vm, 5: all five,
-    // 6: posh only); the rest are issued at the top of the body and have the distance/rsqrt chain to arrive.
     if (ONEF) {   // the one-fluid dust instantiations have no registers to spare: direct loads
       walk_list(col, cnt, [&](int n, int k, int k1, int k2) { body(k, ld4(G.posh + k), ld4(G.vm + k), ld4(I.thermo + k), ld4(I.gal + k), MHD ? ld4(I.bpsi + k) : zero4); });
     } else {
-#if ND_RATES_STAGE == 5
-    // All five records of the next neighbour are in flight while this pair is evaluated.  The list column is read two entries
-    // ahead with plain rotation (k <- k1 <- k2 <- load): one coalesced load per pair and no branch in the loop besides its own.
-    const int last = cnt - 1;
-    int k = (int)__ldcs(col), k1 = (int)__ldcs(col + (size_t)min(1, last) * 32);
-    double4 pn = ld4(G.posh + k), vn = ld4(G.vm + k), tn = ld4(I.thermo + k), gn = ld4(I.gal + k), bn = MHD ? ld4(I.bpsi + k) : zero4;
+      // Register software pipeline: all five records of the next neighbour are in flight while this pair is evaluated.  The list
+      // column is read two entries ahead with plain rotation (k <- k1 <- k2 <- load): one coalesced load per pair and no branch in
+      // the loop besides its own.
+      const int last = cnt - 1;
+      int k = (int)__ldcs(col), k1 = (int)__ldcs(col + (size_t)min(1, last) * 32);
+      double4 pn = ld4(G.posh + k), vn = ld4(G.vm + k), tn = ld4(I.thermo + k), gn = ld4(I.gal + k), bn = MHD ? ld4(I.bpsi + k) : zero4;
 #pragma unroll 1
-    for (int n = 0; n < cnt; n++) {
-      const int k2 = (int)__ldcs(col + (size_t)min(n + 2, last) * 32);
-      const double4 pc = pn, vc = vn, tc = tn, gc = gn, bc = bn;
-      pn = ld4(G.posh + k1); vn = ld4(G.vm + k1); tn = ld4(I.thermo + k1); gn = ld4(I.gal + k1); bn = MHD ? ld4(I.bpsi + k1) : zero4;
-      body(k, pc, vc, tc, gc, bc);
-      k = k1; k1 = k2;
+      for (int n = 0; n < cnt; n++) {
+        const int k2 = (int)__ldcs(col + (size_t)min(n + 2, last) * 32);
+        const double4 pc = pn, vc = vn, tc = tn, gc = gn, bc = bn;
+        pn = ld4(G.posh + k1); vn = ld4(G.vm + k1); tn = ld4(I.thermo + k1); gn = ld4(I.gal + k1); bn = MHD ? ld4(I.bpsi + k1) : zero4;
+        body(k, pc, vc, tc, gc, bc);
+        k = k1; k1 = k2;
+      }
     }
-#else
-    const int kf = (int)col[0];
-    double4 pn = ld4(G.posh + kf);
-#if ND_RATES_STAGE != 6
-    double4 vn = ld4(G.vm + kf);
-#endif
-    walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
-      const double4 pc = pn;
-      pn = ld4(G.posh + k1);
-#if ND_RATES_STAGE != 6
-      const double4 vc = vn;
-      vn = ld4(G.vm + k1);
-#else
-      const double4 vc = ld4(G.vm + k);
-#endif
-      body(k, pc, vc, ld4(I.thermo + k), ld4(I.gal + k), MHD ? ld4(I.bpsi + k) : zero4);
-    });
-#endif
-    }
-#else
-    walk_list(col, cnt, [&](int n, int k, int k1, int k2) {
-#if ND_RATES_STAGE >= 1
-      // register-free L1 prefetch of the records ND_RATES_STAGE pairs ahead
-      const int kp = ND_RATES_STAGE == 1 ? k1 : k2;
-      prefetch_l1(G.posh + kp); prefetch_l1(G.vm + kp); prefetch_l1(I.thermo + kp); prefetch_l1(I.gal + kp);
-      if (MHD) prefetch_l1(I.bpsi + kp);
-#endif
-      body(k, ld4(G.posh + k), ld4(G.vm + k), ld4(I.thermo + k), ld4(I.gal + k), MHD ? ld4(I.bpsi + k) : zero4);
-    });
-#endif
   }
 
   if (vsig_det_bad) atomicCAS(R.err, 0, 6 /*ND_ERR_VSIG_DET*/);
