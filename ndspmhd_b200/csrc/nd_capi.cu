@@ -78,7 +78,7 @@ struct nd_ctx {
   int itsdensity = 0, ncalc = 0, nrelink = 0; long long ncalctotal = 0, ncalc_g = 0; bool redolink = false;
   nd_scalars sc;
   // ---- slab decomposition (nd_comm): halo send lists and staging buffers ----
-  nd_comm comm; bool has_comm = false;
+  nd_comm comm; bool has_comm = false; bool slab_too_narrow = false;
   int *sendlist[2] = {nullptr, nullptr}; int sendcap[2] = {0, 0}, nsend[2] = {0, 0}, nrecv[2] = {0, 0};
   void *sendbuf[2] = {nullptr, nullptr}, *recvbuf[2] = {nullptr, nullptr}; size_t sendbufcap[2] = {0, 0}, recvbufcap[2] = {0, 0};
   cudaEvent_t ev[8];
@@ -495,6 +495,8 @@ int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int
   c->npart = npart; c->ntotal = ntotal; c->nown = npart;
   c->uploaded = true; c->linked = c->density_done = c->prim_done = c->rates_done = false;
   CU(cudaStreamWaitEvent(c->stream, c->ev_in[0], 0));
+  // slab contexts pack en, Bevol, alpha, psi into the halo records during the link (k_halo_pack1): group 2 must have landed too
+  if (c->has_comm) CU(cudaStreamWaitEvent(c->stream, c->ev_in[1], 0));
   CU(cudaEventRecord(c->ev[0], c->stream));
   int e = DISPATCH_NDIM(c, do_link<1>(c), do_link<2>(c), do_link<3>(c));
   bool light = false;

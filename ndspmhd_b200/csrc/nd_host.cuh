@@ -183,6 +183,10 @@ int halo_exchange_inputs(nd_ctx *c) {
   HaloSelArgs SA;
   SA.x = c->x; SA.nown = np; SA.ndim = c->ndim; SA.lo = c->comm.slab_lo; SA.hi = c->comm.slab_hi;
   SA.reach = c->T->radkern * c->hhmax * (1.0 + 1.e-10);
+  // Halos come from the two adjacent ranks only: a slab narrower than the reach would miss neighbours two ranks away, and on a
+  // periodic ring of two ranks a pair could be within reach through both faces (two copies of one particle).  Flagged here,
+  // raised by do_link after the ranks' error flags have been all-reduced, so that every rank leaves together.
+  c->slab_too_narrow = (SA.hi - SA.lo) < ((periodic && nr == 2) ? 2. : 1.) * SA.reach;
   SA.tol = 1.e-9 * std::max(1.0, std::fabs(SA.hi - SA.lo));
   SA.left_on = (periodic || rank > 0) ? 1 : 0; SA.right_on = (periodic || rank < nr - 1) ? 1 : 0;
   SA.flagL = c->cellOfOrig; SA.flagR = c->ghostcount; SA.err = c->flags + 1;   // scratch: both are rewritten later in this link
@@ -345,12 +349,14 @@ template <int NDIM> int do_link(nd_ctx *c) {
   if (int e = build_cells<NDIM>(c)) return e;
   if (int e = sync_flags(c)) return e;
   c->mixed_types = c->h_flags[6] != 0;
-  double ef = c->h_flags[1];
+  double ef = (c->h_flags[1] != 0 || (c->has_comm && c->slab_too_narrow)) ? 1. : 0.;
   if (int e = comm_allreduce(c, &ef, 1, 0)) return e;   // every rank leaves together
   if (ef != 0.) {
-    int code = c->h_flags[1] ? c->h_flags[1] : ND_ERR_COMM;
     CU(cudaMemsetAsync(c->flags, 0, sizeof(int) * 16, c->stream));
-    return set_err(c, code, c->h_flags[1] ? "link: particle outside the boundary / its slab" : "link: another rank reported an error");
+    if (c->h_flags[1]) return set_err(c, c->h_flags[1], "link: particle outside the boundary / its slab");
+    if (c->has_comm && c->slab_too_narrow)
+      return set_err(c, ND_ERR_INVALID_ARG, "link: slab narrower than the interaction reach radkern*hhmax (twice that on a periodic ring of 2 ranks): repartition with fewer ranks");
+    return set_err(c, ND_ERR_COMM, "link: another rank reported an error");
   }
   c->linked = true;
   return 0;

@@ -132,9 +132,22 @@ def read_dump(path: str):
                   "iformat": iformat, "ibound": ibound, "xmin": xmin, "xmax": xmax, "geom": geom}
         if not geom.startswith("cart"):
             raise ValueError(f"geometry {geom!r}: only cartesian dumps are read")
-        imhd = 1 if iformat in (2, 4) else 0
         onef = iformat == 5
+        if onef:
+            # the reference writes iformat = 5 for one-fluid dust with or without the MHD columns (:65-86): only the column
+            # count tells the two layouts apart
+            if ncol == ncolumns(ndim, 1, True):
+                imhd = 1
+            elif ncol == ncolumns(ndim, 0, True):
+                imhd = 0
+            else:
+                raise ValueError(f"iformat 5 dump with {ncol} columns: neither the MHD ({ncolumns(ndim, 1, True)}) nor the hydro "
+                                 f"({ncolumns(ndim, 0, True)}) one-fluid dust layout")
+        else:
+            imhd = 1 if iformat in (2, 4) else 0
         names = column_names(ndim, imhd, onef)
+        if not onef and ncol != len(names):
+            raise ValueError(f"iformat {iformat} dump with {ncol} columns, expected {len(names)} (extra columns: igravity, del2v, imhd<0?)")
         cols = {}
         for nm in names:
             rec = _read_rec(f)
@@ -142,6 +155,8 @@ def read_dump(path: str):
                 raise ValueError(f"column {nm}: {len(rec)} bytes, expected {8 * nprint} (a dump with extra columns: igravity, del2v, imhd<0?)")
             cols[nm] = np.frombuffer(rec, dtype="<f8").copy()
         rec = _read_rec(f)
+        if len(rec) != 4 * nprint:
+            raise ValueError(f"itype record: {len(rec)} bytes, expected {4 * nprint} (a real-valued column read as itype?)")
         cols["itype"] = np.frombuffer(rec, dtype="<i4").copy()
         header["imhd_in_file"] = imhd
         header["onef_dust_in_file"] = onef

@@ -123,6 +123,11 @@ module ndspmhd_b200
 
  type(c_ptr), save :: b200_ctx = c_null_ptr     ! one context per process (the reference is single-threaded)
  logical, save     :: b200_resident = .false.  ! .true. between the shim's link and rates calls of one derivs
+ ! rhoalt, gradhn, gradsoft, gradgradh, graddivv are written by the reference's density/rates but read back only under options
+ ! the library refuses (usenumdens, igravity, ibiascorrection, iavlim(1)=3 ...).  With .false. (default) the library runs the
+ ! first-class tuple on its fast kernels (FAST rates instantiation, LIGHT density rounds: the configuration bench.py times)
+ ! and does not download those arrays; set .true. to get them filled as the reference does.
+ logical, save     :: b200_want_aux = .false.
 
 contains
 
@@ -152,7 +157,7 @@ contains
   o%ivisc = ivisc; o%iquantum = iquantum; o%ind_timesteps = 0   ! no default in defaults.f90; leapfrog never sets it
   o%nsubsteps_divB = 0                                         ! uninitialised under leapfrog (variablesND.f90:261)
   o%device_ghosts = 0                                          ! set_ghost_particles stays on the host in the drop-in mode
-  o%want_aux = 1
+  o%want_aux = merge(1,0,b200_want_aux)                        ! see b200_want_aux
   o%hfact = hfact; o%psep = psep; o%tolh = tolh; o%gamma = gamma; o%polyk = polyk
   o%alphamin = alphamin; o%alphaumin = alphaumin; o%alphaBmin = alphabmin; o%beta = beta
   o%avdecayconst = avdecayconst; o%avfact = avfact
@@ -171,26 +176,55 @@ contains
   use derivB,   only:divB,curlB
   use bound,    only:ireal
   use linklist, only:numneigh
+  use options,  only:iavlim
   type(nd_arrays), intent(out) :: a
-  a%x = c_loc(x); a%vel = c_loc(vel); a%pmass = c_loc(pmass); a%hh_in = c_loc(hh); a%itype = c_loc(itype); a%ireal = c_loc(ireal)
-  a%en = c_loc(en); a%Bevol = c_loc(Bevol); a%alpha = c_loc(alpha); a%psi = c_loc(psi); a%rho_in = c_loc(rho)
-  a%hh = c_loc(hh); a%rho = c_loc(rho); a%gradh = c_loc(gradh); a%drhodt = c_loc(drhodt); a%dhdt = c_loc(dhdt)
-  a%numneigh = c_loc(numneigh); a%rhoalt = c_loc(rhoalt); a%gradhn = c_loc(gradhn); a%gradsoft = c_loc(gradsoft)
-  a%gradgradh = c_loc(gradgradh)
-  a%dens = c_loc(dens); a%uu = c_loc(uu); a%pr = c_loc(pr); a%spsound = c_loc(spsound); a%Bfield = c_loc(Bfield)
-  a%force = c_loc(force); a%dudt = c_loc(dudt); a%dendt = c_loc(dendt); a%dBevoldt = c_loc(dBevoldt); a%daldt = c_loc(daldt)
-  a%dpsidt = c_loc(dpsidt); a%gradpsi = c_loc(gradpsi); a%divB = c_loc(divB); a%curlB = c_loc(curlB)
-  a%graddivv = c_loc(graddivv); a%del2u = c_null_ptr
+  ! The module arrays are plain `allocatable` without TARGET (src/variablesND.f90:174-186), so c_loc may not be applied to
+  ! them directly (gfortran -std=f2008 rejects it).  They are passed to b200_loc_r / b200_loc_i instead, whose assumed-size
+  ! dummies carry TARGET: a whole allocatable array is contiguous, so sequence association hands over its base address
+  ! without a copy and c_loc of the dummy is legal.  No line of the reference's declarations has to change.
+  a%x = b200_loc_r(x); a%vel = b200_loc_r(vel); a%pmass = b200_loc_r(pmass); a%hh_in = b200_loc_r(hh)
+  a%itype = b200_loc_i(itype); a%ireal = b200_loc_i(ireal)
+  a%en = b200_loc_r(en); a%Bevol = b200_loc_r(Bevol); a%alpha = b200_loc_r(alpha); a%psi = b200_loc_r(psi)
+  a%rho_in = b200_loc_r(rho)
+  a%hh = b200_loc_r(hh); a%rho = b200_loc_r(rho)
+  a%gradh = b200_loc_r(gradh); a%drhodt = b200_loc_r(drhodt); a%dhdt = b200_loc_r(dhdt)
+  a%numneigh = b200_loc_i(numneigh)
+  if (b200_want_aux) then   ! companions of the density sums no supported option tuple reads back (see b200_fill_options)
+     a%rhoalt = b200_loc_r(rhoalt); a%gradhn = b200_loc_r(gradhn)
+     a%gradsoft = b200_loc_r(gradsoft); a%gradgradh = b200_loc_r(gradgradh)
+  else
+     a%rhoalt = c_null_ptr; a%gradhn = c_null_ptr; a%gradsoft = c_null_ptr; a%gradgradh = c_null_ptr
+  endif
+  a%graddivv = c_null_ptr
+  if (b200_want_aux .or. iavlim(1)==3) a%graddivv = b200_loc_r(graddivv)   ! read back by the iavlim(1)=3 switch only
+  a%dens = b200_loc_r(dens); a%uu = b200_loc_r(uu)
+  a%pr = b200_loc_r(pr); a%spsound = b200_loc_r(spsound); a%Bfield = b200_loc_r(Bfield)
+  a%force = b200_loc_r(force); a%dudt = b200_loc_r(dudt); a%dendt = b200_loc_r(dendt); a%dBevoldt = b200_loc_r(dBevoldt)
+  a%daldt = b200_loc_r(daldt); a%dpsidt = b200_loc_r(dpsidt); a%gradpsi = b200_loc_r(gradpsi); a%divB = b200_loc_r(divB)
+  a%curlB = b200_loc_r(curlB); a%del2u = c_null_ptr
   a%x_out = c_null_ptr; a%vel_out = c_null_ptr; a%ireal_out = c_null_ptr; a%itype_out = c_null_ptr
   if (onef_dust) then   ! one-fluid dust arrays only exist then (src/allocateND.f90:386-392)
-     a%dustevol = c_loc(dustevol); a%dustfrac_in = c_loc(dustfrac); a%deltav = c_loc(deltav)
-     a%dustfrac = c_loc(dustfrac); a%rhogas = c_loc(rhogas); a%rhodust = c_loc(rhodust)
-     a%ddustevoldt = c_loc(ddustevoldt); a%ddeltavdt = c_loc(ddeltavdt)
+     a%dustevol = b200_loc_r(dustevol); a%dustfrac_in = b200_loc_r(dustfrac); a%deltav = b200_loc_r(deltav)
+     a%dustfrac = b200_loc_r(dustfrac); a%rhogas = b200_loc_r(rhogas); a%rhodust = b200_loc_r(rhodust)
+     a%ddustevoldt = b200_loc_r(ddustevoldt); a%ddeltavdt = b200_loc_r(ddeltavdt)
   else
      a%dustevol = c_null_ptr; a%dustfrac_in = c_null_ptr; a%deltav = c_null_ptr; a%dustfrac = c_null_ptr
      a%rhogas = c_null_ptr; a%rhodust = c_null_ptr; a%ddustevoldt = c_null_ptr; a%ddeltavdt = c_null_ptr
   endif
  end subroutine b200_fill_arrays
+
+!--base address of a contiguous real / integer array of any rank (sequence association onto an assumed-size TARGET dummy)
+ function b200_loc_r(a) result(p)
+  real(c_double), intent(in), target :: a(*)
+  type(c_ptr) :: p
+  p = c_loc(a)
+ end function b200_loc_r
+
+ function b200_loc_i(a) result(p)
+  integer(c_int), intent(in), target :: a(*)
+  type(c_ptr) :: p
+  p = c_loc(a)
+ end function b200_loc_i
 
 !--reference error convention: print to iprint, then `call quit` (emergency dump + stop, src/ndspmhd.f90:369-386)
  subroutine b200_check(ierr,where)

@@ -54,8 +54,9 @@ subroutine b200_sync_to_host
  implicit none
  type(nd_state_out) :: st
  type(nd_arrays)    :: a
- st%x = c_loc(x); st%vel = c_loc(vel); st%hh = c_loc(hh); st%en = c_loc(en)
- st%Bevol = c_loc(Bevol); st%alpha = c_loc(alpha); st%psi = c_loc(psi); st%rho = c_loc(rho)
+ ! b200_loc_r: c_loc through an assumed-size TARGET dummy (the module arrays have no TARGET attribute)
+ st%x = b200_loc_r(x); st%vel = b200_loc_r(vel); st%hh = b200_loc_r(hh); st%en = b200_loc_r(en)
+ st%Bevol = b200_loc_r(Bevol); st%alpha = b200_loc_r(alpha); st%psi = b200_loc_r(psi); st%rho = b200_loc_r(rho)
  st%dustevol = c_null_ptr; st%deltav = c_null_ptr
  call b200_check(ndspmhd_b200_download_state(b200_ctx,st,int(size(hh),c_int)),'download_state')
  call b200_fill_arrays(a)                 ! pointers to dens, pr, ..., force, divB, curlB

@@ -79,3 +79,26 @@ def test_read_rejects_foreign_files(tmp_path):
         f.write(struct.pack("<i", 48) + b"\0" * 48 + struct.pack("<i", 48))
     with pytest.raises(ValueError):
         dumps.read_dump(path)
+
+
+def test_onefluid_dust_mhd_dump_is_told_apart_by_its_column_count(tmp_path):
+    """iformat = 5 is written for one-fluid dust with AND without the 14 MHD columns (readwrite_dumps.f90:65-86): the reader decides by
+    ncolumns, checks the itype record's length, and refuses a column count that fits neither layout."""
+    o, p = _state(lambda: setups.dustywave_onefluid(ndim=3, nx=8, mhd=True))
+    path = str(tmp_path / "dust_00000.dat")
+    n = dumps.write_dump(path, 0.0, o, p)
+    hdr, cols = dumps.read_dump(path)
+    assert hdr["iformat"] == 5 and hdr["imhd_in_file"] == 1 and hdr["ncolumns"] == dumps.ncolumns(3, 1, True)
+    assert np.array_equal(cols["Bz"], p.Bfield[:n, 2]) and np.array_equal(cols["dustfrac"], p.dustfrac[:n])
+    assert cols["itype"].dtype == np.int32 and np.array_equal(cols["itype"], p.itype[:n])
+    o2, p2 = _state(lambda: setups.dustywave_onefluid(ndim=3, nx=8, mhd=False))
+    path2 = str(tmp_path / "dusth_00000.dat")
+    dumps.write_dump(path2, 0.0, o2, p2)
+    hdr2, cols2 = dumps.read_dump(path2)
+    assert hdr2["iformat"] == 5 and hdr2["imhd_in_file"] == 0 and "Bx" not in cols2
+    raw = bytearray(open(path, "rb").read())
+    struct.pack_into("<i", raw, 4 + 32 + 8, hdr["ncolumns"] + 1)   # ncolumns sits after t, npart, nprint, gamma, hfact, ndim, ndimV
+    bad = str(tmp_path / "bad_00000.dat")
+    open(bad, "wb").write(bytes(raw))
+    with pytest.raises(ValueError):
+        dumps.read_dump(bad)
