@@ -34,20 +34,73 @@ sys.path.insert(0, ROOT)
 
 METRIC = "particle-updates/sec (density+rates), 3D MHD Orszag-Tang, 16.8M particles"
 UNIT = "particle-updates/s"
-# compulsory read-once/write-once bytes per particle-update, FP64, 3D MHD tuple
-BYTES_DENSITY = 68 + 44
-BYTES_C2P = 40 + 56
-BYTES_RATES = 164 + 120
-BYTES_TOTAL = BYTES_DENSITY + BYTES_C2P + BYTES_RATES   # 492
+
+# ----------------------------------------------------------------------------------------------------------------------
+# workloads: BASELINE.json configs C2-C5 (C1, the 1000-particle shock tube, is a parity case, not a bench line).  `bytes` = SURVEY.md 8(d)
+# compulsory read-once/write-once bytes per particle-update (density, cons2prim, rates), FP64.
+# ----------------------------------------------------------------------------------------------------------------------
+CONFIGS = {
+    # C5 family, thin slab: the reference's own 3-D MHD problem (src/setup_orszagtang2D_mhd.f90:70-73, default SETUP3D) -- the headline
+    "slab512": dict(kind="ot", ndim=3, nx=512, cube=False, bytes=(68 + 44, 40 + 56, 164 + 120), metric=METRIC,
+                    label="3D Orszag-Tang MHD vortex, thin periodic slab {nx}x{nx}x{nz} = {n} particles (src/setup_orszagtang2D_mhd.f90 in 3D), "
+                          "glass (lattice + 0.2 dp), imhd=11 idivbzero=2 iener=2 iav=2 cubic spline hfact=1.2"),
+    # C5 / C3: the same fields in a periodic CUBE (twice the halo area per face of the thin slab)
+    "cube256": dict(kind="ot", ndim=3, nx=256, cube=True, bytes=(112, 96, 284),
+                    label="3D Orszag-Tang MHD vortex, periodic cube {nx}^3 = {n} particles, glass (lattice + 0.2 dp), imhd=11 idivbzero=2 iener=2 iav=2"),
+    "cube128": dict(kind="ot", ndim=3, nx=128, cube=True, bytes=(112, 96, 284),
+                    label="3D Orszag-Tang MHD vortex, periodic cube {nx}^3 = {n} particles, glass (lattice + 0.2 dp), imhd=11 idivbzero=2 iener=2 iav=2"),
+    # C2: 2-D Orszag-Tang on the close-packed lattice, dp = 1/512 -> 512 x 592 (src/setup_orszagtang2D_mhd.f90:63-96)
+    "ot2d": dict(kind="ot", ndim=2, nx=512, cube=False, bytes=(60 + 44, 40 + 56, 156 + 120),
+                 label="2D Orszag-Tang MHD vortex, close-packed lattice dp=1/{nx} = {n} particles (+0.2 dp), imhd=11 idivbzero=2 iener=2 iav=2"),
+    # C4: two-fluid dust + gas, fat periodic box (the thin 1 x 11 x 11 box is ghost-dominated; it is a parity case)
+    "dust2m": dict(kind="dust", ndim=3, nx=100, cube=True, bytes=(112, 48, 172),
+                   label="3D two-fluid dust+gas box, {nx}^3 gas + {nx}^3 dust = {n} particles, idust=2 idrag_nature=1 K=1, iener=2 iav=2 (src/setup_dustybox.f90 fields, fat box)"),
+}
 
 
-def workload(nx: int, perturb: float = 0.2):
+def cfg_of(args):
+    c = dict(CONFIGS[args.config])
+    if args.nx:
+        c["nx"] = args.nx
+    return c
+
+
+def workload(args_or_cfg, nx=None, slab=None):
+    """(options, particles[, info]) of a config at `nx` particles per unit length (default: the config's own size)."""
     from ndspmhd_b200 import setups
 
-    o, p = setups.orszag_tang(ndim=3, nx=nx, zfrac=0.125, perturb_amp=perturb, evolved=True, imhd=11, idivbzero=2, iener=2)
-    o.device_ghosts = 1
-    o.want_aux = 0
-    return o, p
+    c = args_or_cfg if isinstance(args_or_cfg, dict) else cfg_of(args_or_cfg)
+    nx = nx or c["nx"]
+    if c["kind"] == "dust":
+        if slab is not None:
+            raise SystemExit("bench.py: the dust config is single-GPU")
+        o, p = setups.dustybox(ndim=3, nx=nx, perturb_amp=0.05)
+        o.device_ghosts, o.want_aux = 1, 0
+        return o, p
+    kw = dict(ndim=c["ndim"], nx=nx, perturb_amp=0.2, evolved=True, imhd=11, idivbzero=2, iener=2)
+    if c["ndim"] == 3:
+        kw.update(cube=c["cube"], zfrac=0.125)
+    else:
+        kw.update(lattice="cp")
+    out = setups.orszag_tang(slab=slab, **kw)
+    out[0].device_ghosts, out[0].want_aux = 1, 0
+    return out
+
+
+def npart_of(c, nx=None):
+    nx = nx or c["nx"]
+    if c["kind"] == "dust":
+        return 2 * nx ** 3
+    if c["ndim"] == 2:
+        return None   # the close-packed generator decides (512 x 592 at dp = 1/512)
+    return nx ** 3 if c["cube"] else nx * nx * (nx // 8)
+
+
+def source_sha() -> str:
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_count
+
+    return sass_count.source_sha()
 
 
 def measured_peaks():
@@ -108,15 +161,47 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_oracle_sample(nx: int):
-    """One serial oracle `derivs` on the bounded sample; returns (updates/s, npart, seconds, phase ms)."""
+def cpu_oracle_runs(c, sizes):
+    """Serial oracle `derivs` of the config at several sizes: [(npart, seconds, updates/s, phase ms, its)] -- the reference is serial
+    (docs/about.rst:12), so this IS its execution model; the sizes show that updates/s does not depend on N (the fit SURVEY 8d asks for)."""
     from oracle import oracle
 
-    o, p = workload(nx)
-    t = time.perf_counter()
-    s, ms = oracle.derivs(o, p)
-    dt = time.perf_counter() - t
-    return p.npart / dt, p.npart, dt, ms, s["itsdensity"]
+    runs = []
+    for nx in sizes:
+        o, p = workload(c, nx)
+        t = time.perf_counter()
+        s, ms = oracle.derivs(o, p)
+        dt = time.perf_counter() - t
+        runs.append({"nx": nx, "npart": int(p.npart), "seconds": dt, "updates_per_s": p.npart / dt, "itsdensity": int(s["itsdensity"]),
+                     "phases_ms": dict(zip(["ghosts", "link", "density", "c2p", "rates"], [float(x) for x in ms]))})
+        del p
+    return runs
+
+
+def loglog_slope(runs):
+    """d log(time) / d log(N): 1.0 = throughput independent of N."""
+    import math
+
+    if len(runs) < 2:
+        return None
+    xs = [math.log(r["npart"]) for r in runs]
+    ys = [math.log(r["seconds"]) for r in runs]
+    mx, my = sum(xs) / len(xs), sum(ys) / len(ys)
+    return sum((x - mx) * (y - my) for x, y in zip(xs, ys)) / max(sum((x - mx) ** 2 for x in xs), 1e-300)
+
+
+def sample_sizes(c, budget_s: float, rate: float = 1.0e5):
+    """Sizes of the config family whose serial oracle runs fit `budget_s` seconds in total (largest first dominates)."""
+    cand = {"slab": [256, 224, 192, 160, 128, 96, 64], "cube": [128, 112, 96, 80, 64, 48, 32], "2d": [512, 384, 256, 192, 128],
+            "dust": [100, 80, 64, 50, 40, 32]}["dust" if c["kind"] == "dust" else "2d" if c["ndim"] == 2 else "cube" if c["cube"] else "slab"]
+    est = lambda nx: (npart_of(c, nx) or int(1.155 * nx * nx)) / rate
+    big = next((nx for nx in cand if est(nx) <= 0.7 * budget_s), cand[-1])
+    smaller = [nx for nx in cand if nx < big]
+    out = [big]
+    for nx in (smaller[1:2] + smaller[3:4]):
+        if sum(est(k) for k in out) + est(nx) <= budget_s:
+            out.append(nx)
+    return sorted(out)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -125,10 +210,10 @@ def cpu_oracle_sample(nx: int):
 _W = {}
 
 
-def _ref_init(nx):
-    from oracle import oracle  # noqa: F401  (loads the .so once per worker)
+def _ref_init(cfg, nx):
+    from oracle import oracle  # noqa: F401  (loads the oracle .so once per worker; the product library is never loaded in this arm)
 
-    _W["o"], _W["p"] = workload(nx)
+    _W["o"], _W["p"] = workload(cfg, nx)
 
 
 def _ref_step(_):
@@ -141,33 +226,45 @@ def _ref_step(_):
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the path on all host cores.  The reference is serial Fortran that cannot be built in this image
+    (DESIGN.md), so this times its C++ restatement (oracle/), farmed over the cores as independent serial runs -- the reference's only form of
+    parallelism (scripts/doparallel.pl).  Each step is a bounded sample of the workload (the largest size of the same family that keeps the
+    whole --steps/--warmup run within a few minutes); single-core runs at smaller sizes show updates/s is flat in N."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import multiprocessing as mp
 
+    c = cfg_of(args)
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    nx = args.ref_nx or (128 if cores <= 64 else 96)
+    # time budget: ~200 s for the farmed steps (contention on memory bandwidth costs ~1.4x against a lone core)
+    per_step = 200.0 / max(1, args.steps + args.warmup)
+    nx = args.ref_nx or sample_sizes(c, per_step / 1.4)[-1]
+    fit = cpu_oracle_runs(c, [k for k in sample_sizes(c, 12.0) if k != nx][:2]) if not args.no_fit else []
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_ref_init, initargs=(nx,)) as pool:
+    with ctx.Pool(cores, initializer=_ref_init, initargs=(c, nx)) as pool:
         times = []
         for step in range(args.warmup + args.steps):
             t = time.perf_counter()
             res = pool.map(_ref_step, range(cores), chunksize=1)
             dt = time.perf_counter() - t
             if step >= args.warmup:
-                times.append((dt, sum(r[1] for r in res)))
-    total_t = sum(t for t, _ in times)
-    total_n = sum(n for _, n in times)
+                times.append((dt, sum(r[1] for r in res), sum(r[0] for r in res) / len(res)))
+    total_t = sum(t[0] for t in times)
+    total_n = sum(t[1] for t in times)
     value = total_n / total_t
     npart = times[0][1] // cores
-    sample = (f"{cores} independent serial oracle runs (one per core, the reference's job-farming model, scripts/doparallel.pl), "
-              f"each one full derivs on the same workload at {nx}x{nx}x{nx // 8} = {npart} particles")
+    per_core = npart / (sum(t[2] for t in times) / len(times))
+    sample = (f"{cores} independent serial oracle runs (one per core: the reference's job-farming model, scripts/doparallel.pl), each one full derivs of the "
+              f"same workload at nx={nx} = {npart} particles per run; {per_core:.3g} updates/s per core inside the farm")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": c.get("metric", METRIC_FOR(c)), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total_t / len(times), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": config_dict(args, nx_used=nx),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": config_dict(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "single_core_fit": {"runs": [{k: r[k] for k in ("nx", "npart", "seconds", "updates_per_s")} for r in fit],
+                                             "farm_per_core_updates_per_s": per_core,
+                                             "note": "updates/s of the serial oracle vs N: flat (O(N) cell lists), so the bounded sample stands for the full-size run"}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -175,24 +272,55 @@ def run_reference(args):
     return 0
 
 
-def config_dict(args, nx_used=None, extra=None):
-    nx = args.nx
-    d = {"workload": f"3D Orszag-Tang MHD vortex, thin periodic slab {nx}x{nx}x{nx // 8} = {nx * nx * (nx // 8)} particles "
-                     "(src/setup_orszagtang2D_mhd.f90 in 3D), glass (lattice + 0.2 dp), imhd=11 idivbzero=2 iener=2 iav=2 cubic spline hfact=1.2",
-         "step": "one derivs: ghosts + link + density/h iteration to tolh=1e-3 + cons2prim + rates (pair + final)",
-         "l2": "inputs (>2 GB of particle state) larger than the 126 MB L2; no flush needed",
-         "parallelism": "1 GPU" if args.gpus == 1 else f"x-slabs over {args.gpus} GPUs, NCCL halo exchange"}
-    if nx_used and nx_used != nx:
-        d["reference_sample_nx"] = nx_used
-    if extra:
-        d.update(extra)
-    return d
+def METRIC_FOR(c):
+    return "particle-updates/sec (density+rates), " + c["label"].split(",")[0]
+
+
+def config_dict(args):
+    """The same dict in both arms (the driver compares them): the workload by name and size, nothing run-specific."""
+    c = cfg_of(args)
+    nx = c["nx"]
+    n = npart_of(c) or 512 * 592 * (nx * nx) // (512 * 512)
+    return {"workload": args.config + ": " + c["label"].format(nx=nx, nz=nx // 8, n=n),
+            "step": "one derivs: ghosts + link + density/h iteration to tolh=1e-3 + cons2prim + rates (pair + final)",
+            "l2": "inputs (>2 GB of particle state at the headline size) larger than the 126 MB L2; no flush needed",
+            "parallelism": "1 GPU" if args.gpus == 1 else f"x-slabs over {args.gpus} GPUs, NCCL halo exchange"}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
+UP_NAMES = ["x", "vel", "pmass", "hh", "itype", "ireal", "en", "Bevol", "alpha", "psi", "rho"]
+DN_FULL = ["hh", "rho", "gradh", "numneigh", "dens", "uu", "pr", "spsound", "Bfield", "drhodt", "dhdt", "force", "dudt", "dendt",
+           "dBevoldt", "daldt", "dpsidt", "gradpsi", "divB", "curlB"]
+# what neither the leapfrog integrator (src/stepND_leapfrog_mhd.f90:70-216) nor evwrite (src/evwrite_mhd.f90:124-284) reads between two derivs:
+# a dump step fetches them with ndspmhd_b200_download.  The Fortran shim's default contract (b200_lean_download, INTEGRATION.md).
+LEAN_SKIP = ["gradh", "numneigh", "dens", "spsound", "gradpsi", "dudt"]
+HYDRO_SKIP = ["Bfield", "dBevoldt", "dpsidt", "gradpsi", "divB", "curlB"]
+
+
+def fp64_roofline(kernel_label, ntrips, kernel_ms, sm_mhz, num_smsp=592):
+    """FP64-pipe floor of the pair kernel: FP64-pipe instructions per pair-loop trip (from the SASS of THIS build, tools/sass_count.py) x the
+    warp trips the kernel made (nd_scalars.ntrips_rates) x 2 issue cycles (measured 0.49 warp-instr/clk/SMSP, profiles/r01/fp64_pipe_microbench.txt)
+    over 592 SMSPs.  frac = floor / measured kernel time = how busy the binding unit can be at best."""
+    try:
+        sj = json.load(open(os.path.join(ROOT, "profiles", "sass_fp64.json")))
+        if sj.get("source_sha") != source_sha():
+            return {"error": "profiles/sass_fp64.json is from another build (run tools/sass_count.py --write)"}
+        k = sj["kernels"][kernel_label]
+    except Exception as ex:
+        return {"error": str(ex)[:120]}
+    clk = (sm_mhz or 1965.0) * 1e6
+    floor_ms = 1e3 * ntrips * k["fp64_pipe_instructions"] * (1.0 / 0.49) / (num_smsp * clk)
+    return {"bound": "fp64_pipe", "kernel": kernel_label, "fp64_pipe_instructions_per_trip": k["fp64_pipe_instructions"], "loop_instructions_per_trip": k["loop_instructions"],
+            "warp_trips": int(ntrips), "issue_rate_warp_instr_per_clk_per_smsp": 0.49, "sm_mhz": clk / 1e6,
+            "fp64_issue_floor_ms": floor_ms, "kernel_ms": kernel_ms, "frac": floor_ms / kernel_ms if kernel_ms > 0 else None}
+
+
 def run_single(args):
+    import ctypes as C
+
+    import numpy as np
     import torch
 
     from ndspmhd_b200 import abi, lib
@@ -201,53 +329,53 @@ def run_single(args):
         raise SystemExit("bench.py: no CUDA device; ndspmhd_b200 has no CPU fallback")
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
-    o, p0 = workload(args.nx)
-    n = p0.npart
+    c = cfg_of(args)
+    o, p0 = workload(c)
+    n, ndim = p0.npart, c["ndim"]
+    mhd = o.imhd != 0
     # host arrays in page-locked memory (the Fortran module arrays, registered once)
-    p = lib.pinned_particles(3, n, p0.idim)
+    p = lib.pinned_particles(ndim, n, p0.idim)
     for k, v in p0.arrays.items():
         p.arrays[k][...] = v
     p.ntotal = n
     del p0
     # derivs overwrites hh with the converged smoothing lengths; every step must start from the same guess
     L = lib.load()
-    import ctypes as C
-    import numpy as np
     nb = p.arrays["hh"].nbytes
     ptr = L.ndspmhd_b200_host_alloc(nb)
     guess = np.frombuffer((C.c_char * nb).from_address(ptr), dtype=np.float64, count=p.idim)
     guess[...] = p.arrays["hh"]
     p.arrays["hh_guess"] = guess
     p.__dict__["_pinned"].append(ptr)
-    hot = lib.Hotpath(o, 3, dev)
+    hot = lib.Hotpath(o, ndim, dev)
     stream = torch.cuda.ExternalStream(hot.stream(), device=dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    # ---- e2e: host arrays in, host arrays out ----
-    mask = abi.DL_DENSITY | abi.DL_PRIM | abi.DL_RATES
-    if args.e2e_real_rows:
-        mask |= abi.DL_REAL_ROWS            # informational variant: the ghost rows of the output arrays stay on the device
-    def e2e_step():
-        p.ntotal = n
-        return hot.derivs_host(p, mask)     # ndspmhd_b200_derivs_host: upload + derivs + download, copies overlapped with kernels
-    for _ in range(max(1, min(args.warmup, 2))):
-        s = e2e_step()
-    nt = s["ntotal"]
-    e2e_steps = max(1, min(args.steps, 3))
     a, b = ev(), ev()
-    torch.cuda.synchronize()
-    a.record(stream)
-    for _ in range(e2e_steps):
-        e2e_step()
-    b.record(stream)
-    torch.cuda.synchronize()
-    e2e_ms = a.elapsed_time(b) / e2e_steps
-    up_names = ["x", "vel", "pmass", "hh", "itype", "ireal", "en", "Bevol", "alpha", "psi", "rho"]
-    dn_names = ["hh", "rho", "gradh", "numneigh", "dens", "uu", "pr", "spsound", "Bfield", "drhodt", "dhdt", "force", "dudt", "dendt",
-                "dBevoldt", "daldt", "dpsidt", "gradpsi", "divB", "curlB"]
     rowbytes = lambda nm: p.arrays[nm].nbytes // p.idim
-    h2d = sum(rowbytes(nm) for nm in up_names) * n
-    d2h = sum(rowbytes(nm) for nm in dn_names) * (n if args.e2e_real_rows else nt)
+
+    # ---- e2e: host arrays in, host arrays out, through ndspmhd_b200_derivs_host (upload + derivs + download, copies overlapped with kernels) ----
+    def e2e(skip, real_rows):
+        mask = abi.DL_DENSITY | abi.DL_PRIM | abi.DL_RATES | (abi.DL_REAL_ROWS if real_rows else 0)
+        def one():
+            p.ntotal = n
+            return hot.derivs_host(p, mask, skip=skip)
+        for _ in range(max(1, min(args.warmup, 2))):
+            s_ = one()
+        k = max(1, min(args.steps, 3))
+        torch.cuda.synchronize()
+        a.record(stream)
+        for _ in range(k):
+            one()
+        b.record(stream)
+        torch.cuda.synchronize()
+        ms_ = a.elapsed_time(b) / k
+        names = [nm for nm in DN_FULL if nm not in skip and (mhd or nm not in HYDRO_SKIP)]
+        up = [nm for nm in UP_NAMES if mhd or nm not in ("Bevol", "psi")]
+        return {"value": n / (ms_ * 1e-3), "unit": UNIT, "h2d_bytes_per_step": sum(rowbytes(nm) for nm in up) * n,
+                "d2h_bytes_per_step": sum(rowbytes(nm) for nm in names) * (n if real_rows else s_["ntotal"]), "ms_per_step": ms_, "steps": k}, s_
+    e2e_full, s = e2e([], False)
+    e2e_lean, s = e2e(LEAN_SKIP, True)
+    nt = s["ntotal"]
 
     # ---- device-resident ----
     p.ntotal = n
@@ -277,32 +405,41 @@ def run_single(args):
     value = n / (ms * 1e-3)
     peak, peak_src = measured_peaks()
     pair_ms = phases.pop("rates_pair_kernel")       # CUDA events around the pair kernel's launch alone, on the library's stream
-    achieved = BYTES_RATES * n / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else 0.0
+    b_dens, b_c2p, b_rates = c["bytes"]
+    b_total = b_dens + b_c2p + b_rates
+    achieved = b_rates * n / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else 0.0
+    kern = ("rates_pair_kernel<%d,%s>" % (ndim, "hydro,DRAG" if c["kind"] == "dust" else "MHD,FAST=2"))
     traffic, ncu_extra = None, {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            if int(tj.get("nx", 0)) == args.nx:
-                traffic = tj.get("rates_pair_kernel_dram_bytes_per_launch")
-                ncu_extra = {k: tj[k] for k in ("fp64_pipe_active_pct", "issue_active_pct", "l1tex_throughput_pct", "ncu_report") if k in tj}
+            if tj.get("config") == args.config and int(tj.get("nx", 0)) == c["nx"]:
+                if tj.get("source_sha") == source_sha():
+                    traffic = tj.get("rates_pair_kernel_dram_bytes_per_launch")
+                    ncu_extra = {k: tj[k] for k in ("fp64_pipe_active_pct", "issue_active_pct", "l1tex_throughput_pct", "gpu_time_ms_under_ncu", "ncu_report") if k in tj}
+                else:
+                    ncu_extra = {"stale": "profiles/traffic.json was captured from another build of the kernels (source_sha differs): not reported"}
         except Exception:
             pass
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "metric": c.get("metric", METRIC_FOR(c)), "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, extra={"npart": n, "ntotal_with_ghosts": nt, "itsdensity": s["itsdensity"], "nneigh_min": s["nneigh_min"],
-                                           "nneigh_max": s["nneigh_max"]}),
-        "e2e": {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                "steps": e2e_steps},
+        "config": config_dict(args),
+        "run": {"npart": n, "ntotal_with_ghosts": nt, "itsdensity": s["itsdensity"], "nrelink": s["nrelink"], "nneigh_min": s["nneigh_min"], "nneigh_max": s["nneigh_max"],
+                "npairs_rates": s["npairs_rates"], "lmax": s["lmax"], "source_sha": source_sha()},
+        # headline e2e: the contract the Fortran shim uses on ordinary steps (rows [0,npart); arrays no host code reads between two derivs stay
+        # on the device); full_contract: every output array of the reference's density/cons2prim/get_rates, ghost rows included
+        "e2e": dict(e2e_lean, contract="lean: skips " + ",".join(LEAN_SKIP) + " + ghost rows (ND_DL_REAL_ROWS)", full_contract=e2e_full),
         "gpu_launches": launches,
         "clocks": ck,
-        "roofline": {"bound": "hbm", "kernel": "rates_pair_kernel<3,MHD>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": BYTES_RATES * n, "kernel_ms": pair_ms, "kernel_share_of_step": pair_ms / ms,
+                     "algorithmic_bytes_per_launch": b_rates * n, "kernel_ms": pair_ms, "kernel_share_of_step": pair_ms / ms,
                      "ncu": ncu_extra,
-                     "whole_step_GBps": BYTES_TOTAL * n / (ms * 1e-3) / 1e9, "whole_step_frac": BYTES_TOTAL * n / (ms * 1e-3) / 1e9 / peak,
-                     "note": "FP64 pairwise gather: the FP64 pipe and L1/shared gather bandwidth bind long before HBM (DESIGN.md); no tensor cores"},
+                     "whole_step_GBps": b_total * n / (ms * 1e-3) / 1e9, "whole_step_frac": b_total * n / (ms * 1e-3) / 1e9 / peak,
+                     "fp64": fp64_roofline(kern, s["ntrips_rates"], pair_ms, ck.get("sm_mhz")),
+                     "note": "FP64 pairwise gather: the FP64 pipe and L1 gather bandwidth bind long before HBM (DESIGN.md); no tensor cores"},
         "phases_ms": phases,
     }
     # ---- whole leapfrog steps on the resident state: ndspmhd_b200_step = predictor + derivs + corrector;
@@ -324,14 +461,17 @@ def run_single(args):
                                  "itsdensity": its_seen, "pcie_bytes_per_step": 0}
     except Exception as ex:  # never lose the headline line over the extra
         line["step_resident"] = {"error": str(ex)[:200]}
-    if not args.no_cpu:
-        v, npc, dt, pms, its = cpu_oracle_sample(args.cpu_nx)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": f"one serial oracle derivs of the same workload at {args.cpu_nx}x{args.cpu_nx}x{args.cpu_nx // 8} = {npc} particles "
-                                          f"({dt:.1f} s, {its} density rounds); the reference is serial (docs/about.rst:12)",
-                                "phases_ms": dict(zip(["ghosts", "link", "density", "c2p", "rates"], pms))}
     hot.close()
     lib.free_pinned(p)
+    if not args.no_cpu:
+        runs = cpu_oracle_runs(c, [args.cpu_nx] if args.cpu_nx else sample_sizes(c, 24.0))
+        big = runs[-1]
+        line["cpu_baseline"] = {"value": big["updates_per_s"], "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"one serial oracle derivs of the same workload at nx={big['nx']} = {big['npart']} particles ({big['seconds']:.1f} s, "
+                                          f"{big['itsdensity']} density rounds); the reference is serial (docs/about.rst:12)",
+                                "phases_ms": big["phases_ms"],
+                                "fit": {"runs": [{k: r[k] for k in ("nx", "npart", "seconds", "updates_per_s")} for r in runs], "loglog_slope_time_vs_n": loglog_slope(runs),
+                                        "note": "slope 1.0 = updates/s independent of N: the bounded sample stands for the full-size run"}}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -342,24 +482,27 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nx", type=int, default=512, help="particles along x (thin slab nx * nx * nx/8)")
-    ap.add_argument("--cpu-nx", type=int, default=224, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--config", default="slab512", choices=sorted(CONFIGS), help="workload (BASELINE.json configs); default = the headline 16.8 M thin slab")
+    ap.add_argument("--nx", type=int, default=0, help="override the config's particles per unit length")
+    ap.add_argument("--cpu-nx", type=int, default=0, help="size of the bounded CPU-baseline sample (default: three sizes within ~25 s)")
     ap.add_argument("--ref-nx", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-real-rows", action="store_true", help="e2e downloads rows [0,npart) only (ND_DL_REAL_ROWS); default: the full contract")
+    ap.add_argument("--no-fit", action="store_true", help="--impl reference: skip the single-core runs at smaller sizes")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the single-GPU re-run that fills parity_vs_single")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     import __graft_entry__ as g
 
-    g.build()
     if args.impl == "reference":
+        g.build(load=False)   # compiles; the product library is not loaded into this process
         return run_reference(args)
+    g.build()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 or world > 1:
         from ndspmhd_b200 import slab_bench
 
-        return slab_bench.run(args, METRIC, UNIT, config_dict, ClockSampler, measured_peaks)
+        return slab_bench.run(args, cfg_of(args), workload, UNIT, config_dict, ClockSampler, measured_peaks)
     return run_single(args)
 
 

@@ -183,7 +183,16 @@ typedef struct nd_scalars {
   int itsdensity, nneigh_min, nneigh_max, nclumped;
   int ntotal, ncells, ncellsx[3], nrelink;
   long long ncalctotal;   /* total particle-density evaluations over all rounds (iterate_density.f90:154) */
-  int reserved_i[8];
+  /* diagnostics of the list machinery (no reference counterpart): column capacity of the neighbour lists, how many list builds had
+     to be repeated with a larger capacity since create, and in how many row chunks the last get_rates ran (derivs_host pipelines
+     the download of one chunk with the pair kernel of the next) */
+  int lmax, list_overflows, rate_chunks;
+  int reserved_i[5];
+  /* ordered pairs (i real, j any row) the last get_rates evaluated = sum of the rates list lengths: an order-independent integer
+     checksum of the neighbour finding (summed over ranks with slabs; bench.py --gpus N compares it with the single-GPU run) */
+  long long npairs_rates;
+  /* warp trips of the rates pair loop on THIS context (sum over 32-target list blocks of the longest list): bench.py's FP64-pipe floor */
+  long long ntrips_rates;
 } nd_scalars;
 
 typedef struct nd_ctx nd_ctx;

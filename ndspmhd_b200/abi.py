@@ -117,7 +117,9 @@ class NdScalars(C.Structure):
         ("itsdensity", C.c_int), ("nneigh_min", C.c_int), ("nneigh_max", C.c_int), ("nclumped", C.c_int),
         ("ntotal", C.c_int), ("ncells", C.c_int), ("ncellsx", C.c_int * 3), ("nrelink", C.c_int),
         ("ncalctotal", C.c_longlong),
-        ("reserved_i", C.c_int * 8),
+        ("lmax", C.c_int), ("list_overflows", C.c_int), ("rate_chunks", C.c_int),
+        ("reserved_i", C.c_int * 5),
+        ("npairs_rates", C.c_longlong), ("ntrips_rates", C.c_longlong),
     ]
 
     def as_dict(self):

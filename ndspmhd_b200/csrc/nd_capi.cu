@@ -84,7 +84,7 @@ struct nd_ctx {
   cudaEvent_t ev[8];
   // rates in row chunks (ndspmhd_b200_derivs_host): chunk q = original rows [q*rows, (q+1)*rows) so that its results can be
   // downloaded while the next chunk's pair kernel runs
-  int rate_chunks = 1; int *rlist = nullptr; size_t rlistcap = 0;
+  int rate_chunks = 1, rate_chunks_used = 1, list_overflows = 0; int *rlist = nullptr; size_t rlistcap = 0;
   std::function<int(int, int, int)> on_rates_chunk;   // (chunk, row0, row1) after the chunk's finalisation is enqueued
   std::vector<cudaEvent_t> chunk_events;
   double *evpartial = nullptr, *h_ev = nullptr;        // evwrite reductions

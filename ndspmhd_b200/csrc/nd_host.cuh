@@ -371,6 +371,7 @@ int ensure_lists(nd_ctx *c, int ntargets) {
     double r = c->T->radkern * std::max(c->o.hfact, 1.0);
     double nn = v * (c->ndim == 1 ? r : c->ndim == 2 ? r * r : r * r * r);
     c->lmax = std::max(16, (int)(2.2 * nn) + 8);
+    if (const char *ev = getenv("NDSPMHD_B200_LMAX0")) c->lmax = std::max(1, atoi(ev));   // test hook: start small, exercise the overflow retry
   }
   const size_t need = ((size_t)(ntargets + 31) / 32) * 32 * (size_t)c->lmax;
   if (need > c->nbrcap) {
@@ -400,6 +401,7 @@ template <int NDIM, int MODE> int build_lists(nd_ctx *c, const Grid &G, ListArgs
     const int big = c->h_flags[20];
     if (big == 0) return 0;
     c->lmax = big + big / 4 + 8;
+    c->list_overflows++;
     CU(cudaMemsetAsync(c->flags + 5, 0, sizeof(int), c->stream));
   }
   return set_err(c, ND_ERR_NEIGHBOUR_OVERFLOW, "neighbour list overflow");
@@ -540,7 +542,7 @@ RatesOpts make_rates_opts(const nd_ctx *c) {
   return O;
 }
 
-enum { RED_DTC = 0, RED_VSIG = 1, RED_DTAV = 2, RED_TS = 3, RED_HCS = 4, RED_FH = 5, RED_DTF = 6, RED_STRESS = 7 };
+enum { RED_DTC = 0, RED_VSIG = 1, RED_DTAV = 2, RED_TS = 3, RED_HCS = 4, RED_FH = 5, RED_DTF = 6, RED_STRESS = 7, RED_NPAIRS = 8, RED_NTRIPS = 9 /* plain sums, not keys */ };
 
 template <int NDIM, bool MHD, bool DRAG, int FAST, bool ONEF> int launch_rates_pair(nd_ctx *c, const RatesIn &I, const RatesOpts &O, const RatesSums &S, const RatesRed &R, int *pi, int *pj,
                                                                           unsigned long long *pc, long long cap, const int *targets, int ntargets) {
@@ -553,6 +555,7 @@ template <int NDIM, bool MHD, bool DRAG, int FAST, bool ONEF> int launch_rates_p
     LA.pair_out_i = pi; LA.pair_out_j = pj; LA.pair_count = pc; LA.pair_cap = cap;
     NbrLists L;
     if (int e = build_lists<NDIM, LIST_RATES>(c, G, LA, L)) return e;
+    LAUNCH(c, k_sum_counts, std::min(nblocks(m, 256), 1184), 256, 0, L.cnt, m, c->red + RED_NPAIRS, c->red + RED_NTRIPS);
     // persistent blocks: one per resident slot (the 64 KB shared-memory table is loaded once per block)
     static int resident = 0, carveout = 100;
     auto kfn = rates_pair_kernel<NDIM, MHD, DRAG, FAST, ONEF>;
@@ -585,6 +588,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   for (int k = 0; k < 16; k++) init[k] = 0x8000000000000000ull;                       // key(+0.0)
   union { double d; unsigned long long u; } cv;
   auto keyof = [&](double v) { cv.d = v; return cv.u | 0x8000000000000000ull; };     // v >= 0
+  init[RED_NPAIRS] = init[RED_NTRIPS] = 0ull;
   init[RED_DTC] = keyof(1.e6); init[RED_DTAV] = keyof(DBL_MAX); init[RED_TS] = keyof(DBL_MAX); init[RED_DTF] = keyof(DBL_MAX);
   CU(cudaMemcpyAsync(c->red, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemsetAsync(c->fmean, 0, sizeof(double) * 4, c->stream));
@@ -637,6 +641,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   FA.dusta = o.onef_dust ? c->dusta : nullptr; FA.dustb = c->dustb; FA.fineStart = c->cellStart; FA.cellOf = c->cellOf;
   FA.ddustevoldt = c->ddustevoldt; FA.ddeltavdt = c->ddeltavdt;
   const int nchunk = (c->rate_chunks > 1 && !c->has_comm && !pi) ? c->rate_chunks : 1;
+  c->rate_chunks_used = nchunk;
   if (nchunk == 1) {
     if (int e = pair(nullptr, 0)) return e;
     CU(cudaEventRecord(c->ev[4], c->stream));
@@ -695,9 +700,10 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   double ef = c->h_flags[1];
   if (c->has_comm) {   // two all-reduces: {error flag, maxima, minima} and the sums
     double mx[4] = {ef, s.vsigmax, s.h_on_csts_max, s.fhmax}, mn[4] = {s.dtcourant, s.dtav, s.ts_min, dkey_inv(c->h_red[RED_DTF])};
-    double sm[4] = {c->h_fmean[0], c->h_fmean[1], c->h_fmean[2], (double)c->h_flags[4]};
+    double sm[5] = {c->h_fmean[0], c->h_fmean[1], c->h_fmean[2], (double)c->h_flags[4], (double)c->h_red[RED_NPAIRS] /* < 2^53 */};
     if (int e3 = comm_allreduce_maxmin(c, mx, 4, mn, 4)) return e3;
-    if (int e3 = comm_allreduce(c, sm, 4, 2)) return e3;
+    if (int e3 = comm_allreduce(c, sm, 5, 2)) return e3;
+    c->h_red[RED_NPAIRS] = (unsigned long long)(sm[4] + 0.5);
     ef = mx[0]; s.vsigmax = mx[1]; s.h_on_csts_max = mx[2]; s.fhmax = mx[3];
     s.dtcourant = mn[0]; s.dtav = mn[1]; s.ts_min = mn[2];
     c->h_fmean[0] = sm[0]; c->h_fmean[1] = sm[1]; c->h_fmean[2] = sm[2]; c->h_flags[4] = (int)(sm[3] + 0.5);
@@ -718,6 +724,8 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   else if (o.idust == 1) { s.dtdrag = std::min(s.dtdrag, s.ts_min); s.ts_min = DBL_MAX; }   // :561: the key carried min tstop; module ts_min is two-fluid only
   for (int k = 0; k < 3; k++) s.fmean[k] = c->h_fmean[k];
   s.nclumped = c->h_flags[4];
+  s.npairs_rates = (long long)c->h_red[RED_NPAIRS];
+  s.ntrips_rates = (long long)c->h_red[RED_NTRIPS];
   c->rates_done = true;
   return 0;
 }
@@ -725,6 +733,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
 void fill_link_scalars(nd_ctx *c) {
   nd_scalars &s = c->sc;
   s.hhmax = c->hhmax; s.dxcell = c->dxcell; s.ntotal = c->ntotal; s.ncells = c->ncells;
+  s.lmax = c->lmax; s.list_overflows = c->list_overflows; s.rate_chunks = c->rate_chunks_used;
   for (int d = 0; d < 3; d++) s.ncellsx[d] = c->ncellsx[d];
 }
 

@@ -97,14 +97,24 @@ subroutine get_rates
  implicit none
  type(nd_arrays)  :: a
  type(nd_scalars) :: s
+ integer(c_int)   :: mask
  if (.not.b200_resident) then
     call get_rates_cpu
     return
  endif
  call b200_check(ndspmhd_b200_get_rates(b200_ctx,s),'get_rates')
  dtcourant = s%dtcourant; dtforce = s%dtforce; dtav = s%dtav; dtdrag = s%dtdrag; dtvisc = s%dtvisc; vsig2max = s%vsig2max
- !--everything the integrator, evwrite and write_dump read goes back to the module arrays
+ !--what the integrator (src/stepND_leapfrog_mhd.f90:70-216) and evwrite (src/evwrite_mhd.f90:124-284) read goes back to the
+ !  module arrays.  With b200_lean_download (default) the arrays only a dump reads -- gradh, dens, spsound, gradpsi, dudt,
+ !  numneigh -- and the ghost rows of every output array stay on the device: 192 instead of 252 bytes per particle and no
+ !  ghost rows over PCIe; call b200_sync_to_host (step_b200.f90) before `output` to fetch everything.
  call b200_fill_arrays(a)
- call b200_check(ndspmhd_b200_download(b200_ctx,a,ior(ior(ND_DL_DENSITY,ND_DL_PRIM),ND_DL_RATES),int(size(pmass),c_int)),'download')
+ mask = ior(ior(ND_DL_DENSITY,ND_DL_PRIM),ND_DL_RATES)
+ if (b200_lean_download) then
+    a%gradh = c_null_ptr; a%dens = c_null_ptr; a%spsound = c_null_ptr; a%gradpsi = c_null_ptr
+    a%dudt = c_null_ptr; a%numneigh = c_null_ptr
+    mask = ior(mask,ND_DL_REAL_ROWS)
+ endif
+ call b200_check(ndspmhd_b200_download(b200_ctx,a,mask,int(size(pmass),c_int)),'download')
  b200_resident = .false.
 end subroutine get_rates

@@ -59,7 +59,9 @@ module ndspmhd_b200
     integer(c_int) :: itsdensity,nneigh_min,nneigh_max,nclumped
     integer(c_int) :: ntotal,ncells,ncellsx(3),nrelink
     integer(c_long_long) :: ncalctotal
-    integer(c_int) :: reserved_i(8)
+    integer(c_int) :: lmax,list_overflows,rate_chunks
+    integer(c_int) :: reserved_i(5)
+    integer(c_long_long) :: npairs_rates,ntrips_rates
  end type nd_scalars
 
  type, bind(C) :: nd_step_opts
@@ -128,6 +130,9 @@ module ndspmhd_b200
  ! first-class tuple on its fast kernels (FAST rates instantiation, LIGHT density rounds: the configuration bench.py times)
  ! and does not download those arrays; set .true. to get them filled as the reference does.
  logical, save     :: b200_want_aux = .false.
+ ! .true. (default): get_rates downloads only what the integrator and evwrite read between two derivs, rows 1..npart
+ ! (derivs_hotpath_b200.f90); .false.: every output array of the reference's density/cons2prim/get_rates, ghost rows included
+ logical, save     :: b200_lean_download = .true.
 
 contains
 

@@ -243,9 +243,12 @@ class Hotpath:
         self._chk(self.L.ndspmhd_b200_selftest_math(self.ctx, x.ctypes.data_as(_DP), s.ctypes.data_as(_DP), r.ctypes.data_as(_DP), x.size))
         return s, r
 
-    def derivs_host(self, p: Particles, mask: int = abi.DL_ALL) -> dict:
-        """upload + derivs + download in one call with the copies overlapped with the kernels (host arrays in, host arrays out)."""
+    def derivs_host(self, p: Particles, mask: int = abi.DL_ALL, skip=()) -> dict:
+        """upload + derivs + download in one call with the copies overlapped with the kernels (host arrays in, host arrays out).
+        `skip`: output arrays handed over as NULL pointers -- the library leaves them on the device (include/ndspmhd_b200.h, nd_arrays)."""
         a = arrays_struct(p)
+        for nm in skip:
+            setattr(a, nm, None)
         s = NdScalars()
         self._chk(self.L.ndspmhd_b200_derivs_host(self.ctx, C.byref(a), p.npart, p.ntotal, p.idim, mask, C.byref(s)))
         p.ntotal = s.ntotal if not getattr(self, "_comm", None) else p.ntotal

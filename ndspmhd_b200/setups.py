@@ -355,3 +355,53 @@ def dustywave_onefluid(ndim=3, nx=12, perturb_amp=0.1, dust_to_gas=1.0, Kdrag=1.
     p.rho[:n] = p.rho[:n] / (1.0 - eps0)
     p.hh[:n] = o.hfact * (p.pmass[:n] / p.rho[:n]) ** (1.0 / ndim)
     return o, p
+
+
+# ---------------------------------------------------------------------------------------------------------
+# C4 as the reference sets it up: DUSTYBOX in the thin periodic box 1 x 11dp x 11dp (src/setup_dustybox.f90:46-107), gas lattice
+# with the dust lattice on top of it (:58-69), gas moving at v_x = 1 through dust at rest.  In this box the periodic y/z ghosts
+# outnumber the real particles.
+# ---------------------------------------------------------------------------------------------------------
+def dustybox_thin(nx=64, ny=11, Kdrag=1.0, idrag_nature=1, perturb_amp=0.0, seed=11):
+    o = default_options(3)
+    o.idust, o.idrag_nature, o.Kdrag = 2, idrag_nature, Kdrag
+    o.iener = 2
+    psep = 1.0 / nx
+    o.psep = psep
+    xmin, xmax = [0.0, 0.0, 0.0], [1.0, ny * psep, ny * psep]
+    for d in range(3):
+        o.ibound[d] = 3
+        o.xmin[d], o.xmax[d] = xmin[d], xmax[d]
+    xg, _ = cubic_lattice(xmin, xmax, psep)
+    xg = perturb(xg, psep, perturb_amp, seed)
+    xd = xg.copy()                                                             # :58-69: dust on top of gas
+    x = wrap_periodic(np.concatenate([xg, xd], axis=0), o)
+    ngas, n = xg.shape[0], 2 * xg.shape[0]
+    massp = 1.0 * np.prod([xmax[d] - xmin[d] for d in range(3)]) / ngas        # rho_gas = rho_dust = 1
+    p = _alloc(3, x, o, o.hfact * psep)
+    p.itype[:ngas] = ITYPE_GAS
+    p.itype[ngas:n] = ITYPE_DUST
+    p.pmass[:n] = massp
+    p.vel[:ngas, 0] = 1.0
+    dens = np.ones(n)
+    uu = np.where(np.arange(n) < ngas, 1.0, 0.0)
+    _finish(p, o, dens, uu, None)
+    return o, p
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reflecting walls (ibound = 2, src/ghostND_mhd.f90:173, :226-228: ghost at xbound - (x - xbound), normal velocity flipped),
+# optionally mixed with periodic directions
+# ---------------------------------------------------------------------------------------------------------
+def reflecting_box(ndim=3, nx=12, perturb_amp=0.2, mhd=True, ibound=None, seed=5):
+    o, p = orszag_tang(ndim=ndim, nx=nx, perturb_amp=perturb_amp, imhd=11 if mhd else 0, idivbzero=2 if mhd else 0, iener=2,
+                       evolved=True, seed=seed, cube=(ndim == 3)) if ndim > 1 else shock1d(nright=40, mhd=mhd)
+    ib = ibound or [2] * ndim
+    n = p.npart
+    if ndim == 1:
+        # the shock tube without its fixed end particles: the walls reflect instead
+        p.itype[:n] = ITYPE_GAS
+        p.ireal[:n] = 0
+    for d in range(ndim):
+        o.ibound[d] = ib[d]
+    return o, p

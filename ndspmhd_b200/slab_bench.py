@@ -12,7 +12,47 @@ import os
 import numpy as np
 
 
-def run(args, METRIC, UNIT, config_dict, ClockSampler, measured_peaks):
+def parity_vs_single(cfg, workload, hot, p, n, s, info, rank, local, torch, dist):
+    """The slab-decomposed result against the single-GPU result of the same global particle set, computed in the same run (outside the
+    timed region): order-independent integer checksums over ALL ranks -- sum numneigh, ncalctotal, the rates pair count, itsdensity,
+    relinks -- must be bit-equal, and rho, h, force, dB/dt, du/dt, div B on rank 0's own rows must agree with the single-GPU run to the
+    summation-order tolerance (max-norm error relative to the field's max-norm).  The single-GPU run uses a second context on rank 0's GPU."""
+    from . import abi, lib, setups
+
+    hot.download(p, abi.DL_DENSITY | abi.DL_RATES)                     # this rank's own rows of the last timed derivs
+    sums = torch.tensor([float(p.arrays["numneigh"][:n].astype(np.int64).sum())], dtype=torch.float64, device="cuda")
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    out = None
+    if rank == 0:
+        o1, p1 = workload(cfg)
+        n1 = p1.npart
+        hot1 = lib.Hotpath(o1, 3, local)
+        try:
+            hot1.upload(p1)
+            s1 = hot1.derivs()
+            hot1.download(p1, abi.DL_DENSITY | abi.DL_RATES)
+        finally:
+            hot1.close()
+        rows = info["rows"]
+        ints = {"sum_numneigh": (int(sums[0].item()), int(p1.arrays["numneigh"][:n1].astype(np.int64).sum())),
+                "ncalctotal": (int(s["ncalctotal"]), int(s1["ncalctotal"])), "npairs_rates": (int(s["npairs_rates"]), int(s1["npairs_rates"])),
+                "itsdensity": (int(s["itsdensity"]), int(s1["itsdensity"])), "nrelink": (int(s["nrelink"]), int(s1["nrelink"])),
+                "nneigh_min": (int(s["nneigh_min"]), int(s1["nneigh_min"])), "nneigh_max": (int(s["nneigh_max"]), int(s1["nneigh_max"]))}
+        errs = {}
+        for f in ("rho", "hh", "force", "dBevoldt", "dudt", "divB"):
+            a, b = np.asarray(p.arrays[f][:n]), np.asarray(p1.arrays[f][rows])
+            errs[f] = float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+        out = {"integers_equal": all(a == b for a, b in ints.values()), "integers_slab_vs_single": {k: list(v) for k, v in ints.items()},
+               "numneigh_rows_equal_rank0": bool(np.array_equal(p.arrays["numneigh"][:n], p1.arrays["numneigh"][rows])),
+               "max_norm_rel_err_rank0_rows": errs, "tolerance": 1e-12, "ok": None,
+               "scalars_rel_err": {k: abs(s[k] - s1[k]) / max(abs(s1[k]), 1e-300) for k in ("dtcourant", "dtforce", "vsigmax")}}
+        out["ok"] = bool(out["integers_equal"] and out["numneigh_rows_equal_rank0"] and max(errs.values()) <= 1e-12)
+        del p1
+    dist.barrier()
+    return out
+
+
+def run(args, cfg, workload, UNIT, config_dict, ClockSampler, measured_peaks):
     import torch
     import torch.distributed as dist
 
@@ -29,10 +69,9 @@ def run(args, METRIC, UNIT, config_dict, ClockSampler, measured_peaks):
     weak = args.scaling == "weak"
     if weak:
         raise SystemExit("weak scaling is not implemented for the slab bench: the Orszag-Tang box is fixed; use --scaling strong")
-    o, p0, info = setups.orszag_tang(ndim=3, nx=args.nx, zfrac=0.125, perturb_amp=0.2, evolved=True, imhd=11, idivbzero=2, iener=2,
-                                     slab=(rank, world))
-    o.device_ghosts = 1
-    o.want_aux = 0
+    if cfg["kind"] != "ot" or cfg["ndim"] != 3:
+        raise SystemExit("bench.py --gpus N: the slab decomposition is benchmarked on the 3-D MHD configs (slab512, cube256, cube128)")
+    o, p0, info = workload(cfg, slab=(rank, world))
     n, nglobal = p0.npart, int(info["nglobal"])
     lo, hi = float(info["edges"][rank]), float(info["edges"][rank + 1])
     p = lib.pinned_particles(3, n, p0.idim)
@@ -62,21 +101,27 @@ def run(args, METRIC, UNIT, config_dict, ClockSampler, measured_peaks):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), out
 
-    def e2e_step():
-        p.arrays["hh"][:n] = guess[:n]       # host-side restore of the guess (the integrator's predictor would do this)
-        p.ntotal = n
-        return hot.derivs_host(p, mask)
-
-    for _ in range(2):
-        s = e2e_step()
-    e2e_steps = max(1, min(args.steps, 3))
-    e2e_ms, s = timed(e2e_step, e2e_steps)
-    nown, nsrc, nt = slab.row_counts(hot)
     up_names = ["x", "vel", "pmass", "hh", "itype", "ireal", "en", "Bevol", "alpha", "psi", "rho"]
     dn_names = ["hh", "rho", "gradh", "numneigh", "dens", "uu", "pr", "spsound", "Bfield", "drhodt", "dhdt", "force", "dudt", "dendt",
                 "dBevoldt", "daldt", "dpsidt", "gradpsi", "divB", "curlB"]
+    lean_skip = ["gradh", "numneigh", "dens", "spsound", "gradpsi", "dudt"]   # bench.py LEAN_SKIP: the Fortran shim's contract on ordinary steps
     rowbytes = lambda nm: p.arrays[nm].nbytes // p.idim
-    bytes_t = torch.tensor([sum(rowbytes(nm) for nm in up_names) * n, sum(rowbytes(nm) for nm in dn_names) * n, nsrc - nown, nt - nsrc],
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e(skip):
+        def e2e_step():
+            p.arrays["hh"][:n] = guess[:n]       # host-side restore of the guess (the integrator's predictor would do this)
+            p.ntotal = n
+            return hot.derivs_host(p, mask, skip=skip)
+        for _ in range(2):
+            e2e_step()
+        ms_, s_ = timed(e2e_step, e2e_steps)
+        return ms_, s_, sum(rowbytes(nm) for nm in dn_names if nm not in skip) * n
+
+    e2e_full_ms, s, dn_full = e2e([])
+    e2e_ms, s, dn_lean = e2e(lean_skip)
+    nown, nsrc, nt = slab.row_counts(hot)
+    bytes_t = torch.tensor([sum(rowbytes(nm) for nm in up_names) * n, dn_lean, nsrc - nown, nt - nsrc, dn_full],
                            dtype=torch.float64, device="cuda")
     dist.all_reduce(bytes_t, op=dist.ReduceOp.SUM)
 
@@ -105,26 +150,31 @@ def run(args, METRIC, UNIT, config_dict, ClockSampler, measured_peaks):
     dist.all_reduce(ph, op=dist.ReduceOp.MAX)
     launches_t = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
     dist.all_reduce(launches_t, op=dist.ReduceOp.SUM)
+    check = parity_vs_single(cfg, workload, hot, p, n, s, info, rank, local, torch, dist) if not args.no_parity_check else None
     if rank == 0:
         peak, peak_src = measured_peaks()
         pair_ms = float(ph[5].item())     # the pair kernel alone (CUDA events on the library's stream), max over ranks
         bytes_rates = 284
         ach = bytes_rates * (nglobal / world) / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else 0.0
         line = {
-            "metric": METRIC, "value": nglobal / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": cfg.get("metric") or ("particle-updates/sec (density+rates), " + cfg["label"].split(",")[0]), "value": nglobal / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args, extra={"npart": nglobal, "npart_per_rank": nglobal // world, "halo_rows_total": int(bytes_t[2].item()),
-                                               "ghost_rows_total": int(bytes_t[3].item()), "itsdensity": s["itsdensity"],
-                                               "nneigh_min": s["nneigh_min"], "nneigh_max": s["nneigh_max"],
-                                               "halo_bytes_per_step_all_ranks": float(halo_bytes.item())}),
+            "config": config_dict(args),
+            "run": {"npart": nglobal, "npart_per_rank": nglobal // world, "halo_rows_total": int(bytes_t[2].item()),
+                    "ghost_rows_total": int(bytes_t[3].item()), "itsdensity": s["itsdensity"], "nrelink": s["nrelink"],
+                    "nneigh_min": s["nneigh_min"], "nneigh_max": s["nneigh_max"], "npairs_rates": s["npairs_rates"],
+                    "halo_bytes_per_step_all_ranks": float(halo_bytes.item())},
             "e2e": {"value": nglobal / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(bytes_t[0].item()),
-                    "d2h_bytes_per_step": int(bytes_t[1].item()), "ms_per_step": e2e_ms, "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(bytes_t[1].item()), "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "contract": "lean: skips " + ",".join(lean_skip) + "; each rank moves its own rows",
+                    "full_contract": {"value": nglobal / (e2e_full_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_full_ms, "d2h_bytes_per_step": int(bytes_t[4].item())}},
             "gpu_launches": int(launches_t.item()),
             "clocks": ck,
             "roofline": {"bound": "hbm", "kernel": "rates_pair_kernel<3,MHD,FAST> (per rank, max over ranks)", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": pair_ms},
             "phases_ms": dict(zip(["link", "density", "c2p_gather", "rates_pair", "rates_final"], [float(v) for v in ph.tolist()[:5]])),
-            "comm": {"allreduces_per_step": comm.n_allreduce // max(1, args.steps + args.warmup + 2 + e2e_steps), "backend": "nccl send/recv + all_reduce"},
+            "comm": {"allreduces_per_step": comm.n_allreduce // max(1, args.steps + args.warmup + 2 * (2 + e2e_steps)), "backend": "nccl send/recv + all_reduce"},
+            "parity_vs_single": check,
         }
         print(json.dumps(line), flush=True)
     hot.close()

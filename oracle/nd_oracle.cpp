@@ -268,6 +268,7 @@ struct St {
   double dtcourant, dtforce, dtav, dtdrag, dtvisc, vsig2max, vsigmax_out, stressmax_out, ts_min_out, h_on_csts_max_out, fhmax_out;
   double fmean[3];
   int nclumped;
+  long long npairs_rates;   // ordered pairs evaluated by get_rates, counted on the side(s) that are real particles (test checksum, no reference counterpart)
   int err;
 };
 
@@ -967,6 +968,7 @@ int get_rates(St &S, std::vector<int> *pairs_i, std::vector<int> *pairs_j) {
   double vsigmax = 0.;
   double dr[3] = {0., 0., 0.};
   int nclumped = 0;
+  long long npairs_rates = 0;
   for (int i = 1; i <= ntotal; i++) {                           // :194-226
     for (int k = 1; k <= 3; k++) { V3(force, k, i) = 0.; V3(dBevoldt, k, i) = 0.; V3(daldt, k, i) = 0.; V3(gradpsi, k, i) = 0.; V3(fmag, k, i) = 0.; V3(xsphterm, k, i) = 0.; V3(graddivv, k, i) = 0.; }
     A1(dudt, i) = 0.; A1(dendt, i) = 0.; A1(dpsidt, i) = 0.; A1(divB, i) = 0.;
@@ -1069,6 +1071,7 @@ int get_rates(St &S, std::vector<int> *pairs_i, std::vector<int> *pairs_j) {
           for (int k = 0; k < ndim; k++) dr[k] = dx[k] / rij;
         }
         int itypej = A1(itype, j);
+        if (types_interact(itypei, itypej) || (o.idust == 2 && o.idrag_nature > 0)) npairs_rates += (i <= npart ? 1 : 0) + (j <= npart ? 1 : 0);
         if (types_interact(itypei, itypej)) {
           // ===================== rates_core :1175-1690 =====================
           double pmassj = A1(pmass, j);
@@ -1449,6 +1452,7 @@ int get_rates(St &S, std::vector<int> *pairs_i, std::vector<int> *pairs_j) {
     }
   }
   S.nclumped = nclumped;
+  S.npairs_rates = npairs_rates;
   S.vsigmax_out = vsigmax;
   S.ts_min_out = ts_min;
   S.h_on_csts_max_out = h_on_csts_max;
@@ -1616,6 +1620,7 @@ int ndo_derivs(const nd_options *o, int ndim, ndo_arrays *a, int npart, int *nto
     for (int k = 0; k < 3; k++) { s->fmean[k] = S.fmean[k]; s->ncellsx[k] = S.ncellsx[k]; }
     s->itsdensity = S.itsdensity; s->nclumped = S.nclumped; s->ntotal = S.ntotal; s->ncells = S.ncells;
     s->ncalctotal = S.ncalctotal;
+    s->npairs_rates = S.npairs_rates;
     int mn = 1 << 30, mx = 0;
     for (int i = 0; i < npart; i++) { mn = std::min(mn, a->numneigh[i]); mx = std::max(mx, a->numneigh[i]); }
     s->nneigh_min = mn; s->nneigh_max = mx;
