@@ -159,6 +159,9 @@ typedef struct nd_arrays {
   double *rhodust;           /* (idim)   out: part:rhodust(1,:) */
   double *ddustevoldt;       /* (idim)   out: rates:ddustevoldt(1,:) */
   double *ddeltavdt;         /* (3,idim) out: rates:ddeltavdt */
+  /* --- iavlim(3) = 2: conservative2primitive rewrites part:alpha(3,:) (Tricco & Price resistivity switch, conservative2primitive.f90:299-311);
+         normally the same memory as `alpha`.  Comes down with ND_DL_PRIM; NULL = not wanted --- */
+  double *alpha_out;         /* (3,idim) */
 } nd_arrays;
 
 /* download masks */
@@ -316,6 +319,16 @@ typedef struct nd_evwrite {
   double reserved[8];
 } nd_evwrite;
 int ndspmhd_b200_evwrite(nd_ctx *c, nd_evwrite *ev);
+
+/*
+ * `get_curl` (src/get_curl.f90:64-287) as an operator on the resident state, on the same cell grid / neighbour-list / pair
+ * engine as the rates: curl of Bvec (host, (3,idim), rows [0,npart) read; ghost rows take their parent's value) into curlB (host, (3,idim),
+ * rows [0,npart) written) and, for icurltype = 1, optionally grad Bvec into gradB ((3,3,idim), gradB(l,k,i) = d Bvec_k / d x_l).
+ * icurltype: 1 differenced, mass-weighted with grad-h (default); 2 symmetric; 3 constant weights; 4 m_j/rho_j^2 weights.
+ * Needs a prior link + iterate_density (it uses the converged rho, h, gradh).  The reference's call site on the path -- the Tricco & Price
+ * resistivity switch inside conservative2primitive, iavlim(3) = 2 -- is run by ndspmhd_b200_cons2prim / _derivs themselves.
+ */
+int ndspmhd_b200_get_curl(nd_ctx *c, int icurltype, const double *Bvec, double *curlB, double *gradB, int idim);
 
 /* page-locked host memory for the caller's particle arrays (makes upload/download run at PCIe speed) */
 void *ndspmhd_b200_host_alloc(size_t bytes);

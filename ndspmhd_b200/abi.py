@@ -77,6 +77,7 @@ class NdArrays(C.Structure):
         ("x_out", _DP), ("vel_out", _DP), ("ireal_out", _IP), ("itype_out", _IP),
         ("dustevol", _DP), ("dustfrac_in", _DP), ("deltav", _DP),
         ("dustfrac", _DP), ("rhogas", _DP), ("rhodust", _DP), ("ddustevoldt", _DP), ("ddeltavdt", _DP),
+        ("alpha_out", _DP),
     ]
 
 

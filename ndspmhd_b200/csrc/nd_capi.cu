@@ -8,6 +8,7 @@
 #include "nd_device.cuh"
 #include "nd_density.cuh"
 #include "nd_rates.cuh"
+#include "nd_curl.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -41,7 +42,7 @@ struct nd_ctx {
   // ---- original-order arrays (row r = Fortran index r+1) ----
   double *x = nullptr, *vel = nullptr, *pmass = nullptr, *hh = nullptr, *en = nullptr, *Bevol = nullptr, *alpha = nullptr, *psi = nullptr;
   int *itype = nullptr, *ireal = nullptr;
-  double *hhin = nullptr, *hh0 = nullptr;
+  double *hhin = nullptr, *hh0 = nullptr, *alphaB_in = nullptr;
   double *rho = nullptr, *gradh = nullptr, *drhodt = nullptr, *dhdt = nullptr, *rhoalt = nullptr, *gradhn = nullptr, *gradsoft = nullptr, *gradgradh = nullptr;
   int *numneigh = nullptr;
   double *dens = nullptr, *uu = nullptr, *pr = nullptr, *spsound = nullptr, *Bfield = nullptr;
@@ -333,6 +334,7 @@ int download_group(nd_ctx *c, nd_arrays *a, size_t n, int group, unsigned mask, 
   if (group == 2 && (mask & ND_DL_PRIM)) {
     CU(dn(a->dens, c->dens, D * n)); CU(dn(a->uu, c->uu, D * n)); CU(dn(a->pr, c->pr, D * n)); CU(dn(a->spsound, c->spsound, D * n));
     if (c->o.imhd != 0) CU(dn(a->Bfield, c->Bfield, D * 3 * n));
+    if (c->o.imhd != 0 && c->o.iavlim[2] == 2) CU(dn(a->alpha_out, c->alpha, D * 3 * n));   // alpha(3,:) rewritten by the resistivity switch
     if (c->o.onef_dust) CU(dn(a->dustfrac, c->dustfrac, D * n));
   }
   if (group == 3) {
@@ -643,6 +645,31 @@ int ndspmhd_b200_rates_pairs(nd_ctx *c, int *pair_i, int *pair_j, long long cap,
   if (!e && m > 0 && pair_i && pair_j) { cudaMemcpy(pair_i, di, sizeof(int) * m, cudaMemcpyDeviceToHost); cudaMemcpy(pair_j, dj, sizeof(int) * m, cudaMemcpyDeviceToHost); }
   cudaFree(di); cudaFree(dj); cudaFree(dc);
   *npairs = (long long)n;
+  return e;
+}
+
+/* ---- get_curl as an operator on the resident state ---- */
+int ndspmhd_b200_get_curl(nd_ctx *c, int icurltype, const double *Bvec, double *curlB, double *gradB, int idim) {
+  if (!c || !Bvec || !curlB) return ND_ERR_INVALID_ARG;
+  if (!c->density_done) return set_err(c, ND_ERR_STATE, "get_curl needs the linked state and the converged rho, h, gradh of iterate_density");
+  if (icurltype < 1 || icurltype > 4) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "get_curl: icurltype must be 1..4");
+  if (gradB && icurltype != 1) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "get_curl: gradB comes with icurltype = 1 only (src/get_curl.f90:250-255)");
+  if (c->has_comm) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "get_curl is not available on slab-decomposed contexts");
+  if (idim < c->npart) return set_err(c, ND_ERR_INVALID_ARG, "get_curl: idim < npart");
+  CU(cudaSetDevice(c->device));
+  const size_t n = (size_t)c->npart;
+  double *d = nullptr;
+  CU(cudaMalloc(&d, sizeof(double) * n * (3 + 3 + (gradB ? 9 : 0))));
+  double *dB = d, *dC = d + 3 * n, *dG = gradB ? d + 6 * n : nullptr;
+  CU(cudaMemcpyAsync(dB, Bvec, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+  int e = DISPATCH_NDIM(c, do_get_curl<1>(c, icurltype, dB, dC, dG, nullptr), do_get_curl<2>(c, icurltype, dB, dC, dG, nullptr), do_get_curl<3>(c, icurltype, dB, dC, dG, nullptr));
+  if (!e) {
+    CU(cudaMemcpyAsync(curlB, dC, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (gradB) CU(cudaMemcpyAsync(gradB, dG, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(d);
+  // the operator re-used the sorted rates records (bpsi, gal, posh.w): a following get_rates regathers them (k_rates_gather) anyway
   return e;
 }
 

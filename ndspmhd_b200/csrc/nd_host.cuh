@@ -6,6 +6,8 @@
 // =====================================================================================================
 // host orchestration
 // =====================================================================================================
+#define DISPATCH_NDIM(c, expr1, expr2, expr3) ((c)->ndim == 1 ? (expr1) : (c)->ndim == 2 ? (expr2) : (expr3))
+
 template <class T> int dev_alloc(nd_ctx *c, T **p, size_t n) {
   if (*p) { cudaFree(*p); *p = nullptr; }
   if (n == 0) n = 1;
@@ -22,7 +24,7 @@ void register_rows(nd_ctx *c) {
 #define R1(a) v.push_back({(void **)&c->a, D})
 #define RI(a) v.push_back({(void **)&c->a, I})
 #define R4(a) v.push_back({(void **)&c->a, D4})
-  R3(vel); R1(pmass); R1(hh); R1(en); R3(Bevol); R3(alpha); R1(psi); RI(itype); RI(ireal); R1(hhin); R1(hh0);
+  R3(vel); R1(pmass); R1(hh); R1(en); R3(Bevol); R3(alpha); R1(psi); RI(itype); RI(ireal); R1(hhin); R1(hh0); R1(alphaB_in);
   R1(rho); R1(gradh); R1(drhodt); R1(dhdt); R1(rhoalt); R1(gradhn); R1(gradsoft); R1(gradgradh); RI(numneigh);
   R1(dens); R1(uu); R1(pr); R1(spsound); R3(Bfield);
   R3(force); R1(dudt); R1(dendt); R3(dBevoldt); R3(daldt); R1(dpsidt); R3(gradpsi); R1(divB); R3(curlB); R3(graddivv); R1(del2u);
@@ -87,6 +89,10 @@ int check_options(nd_ctx *c, const nd_options &o, int ndim) {
     if (ghosts && !all3) return bad("one-fluid dust with ghost boundaries needs ibound = 3 in every dimension");
   }
   if (o.ikernelalt != o.ikernel) return bad("ikernelalt /= ikernel");
+  // iavlim(3) = 2 (get_curl inside conservative2primitive): with B/rho evolved the reference's get_curl reads the ghosts' Bfield of the
+  // PREVIOUS derivs (the loop of conservative2primitive.f90:190-193 stops at npart); only imhd >= 11 (`Bfield = Bevol`, whole array) is
+  // a function of this call's inputs
+  if (o.iavlim[2] == 2 && o.imhd != 0 && o.imhd < 11) return bad("iavlim(3) = 2 needs imhd >= 11 (B evolved)");
   for (int d = 0; d < ndim; d++) {
     const int b = o.ibound[d];
     if (!(b == 0 || b == 1 || b == 2 || b == 3)) return bad("ibound not in {0,1,2,3}");
@@ -515,6 +521,31 @@ template <int NDIM> int do_iterate_density(nd_ctx *c, int resume) {
   return 0;
 }
 
+// ---- get_curl (src/get_curl.f90:64-287) on the linked, density-converged state: curl (and grad) of `bvec` (device, original order,
+//      3 doubles a row, rows [0,npart)) into curlB / gradB (device, original order); with `alpha` the Tricco & Price switch as well ----
+template <int NDIM> int do_get_curl(nd_ctx *c, int icurltype, const double *bvec, double *curlB, double *gradB, double *alpha) {
+  const int nt = c->ntotal;
+  CurlGatherArgs GA;
+  GA.perm = c->perm; GA.ireal = c->ireal; GA.hh = c->hh; GA.pmass = c->pmass; GA.rho = c->rho; GA.gradh = c->gradh; GA.bvec = bvec;
+  GA.posh = c->posh; GA.vm = c->vm; GA.gal = c->gal; GA.bsorted = c->bpsi; GA.p32 = c->p32; GA.srho = c->srho; GA.hhmax1 = 1.0 / c->hhmax;
+  GA.npart = c->npart; GA.ntotal = nt;
+  LAUNCH(c, k_curl_gather, nblocks(nt, 256), 256, 0, GA);
+  Grid G = make_grid(c);
+  for (int c0 = 0; c0 < nt; c0 += LIST_CHUNK) {
+    const int m = std::min(LIST_CHUNK, nt - c0);
+    ListArgs LA;
+    LA.hh = c->hh; LA.targets = nullptr; LA.s0 = c0; LA.ntargets = m; LA.numneigh = nullptr; LA.drag = 0;   // type rule of get_curl.f90:161-167
+    LA.pair_out_i = LA.pair_out_j = nullptr; LA.pair_count = nullptr; LA.pair_cap = 0;
+    NbrLists L;
+    if (int e = build_lists<NDIM, LIST_RATES>(c, G, LA, L)) return e;
+    CurlArgs A;
+    A.bvec = c->bpsi; A.srho = c->srho; A.gal = c->gal; A.curlB = curlB; A.gradB = gradB; A.alpha = alpha; A.hh = c->hh; A.icurltype = icurltype;
+    A.weight = 1.0 / std::pow(c->o.hfact, NDIM); A.s0 = c0; A.ntargets = m; A.targets = nullptr;
+    LAUNCH(c, (curl_pair_kernel<NDIM>), nblocks(m, 128), 128, 0, G, A, L);
+  }
+  return 0;
+}
+
 int do_cons2prim(nd_ctx *c) {
   const nd_options &o = c->o;
   C2PArgs A;
@@ -525,6 +556,16 @@ int do_cons2prim(nd_ctx *c) {
   A.npart = c->npart; A.ntotal = c->ntotal; A.imhd = o.imhd; A.iener = o.iener; A.gamma = o.gamma; A.polyk = o.polyk; A.aux = o.want_aux != 0;
   A.dustevol = o.onef_dust ? c->dustevol : nullptr; A.dustfrac = c->dustfrac; A.rhogas = c->rhogas; A.rhodust = c->rhodust;
   LAUNCH(c, k_c2p, nblocks(c->npart, 256), 256, 0, A);
+  if (o.imhd != 0 && o.iavlim[2] == 2 && c->has_comm)
+    return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "iavlim(3) = 2 (resistivity switch) is not available on slab-decomposed contexts: halo rows would need the owners' alpha_B");
+  if (o.imhd != 0 && o.iavlim[2] == 2) {
+    // conservative2primitive.f90:299-311: J and grad B by the differenced curl operator, then alpha_B = min(h |grad B| / |B|, 1).  It sits
+    // between the B-field assignment and the copies to fixed particles and ghosts, like the reference's.  The old alpha_B is kept for
+    // ghost rows that do not get copy_particle (k_rates_gather).
+    LAUNCH(c, k_take_column, nblocks(c->npart, 256), 256, 0, c->alpha, 3, 2, c->alphaB_in, c->npart);
+    if (int e = DISPATCH_NDIM(c, do_get_curl<1>(c, 1, c->Bfield, c->curlB, nullptr, c->alpha), do_get_curl<2>(c, 1, c->Bfield, c->curlB, nullptr, c->alpha),
+                              do_get_curl<3>(c, 1, c->Bfield, c->curlB, nullptr, c->alpha))) return e;
+  }
   if (any_fixed_bound(c)) LAUNCH(c, k_c2p_fixed, nblocks(c->npart, 256), 256, 0, A);
   if (any_ghost_bound(c)) LAUNCH(c, k_c2p_ghost, nblocks(c->ntotal - c->npart, 256), 256, 0, A);
   c->prim_done = true;
@@ -599,6 +640,11 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   GA.p32 = c->p32; GA.hhmax1 = 1.0 / c->hhmax;
   GA.dustfrac = c->dustfrac; GA.deltav = c->deltav; GA.rhogas = c->rhogas; GA.rhodust = c->rhodust;
   GA.dusta = o.onef_dust ? c->dusta : nullptr; GA.dustb = c->dustb; GA.use_smoothed_rhodust = o.use_smoothed_rhodust;
+  {
+    bool all3 = true;
+    for (int d = 0; d < c->ndim; d++) if (o.ibound[d] != 3) all3 = false;
+    GA.alphaB_ghost = (o.imhd != 0 && o.iavlim[2] == 2 && any_ghost_bound(c) && !all3) ? c->alphaB_in : nullptr;
+  }
   GA.posh = c->posh; GA.vm = c->vm; GA.bpsi = c->bpsi; GA.thermo = c->thermo; GA.gal = c->gal; GA.npart = c->npart; GA.ntotal = nt; GA.imhd = o.imhd;
   GA.stress_key = c->red + RED_STRESS; GA.imagforce = o.imagforce; GA.srho = c->srho; GA.pext = o.pext; GA.err = c->flags + 1;
   GA.Bconstmax = std::max(o.Bconst[0], std::max(o.Bconst[1], o.Bconst[2]));
@@ -753,5 +799,4 @@ int fill_density_scalars(nd_ctx *c) {
   return 0;
 }
 
-#define DISPATCH_NDIM(c, expr1, expr2, expr3) ((c)->ndim == 1 ? (expr1) : (c)->ndim == 2 ? (expr2) : (expr3))
 

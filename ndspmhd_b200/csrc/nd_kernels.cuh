@@ -461,6 +461,30 @@ __global__ void k_c2p_ghost(C2PArgs A) {                                        
   if (A.dustevol) { A.dustfrac[i] = A.dustfrac[j]; A.rhogas[i] = A.rhogas[j]; A.rhodust[i] = A.rhodust[j]; }
 }
 
+// get_curl (nd_curl.cuh): the sorted records the operator reads -- converged 1/h, mass, rho, gradh and the vector field; ghost slots carry
+// their parent's values (for imhd >= 11 that is what `Bfield = Bevol` leaves in the ghost rows, conservative2primitive.f90:151-152)
+struct CurlGatherArgs {
+  const int *perm, *ireal; const double *hh, *pmass, *rho, *gradh, *bvec;
+  double4 *posh, *vm, *gal, *bsorted; float4 *p32; double *srho; double hhmax1; int npart, ntotal;
+};
+__global__ void k_curl_gather(CurlGatherArgs A) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= A.ntotal) return;
+  const int r = A.perm[s];
+  const int st = (r < A.npart) ? r : A.ireal[r] - 1;
+  const double h = A.hh[st];
+  A.posh[s].w = 1.0 / h;
+  A.p32[s].w = screen_h2(h, A.hhmax1);
+  A.vm[s].w = A.pmass[st];
+  A.srho[s] = A.rho[st];
+  A.gal[s].x = A.gradh[st];
+  A.bsorted[s] = make_double4(A.bvec[(size_t)st * 3], A.bvec[(size_t)st * 3 + 1], A.bvec[(size_t)st * 3 + 2], 0.);
+}
+__global__ void k_take_column(const double *a, int stride, int col, double *out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[(size_t)i * stride + col];
+}
+
 // =====================================================================================================
 // rates: gather of the sorted inputs, finalisation loop (src/ratesND_mhd.f90:532-965)
 // =====================================================================================================
@@ -470,6 +494,9 @@ struct RGatherArgs {
   int *err;
   // one-fluid dust (dusta NULL otherwise)
   const double *dustfrac, *deltav, *rhogas, *rhodust; double4 *dusta; double2 *dustb; int use_smoothed_rhodust;
+  // iavlim(3) = 2 with ghosts that are not all periodic: the ghosts keep the alpha_B they were created with (copy_particle runs for
+  // them only when every boundary is periodic, conservative2primitive.f90:465), i.e. the parent's value BEFORE the switch of this call
+  const double *alphaB_ghost;
 };
 __global__ void k_rates_gather(RGatherArgs A) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -484,7 +511,8 @@ __global__ void k_rates_gather(RGatherArgs A) {
     A.vm[s].w = A.pmass[st];
     A.srho[s] = rho;
     A.thermo[s] = make_double4(1.0 / rho, fmax(A.pr[st] - A.pext, 0.), A.spsound[st], A.uu[st]);   // rho1i, :325; pri = max(pr - pext, 0), :328
-    A.gal[s] = make_double4(A.gradh[st], A.alpha[(size_t)st * 3], A.alpha[(size_t)st * 3 + 1], A.alpha[(size_t)st * 3 + 2]);
+    A.gal[s] = make_double4(A.gradh[st], A.alpha[(size_t)st * 3], A.alpha[(size_t)st * 3 + 1],
+                            (A.alphaB_ghost && r >= A.npart) ? A.alphaB_ghost[st] : A.alpha[(size_t)st * 3 + 2]);
     if (A.dusta) {                                                                  // :344-356
       const double eps = A.dustfrac[st];
       A.dusta[s] = make_double4(eps, A.deltav[(size_t)st * 3], A.deltav[(size_t)st * 3 + 1], A.deltav[(size_t)st * 3 + 2]);

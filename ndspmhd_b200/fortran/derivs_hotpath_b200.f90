@@ -25,9 +25,11 @@ subroutine set_linklist
  type(nd_arrays)  :: a
  integer(c_int)   :: ierr
  logical, save    :: cpu_only = .false.
- !--CPU consumers of ll/ifirstincell/iamincell (get_curl, get_divB, smooth, dust_diffusion, get_2ndderivs) need the
- !  host link list: keep the original routine for those option values (SURVEY.md 8b)
- if (cpu_only .or. iavlim(3)==2 .or. idust==3 .or. icompute_d2v>0 .or. imhd<0 .or. iprterm==12 .or. ibiascorrection>0) then
+ !--CPU consumers of ll/ifirstincell/iamincell (get_divB, smooth, dust_diffusion, get_2ndderivs) need the host link
+ !  list: keep the original routine for those option values (SURVEY.md 8b).  iavlim(3)=2 (get_curl inside
+ !  conservative2primitive) runs on the device when B is the evolved variable (imhd >= 11); with B/rho the library
+ !  refuses the tuple (ND_ERR_UNSUPPORTED_OPTION below) and the CPU routines take over.
+ if (cpu_only .or. idust==3 .or. icompute_d2v>0 .or. imhd<0 .or. iprterm==12 .or. ibiascorrection>0) then
     call set_linklist_cpu
     b200_resident = .false.
     return

@@ -49,6 +49,7 @@ module ndspmhd_b200
     type(c_ptr) :: force,dudt,dendt,dBevoldt,daldt,dpsidt,gradpsi,divB,curlB,graddivv,del2u
     type(c_ptr) :: x_out,vel_out,ireal_out,itype_out
     type(c_ptr) :: dustevol,dustfrac_in,deltav,dustfrac,rhogas,rhodust,ddustevoldt,ddeltavdt
+    type(c_ptr) :: alpha_out
  end type nd_arrays
 
  type, bind(C) :: nd_scalars
@@ -208,6 +209,9 @@ contains
   a%daldt = b200_loc_r(daldt); a%dpsidt = b200_loc_r(dpsidt); a%gradpsi = b200_loc_r(gradpsi); a%divB = b200_loc_r(divB)
   a%curlB = b200_loc_r(curlB); a%del2u = c_null_ptr
   a%x_out = c_null_ptr; a%vel_out = c_null_ptr; a%ireal_out = c_null_ptr; a%itype_out = c_null_ptr
+  a%alpha_out = c_null_ptr
+  ! the resistivity switch rewrites alpha(3,:) (conservative2primitive.f90:299-311)
+  if (iavlim(3)==2) a%alpha_out = b200_loc_r(alpha)
   if (onef_dust) then   ! one-fluid dust arrays only exist then (src/allocateND.f90:386-392)
      a%dustevol = b200_loc_r(dustevol); a%dustfrac_in = b200_loc_r(dustfrac); a%deltav = b200_loc_r(deltav)
      a%dustfrac = b200_loc_r(dustfrac); a%rhogas = b200_loc_r(rhogas); a%rhodust = b200_loc_r(rhodust)

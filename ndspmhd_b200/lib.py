@@ -33,7 +33,7 @@ EXPORTS = [
     "ndspmhd_b200_cons2prim", "ndspmhd_b200_get_rates", "ndspmhd_b200_derivs", "ndspmhd_b200_download",
     "ndspmhd_b200_host_alloc", "ndspmhd_b200_host_free", "ndspmhd_b200_last_timings", "ndspmhd_b200_launch_count",
     "ndspmhd_b200_stream", "ndspmhd_b200_rates_pairs", "ndspmhd_b200_rewind", "ndspmhd_b200_set_comm", "ndspmhd_b200_row_counts", "ndspmhd_b200_selftest_math", "ndspmhd_b200_derivs_host",
-    "ndspmhd_b200_step", "ndspmhd_b200_download_state", "ndspmhd_b200_evwrite",
+    "ndspmhd_b200_step", "ndspmhd_b200_download_state", "ndspmhd_b200_evwrite", "ndspmhd_b200_get_curl",
 ]
 
 
@@ -84,6 +84,7 @@ def load():
     L.ndspmhd_b200_step.argtypes = [vp, C.POINTER(NdStepOpts), _DP, C.POINTER(NdScalars)]
     L.ndspmhd_b200_download_state.argtypes = [vp, C.POINTER(NdStateOut), C.c_int]
     L.ndspmhd_b200_evwrite.argtypes = [vp, C.POINTER(NdEvwrite)]
+    L.ndspmhd_b200_get_curl.argtypes = [vp, C.c_int, _DP, _DP, _DP, C.c_int]
     _LIB = L
     return L
 
@@ -136,6 +137,7 @@ def arrays_struct(p: Particles) -> NdArrays:
     a.dustevol, a.dustfrac_in, a.deltav = p.ptr("dustevol"), p.ptr("dustfrac"), p.ptr("deltav")
     for n in ("dustfrac", "rhogas", "rhodust", "ddustevoldt", "ddeltavdt"):
         setattr(a, n, p.ptr(n))
+    a.alpha_out = p.ptr("alpha")   # iavlim(3) = 2: conservative2primitive rewrites alpha(3,:) in place, like the module array
     return a
 
 
@@ -234,6 +236,17 @@ class Hotpath:
         ev = NdEvwrite()
         self._chk(self.L.ndspmhd_b200_evwrite(self.ctx, C.byref(ev)))
         return ev.as_dict()
+
+    def get_curl(self, Bvec: np.ndarray, icurltype: int = 1, want_gradB: bool = False):
+        """`get_curl` (src/get_curl.f90:64) of Bvec[(idim,3)] on the resident state after iterate_density.  Returns (curlB[(idim,3)],
+        gradB[(idim,3,3)] or None) with rows [0,npart) filled; gradB[i, k, l] = d Bvec_k / d x_l."""
+        Bvec = np.ascontiguousarray(Bvec, dtype=np.float64)
+        idim = Bvec.shape[0]
+        curlB = np.zeros((idim, 3))
+        gradB = np.zeros((idim, 3, 3)) if want_gradB else None
+        self._chk(self.L.ndspmhd_b200_get_curl(self.ctx, icurltype, Bvec.ctypes.data_as(_DP), curlB.ctypes.data_as(_DP),
+                                               gradB.ctypes.data_as(_DP) if want_gradB else None, idim))
+        return curlB, gradB
 
     def selftest_math(self, x: np.ndarray):
         """sqrt_nr / rsqrt_nr of the pair kernels evaluated on the device for the given arguments."""

@@ -268,6 +268,7 @@ struct St {
   double dtcourant, dtforce, dtav, dtdrag, dtvisc, vsig2max, vsigmax_out, stressmax_out, ts_min_out, h_on_csts_max_out, fhmax_out;
   double fmean[3];
   int nclumped;
+  std::vector<double> gradB;   // module derivB: gradB(3,3,idim), filled by get_curl when iavlim(3) = 2
   long long npairs_rates;   // ordered pairs evaluated by get_rates, counted on the side(s) that are real particles (test checksum, no reference counterpart)
   int err;
 };
@@ -866,6 +867,137 @@ void equation_of_state(St &S, const double *rho /*0-based*/) {
 }
 
 // src/conservative2primitive.f90:42-470, element-wise branches only
+inline void cross_product3D(const double *a, const double *b, double *c) {   // src/utils.f90:60-68
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline double dot3(const double *a, const double *b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+
+// src/kernelND.f90:4643-4672 interpolate_kernel_curl
+inline void interpolate_kernel_curl(const Kern &K, double q2, double &gradwalt, double &gradgradwalt) {
+  int index, index1; kindex(K, q2, index, index1);
+  double dxx = q2 - index * K.dq2table;
+  gradwalt = K.grwijalt[index];
+  double dgrwaltdx = (K.grwijalt[index1] - gradwalt) * K.ddq2table;
+  gradwalt = gradwalt + dgrwaltdx * dxx;
+  gradgradwalt = K.grgrwijalt[index];
+  double dgrgrwaltdx = (K.grgrwijalt[index1] - gradgradwalt) * K.ddq2table;
+  gradgradwalt = gradgradwalt + dgrgrwaltdx * dxx;
+}
+
+// src/get_curl.f90:64-287 get_curl, icurltype 1 (default, optional gradB) .. 4; the optional curlBgradh (vector potential) is not restated.
+// Bvec, curlB: (3, idim) 1-based rows like the module arrays; gradB: (3,3,idim) column-major gradB(:,k,i) or NULL.
+// Reads whatever the rows npart+1..ntotal of Bvec hold, as the reference does (the caller decides what the ghosts carry).
+void get_curl(St &S, int icurltype, const double *Bvec, double *curlB, double *gradB) {
+  const nd_options &o = *S.o;
+  const Kern &K = S.K;
+  const int ndim = S.ndim, npart = S.npart, ntotal = S.ntotal;
+  auto BV = [&](int k, int i) { return Bvec[(size_t)(i - 1) * 3 + (k - 1)]; };
+  auto CB = [&](int k, int i) -> double & { return curlB[(size_t)(i - 1) * 3 + (k - 1)]; };
+  auto GB = [&](int l, int k, int i) -> double & { return gradB[((size_t)(i - 1) * 3 + (k - 1)) * 3 + (l - 1)]; };
+  std::vector<int> listneigh(S.idim + 1);
+  std::vector<double> h1(ntotal + 1);
+  for (int i = 1; i <= S.idim; i++) for (int k = 1; k <= 3; k++) CB(k, i) = 0.;     // :113
+  double dr[3] = {0., 0., 0.};
+  const double weight = 1. / powi(o.hfact, ndim);                                   // :115
+  for (int i = 1; i <= ntotal; i++) h1[i] = 1. / A1(hh, i);
+  if (gradB) for (size_t q = 0; q < (size_t)S.idim * 9; q++) gradB[q] = 0.;
+  int nneigh = 0;
+  for (int icell = 1; icell <= S.ncellsloop; icell++) {                             // :124
+    get_neighbour_list(S, icell, listneigh.data(), nneigh);
+    int i = S.ifirstincell[icell];
+    int idone = -1;
+    while (i != -1) {                                                               // :137
+      idone = idone + 1;
+      double hi1 = h1[i];
+      double hi21 = hi1 * hi1;
+      double hfacwabi = powi(hi1, ndim);
+      double pmassi = A1(pmass, i);
+      double Bi[3] = {BV(1, i), BV(2, i), BV(3, i)};
+      double rho21i = 1. / (A1(rho, i) * A1(rho, i));
+      double rho21gradhi = rho21i * A1(gradh, i);
+      double curlBi[3] = {0., 0., 0.}, gradBi[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};   // gradBi[k][l] = gradBi(l,k)
+      int itypei = A1(itype, i);
+      for (int n = idone + 1; n <= nneigh; n++) {                                   // :158
+        int j = listneigh[n - 1];
+        int itypej = A1(itype, j);
+        if (!types_interact(itypei, itypej)) continue;                              // :161-167
+        if (!((j != i) && !(j > npart && i > npart))) continue;                     // :168
+        double dx[3] = {0., 0., 0.};
+        for (int k = 1; k <= ndim; k++) dx[k - 1] = X_(k, i) - X_(k, j);
+        double hj1 = h1[j];
+        double rij2 = 0.;
+        for (int k = 0; k < ndim; k++) rij2 = rij2 + dx[k] * dx[k];
+        double q2i = rij2 * hi21;
+        double q2j = rij2 * hj1 * hj1;
+        if (!((q2i < K.radkern2) || (q2j < K.radkern2))) continue;                  // :183
+        double hfacwabj = powi(hj1, ndim);
+        double rij = std::sqrt(rij2);
+        for (int k = 0; k < ndim; k++) dr[k] = dx[k] / (rij + DBL_MIN);             // :187 tiny(rij)
+        double grkerni, grgrkerni, grkernj, grgrkernj;
+        interpolate_kernel_curl(K, q2i, grkerni, grgrkerni);
+        interpolate_kernel_curl(K, q2j, grkernj, grgrkernj);
+        double dB[3], curlBterm[3], Bj[3] = {BV(1, j), BV(2, j), BV(3, j)};
+        switch (icurltype) {
+          case 2: {                                                                 // :202-211
+            grkerni = grkerni * hfacwabi * hi1;
+            grkernj = grkernj * hfacwabj * hj1 * A1(gradh, j);
+            double ti_[3], tj_[3];
+            cross_product3D(Bi, dr, ti_);
+            cross_product3D(Bj, dr, tj_);
+            for (int k = 0; k < 3; k++) curlBterm[k] = (ti_[k] * rho21gradhi * grkerni + tj_[k] / (A1(rho, j) * A1(rho, j)) * grkernj);
+            for (int k = 0; k < 3; k++) curlBi[k] = curlBi[k] + A1(pmass, j) * curlBterm[k];
+            for (int k = 0; k < 3; k++) CB(k + 1, j) = CB(k + 1, j) - pmassi * curlBterm[k];
+          } break;
+          case 3:                                                                   // :213-220
+            grkerni = grkerni * hi1;
+            grkernj = grkernj * hj1;
+            for (int k = 0; k < 3; k++) dB[k] = Bi[k] - Bj[k];
+            cross_product3D(dB, dr, curlBterm);
+            for (int k = 0; k < 3; k++) curlBi[k] = curlBi[k] + curlBterm[k] * grkerni;
+            for (int k = 0; k < 3; k++) CB(k + 1, j) = CB(k + 1, j) + curlBterm[k] * grkernj;
+            break;
+          case 4:                                                                   // :222-230
+            grkerni = grkerni * hfacwabi * hi1;
+            grkernj = grkernj * hfacwabj * hj1;
+            for (int k = 0; k < 3; k++) dB[k] = Bi[k] - Bj[k];
+            cross_product3D(dB, dr, curlBterm);
+            for (int k = 0; k < 3; k++) curlBi[k] = curlBi[k] + A1(pmass, j) / (A1(rho, j) * A1(rho, j)) * curlBterm[k] * grkerni;
+            for (int k = 0; k < 3; k++) CB(k + 1, j) = CB(k + 1, j) + pmassi * rho21i * curlBterm[k] * grkernj;
+            break;
+          default:                                                                  // :232-255
+            grkerni = grkerni * hfacwabi * hi1;
+            grkernj = grkernj * hfacwabj * hj1;
+            for (int k = 0; k < 3; k++) dB[k] = Bi[k] - Bj[k];
+            cross_product3D(dB, dr, curlBterm);
+            for (int k = 0; k < 3; k++) curlBi[k] = curlBi[k] + A1(pmass, j) * curlBterm[k] * grkerni;
+            for (int k = 0; k < 3; k++) CB(k + 1, j) = CB(k + 1, j) + pmassi * curlBterm[k] * grkernj;
+            if (gradB) {
+              for (int k = 0; k < 3; k++) for (int l = 0; l < 3; l++) {
+                gradBi[k][l] = gradBi[k][l] + A1(pmass, j) * dB[k] * dr[l] * grkerni;
+                GB(l + 1, k + 1, j) = GB(l + 1, k + 1, j) + pmassi * dB[k] * dr[l] * grkernj;
+              }
+            }
+        }
+      }
+      for (int k = 0; k < 3; k++) CB(k + 1, i) = CB(k + 1, i) + curlBi[k];          // :262
+      if (gradB) for (int k = 0; k < 3; k++) for (int l = 0; l < 3; l++) GB(l + 1, k + 1, i) = GB(l + 1, k + 1, i) + gradBi[k][l];
+      i = S.ll[i];
+    }
+  }
+  for (int i = 1; i <= npart; i++) {                                                // :275-290
+    switch (icurltype) {
+      case 4: for (int k = 1; k <= 3; k++) CB(k, i) = A1(rho, i) * CB(k, i); break;
+      case 3: for (int k = 1; k <= 3; k++) CB(k, i) = weight * CB(k, i); break;
+      case 2: for (int k = 1; k <= 3; k++) CB(k, i) = -A1(rho, i) * CB(k, i); break;
+      default:
+        for (int k = 1; k <= 3; k++) CB(k, i) = CB(k, i) * A1(gradh, i) / A1(rho, i);
+        if (gradB) for (int k = 1; k <= 3; k++) for (int l = 1; l <= 3; l++) GB(l, k, i) = -GB(l, k, i) * A1(gradh, i) / A1(rho, i);
+    }
+  }
+}
+
 int conservative2primitive(St &S) {
   const nd_options &o = *S.o;
   const int npart = S.npart, ntotal = S.ntotal;
@@ -883,6 +1015,22 @@ int conservative2primitive(St &S) {
   } else if (o.imhd >= 1 && o.imhd <= 9) {                      // :190-193
     for (int i = 1; i <= npart; i++) for (int k = 1; k <= 3; k++) V3(Bfield, k, i) = V3(Bevol, k, i) * A1(rho, i);
   } else if (o.imhd != 0) return fail(S, ND_ERR_UNSUPPORTED_OPTION, "c2p: imhd not supported");
+  if (o.imhd != 0 && o.iavlim[2] == 2) {                        // :299-323 (iambipolar = 0, iresist /= 4: only the switch branch)
+    // J and grad(B) by the standard (differenced) curl operator, then the Tricco & Price (2013) resistivity switch.  The ghost rows
+    // of Bfield are whatever they hold at this point: Bevol's for imhd >= 11 (whole-array assignment above), the copies made when the
+    // ghosts were created for imhd 1..9 (the loop above stops at npart) -- the ghost copies of :441-467 come later.
+    S.gradB.assign((size_t)S.idim * 9, 0.);
+    get_curl(S, 1, S.a.Bfield, S.a.curlB, S.gradB.data());
+    for (int i = 1; i <= npart; i++) {
+      double B2i = 0.;
+      for (int k = 1; k <= 3; k++) B2i = B2i + V3(Bfield, k, i) * V3(Bfield, k, i);
+      if (B2i > 1.e-8) {
+        double g2 = 0.;
+        for (int q = 0; q < 9; q++) g2 = g2 + S.gradB[(size_t)(i - 1) * 9 + q] * S.gradB[(size_t)(i - 1) * 9 + q];   // norm2 of the 3x3 block
+        V3(alpha, 3, i) = std::min(A1(hh, i) * std::sqrt(g2) / std::sqrt(B2i + DBL_EPSILON), 1.0);
+      } else V3(alpha, 3, i) = 0.;
+    }
+  }
   if (o.iener == 3) {                                           // :329-346
     for (int i = 1; i <= npart; i++) {
       double v2i = 0., B2i = 0.;
@@ -933,12 +1081,6 @@ inline double get_tstop(int idrag_nature, double rhogas, double rhodust, double 
   }
 }
 
-inline void cross_product3D(const double *a, const double *b, double *c) {   // src/utils.f90:60-68
-  c[0] = a[1] * b[2] - a[2] * b[1];
-  c[1] = a[2] * b[0] - a[0] * b[2];
-  c[2] = a[0] * b[1] - a[1] * b[0];
-}
-inline double dot3(const double *a, const double *b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
 
 // src/ratesND_mhd.f90:29-979 get_rates with rates_core (:1175), artificial_dissipation (:1700),
 // artificial_dissipation_phantom (:1903), mhd_terms (:2377, default tensor force), drag_forces (:1074).
@@ -1715,6 +1857,18 @@ long long ndo_linklist_pairs(const nd_options *o, int ndim, ndo_arrays *a, int n
   long long n = (long long)vi.size();
   for (long long k = 0; k < n && k < cap; k++) { pi[k] = vi[k]; pj[k] = vj[k]; }
   return n;
+}
+
+/* src/get_curl.f90:64-287 on the arrays as they stand (rho, hh, gradh of a previous derivs; rows npart+1..ntotal are the ghosts of that
+ * derivs): re-links and runs the operator.  Bvec, curlB (3,idim); gradB (3,3,idim) or NULL (icurltype 1 only). */
+int ndo_get_curl(const nd_options *o, int ndim, ndo_arrays *a, int npart, int ntotal, int idim, int icurltype, const double *Bvec, double *curlB,
+                 double *gradB) {
+  static St S;
+  g_err.clear();
+  if (int e = init_state(S, o, ndim, a, npart, ntotal, idim)) return e;
+  if (int e = set_linklist(S)) return e;
+  get_curl(S, icurltype, Bvec, curlB, icurltype == 1 ? gradB : nullptr);
+  return 0;
 }
 
 /* One leapfrog step: `step` (src/stepND_leapfrog_mhd.f90:39-300) with its `call derivs` (:167) and `call boundary`

@@ -65,6 +65,11 @@ long long ndo_bruteforce_pairs(int ndim, const double *x, const double *hh, int 
 long long ndo_linklist_pairs(const nd_options *o, int ndim, ndo_arrays *a, int npart, int ntotal, int idim,
                              int *pi, int *pj, long long cap);
 
+/* `get_curl` (src/get_curl.f90:64-287) on the arrays as they stand after a derivs (rho, hh, gradh; rows npart..ntotal-1
+ * are that derivs' ghosts): icurltype 1..4; Bvec and curlB are (3,idim), gradB (3,3,idim) or NULL (filled for icurltype 1 only). */
+int ndo_get_curl(const nd_options *o, int ndim, ndo_arrays *a, int npart, int ntotal, int idim, int icurltype, const double *Bvec,
+                 double *curlB, double *gradB);
+
 const char *ndo_last_error(void);
 
 #ifdef __cplusplus

@@ -65,6 +65,8 @@ def lib():
         _LIB.ndo_linklist_pairs.restype = C.c_longlong
         _LIB.ndo_linklist_pairs.argtypes = [C.POINTER(NdOptions), C.c_int, C.POINTER(NdoArrays), C.c_int, C.c_int, C.c_int,
                                             _IP, _IP, C.c_longlong]
+        _LIB.ndo_get_curl.restype = C.c_int
+        _LIB.ndo_get_curl.argtypes = [C.POINTER(NdOptions), C.c_int, C.POINTER(NdoArrays), C.c_int, C.c_int, C.c_int, C.c_int, _DP, _DP, _DP]
         _LIB.ndo_last_error.restype = C.c_char_p
     return _LIB
 
@@ -120,6 +122,25 @@ def evwrite(opts: NdOptions, p: Particles) -> dict:
     if e != 0:
         raise OracleError(e, "evwrite")
     return ev.as_dict()
+
+
+def get_curl(opts: NdOptions, p: Particles, Bvec: np.ndarray, icurltype: int = 1, want_gradB: bool = False, hhmax: float | None = None):
+    """`get_curl` (src/get_curl.f90:64-287) of Bvec[(idim,3)] on the arrays of `p` as a previous derivs left them (rho, hh, gradh, ghosts).
+    Returns (curlB[(idim,3)], gradB[(idim,3,3)] or None); gradB[i, k, l] = gradB(l,k,i) of the reference = d B_k / d x_l."""
+    L = lib()
+    o2 = NdOptions.from_buffer_copy(opts)   # bound:hhmax as set_ghost_particles left it (the cell size of the re-link)
+    o2.hhmax = float(np.max(p.hh[: p.npart])) if hhmax is None else hhmax
+    opts = o2
+    a = _arrays(p)
+    Bvec = np.ascontiguousarray(Bvec, dtype=np.float64)
+    assert Bvec.shape == (p.idim, 3)
+    curlB = np.zeros((p.idim, 3))
+    gradB = np.zeros((p.idim, 3, 3)) if want_gradB else None
+    e = L.ndo_get_curl(C.byref(opts), p.ndim, C.byref(a), p.npart, p.ntotal, p.idim, icurltype, Bvec.ctypes.data_as(_DP), curlB.ctypes.data_as(_DP),
+                       gradB.ctypes.data_as(_DP) if want_gradB else None)
+    if e != 0:
+        raise OracleError(e, L.ndo_last_error().decode())
+    return curlB, gradB
 
 
 def kernel_tables(ikernel: int, ikerneldrag: int, ndim: int):

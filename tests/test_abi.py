@@ -33,7 +33,7 @@ def test_header_is_plain_c_and_struct_layout_matches_ctypes():
     """Compile the header as C (gcc) and compare sizeof/offsetof with the ctypes mirror."""
     fields = {
         "nd_options": ["iener", "iavlim", "ibound", "device_ghosts", "idustevol", "hfact", "gamma", "xmin", "Bconst", "hhmax", "reserved_d"],
-        "nd_arrays": ["x", "rho_in", "hh", "dens", "force", "del2u", "x_out", "dustevol", "dustfrac_in", "dustfrac", "ddeltavdt"],
+        "nd_arrays": ["x", "rho_in", "hh", "dens", "force", "del2u", "x_out", "dustevol", "dustfrac_in", "dustfrac", "ddeltavdt", "alpha_out"],
         "nd_scalars": ["dtcourant", "fmean", "itsdensity", "ncellsx", "nrelink", "ncalctotal", "lmax", "list_overflows", "rate_chunks", "reserved_i", "npairs_rates", "ntrips_rates"],
         "nd_step_opts": ["C_cour", "C_force", "dtfixed", "reserved"],
         "nd_state_out": ["x", "rho", "dustevol", "deltav"],
