@@ -54,6 +54,7 @@ struct nd_ctx {
   bool slab_light = false;   // NDSPMHD_B200_SLAB_LIGHT=1: LIGHT rounds in slab-decomposed contexts too (off until it has run on >= 2 GPUs)
   bool drho_pairs = false;   // the density rounds of this derivs ran LIGHT: k_rates_final takes drho/dt from the pair sums and makes dh/dt
   float4 *p32 = nullptr;   // FP32 screening records of the list builder (nd_device.cuh)
+  double4 *rec = nullptr;  // [4*slot + 0..3] = {posh, vm, thermo, bpsi}: the packed neighbour record of the rates pair kernel
   double *srho = nullptr;
   // ---- one-fluid dust (idust=1; allocated only then) ----
   double *dustevol = nullptr, *dustfrac = nullptr, *deltav = nullptr, *rhogas = nullptr, *rhodust = nullptr, *ddustevoldt = nullptr, *ddeltavdt = nullptr;

@@ -29,6 +29,7 @@ void register_rows(nd_ctx *c) {
   R1(dens); R1(uu); R1(pr); R1(spsound); R3(Bfield);
   R3(force); R1(dudt); R1(dendt); R3(dBevoldt); R3(daldt); R1(dpsidt); R3(gradpsi); R1(divB); R3(curlB); R3(graddivv); R1(del2u);
   v.push_back({(void **)&c->p32, sizeof(float4)});
+  v.push_back({(void **)&c->rec, 4 * sizeof(double4)});
   R1(srho); R4(posh); R4(vm); R4(posm); R4(bpsi); R4(thermo); R4(gal); R4(sF); R4(sdB); R4(sC); R4(sP); R4(sV);
   RI(typ); RI(perm); RI(permtmp); RI(inv); RI(cellOf); RI(cellOfOrig); RI(redo); RI(list); RI(ghostcount);
   if (c->o.onef_dust) {
@@ -646,6 +647,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
     GA.alphaB_ghost = (o.imhd != 0 && o.iavlim[2] == 2 && any_ghost_bound(c) && !all3) ? c->alphaB_in : nullptr;
   }
   GA.posh = c->posh; GA.vm = c->vm; GA.bpsi = c->bpsi; GA.thermo = c->thermo; GA.gal = c->gal; GA.npart = c->npart; GA.ntotal = nt; GA.imhd = o.imhd;
+  GA.rec = (ND_RATES_QUAD && !o.onef_dust) ? c->rec : nullptr;
   GA.stress_key = c->red + RED_STRESS; GA.imagforce = o.imagforce; GA.srho = c->srho; GA.pext = o.pext; GA.err = c->flags + 1;
   GA.Bconstmax = std::max(o.Bconst[0], std::max(o.Bconst[1], o.Bconst[2]));
   LAUNCH(c, k_rates_gather, nblocks(nt, 256), 256, 0, GA);
@@ -656,7 +658,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
     O.stressmax = dkey_inv(c->h_red[0]);
     if (int e = comm_allreduce(c, &O.stressmax, 1, 0)) return e;
   }
-  RatesIn I; I.bpsi = c->bpsi; I.thermo = c->thermo; I.gal = c->gal; I.srho = c->srho; I.dusta = c->dusta; I.dustb = c->dustb;
+  RatesIn I; I.bpsi = c->bpsi; I.thermo = c->thermo; I.gal = c->gal; I.srho = c->srho; I.dusta = c->dusta; I.dustb = c->dustb; I.rec = c->rec;
   RatesSums S; S.F = c->sF; S.dB = c->sdB; S.C = c->sC; S.P = c->sP; S.V = c->sV; S.D = c->sD;
   RatesRed R;
   R.dtcourant_min = c->red + RED_DTC; R.vsigmax_max = c->red + RED_VSIG; R.dtav_min = c->red + RED_DTAV; R.ts_min = c->red + RED_TS;
