@@ -490,6 +490,7 @@ def main():
     ap.add_argument("--no-fit", action="store_true", help="--impl reference: skip the single-core runs at smaller sizes")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the single-GPU re-run that fills parity_vs_single")
+    ap.add_argument("--transport", default="nccl", choices=["nccl", "callbacks"], help="N > 1: native NCCL in the library (default) or the nd_comm host callbacks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     import __graft_entry__ as g

@@ -277,6 +277,16 @@ typedef struct nd_comm {
 
 /* attach (or detach with NULL) the transport; call before upload.  upload then takes only this rank's own rows. */
 int ndspmhd_b200_set_comm(nd_ctx *c, const nd_comm *comm);
+/*
+ * The native transport: the library calls NCCL itself, on its own stream (all-reduces of device scalars, grouped ncclSend/ncclRecv of the
+ * halo buffers, all-gather of the halo byte counts) -- no host callback on the path.  libnccl.so.2 is opened with dlopen at the first call
+ * (the copy the host process already holds, e.g. torch's, or NDSPMHD_B200_NCCL_LIB).  Rank 0 makes the 128-byte id, the host program
+ * broadcasts it by its own means (torch.distributed, MPI_Bcast), every rank then calls set_comm_nccl (collective: ncclCommInitRank).
+ */
+int ndspmhd_b200_nccl_unique_id(unsigned char id[128]);
+int ndspmhd_b200_set_comm_nccl(nd_ctx *c, const unsigned char id[128], int rank, int nranks, double slab_lo, double slab_hi, long long nglobal);
+/* counters since create: all-reduces issued (either transport), halo payload bytes this rank sent */
+int ndspmhd_b200_comm_stats(const nd_ctx *c, long long *n_allreduce, long long *halo_bytes_sent);
 /* rows after the last link: own rows [0,nown), halo rows [nown,nsrc), ghosts [nsrc,ntotal) */
 int ndspmhd_b200_row_counts(const nd_ctx *c, int *nown, int *nsrc, int *ntotal);
 

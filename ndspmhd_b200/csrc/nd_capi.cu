@@ -9,6 +9,7 @@
 #include "nd_density.cuh"
 #include "nd_rates.cuh"
 #include "nd_curl.cuh"
+#include "nd_nccl.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -51,10 +52,9 @@ struct nd_ctx {
   // ---- sorted-order arrays ----
   double4 *posh = nullptr, *vm = nullptr, *posm = nullptr, *bpsi = nullptr, *thermo = nullptr, *gal = nullptr;
   bool dens_light = false;   // set by the fused entry points: the rates kernel of the same derivs makes drho/dt (fast tuple)
-  bool slab_light = false;   // NDSPMHD_B200_SLAB_LIGHT=1: LIGHT rounds in slab-decomposed contexts too (off until it has run on >= 2 GPUs)
+  bool slab_light = true;    // LIGHT rounds in slab-decomposed contexts too (NDSPMHD_B200_SLAB_LIGHT=0 turns them off: the A/B of tools/gpu_slab_ab.sh)
   bool drho_pairs = false;   // the density rounds of this derivs ran LIGHT: k_rates_final takes drho/dt from the pair sums and makes dh/dt
   float4 *p32 = nullptr;   // FP32 screening records of the list builder (nd_device.cuh)
-  double4 *rec = nullptr;  // [4*slot + 0..3] = {posh, vm, thermo, bpsi}: the packed neighbour record of the rates pair kernel
   double *srho = nullptr;
   // ---- one-fluid dust (idust=1; allocated only then) ----
   double *dustevol = nullptr, *dustfrac = nullptr, *deltav = nullptr, *rhogas = nullptr, *rhodust = nullptr, *ddustevoldt = nullptr, *ddeltavdt = nullptr;
@@ -81,6 +81,9 @@ struct nd_ctx {
   nd_scalars sc;
   // ---- slab decomposition (nd_comm): halo send lists and staging buffers ----
   nd_comm comm; bool has_comm = false; bool slab_too_narrow = false;
+  // native NCCL transport (nd_nccl.cuh): communicator, a 64-double device block and its pinned mirror for the small collectives
+  nd_ncclComm_t nccl = nullptr; NcclApi *nccl_api = nullptr; double *d_comm = nullptr, *h_comm = nullptr;
+  long long n_allreduce = 0, halo_bytes_sent = 0;
   int *sendlist[2] = {nullptr, nullptr}; int sendcap[2] = {0, 0}, nsend[2] = {0, 0}, nrecv[2] = {0, 0};
   void *sendbuf[2] = {nullptr, nullptr}, *recvbuf[2] = {nullptr, nullptr}; size_t sendbufcap[2] = {0, 0}, recvbufcap[2] = {0, 0};
   cudaEvent_t ev[8];
@@ -236,6 +239,9 @@ int ndspmhd_b200_destroy(nd_ctx *c) {
   if (c->h_red) cudaFreeHost(c->h_red);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->h_fmean) cudaFreeHost(c->h_fmean);
+  if (c->nccl && c->nccl_api) c->nccl_api->CommDestroy(c->nccl);
+  if (c->d_comm) cudaFree(c->d_comm);
+  if (c->h_comm) cudaFreeHost(c->h_comm);
   if (c->stepbuf) cudaFree(c->stepbuf);
   if (c->evpartial) cudaFree(c->evpartial);
   if (c->h_ev) cudaFreeHost(c->h_ev);
@@ -374,6 +380,7 @@ int ndspmhd_b200_upload(nd_ctx *c, const nd_arrays *a, int npart, int ntotal, in
 
 int ndspmhd_b200_set_comm(nd_ctx *c, const nd_comm *comm) {
   if (!c) return ND_ERR_INVALID_ARG;
+  if (c->nccl && c->nccl_api) { c->nccl_api->CommDestroy(c->nccl); c->nccl = nullptr; }   // the callback transport replaces a native one
   if (!comm || comm->nranks <= 1) { c->has_comm = false; return 0; }
   if (!comm->allreduce || !comm->sendrecv_counts || !comm->sendrecv) return set_err(c, ND_ERR_INVALID_ARG, "set_comm: all three callbacks are required");
   if (comm->rank < 0 || comm->rank >= comm->nranks || !(comm->slab_hi > comm->slab_lo) || comm->nglobal < 1) return set_err(c, ND_ERR_INVALID_ARG, "set_comm: bad rank / slab / nglobal");
@@ -381,6 +388,46 @@ int ndspmhd_b200_set_comm(nd_ctx *c, const nd_comm *comm) {
   if (!(c->o.ibound[0] == 0 || c->o.ibound[0] == 1 || c->o.ibound[0] == 3)) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "slab decomposition needs ibound(1) in {0,1,3}");
   c->comm = *comm; c->has_comm = true;
   c->uploaded = c->linked = c->density_done = c->prim_done = c->rates_done = false;
+  return 0;
+}
+
+int ndspmhd_b200_nccl_unique_id(unsigned char id[128]) {
+  if (!id) return ND_ERR_INVALID_ARG;
+  NcclApi *api = nccl_api();
+  if (!api) return ND_ERR_COMM;
+  nd_ncclUniqueId u;
+  if (api->GetUniqueId(&u) != 0) return ND_ERR_COMM;
+  memcpy(id, u.internal, 128);
+  return 0;
+}
+
+int ndspmhd_b200_set_comm_nccl(nd_ctx *c, const unsigned char id[128], int rank, int nranks, double slab_lo, double slab_hi, long long nglobal) {
+  if (!c || !id) return ND_ERR_INVALID_ARG;
+  if (nranks <= 1) { c->has_comm = false; return 0; }
+  if (rank < 0 || rank >= nranks || !(slab_hi > slab_lo) || nglobal < 1) return set_err(c, ND_ERR_INVALID_ARG, "set_comm_nccl: bad rank / slab / nglobal");
+  if (nranks > 31) return set_err(c, ND_ERR_INVALID_ARG, "set_comm_nccl: at most 31 ranks");
+  if (!c->o.device_ghosts) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "slab decomposition needs device_ghosts = 1");
+  if (!(c->o.ibound[0] == 0 || c->o.ibound[0] == 1 || c->o.ibound[0] == 3)) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "slab decomposition needs ibound(1) in {0,1,3}");
+  NcclApi *api = nccl_api();
+  if (!api) return set_err(c, ND_ERR_COMM, "libnccl could not be opened (set NDSPMHD_B200_NCCL_LIB, or use the callback transport ndspmhd_b200_set_comm)");
+  CU(cudaSetDevice(c->device));
+  if (c->nccl) { api->CommDestroy(c->nccl); c->nccl = nullptr; }
+  nd_ncclUniqueId u;
+  memcpy(u.internal, id, 128);
+  c->nccl_api = api;
+  NCCLCHK(api->CommInitRank(&c->nccl, nranks, u, rank));
+  if (!c->d_comm) { CU(cudaMalloc(&c->d_comm, sizeof(double) * 64)); CU(cudaMallocHost(&c->h_comm, sizeof(double) * 96)); }
+  memset(&c->comm, 0, sizeof(c->comm));
+  c->comm.rank = rank; c->comm.nranks = nranks; c->comm.slab_lo = slab_lo; c->comm.slab_hi = slab_hi; c->comm.nglobal = nglobal;
+  c->has_comm = true;
+  c->uploaded = c->linked = c->density_done = c->prim_done = c->rates_done = false;
+  return 0;
+}
+
+int ndspmhd_b200_comm_stats(const nd_ctx *c, long long *n_allreduce, long long *halo_bytes_sent) {
+  if (!c) return ND_ERR_INVALID_ARG;
+  if (n_allreduce) *n_allreduce = c->n_allreduce;
+  if (halo_bytes_sent) *halo_bytes_sent = c->halo_bytes_sent;
   return 0;
 }
 
@@ -513,15 +560,19 @@ int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int
   if (e) { cudaStreamSynchronize(c->stream_h2d); return e; }
   if (idim < c->ntotal) { cudaStreamSynchronize(c->stream_h2d); return set_err(c, ND_ERR_INVALID_ARG, "derivs_host: idim < ntotal after ghost generation"); }
   const size_t nout = (size_t)(c->has_comm ? c->nown : ((mask & ND_DL_REAL_ROWS) ? c->npart : c->ntotal));
+  // the density outputs leave while cons2prim and the rates run -- unless fixed particles take their partner's gradgradh in cons2prim
+  // (copy_particle, conservative2primitive.f90:424-437): then that group goes after cons2prim
+  const bool dens_after_c2p = any_fixed_bound(c) && c->o.want_aux;
   CU(cudaEventRecord(c->ev_out[0], c->stream));
   CU(cudaStreamWaitEvent(c->stream_d2h, c->ev_out[0], 0));
-  if (int e2 = download_group(c, a, nout, 1, mask, c->stream_d2h)) return e2;
+  if (!dens_after_c2p) { if (int e2 = download_group(c, a, nout, 1, mask, c->stream_d2h)) return e2; }
   CU(cudaStreamWaitEvent(c->stream, c->ev_in[1], 0));
   CU(cudaEventRecord(c->ev[2], c->stream));
   e = do_cons2prim(c);
   if (e) { cudaStreamSynchronize(c->stream_h2d); cudaStreamSynchronize(c->stream_d2h); return e; }
   CU(cudaEventRecord(c->ev_out[1], c->stream));
   CU(cudaStreamWaitEvent(c->stream_d2h, c->ev_out[1], 0));
+  if (dens_after_c2p) { if (int e2 = download_group(c, a, nout, 1, mask, c->stream_d2h)) return e2; }
   if (int e2 = download_group(c, a, nout, 2, mask, c->stream_d2h)) return e2;
   // The rates run in row chunks (do_get_rates) so that a chunk's rows go down the wire while the next chunk's pair kernel
   // runs; what is left after the last kernel is one chunk, dpsidt and the (zero) ghost rows instead of the whole 168 B/row.

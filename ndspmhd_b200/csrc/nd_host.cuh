@@ -29,7 +29,6 @@ void register_rows(nd_ctx *c) {
   R1(dens); R1(uu); R1(pr); R1(spsound); R3(Bfield);
   R3(force); R1(dudt); R1(dendt); R3(dBevoldt); R3(daldt); R1(dpsidt); R3(gradpsi); R1(divB); R3(curlB); R3(graddivv); R1(del2u);
   v.push_back({(void **)&c->p32, sizeof(float4)});
-  v.push_back({(void **)&c->rec, 4 * sizeof(double4)});
   R1(srho); R4(posh); R4(vm); R4(posm); R4(bpsi); R4(thermo); R4(gal); R4(sF); R4(sdB); R4(sC); R4(sP); R4(sV);
   RI(typ); RI(perm); RI(permtmp); RI(inv); RI(cellOf); RI(cellOfOrig); RI(redo); RI(list); RI(ghostcount);
   if (c->o.onef_dust) {
@@ -122,9 +121,27 @@ bool any_ghost_bound(const nd_ctx *c) { for (int d = 0; d < c->ndim; d++) if (lo
 bool any_fixed_bound(const nd_ctx *c) { for (int d = 0; d < c->ndim; d++) if (c->o.ibound[d] == 1) return true; return false; }
 bool has_copies(const nd_ctx *c) { return any_ghost_bound(c) || c->has_comm; }
 
+#define NCCLCHK(call)                                                                                                   \
+  do {                                                                                                                  \
+    int r_ = (call);                                                                                                    \
+    if (r_ != 0) return set_err(c, ND_ERR_COMM, std::string(#call) + ": " + (c->nccl_api->GetErrorString ? c->nccl_api->GetErrorString(r_) : "nccl error")); \
+  } while (0)
+
 int comm_allreduce(nd_ctx *c, double *v, int n, int op) {
   if (!c->has_comm) return 0;
+  if (c->nccl) {   // native: H2D of the n doubles, ncclAllReduce on the compute stream, store to pinned memory, one synchronise
+    if (n > 16) return set_err(c, ND_ERR_INVALID_ARG, "comm_allreduce: at most 16 values");
+    for (int k = 0; k < n; k++) c->h_comm[k] = v[k];
+    CU(cudaMemcpyAsync(c->d_comm, c->h_comm, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    NCCLCHK(c->nccl_api->AllReduce(c->d_comm, c->d_comm, (size_t)n, ND_NCCL_FLOAT64, op == 0 ? ND_NCCL_MAX : op == 1 ? ND_NCCL_MIN : ND_NCCL_SUM, c->nccl, c->stream));
+    SMALL_D2H(c, c->h_comm + 16, c->d_comm, sizeof(double) * n);
+    CU(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < n; k++) v[k] = c->h_comm[16 + k];
+    c->n_allreduce++;
+    return 0;
+  }
   if (c->comm.allreduce(c->comm.user, v, n, op)) return set_err(c, ND_ERR_COMM, "allreduce callback failed");
+  c->n_allreduce++;
   return 0;
 }
 
@@ -171,6 +188,21 @@ template <class T> int grow_buf(nd_ctx *c, T **p, size_t *cap, size_t need) {
 int halo_sendrecv(nd_ctx *c, const long long sb[2], const long long rb[2]) {
   void *const sbuf[2] = {c->sendbuf[0], c->sendbuf[1]};
   void *const rbuf[2] = {c->recvbuf[0], c->recvbuf[1]};
+  c->halo_bytes_sent += sb[0] + sb[1];
+  if (c->nccl) {
+    // Grouped point-to-point on the compute stream, after the pack kernels and before the unpack kernels.  Posting order
+    // [send->right, send->left, recv<-left, recv<-right]: on a ring of two ranks both neighbours are the same peer, and NCCL matches the
+    // sends and receives between one pair of ranks in posting order -- the peer's first send (to ITS right = my left side) meets my first
+    // receive (from my left).
+    const int nr = c->comm.nranks, left = (c->comm.rank - 1 + nr) % nr, right = (c->comm.rank + 1) % nr;
+    NCCLCHK(c->nccl_api->GroupStart());
+    if (sb[1] > 0) NCCLCHK(c->nccl_api->Send(sbuf[1], (size_t)sb[1], ND_NCCL_CHAR, right, c->nccl, c->stream));
+    if (sb[0] > 0) NCCLCHK(c->nccl_api->Send(sbuf[0], (size_t)sb[0], ND_NCCL_CHAR, left, c->nccl, c->stream));
+    if (rb[0] > 0) NCCLCHK(c->nccl_api->Recv(rbuf[0], (size_t)rb[0], ND_NCCL_CHAR, left, c->nccl, c->stream));
+    if (rb[1] > 0) NCCLCHK(c->nccl_api->Recv(rbuf[1], (size_t)rb[1], ND_NCCL_CHAR, right, c->nccl, c->stream));
+    NCCLCHK(c->nccl_api->GroupEnd());
+    return 0;
+  }
   if (c->comm.sendrecv(c->comm.user, sbuf, sb, rbuf, rb, (void *)c->stream)) return set_err(c, ND_ERR_COMM, "sendrecv callback failed");
   return 0;
 }
@@ -212,7 +244,17 @@ int halo_exchange_inputs(nd_ctx *c) {
   }
   const long long rec = 8LL * (c->ndim + 14) + 4;
   long long sb[2] = {c->nsend[0] * rec, c->nsend[1] * rec}, rb[2] = {0, 0};
-  if (c->comm.sendrecv_counts(c->comm.user, sb, rb)) return set_err(c, ND_ERR_COMM, "sendrecv_counts callback failed");
+  if (c->nccl) {   // byte counts of every rank by one all-gather; mine come from my left neighbour's right side and vice versa
+    const int nr_ = c->comm.nranks;
+    long long *h = reinterpret_cast<long long *>(c->h_comm);          // pinned: [0,2) mine, [2, 2 + 2 nranks) everybody's
+    h[0] = sb[0]; h[1] = sb[1];
+    CU(cudaMemcpyAsync(c->d_comm, h, sizeof(long long) * 2, cudaMemcpyHostToDevice, c->stream));
+    NCCLCHK(c->nccl_api->AllGather(c->d_comm, c->d_comm + 2, 2, ND_NCCL_INT64, c->nccl, c->stream));
+    SMALL_D2H(c, h + 2, c->d_comm + 2, sizeof(long long) * 2 * nr_);
+    CU(cudaStreamSynchronize(c->stream));
+    const int left = (rank - 1 + nr_) % nr_, right = (rank + 1) % nr_;
+    rb[0] = h[2 + 2 * left + 1]; rb[1] = h[2 + 2 * right + 0];
+  } else if (c->comm.sendrecv_counts(c->comm.user, sb, rb)) return set_err(c, ND_ERR_COMM, "sendrecv_counts callback failed");
   if (rb[0] % rec || rb[1] % rec) return set_err(c, ND_ERR_COMM, "halo record size mismatch between ranks");
   c->nrecv[0] = (int)(rb[0] / rec); c->nrecv[1] = (int)(rb[1] / rec);
   for (int side = 0; side < 2; side++) {
@@ -647,7 +689,6 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
     GA.alphaB_ghost = (o.imhd != 0 && o.iavlim[2] == 2 && any_ghost_bound(c) && !all3) ? c->alphaB_in : nullptr;
   }
   GA.posh = c->posh; GA.vm = c->vm; GA.bpsi = c->bpsi; GA.thermo = c->thermo; GA.gal = c->gal; GA.npart = c->npart; GA.ntotal = nt; GA.imhd = o.imhd;
-  GA.rec = (ND_RATES_QUAD && !o.onef_dust) ? c->rec : nullptr;
   GA.stress_key = c->red + RED_STRESS; GA.imagforce = o.imagforce; GA.srho = c->srho; GA.pext = o.pext; GA.err = c->flags + 1;
   GA.Bconstmax = std::max(o.Bconst[0], std::max(o.Bconst[1], o.Bconst[2]));
   LAUNCH(c, k_rates_gather, nblocks(nt, 256), 256, 0, GA);
@@ -658,7 +699,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
     O.stressmax = dkey_inv(c->h_red[0]);
     if (int e = comm_allreduce(c, &O.stressmax, 1, 0)) return e;
   }
-  RatesIn I; I.bpsi = c->bpsi; I.thermo = c->thermo; I.gal = c->gal; I.srho = c->srho; I.dusta = c->dusta; I.dustb = c->dustb; I.rec = c->rec;
+  RatesIn I; I.bpsi = c->bpsi; I.thermo = c->thermo; I.gal = c->gal; I.srho = c->srho; I.dusta = c->dusta; I.dustb = c->dustb;
   RatesSums S; S.F = c->sF; S.dB = c->sdB; S.C = c->sC; S.P = c->sP; S.V = c->sV; S.D = c->sD;
   RatesRed R;
   R.dtcourant_min = c->red + RED_DTC; R.vsigmax_max = c->red + RED_VSIG; R.dtav_min = c->red + RED_DTAV; R.ts_min = c->red + RED_TS;

@@ -490,7 +490,7 @@ __global__ void k_take_column(const double *a, int stride, int col, double *out,
 // =====================================================================================================
 struct RGatherArgs {
   const int *perm, *ireal; const double *hh, *pmass, *rho, *pr, *spsound, *uu, *gradh, *alpha, *psi, *Bfield;
-  double4 *posh, *vm, *bpsi, *thermo, *gal, *rec; float4 *p32; double hhmax1; double *srho; int npart, ntotal, imhd; unsigned long long *stress_key; int imagforce; double Bconstmax, pext;
+  double4 *posh, *vm, *bpsi, *thermo, *gal; float4 *p32; double hhmax1; double *srho; int npart, ntotal, imhd; unsigned long long *stress_key; int imagforce; double Bconstmax, pext;
   int *err;
   // one-fluid dust (dusta NULL otherwise)
   const double *dustfrac, *deltav, *rhogas, *rhodust; double4 *dusta; double2 *dustb; int use_smoothed_rhodust;
@@ -506,15 +506,11 @@ __global__ void k_rates_gather(RGatherArgs A) {
     const int st = (r < A.npart) ? r : A.ireal[r] - 1;
     const double h = A.hh[st], rho = A.rho[st];
     if (h <= 0.) atomicCAS(A.err, 0, ND_ERR_H_NONPOSITIVE);                         // :384-387
-    double4 ph = A.posh[s], vmass = A.vm[s];
-    ph.w = 1.0 / h; vmass.w = A.pmass[st];
-    A.posh[s].w = ph.w;
+    A.posh[s].w = 1.0 / h;
     A.p32[s].w = screen_h2(h, A.hhmax1);
-    A.vm[s].w = vmass.w;
+    A.vm[s].w = A.pmass[st];
     A.srho[s] = rho;
-    const double4 th = make_double4(1.0 / rho, fmax(A.pr[st] - A.pext, 0.), A.spsound[st], A.uu[st]);   // rho1i, :325; pri = max(pr - pext, 0), :328
-    A.thermo[s] = th;
-    double4 bp = make_double4(0., 0., 0., 0.);
+    A.thermo[s] = make_double4(1.0 / rho, fmax(A.pr[st] - A.pext, 0.), A.spsound[st], A.uu[st]);   // rho1i, :325; pri = max(pr - pext, 0), :328
     A.gal[s] = make_double4(A.gradh[st], A.alpha[(size_t)st * 3], A.alpha[(size_t)st * 3 + 1],
                             (A.alphaB_ghost && r >= A.npart) ? A.alphaB_ghost[st] : A.alpha[(size_t)st * 3 + 2]);
     if (A.dusta) {                                                                  // :344-356
@@ -524,14 +520,9 @@ __global__ void k_rates_gather(RGatherArgs A) {
     }
     if (A.imhd != 0) {
       const double bx = A.Bfield[(size_t)st * 3], by = A.Bfield[(size_t)st * 3 + 1], bz = A.Bfield[(size_t)st * 3 + 2];
-      bp = make_double4(bx, by, bz, A.psi[st]);
-      A.bpsi[s] = bp;
+      A.bpsi[s] = make_double4(bx, by, bz, A.psi[st]);
       const double B2i = (bx * bx + by * by) + bz * bz;
       stress = fmax(fmax(0.5 * B2i - A.pr[st], 0.), A.Bconstmax);                   // :240-241
-    }
-    if (A.rec) {   // the packed neighbour record of the pair kernel: the four sectors of a slot in one 128-byte line
-      double4 *r4 = A.rec + 4 * (size_t)s;
-      st4(r4, ph); st4(r4 + 1, vmass); st4(r4 + 2, th); st4(r4 + 3, bp);
     }
   }
   if (A.imhd != 0) {                                                                // stressmax over 1..ntotal, :231-245

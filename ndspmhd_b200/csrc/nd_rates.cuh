@@ -25,7 +25,6 @@ struct RatesIn {
   const double4 *bpsi;     // {Bx,By,Bz,psi}
   const double4 *thermo;   // {1/rho, max(pr - pext, 0), spsound, uu}   (1/rho correctly rounded: rho1i = 1./rhoi, ratesND_mhd.f90:325)
   const double4 *gal;      // {gradh, alpha, alphau, alphaB}
-  const double4 *rec;      // [4*slot + 0..3] = {posh, vm, thermo, bpsi} of the slot: one 128-byte line a neighbour (quad-cooperative loads)
   const double *srho;      // rho by sorted slot (drag and phantom-AV branches only)
   const double4 *dusta;    // one-fluid dust: {dustfrac, deltav xyz}
   const double2 *dustb;    // one-fluid dust: {rhogas, rhodust} (smoothed sums or rho*(1-eps), rho*eps: ratesND_mhd.f90:346-352)
@@ -54,9 +53,6 @@ __device__ __forceinline__ double fmax_nonneg(double a, double b) { return __dou
 #define ND_FMAX(a, b) fmax_nonneg(a, b)
 #ifndef ND_RATES_MINB
 #define ND_RATES_MINB 2
-#endif
-#ifndef ND_RATES_QUAD
-#define ND_RATES_QUAD 1   // quad-cooperative loads of the packed neighbour record (rates_pair_kernel); 0 = per-lane gathers of the five records
 #endif
 #ifndef ND_RATES_BLOCK
 #define ND_RATES_BLOCK 128
@@ -481,50 +477,6 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
     }
   };
 
-#if ND_RATES_QUAD
-  if (!ONEF) {
-    // Quad-cooperative record loads.  A per-lane 32-byte gather costs the L1 one wavefront per lane and instruction (every lane hits
-    // another 128-byte line: 5 records x ~22 distinct lines a trip, and the queue of those wavefronts -- not DRAM -- was the latency the
-    // 8 resident warps could not hide).  Here the four sectors {posh, vm, thermo, bpsi} of a neighbour lie in ONE 128-byte line
-    // (I.rec), and the 4 lanes of a quad fetch it together: in load m every lane of the quad reads the record of member m's neighbour,
-    // lane q its sector q^m -- one line per quad and instruction, 8 lines a warp instead of ~22.  Lane q then holds R[m] = sector q^m
-    // of member m's record; two levels of conditional swaps give P[j] = R[j^q] = sector j of member (q^j)'s record, and
-    // S[j] = shfl_xor(P[j], j) hands every lane sector j of its OWN neighbour.  64 SEL + 24 SHFL a trip for 55 fewer L1 wavefronts.
-    // The gal record (gradh, alphas) is a fifth sector and stays a per-lane gather.  The trip count is the warp's longest list
-    // (what the divergent per-lane loop amounted to); finished lanes keep loading their last entry and skip the body.
-    const unsigned *col = L.nbr + ((size_t)(tix >> 5) * L.lmax) * 32 + (tix & 31);
-    const int q = lane & 3, qbase = lane & ~3, last = cnt - 1;
-    int cntmax = cnt;
-    for (int o = 16; o; o >>= 1) cntmax = max(cntmax, __shfl_xor_sync(FULL, cntmax, o));
-    auto entry = [&](int n) { return cnt > 0 ? (int)__ldcs(col + (size_t)min(n, last) * 32) : 0; };   // lanes without a list point at slot 0
-    int k = entry(0), k1 = entry(1);
-    double4 R0, R1, R2, R3, gn;
-    auto fetch = [&](int kme) {
-      const int k_0 = __shfl_sync(FULL, kme, qbase), k_1 = __shfl_sync(FULL, kme, qbase + 1), k_2 = __shfl_sync(FULL, kme, qbase + 2),
-                k_3 = __shfl_sync(FULL, kme, qbase + 3);
-      R0 = ld4(I.rec + 4 * (size_t)k_0 + q); R1 = ld4(I.rec + 4 * (size_t)k_1 + (q ^ 1)); R2 = ld4(I.rec + 4 * (size_t)k_2 + (q ^ 2));
-      R3 = ld4(I.rec + 4 * (size_t)k_3 + (q ^ 3));
-      gn = ld4(I.gal + kme);
-    };
-    auto sel4 = [](bool c, const double4 &a, const double4 &b) { return c ? a : b; };
-    auto xor4 = [](const double4 &v, int m) {
-      return make_double4(__shfl_xor_sync(FULL, v.x, m), __shfl_xor_sync(FULL, v.y, m), __shfl_xor_sync(FULL, v.z, m), __shfl_xor_sync(FULL, v.w, m));
-    };
-    fetch(k);
-#pragma unroll 1
-    for (int n = 0; n < cntmax; n++) {
-      const int k2 = entry(n + 2);
-      const bool b0 = q & 1, b1 = q & 2;
-      const double4 T0 = sel4(b0, R1, R0), T1 = sel4(b0, R0, R1), T2 = sel4(b0, R3, R2), T3 = sel4(b0, R2, R3);   // T[j] = R[j ^ (q&1)]
-      const double4 pc = sel4(b1, T2, T0);                                                                         // P[j] = T[j ^ (q&2)]
-      const double4 vc = xor4(sel4(b1, T3, T1), 1), tc = xor4(sel4(b1, T0, T2), 2), bc = xor4(sel4(b1, T1, T3), 3);
-      const double4 gc = gn;
-      fetch(k1);
-      if (n < cnt) body(k, pc, vc, tc, gc, bc);
-      k = k1; k1 = k2;
-    }
-  } else
-#endif
   if (cnt > 0) {
     const unsigned *col = L.nbr + ((size_t)(tix >> 5) * L.lmax) * 32 + (tix & 31);
     const double4 zero4 = make_double4(0., 0., 0., 0.);

@@ -34,6 +34,7 @@ EXPORTS = [
     "ndspmhd_b200_host_alloc", "ndspmhd_b200_host_free", "ndspmhd_b200_last_timings", "ndspmhd_b200_launch_count",
     "ndspmhd_b200_stream", "ndspmhd_b200_rates_pairs", "ndspmhd_b200_rewind", "ndspmhd_b200_set_comm", "ndspmhd_b200_row_counts", "ndspmhd_b200_selftest_math", "ndspmhd_b200_derivs_host",
     "ndspmhd_b200_step", "ndspmhd_b200_download_state", "ndspmhd_b200_evwrite", "ndspmhd_b200_get_curl",
+    "ndspmhd_b200_nccl_unique_id", "ndspmhd_b200_set_comm_nccl", "ndspmhd_b200_comm_stats",
 ]
 
 
@@ -85,6 +86,9 @@ def load():
     L.ndspmhd_b200_download_state.argtypes = [vp, C.POINTER(NdStateOut), C.c_int]
     L.ndspmhd_b200_evwrite.argtypes = [vp, C.POINTER(NdEvwrite)]
     L.ndspmhd_b200_get_curl.argtypes = [vp, C.c_int, _DP, _DP, _DP, C.c_int]
+    L.ndspmhd_b200_nccl_unique_id.argtypes = [C.c_char_p]
+    L.ndspmhd_b200_set_comm_nccl.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_longlong]
+    L.ndspmhd_b200_comm_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     _LIB = L
     return L
 

@@ -244,6 +244,28 @@ def attach(hot, comm: SlabComm, slab_lo: float, slab_hi: float, nglobal: int) ->
     hot._chk(L.ndspmhd_b200_set_comm(hot.ctx, C.byref(nc)))
 
 
+def attach_nccl(hot, rank: int, nranks: int, slab_lo: float, slab_hi: float, nglobal: int, group=None) -> None:
+    """The native transport (ndspmhd_b200_set_comm_nccl): the library runs its collectives itself over NCCL on its own stream; the host
+    only carries the 128-byte communicator id from rank 0 to the others (here through torch.distributed's object broadcast)."""
+    import torch.distributed as dist
+
+    L = hot.L
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        hot._chk(L.ndspmhd_b200_nccl_unique_id(buf))
+    obj = [buf.raw]
+    dist.broadcast_object_list(obj, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    hot._chk(L.ndspmhd_b200_set_comm_nccl(hot.ctx, obj[0], rank, nranks, slab_lo, slab_hi, nglobal))
+    hot._comm = "nccl"
+
+
+def comm_stats(hot):
+    """(all-reduces issued, halo payload bytes sent by this rank) since the context was created -- either transport."""
+    a, b = C.c_longlong(), C.c_longlong()
+    hot.L.ndspmhd_b200_comm_stats(hot.ctx, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
 def row_counts(hot):
     a, b, c = C.c_int(), C.c_int(), C.c_int()
     hot.L.ndspmhd_b200_row_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]

@@ -81,8 +81,12 @@ def run(args, cfg, workload, UNIT, config_dict, ClockSampler, measured_peaks):
     del p0
     guess = np.array(p.arrays["hh"], copy=True)
     hot = lib.Hotpath(o, 3, local)
-    comm = slab.SlabComm(device="cuda")
-    slab.attach(hot, comm, lo, hi, nglobal)
+    native = args.transport == "nccl"
+    if native:      # the library drives NCCL itself (nd_nccl.cuh); torch.distributed only carries the communicator id and the timing barriers
+        slab.attach_nccl(hot, rank, world, lo, hi, nglobal)
+    else:           # host-callback transport over torch.distributed (the portable route, what an MPI host would supply)
+        comm = slab.SlabComm(device="cuda")
+        slab.attach(hot, comm, lo, hi, nglobal)
     stream = torch.cuda.ExternalStream(hot.stream(), device=local)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     mask = abi.DL_DENSITY | abi.DL_PRIM | abi.DL_RATES
@@ -138,10 +142,11 @@ def run(args, cfg, workload, UNIT, config_dict, ClockSampler, measured_peaks):
     clocks = ClockSampler(local)
     clocks.start()
     l0 = hot.launch_count()
-    sb0 = comm.bytes_sent
+    ar0, sb0 = slab.comm_stats(hot)
     ms, s = timed(step, args.steps)
     launches = hot.launch_count() - l0
-    halo_bytes = torch.tensor([float(comm.bytes_sent - sb0) / args.steps], dtype=torch.float64, device="cuda")
+    ar1, sb1 = slab.comm_stats(hot)
+    halo_bytes = torch.tensor([float(sb1 - sb0) / args.steps], dtype=torch.float64, device="cuda")
     dist.all_reduce(halo_bytes, op=dist.ReduceOp.SUM)
     ck = clocks.stop()
     phases = hot.timings()
@@ -173,7 +178,9 @@ def run(args, cfg, workload, UNIT, config_dict, ClockSampler, measured_peaks):
             "roofline": {"bound": "hbm", "kernel": "rates_pair_kernel<3,MHD,FAST> (per rank, max over ranks)", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": pair_ms},
             "phases_ms": dict(zip(["link", "density", "c2p_gather", "rates_pair", "rates_final"], [float(v) for v in ph.tolist()[:5]])),
-            "comm": {"allreduces_per_step": comm.n_allreduce // max(1, args.steps + args.warmup + 2 * (2 + e2e_steps)), "backend": "nccl send/recv + all_reduce"},
+            "comm": {"allreduces_per_step": (ar1 - ar0) // max(1, args.steps),
+                     "transport": "native: ncclAllReduce / grouped ncclSend+ncclRecv / ncclAllGather issued by the library on its stream" if native
+                                  else "host callbacks (nd_comm) over torch.distributed NCCL"},
             "parity_vs_single": check,
         }
         print(json.dumps(line), flush=True)

@@ -355,3 +355,17 @@ def test_big_matches_oracle_on_a_sampled_subvolume(big):
     o2.want_aux = 0
     so, _ = oracle.derivs(o2, p2)
     parity.assert_parity(p, p2, s, so, o2, aux=False)
+
+
+@pytest.mark.parametrize("name", ["briowu1d", "sod1d", "ot3d_glass", "ot3d_glass_noaux", "dustybox3d", "onefluid_dust3d"])
+def test_pipelined_derivs_host_parity(name):
+    """ndspmhd_b200_derivs_host (copies overlapped with the kernels) against the oracle, including what only this entry point does: density
+    outputs downloaded while cons2prim and the rates run (fixed particles: after cons2prim, which gives them their partner's gradgradh)."""
+    make, aux = CASES[name]
+    o, p = make()
+    o.device_ghosts = 1
+    o.want_aux = aux
+    po, pg = p.copy(), p.copy()
+    so, _ = oracle.derivs(o, po)
+    sg = lib.derivs_host(o, pg, pipelined=True)
+    parity.assert_parity(pg, po, sg, so, o, aux=bool(aux))

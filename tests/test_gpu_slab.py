@@ -12,11 +12,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("transport", ["nccl", "callbacks"])
 @pytest.mark.parametrize("nranks", [2, 4])
-def test_slab_decomposition_matches_single_gpu(nranks):
+def test_slab_decomposition_matches_single_gpu(nranks, transport):
     if lib.device_count() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29530 + nranks), os.path.join(ROOT, "tools", "slab_check.py"), "32"]
+           "--master-port", str(29530 + nranks), os.path.join(ROOT, "tools", "slab_check.py"), "32", transport]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
-    assert r.returncode == 0 and "SLAB CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

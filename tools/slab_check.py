@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N tools/slab_check.py [nx]: slab-decomposed derivs on N GPUs vs the single-GPU result and the oracle."""
+"""torchrun --nproc-per-node N tools/slab_check.py [nx] [nccl|callbacks]: slab-decomposed derivs on N GPUs vs the single-GPU result and the oracle."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -11,6 +11,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nx = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+    transport = sys.argv[2] if len(sys.argv) > 2 else "nccl"      # "nccl": the library's own NCCL calls; "callbacks": nd_comm over torch.distributed
     ok = True
     for name, kw in [("ot3d_glass", dict(ndim=3, nx=nx, zfrac=0.25, perturb_amp=0.2, evolved=True)),
                      ("ot3d_small_h", dict(ndim=3, nx=nx, zfrac=0.25, perturb_amp=0.3, evolved=True)),
@@ -20,8 +21,11 @@ def main():
         if name == "ot3d_small_h":
             pl.hh[: pl.npart] *= 0.6          # forces relinks (h grows past hhmax) and several `density` rounds over all particles
         hot = lib.Hotpath(o, pl.ndim, local)
-        comm = slab.SlabComm(device="cuda")
-        slab.attach(hot, comm, float(info["edges"][rank]), float(info["edges"][rank + 1]), int(info["nglobal"]))
+        if transport == "nccl":
+            slab.attach_nccl(hot, rank, world, float(info["edges"][rank]), float(info["edges"][rank + 1]), int(info["nglobal"]))
+        else:
+            comm = slab.SlabComm(device="cuda")
+            slab.attach(hot, comm, float(info["edges"][rank]), float(info["edges"][rank + 1]), int(info["nglobal"]))
         hot.upload(pl)
         s = hot.derivs()
         hot.download(pl)
@@ -60,7 +64,7 @@ def main():
             print({k: (s[k], sg[k]) for k in ("dtcourant", "dtforce", "dtav", "vsigmax", "stressmax", "fhmax", "hhmax", "itsdensity", "nneigh_min", "nneigh_max", "ncalctotal", "nrelink")})
     dist.barrier(); dist.destroy_process_group()
     if rank == 0:
-        print("SLAB CHECK", "PASSED" if ok else "FAILED")
+        print(f"SLAB CHECK ({transport}, light={os.environ.get('NDSPMHD_B200_SLAB_LIGHT', '0')})", "PASSED" if ok else "FAILED")
     sys.exit(0 if ok else 1)
 
 if __name__ == "__main__":
