@@ -287,6 +287,18 @@ int ndspmhd_b200_nccl_unique_id(unsigned char id[128]);
 int ndspmhd_b200_set_comm_nccl(nd_ctx *c, const unsigned char id[128], int rank, int nranks, double slab_lo, double slab_hi, long long nglobal);
 /* counters since create: all-reduces issued (either transport), halo payload bytes this rank sent */
 int ndspmhd_b200_comm_stats(const nd_ctx *c, long long *n_allreduce, long long *halo_bytes_sent);
+/*
+ * Row ids.  upload gives every row its row number; a slab-decomposed run sets global ids after upload.  ndspmhd_b200_step on a
+ * slab-decomposed context re-owns the rows whose x left [slab_lo, slab_hi) after the predictor and the periodic wrap
+ * (src/stepND_leapfrog_mhd.f90:145, src/boundaryND.f90:65-93): they travel to the adjacent rank with their evolved state and the
+ * integrator's `*in` copies, holes are filled from the tail of the own rows and arrivals are appended -- so row numbers change and the
+ * ids are how a caller follows a particle.  Moving farther than the adjacent slab in one step is ND_ERR_INVALID_ARG; fixed-particle
+ * boundaries are refused on slab contexts (fixed rows are tied to their partners' row numbers).
+ */
+int ndspmhd_b200_set_row_ids(nd_ctx *c, const long long *ids, int n);
+int ndspmhd_b200_get_row_ids(nd_ctx *c, long long *ids, int cap);
+/* counters since create: rows that left / arrived, payload bytes this rank sent for them */
+int ndspmhd_b200_migration_stats(const nd_ctx *c, long long *rows_out, long long *rows_in, long long *bytes_sent);
 /* rows after the last link: own rows [0,nown), halo rows [nown,nsrc), ghosts [nsrc,ntotal) */
 int ndspmhd_b200_row_counts(const nd_ctx *c, int *nown, int *nsrc, int *ntotal);
 

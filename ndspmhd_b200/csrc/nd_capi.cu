@@ -83,7 +83,9 @@ struct nd_ctx {
   nd_comm comm; bool has_comm = false; bool slab_too_narrow = false;
   // native NCCL transport (nd_nccl.cuh): communicator, a 64-double device block and its pinned mirror for the small collectives
   nd_ncclComm_t nccl = nullptr; NcclApi *nccl_api = nullptr; double *d_comm = nullptr, *h_comm = nullptr;
-  long long n_allreduce = 0, halo_bytes_sent = 0;
+  long long n_allreduce = 0, halo_bytes_sent = 0, migrated_bytes_sent = 0, nmigrated_out = 0, nmigrated_in = 0;
+  std::vector<double> edges;   // every rank's slab faces (migration)
+  long long *gid = nullptr;    // row ids (ndspmhd_b200_set_row_ids; rows keep theirs when they migrate between slabs)
   int *sendlist[2] = {nullptr, nullptr}; int sendcap[2] = {0, 0}, nsend[2] = {0, 0}, nrecv[2] = {0, 0};
   void *sendbuf[2] = {nullptr, nullptr}, *recvbuf[2] = {nullptr, nullptr}; size_t sendbufcap[2] = {0, 0}, recvbufcap[2] = {0, 0};
   cudaEvent_t ev[8];
@@ -372,9 +374,36 @@ int ndspmhd_b200_upload(nd_ctx *c, const nd_arrays *a, int npart, int ntotal, in
   if (int e = ensure_capacity(c, want, 0)) return e;
   if (int e = upload_group(c, a, (size_t)ntotal, 1, c->stream)) return e;
   if (int e = upload_group(c, a, (size_t)ntotal, 2, c->stream)) return e;
+  LAUNCH(c, k_iota_ll, nblocks(npart, 256), 256, 0, c->gid, npart, 0LL);   // default row ids: the row number
   CU(cudaStreamSynchronize(c->stream));
   c->npart = npart; c->ntotal = ntotal; c->nown = npart;
   c->uploaded = true; c->linked = c->density_done = c->prim_done = c->rates_done = false;
+  return 0;
+}
+
+int ndspmhd_b200_set_row_ids(nd_ctx *c, const long long *ids, int n) {
+  if (!c || !ids) return ND_ERR_INVALID_ARG;
+  if (!c->uploaded || n != c->nown) return set_err(c, ND_ERR_STATE, "set_row_ids: call after upload with n = the rows uploaded");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(c->gid, ids, sizeof(long long) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int ndspmhd_b200_get_row_ids(nd_ctx *c, long long *ids, int cap) {
+  if (!c || !ids) return ND_ERR_INVALID_ARG;
+  if (!c->uploaded || cap < c->nown) return set_err(c, ND_ERR_INVALID_ARG, "get_row_ids: cap < own rows");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(ids, c->gid, sizeof(long long) * (size_t)c->nown, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int ndspmhd_b200_migration_stats(const nd_ctx *c, long long *rows_out, long long *rows_in, long long *bytes_sent) {
+  if (!c) return ND_ERR_INVALID_ARG;
+  if (rows_out) *rows_out = c->nmigrated_out;
+  if (rows_in) *rows_in = c->nmigrated_in;
+  if (bytes_sent) *bytes_sent = c->migrated_bytes_sent;
   return 0;
 }
 
@@ -734,15 +763,15 @@ int ndspmhd_b200_step(nd_ctx *c, const nd_step_opts *so, double *dt_inout, nd_sc
   bool ghost_bound = false;
   for (int d = 0; d < c->ndim; d++) if (o.ibound[d] >= 2) ghost_bound = true;
   if (ghost_bound && !o.device_ghosts) return set_err(c, ND_ERR_STATE, "step on the resident state needs device_ghosts = 1 (derivs regenerates the ghosts, src/derivs.f90:78)");
-  if (c->has_comm) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "step: slab-decomposed contexts need particle migration, not available yet");
+  if (c->has_comm && any_fixed_bound(c)) return set_err(c, ND_ERR_UNSUPPORTED_OPTION, "step: slab-decomposed contexts with fixed-particle boundaries (rows tied to partner rows cannot migrate)");
   CU(cudaSetDevice(c->device));
-  const int np = c->npart;
-  const int planes = o.onef_dust ? STEP_NIN_DUST : STEP_NIN;
+  int np = c->nown;                                            // own rows (= npart without slabs; halo rows are remade by derivs)
   if (c->stepbufrows < (size_t)np) {
     if (c->stepbuf) cudaFree(c->stepbuf);
     c->stepbuf = nullptr; c->stepbufrows = 0;
-    CU(cudaMalloc(&c->stepbuf, sizeof(double) * (size_t)STEP_NIN_DUST * (size_t)np));
-    c->stepbufrows = (size_t)np;
+    const size_t rows = c->has_comm ? (size_t)np + (size_t)np / 8 + 1024 : (size_t)np;   // room for arrivals
+    CU(cudaMalloc(&c->stepbuf, sizeof(double) * (size_t)STEP_NIN_DUST * rows));
+    c->stepbufrows = rows;
   }
   auto args = [&]() {
     StepArgs A;
@@ -750,28 +779,34 @@ int ndspmhd_b200_step(nd_ctx *c, const nd_step_opts *so, double *dt_inout, nd_sc
     A.dustevol = c->dustevol; A.deltav = c->deltav;
     A.force = c->force; A.dBevoldt = c->dBevoldt; A.drhodt = c->drhodt; A.dhdt = c->dhdt; A.dendt = c->dendt; A.daldt = c->daldt; A.dpsidt = c->dpsidt;
     A.ddustevoldt = c->ddustevoldt; A.ddeltavdt = c->ddeltavdt;
-    A.itype = c->itype; A.ireal = c->ireal; A.in = c->stepbuf; A.n = (size_t)np; A.npart = np; A.ndim = c->ndim;
+    A.itype = c->itype; A.ireal = c->ireal; A.in = c->stepbuf; A.n = c->stepbufrows; A.npart = np; A.ndim = c->ndim;
     A.imhd = o.imhd; A.iresist = o.iresist; A.icty = o.icty; A.ihvar = o.ihvar; A.iener = o.iener; A.idivbzero = o.idivbzero; A.idust = o.idust; A.onef = o.onef_dust;
     for (int d = 0; d < 3; d++) { A.iavlim[d] = o.iavlim[d]; A.ibound[d] = d < c->ndim ? o.ibound[d] : 0; A.xmin[d] = o.xmin[d]; A.xmax[d] = o.xmax[d]; }
     A.dt = *dt_inout; A.damp = o.damp; A.flags = c->flags;
     return A;
   };
-  (void)planes;
   StepArgs A = args();
   LAUNCH(c, k_step_save, nblocks(np, 256), 256, 0, A);
   LAUNCH(c, k_step_predict, nblocks(np, 256), 256, 0, A);
   LAUNCH(c, k_step_boundary, nblocks(np, 256), 256, 0, A);     // src/derivs.f90:74
   c->linked = c->density_done = c->prim_done = c->rates_done = false;
-  c->ntotal = ghost_bound ? np : c->ntotal;                    // the ghost rows are stale: derivs makes new ones from rows [0,npart)
+  if (c->has_comm) {                                           // rows that left the slab change owner before the link (the corrector does not move x)
+    c->npart = c->ntotal = np;
+    if (int e = migrate_rows(c)) return e;
+    np = c->nown;
+  }
+  c->ntotal = (ghost_bound || c->has_comm) ? np : c->ntotal;   // the ghost rows are stale: derivs makes new ones from rows [0,npart)
   if (int e = ndspmhd_b200_derivs(c, s)) return e;
   A = args();                                                  // derivs may have re-allocated the arrays (more ghosts)
   LAUNCH(c, k_step_correct, nblocks(np, 256), 256, 0, A);
   LAUNCH(c, k_step_boundary, nblocks(np, 256), 256, 0, A);     // :216
   if (int e = sync_flags(c)) return e;
-  if (c->h_flags[1]) {
-    const int code = c->h_flags[1];
+  double bad = c->h_flags[1] ? 1. : 0.;
+  if (int e = comm_allreduce(c, &bad, 1, 0)) return e;         // every rank leaves together
+  if (bad != 0.) {
+    const int code = c->h_flags[1] ? c->h_flags[1] : ND_ERR_COMM;
     CU(cudaMemsetAsync(c->flags, 0, sizeof(int) * 16, c->stream));
-    return set_err(c, code, code == ND_ERR_H_NONPOSITIVE ? "step: hh -ve" : "step: itypebnd2 (cylindrical fixed particles) is not supported");
+    return set_err(c, code, code == ND_ERR_H_NONPOSITIVE ? "step: hh -ve" : code == ND_ERR_COMM ? "step: another rank reported an error" : "step: itypebnd2 (cylindrical fixed particles) is not supported");
   }
   // new timestep, :239-253
   if (!so->dtfixed) *dt_inout = std::min(std::min(so->C_force * c->sc.dtforce, so->C_cour * c->sc.dtcourant), std::min(0.9 * c->sc.dtdrag, so->C_force * c->sc.dtvisc));
@@ -782,9 +817,9 @@ int ndspmhd_b200_step(nd_ctx *c, const nd_step_opts *so, double *dt_inout, nd_sc
 int ndspmhd_b200_download_state(nd_ctx *c, const nd_state_out *st, int idim) {
   if (!c || !st) return ND_ERR_INVALID_ARG;
   if (!c->uploaded) return set_err(c, ND_ERR_STATE, "download_state before upload");
-  if (idim < c->npart) return set_err(c, ND_ERR_INVALID_ARG, "download_state: idim < npart");
+  if (idim < c->nown) return set_err(c, ND_ERR_INVALID_ARG, "download_state: idim < npart");
   CU(cudaSetDevice(c->device));
-  const size_t n = (size_t)c->npart, D = sizeof(double);
+  const size_t n = (size_t)c->nown, D = sizeof(double);   // own rows (slab contexts: ndspmhd_b200_row_counts tells how many there are now)
   auto dn = [&](void *dst, const void *src, size_t bytes) -> cudaError_t { return (dst && src) ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess; };
   CU(dn(st->x, c->x, D * c->ndim * n)); CU(dn(st->vel, c->vel, D * 3 * n)); CU(dn(st->hh, c->hh, D * n)); CU(dn(st->en, c->en, D * n));
   CU(dn(st->Bevol, c->Bevol, D * 3 * n)); CU(dn(st->alpha, c->alpha, D * 3 * n)); CU(dn(st->psi, c->psi, D * n)); CU(dn(st->rho, c->rho, D * n));

@@ -30,6 +30,7 @@ void register_rows(nd_ctx *c) {
   R3(force); R1(dudt); R1(dendt); R3(dBevoldt); R3(daldt); R1(dpsidt); R3(gradpsi); R1(divB); R3(curlB); R3(graddivv); R1(del2u);
   v.push_back({(void **)&c->p32, sizeof(float4)});
   R1(srho); R4(posh); R4(vm); R4(posm); R4(bpsi); R4(thermo); R4(gal); R4(sF); R4(sdB); R4(sC); R4(sP); R4(sV);
+  v.push_back({(void **)&c->gid, sizeof(long long)});
   RI(typ); RI(perm); RI(permtmp); RI(inv); RI(cellOf); RI(cellOfOrig); RI(redo); RI(list); RI(ghostcount);
   if (c->o.onef_dust) {
     R1(dustevol); R1(dustfrac); R3(deltav); R1(rhogas); R1(rhodust); R1(ddustevoldt); R3(ddeltavdt); R1(sdf); R4(dusta); R4(sD);
@@ -130,13 +131,13 @@ bool has_copies(const nd_ctx *c) { return any_ghost_bound(c) || c->has_comm; }
 int comm_allreduce(nd_ctx *c, double *v, int n, int op) {
   if (!c->has_comm) return 0;
   if (c->nccl) {   // native: H2D of the n doubles, ncclAllReduce on the compute stream, store to pinned memory, one synchronise
-    if (n > 16) return set_err(c, ND_ERR_INVALID_ARG, "comm_allreduce: at most 16 values");
+    if (n > 32) return set_err(c, ND_ERR_INVALID_ARG, "comm_allreduce: at most 32 values");
     for (int k = 0; k < n; k++) c->h_comm[k] = v[k];
     CU(cudaMemcpyAsync(c->d_comm, c->h_comm, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     NCCLCHK(c->nccl_api->AllReduce(c->d_comm, c->d_comm, (size_t)n, ND_NCCL_FLOAT64, op == 0 ? ND_NCCL_MAX : op == 1 ? ND_NCCL_MIN : ND_NCCL_SUM, c->nccl, c->stream));
-    SMALL_D2H(c, c->h_comm + 16, c->d_comm, sizeof(double) * n);
+    SMALL_D2H(c, c->h_comm + 32, c->d_comm, sizeof(double) * n);
     CU(cudaStreamSynchronize(c->stream));
-    for (int k = 0; k < n; k++) v[k] = c->h_comm[16 + k];
+    for (int k = 0; k < n; k++) v[k] = c->h_comm[32 + k];
     c->n_allreduce++;
     return 0;
   }
@@ -207,6 +208,25 @@ int halo_sendrecv(nd_ctx *c, const long long sb[2], const long long rb[2]) {
   return 0;
 }
 
+// byte counts of a neighbour exchange: what I send to {left, right} -> what I receive from {left, right}
+int exchange_counts(nd_ctx *c, const long long sb[2], long long rb[2]) {
+  if (c->nccl) {   // byte counts of every rank by one all-gather; mine come from my left neighbour's right side and vice versa
+    const int nr_ = c->comm.nranks, rank = c->comm.rank;
+    long long *h = reinterpret_cast<long long *>(c->h_comm);          // pinned: [0,2) mine, [2, 2 + 2 nranks) everybody's
+    h[0] = sb[0]; h[1] = sb[1];
+    CU(cudaMemcpyAsync(c->d_comm, h, sizeof(long long) * 2, cudaMemcpyHostToDevice, c->stream));
+    NCCLCHK(c->nccl_api->AllGather(c->d_comm, c->d_comm + 2, 2, ND_NCCL_INT64, c->nccl, c->stream));
+    SMALL_D2H(c, h + 2, c->d_comm + 2, sizeof(long long) * 2 * nr_);
+    CU(cudaStreamSynchronize(c->stream));
+    const int left = (rank - 1 + nr_) % nr_, right = (rank + 1) % nr_;
+    rb[0] = h[2 + 2 * left + 1]; rb[1] = h[2 + 2 * right + 0];
+    return 0;
+  }
+  long long sbc[2] = {sb[0], sb[1]};
+  if (c->comm.sendrecv_counts(c->comm.user, sbc, rb)) return set_err(c, ND_ERR_COMM, "sendrecv_counts callback failed");
+  return 0;
+}
+
 HaloPackArgs halo_args(nd_ctx *c) {
   HaloPackArgs A;
   A.ndim = c->ndim; A.x = c->x; A.vel = c->vel; A.pmass = c->pmass; A.hh = c->hh; A.en = c->en; A.Bevol = c->Bevol; A.alpha = c->alpha; A.psi = c->psi;
@@ -244,17 +264,7 @@ int halo_exchange_inputs(nd_ctx *c) {
   }
   const long long rec = 8LL * (c->ndim + 14) + 4;
   long long sb[2] = {c->nsend[0] * rec, c->nsend[1] * rec}, rb[2] = {0, 0};
-  if (c->nccl) {   // byte counts of every rank by one all-gather; mine come from my left neighbour's right side and vice versa
-    const int nr_ = c->comm.nranks;
-    long long *h = reinterpret_cast<long long *>(c->h_comm);          // pinned: [0,2) mine, [2, 2 + 2 nranks) everybody's
-    h[0] = sb[0]; h[1] = sb[1];
-    CU(cudaMemcpyAsync(c->d_comm, h, sizeof(long long) * 2, cudaMemcpyHostToDevice, c->stream));
-    NCCLCHK(c->nccl_api->AllGather(c->d_comm, c->d_comm + 2, 2, ND_NCCL_INT64, c->nccl, c->stream));
-    SMALL_D2H(c, h + 2, c->d_comm + 2, sizeof(long long) * 2 * nr_);
-    CU(cudaStreamSynchronize(c->stream));
-    const int left = (rank - 1 + nr_) % nr_, right = (rank + 1) % nr_;
-    rb[0] = h[2 + 2 * left + 1]; rb[1] = h[2 + 2 * right + 0];
-  } else if (c->comm.sendrecv_counts(c->comm.user, sb, rb)) return set_err(c, ND_ERR_COMM, "sendrecv_counts callback failed");
+  if (int e = exchange_counts(c, sb, rb)) return e;
   if (rb[0] % rec || rb[1] % rec) return set_err(c, ND_ERR_COMM, "halo record size mismatch between ranks");
   c->nrecv[0] = (int)(rb[0] / rec); c->nrecv[1] = (int)(rb[1] / rec);
   for (int side = 0; side < 2; side++) {
@@ -299,6 +309,108 @@ int halo_exchange_density(nd_ctx *c) {
     LAUNCH(c, k_halo_unpack2, nblocks(A.n, 256), 256, 0, A);
     row0 += A.n;
   }
+  return 0;
+}
+
+// ---- particle migration between slabs (ndspmhd_b200_step): rows whose x left [slab_lo, slab_hi) go to the adjacent rank ----
+int grow_stepbuf(nd_ctx *c, size_t rows, int keep) {
+  if (rows <= c->stepbufrows) return 0;
+  const size_t newrows = rows + rows / 8 + 1024;
+  double *nb = nullptr;
+  CU(cudaMalloc(&nb, sizeof(double) * (size_t)STEP_NIN_DUST * newrows));
+  if (c->stepbuf && keep > 0)   // planes keep their contents: the stride changes
+    CU(cudaMemcpy2DAsync(nb, sizeof(double) * newrows, c->stepbuf, sizeof(double) * c->stepbufrows, sizeof(double) * (size_t)keep, STEP_NIN_DUST, cudaMemcpyDeviceToDevice, c->stream));
+  if (c->stepbuf) { CU(cudaStreamSynchronize(c->stream)); cudaFree(c->stepbuf); }
+  c->stepbuf = nb; c->stepbufrows = newrows;
+  return 0;
+}
+
+MigRows mig_rows(nd_ctx *c) {
+  MigRows R;
+  int a = 0;
+  auto put = [&](double *p, int w) { R.arr[a] = p; R.width[a] = w; a++; };
+  put(c->x, c->ndim); put(c->vel, 3); put(c->pmass, 1); put(c->hh, 1); put(c->en, 1); put(c->Bevol, 3); put(c->alpha, 3); put(c->psi, 1); put(c->rho, 1);
+  if (c->o.onef_dust) { put(c->dustevol, 1); put(c->deltav, 3); }
+  R.narr = a;
+  for (; a < 12; a++) { R.arr[a] = nullptr; R.width[a] = 0; }
+  R.in = c->stepbuf; R.instride = c->stepbufrows; R.nplanes = c->o.onef_dust ? STEP_NIN_DUST : STEP_NIN;
+  R.itype = c->itype; R.gid = c->gid;
+  return R;
+}
+
+int migrate_rows(nd_ctx *c) {
+  const nd_options &o = c->o;
+  const int np = c->nown, rank = c->comm.rank, nr = c->comm.nranks;
+  const bool periodic = (o.ibound[0] == 3);
+  if ((int)c->edges.size() != nr + 1) {        // every rank's faces, once: a one-hot sum (the transport has no all-gather of doubles)
+    double v[32];
+    if (nr + 1 > 32) return set_err(c, ND_ERR_INVALID_ARG, "migration: at most 31 ranks");
+    for (int k = 0; k <= nr; k++) v[k] = 0.;
+    v[rank] = c->comm.slab_lo;
+    if (rank == nr - 1) v[nr] = c->comm.slab_hi;
+    if (int e = comm_allreduce(c, v, nr + 1, 2)) return e;
+    c->edges.assign(v, v + nr + 1);
+  }
+  const int left = (rank - 1 + nr) % nr, right = (rank + 1) % nr;
+  MigSelArgs SA;
+  SA.x = c->x; SA.itype = c->itype; SA.nown = np; SA.ndim = c->ndim;
+  SA.lo = c->edges[rank]; SA.hi = c->edges[rank + 1]; SA.hi_closed = rank == nr - 1;
+  SA.llo = c->edges[left]; SA.lhi = c->edges[left + 1]; SA.lhi_closed = left == nr - 1;
+  SA.rlo = c->edges[right]; SA.rhi = c->edges[right + 1]; SA.rhi_closed = right == nr - 1;
+  SA.left_on = (periodic || rank > 0) ? 1 : 0; SA.right_on = (periodic || rank < nr - 1) ? 1 : 0; SA.same_peer = (left == right) ? 1 : 0;
+  SA.flagL = c->cellOfOrig; SA.flagR = c->ghostcount; SA.flagAny = c->redo; SA.err = c->flags + 1;   // scratch: all rewritten by the link that follows
+  LAUNCH(c, k_migrate_flags, nblocks(np, 256), 256, 0, SA);
+  int nside[2] = {0, 0};
+  for (int side = 0; side < 2; side++) {
+    const int *flag = side == 0 ? c->cellOfOrig : c->ghostcount;
+    if (int e = exclusive_scan(c, flag, c->scanout, np)) return e;
+    SMALL_D2H(c, c->h_flags + 24, c->scanout + np, sizeof(int));
+    CU(cudaStreamSynchronize(c->stream));
+    const int n = c->h_flags[24];
+    size_t cap = (size_t)c->sendcap[side];
+    if (int e = grow_buf(c, &c->sendlist[side], &cap, (size_t)n)) return e;
+    c->sendcap[side] = (int)cap;
+    LAUNCH(c, k_halo_compact, nblocks(np, 256), 256, 0, flag, c->scanout, np, c->sendlist[side]);
+    nside[side] = n;
+  }
+  const int nl = nside[0] + nside[1], m = np - nl;
+  if (int e = exclusive_scan(c, c->redo, c->scanout, np)) return e;                       // the holes, ascending
+  LAUNCH(c, k_halo_compact, nblocks(np, 256), 256, 0, c->redo, c->scanout, np, c->list);
+  MigRows R = mig_rows(c);
+  const long long rec = 8LL * mig_nfields(R);
+  long long sb[2] = {nside[0] * rec, nside[1] * rec}, rb[2] = {0, 0};
+  if (int e = exchange_counts(c, sb, rb)) return e;
+  if (rb[0] % rec || rb[1] % rec) return set_err(c, ND_ERR_COMM, "migration record size mismatch between ranks");
+  const int na[2] = {(int)(rb[0] / rec), (int)(rb[1] / rec)};
+  for (int side = 0; side < 2; side++) {
+    char **sp = (char **)&c->sendbuf[side], **rp = (char **)&c->recvbuf[side];
+    if (int e = grow_buf(c, sp, &c->sendbufcap[side], (size_t)sb[side] + 64)) return e;
+    if (int e = grow_buf(c, rp, &c->recvbufcap[side], (size_t)rb[side] + 64)) return e;
+  }
+  for (int side = 0; side < 2; side++) {
+    MigPackArgs A; A.R = R; A.list = c->sendlist[side]; A.n = nside[side]; A.row0 = 0; A.buf = (double *)c->sendbuf[side];
+    LAUNCH(c, k_migrate_pack, nblocks(A.n, 128), 128, 0, A);
+  }
+  if (int e = halo_sendrecv(c, sb, rb)) return e;
+  c->halo_bytes_sent -= sb[0] + sb[1];                       // counted separately
+  c->migrated_bytes_sent += sb[0] + sb[1];
+  if (nl > 0) {                                              // fill the holes below m from the staying rows of the tail [m, np)
+    LAUNCH(c, k_migrate_tailflags, nblocks(nl, 256), 256, 0, c->redo, m, nl, c->permtmp);
+    if (int e = exclusive_scan(c, c->permtmp, c->scanout, nl)) return e;
+    LAUNCH(c, k_migrate_fill, nblocks(nl, 128), 128, 0, R, c->permtmp, c->scanout, c->list, m, nl);
+  }
+  const int nnew = m + na[0] + na[1];
+  if (int e = ensure_capacity(c, nnew + nnew / 8 + 1024, m)) return e;
+  if (int e = grow_stepbuf(c, (size_t)nnew, m)) return e;
+  R = mig_rows(c);                                           // the arrays may have moved
+  int row0 = m;
+  for (int side = 0; side < 2; side++) {
+    MigPackArgs A; A.R = R; A.list = nullptr; A.n = na[side]; A.row0 = row0; A.buf = (double *)c->recvbuf[side];
+    LAUNCH(c, k_migrate_unpack, nblocks(A.n, 128), 128, 0, A);
+    row0 += A.n;
+  }
+  c->nown = c->npart = c->ntotal = nnew;
+  c->nmigrated_out += nl; c->nmigrated_in += na[0] + na[1];
   return 0;
 }
 

@@ -252,6 +252,81 @@ __global__ void k_halo_unpack2(HaloPackArgs A) {
 }
 
 // =====================================================================================================
+// particle migration between slabs (ndspmhd_b200_step on slab-decomposed contexts).  The reference moves every particle in the predictor
+// and wraps it (src/stepND_leapfrog_mhd.f90:145, src/boundaryND.f90:65-93); with x-slabs a row whose x left [slab_lo, slab_hi) is
+// re-owned by the neighbouring rank: its whole evolved state and the integrator's `*in` planes travel, the holes are filled from the
+// tail of the own rows, arrivals are appended.  Rows carry a 64-bit id (ndspmhd_b200_set_row_ids) so a caller can follow them.
+// =====================================================================================================
+struct MigSelArgs {
+  const double *x; const int *itype; int nown, ndim;
+  double lo, hi, llo, lhi, rlo, rhi; int hi_closed, lhi_closed, rhi_closed, left_on, right_on, same_peer;   // [lo,hi) mine, neighbours' slabs; *_closed: x == hi belongs
+  int *flagL, *flagR, *flagAny, *err;
+};
+__device__ __forceinline__ bool mig_inside(double x, double lo, double hi, int closed) { return x >= lo && (x < hi || (closed && x == hi)); }
+__device__ __forceinline__ bool step_fixed_type(int it) { return it == T_BND || it == 11 || it == T_BNDDUST; }
+__global__ void k_migrate_flags(MigSelArgs A) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= A.nown) return;
+  const double xj = A.x[(size_t)j * A.ndim];
+  int fl = 0, fr = 0;
+  if (!mig_inside(xj, A.lo, A.hi, A.hi_closed)) {
+    if (step_fixed_type(A.itype[j])) atomicCAS(A.err, 0, ND_ERR_UNSUPPORTED_OPTION);          // fixed rows are tied to their partners' row numbers
+    else if (A.right_on && mig_inside(xj, A.rlo, A.rhi, A.rhi_closed)) fr = 1;
+    else if (A.left_on && mig_inside(xj, A.llo, A.lhi, A.lhi_closed)) { if (A.same_peer) fr = 1; else fl = 1; }
+    else atomicCAS(A.err, 0, ND_ERR_INVALID_ARG);                                              // farther than the adjacent slab in one step
+  }
+  A.flagL[j] = fl; A.flagR[j] = fr; A.flagAny[j] = fl | fr;
+}
+struct MigRows {
+  double *arr[12]; int width[12]; int narr;     // state arrays, `width` doubles a row
+  double *in; size_t instride; int nplanes;     // leapfrog `*in` planes
+  int *itype; long long *gid;
+};
+__host__ __device__ inline int mig_nfields(const MigRows &R) { int f = R.nplanes + 2; for (int a = 0; a < R.narr; a++) f += R.width[a]; return f; }
+struct MigPackArgs { MigRows R; const int *list; int n, row0; double *buf; };
+__global__ void k_migrate_pack(MigPackArgs A) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= A.n) return;
+  const int j = A.list[q];
+  const size_t n = A.n;
+  int f = 0;
+  for (int a = 0; a < A.R.narr; a++) for (int d = 0; d < A.R.width[a]; d++) A.buf[(f++) * n + q] = A.R.arr[a][(size_t)j * A.R.width[a] + d];
+  for (int pl = 0; pl < A.R.nplanes; pl++) A.buf[(f++) * n + q] = A.R.in[(size_t)pl * A.R.instride + j];
+  A.buf[(f++) * n + q] = (double)A.R.itype[j];
+  A.buf[(f++) * n + q] = __longlong_as_double(A.R.gid[j]);
+}
+__global__ void k_migrate_unpack(MigPackArgs A) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= A.n) return;
+  const int r = A.row0 + q;
+  const size_t n = A.n;
+  int f = 0;
+  for (int a = 0; a < A.R.narr; a++) for (int d = 0; d < A.R.width[a]; d++) A.R.arr[a][(size_t)r * A.R.width[a] + d] = A.buf[(f++) * n + q];
+  for (int pl = 0; pl < A.R.nplanes; pl++) A.R.in[(size_t)pl * A.R.instride + r] = A.buf[(f++) * n + q];
+  A.R.itype[r] = (int)A.buf[(f++) * n + q];
+  A.R.gid[r] = __double_as_longlong(A.buf[(f++) * n + q]);
+}
+// tail rows [m, m + nl) that stay: flag them; k_migrate_fill then moves the k-th of them into the k-th hole (holes ascend, the first
+// `#staying tail rows` of them lie below m)
+__global__ void k_migrate_tailflags(const int *flagAny, int m, int nl, int *tailflag) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nl) tailflag[k] = flagAny[m + k] ? 0 : 1;
+}
+__global__ void k_migrate_fill(MigRows R, const int *tailflag, const int *tailscan, const int *holes, int m, int nl) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nl || !tailflag[k]) return;
+  const int src = m + k, dst = holes[tailscan[k]];
+  for (int a = 0; a < R.narr; a++) for (int d = 0; d < R.width[a]; d++) R.arr[a][(size_t)dst * R.width[a] + d] = R.arr[a][(size_t)src * R.width[a] + d];
+  for (int pl = 0; pl < R.nplanes; pl++) R.in[(size_t)pl * R.instride + dst] = R.in[(size_t)pl * R.instride + src];
+  R.itype[dst] = R.itype[src];
+  R.gid[dst] = R.gid[src];
+}
+__global__ void k_iota_ll(long long *a, int n, long long first) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = first + i;
+}
+
+// =====================================================================================================
 // cell grid (src/linkND.f90:119-145) as a counting sort: cell index, histogram, scan, scatter, per-cell ordering
 // =====================================================================================================
 struct CellArgs { const double *x; int ntotal; double xminpart[3], dxcell; int ncellsx[3]; int *cellOfOrig, *cellCount, *flags; };

@@ -35,6 +35,7 @@ EXPORTS = [
     "ndspmhd_b200_stream", "ndspmhd_b200_rates_pairs", "ndspmhd_b200_rewind", "ndspmhd_b200_set_comm", "ndspmhd_b200_row_counts", "ndspmhd_b200_selftest_math", "ndspmhd_b200_derivs_host",
     "ndspmhd_b200_step", "ndspmhd_b200_download_state", "ndspmhd_b200_evwrite", "ndspmhd_b200_get_curl",
     "ndspmhd_b200_nccl_unique_id", "ndspmhd_b200_set_comm_nccl", "ndspmhd_b200_comm_stats",
+    "ndspmhd_b200_set_row_ids", "ndspmhd_b200_get_row_ids", "ndspmhd_b200_migration_stats",
 ]
 
 
@@ -89,6 +90,9 @@ def load():
     L.ndspmhd_b200_nccl_unique_id.argtypes = [C.c_char_p]
     L.ndspmhd_b200_set_comm_nccl.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_longlong]
     L.ndspmhd_b200_comm_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.ndspmhd_b200_set_row_ids.argtypes = [vp, C.POINTER(C.c_longlong), C.c_int]
+    L.ndspmhd_b200_get_row_ids.argtypes = [vp, C.POINTER(C.c_longlong), C.c_int]
+    L.ndspmhd_b200_migration_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     _LIB = L
     return L
 
@@ -234,6 +238,22 @@ class Hotpath:
         for n in ("x", "vel", "hh", "en", "Bevol", "alpha", "psi", "rho", "dustevol", "deltav"):
             setattr(st, n, p.ptr(n))
         self._chk(self.L.ndspmhd_b200_download_state(self.ctx, C.byref(st), p.idim))
+
+    def set_row_ids(self, ids: np.ndarray) -> None:
+        """Global ids of the uploaded rows (they travel with a row when it migrates to another slab in `step`)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        self._chk(self.L.ndspmhd_b200_set_row_ids(self.ctx, ids.ctypes.data_as(C.POINTER(C.c_longlong)), ids.size))
+
+    def get_row_ids(self, cap: int) -> np.ndarray:
+        ids = np.zeros(cap, np.int64)
+        self._chk(self.L.ndspmhd_b200_get_row_ids(self.ctx, ids.ctypes.data_as(C.POINTER(C.c_longlong)), cap))
+        return ids
+
+    def migration_stats(self):
+        """(rows that left this rank, rows that arrived, payload bytes sent) since the context was created."""
+        a, b, c_ = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        self.L.ndspmhd_b200_migration_stats(self.ctx, C.byref(a), C.byref(b), C.byref(c_))
+        return a.value, b.value, c_.value
 
     def evwrite(self) -> dict:
         """The sums of `evwrite` (src/evwrite_mhd.f90:27) over the resident state, as device reductions."""

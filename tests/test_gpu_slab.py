@@ -21,3 +21,16 @@ def test_slab_decomposition_matches_single_gpu(nranks, transport):
            "--master-port", str(29530 + nranks), os.path.join(ROOT, "tools", "slab_check.py"), "32", transport]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("transport", ["nccl", "callbacks"])
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_slab_step_with_row_migration_matches_single_gpu(nranks, transport):
+    """`ndspmhd_b200_step` on slab contexts: three leapfrog steps with rows changing owner (src/stepND_leapfrog_mhd.f90:145,
+    src/boundaryND.f90:65-93) equal the single-GPU steps particle by particle (1e-12), every particle owned exactly once."""
+    if lib.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29560 + nranks), os.path.join(ROOT, "tools", "slab_step_check.py"), "32", transport, "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
