@@ -30,7 +30,8 @@ struct nd_ctx {
   nd_options o;
   int ndim = 3, device = 0;
   cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;   // compute; copy-in / copy-out of derivs_host
-  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_out[3] = {nullptr, nullptr, nullptr};
+  bool wait_in1b = false;   // derivs_host: vel, pmass, rho are still on their way (ev_in[2]); the link waits for them where it first reads them
   std::string err;
   long long launches = 0;
   ndt::KernelTables *T = nullptr;
@@ -95,6 +96,7 @@ struct nd_ctx {
   std::function<int(int, int, int)> on_rates_chunk;   // (chunk, row0, row1) after the chunk's finalisation is enqueued
   std::vector<cudaEvent_t> chunk_events;
   double *evpartial = nullptr, *h_ev = nullptr;        // evwrite reductions
+  double *finalpart = nullptr; size_t finalpartcap = 0;   // block partials of k_rates_final's scalar reductions
   double *stepbuf = nullptr; size_t stepbufrows = 0;   // leapfrog `*in` copies (ndspmhd_b200_step), rows [0,npart)
   cudaEvent_t ev_pair[2] = {nullptr, nullptr};   // around the rates pair kernel alone (the roofline's kernel time)
   double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -185,7 +187,7 @@ int ndspmhd_b200_create(const nd_options *o, int ndim, int device, nd_ctx **out)
   for (int k = 0; k < 2; k++) CU(cudaEventCreate(&c->ev_pair[k]));
   CU(cudaStreamCreateWithFlags(&c->stream_h2d, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking));
-  for (int k = 0; k < 2; k++) CU(cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
+  for (int k = 0; k < 3; k++) CU(cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
   for (int k = 0; k < 3; k++) CU(cudaEventCreateWithFlags(&c->ev_out[k], cudaEventDisableTiming));
   // kernel tables -> interpolation records
   std::vector<TabRec> tab(IKERN + 1);
@@ -245,13 +247,14 @@ int ndspmhd_b200_destroy(nd_ctx *c) {
   if (c->d_comm) cudaFree(c->d_comm);
   if (c->h_comm) cudaFreeHost(c->h_comm);
   if (c->stepbuf) cudaFree(c->stepbuf);
+  if (c->finalpart) cudaFree(c->finalpart);
   if (c->evpartial) cudaFree(c->evpartial);
   if (c->h_ev) cudaFreeHost(c->h_ev);
   if (c->rlist) cudaFree(c->rlist);
   for (auto x : c->chunk_events) cudaEventDestroy(x);
   for (int k = 0; k < 8; k++) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
   for (int k = 0; k < 2; k++) if (c->ev_pair[k]) cudaEventDestroy(c->ev_pair[k]);
-  for (int k = 0; k < 2; k++) if (c->ev_in[k]) cudaEventDestroy(c->ev_in[k]);
+  for (int k = 0; k < 3; k++) if (c->ev_in[k]) cudaEventDestroy(c->ev_in[k]);
   for (int k = 0; k < 3; k++) if (c->ev_out[k]) cudaEventDestroy(c->ev_out[k]);
   if (c->stream_h2d) cudaStreamDestroy(c->stream_h2d);
   if (c->stream_d2h) cudaStreamDestroy(c->stream_d2h);
@@ -291,17 +294,20 @@ int check_upload_args(nd_ctx *c, const nd_arrays *a, int npart, int &ntotal, int
 // group 1: what link + density read; group 2: what cons2prim + rates read in addition
 int upload_group(nd_ctx *c, const nd_arrays *a, size_t n, int group, cudaStream_t st) {
   auto up = [&](void *dst, const void *src, size_t bytes) -> cudaError_t { return src ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) : cudaMemsetAsync(dst, 0, bytes, st); };
-  if (group == 1) {
+  if (group == 1 || group == 10) {   // 10 = first half of group 1: what hhmax, the ghost count and the cell grid read (40 of the 80 bytes a row)
     CU(up(c->x, a->x, sizeof(double) * c->ndim * n));
-    CU(up(c->vel, a->vel, sizeof(double) * 3 * n));
-    CU(up(c->pmass, a->pmass, sizeof(double) * n));
     CU(up(c->hh, a->hh_in, sizeof(double) * n));
     CU(cudaMemcpyAsync(c->hh0, c->hh, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     CU(up(c->itype, a->itype, sizeof(int) * n));
     CU(up(c->ireal, a->ireal, sizeof(int) * n));
+  }
+  if (group == 1 || group == 11) {   // 11 = second half: first read when the ghost rows are written / the sorted records are gathered
+    CU(up(c->vel, a->vel, sizeof(double) * 3 * n));
+    CU(up(c->pmass, a->pmass, sizeof(double) * n));
     CU(up(c->rho, a->rho_in, sizeof(double) * n));   // fixed particles without a parent keep their density
     if (c->o.onef_dust) CU(up(c->dustfrac, a->dustfrac_in, sizeof(double) * n));   // read by the density sums (density_sums.f90:280-282)
-  } else {
+  }
+  if (group == 2) {
     CU(up(c->en, a->en, sizeof(double) * n));
     CU(up(c->Bevol, a->Bevol, sizeof(double) * 3 * n));
     CU(up(c->alpha, a->alpha, sizeof(double) * 3 * n));
@@ -567,8 +573,10 @@ int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int
   if (c->o.device_ghosts && any_ghost_bound(c)) want = std::max(want, npart + npart / 4 + 1024);
   if (int e = ensure_capacity(c, want, 0)) return e;
   const size_t nin = (size_t)ntotal;
-  if (int e = upload_group(c, a, nin, 1, c->stream_h2d)) return e;
+  if (int e = upload_group(c, a, nin, 10, c->stream_h2d)) return e;
   CU(cudaEventRecord(c->ev_in[0], c->stream_h2d));
+  if (int e = upload_group(c, a, nin, 11, c->stream_h2d)) return e;
+  CU(cudaEventRecord(c->ev_in[2], c->stream_h2d));
   if (int e = upload_group(c, a, nin, 2, c->stream_h2d)) return e;
   CU(cudaEventRecord(c->ev_in[1], c->stream_h2d));
   c->npart = npart; c->ntotal = ntotal; c->nown = npart;
@@ -576,8 +584,10 @@ int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int
   CU(cudaStreamWaitEvent(c->stream, c->ev_in[0], 0));
   // slab contexts pack en, Bevol, alpha, psi into the halo records during the link (k_halo_pack1): group 2 must have landed too
   if (c->has_comm) CU(cudaStreamWaitEvent(c->stream, c->ev_in[1], 0));
+  else c->wait_in1b = true;   // hhmax, the ghost count and its scan run while vel, pmass, rho are still on the wire (wait_second_half)
   CU(cudaEventRecord(c->ev[0], c->stream));
   int e = DISPATCH_NDIM(c, do_link<1>(c), do_link<2>(c), do_link<3>(c));
+  if (c->wait_in1b) { c->wait_in1b = false; cudaStreamWaitEvent(c->stream, c->ev_in[2], 0); }   // the link left early (error): join anyway
   bool light = false;
   if (!e) {
     CU(cudaEventRecord(c->ev[1], c->stream));

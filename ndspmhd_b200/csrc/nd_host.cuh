@@ -159,6 +159,22 @@ int comm_allreduce_maxmin(nd_ctx *c, double *mx, int nmx, double *mn, int nmn) {
   return 0;
 }
 
+// native transport: pack n_max + n_sum device/host values into d_comm[off..), all-reduce the first n_max with MAX and the rest with SUM on
+// the compute stream, and queue the D2H of the results to h_comm[32 + off ..).  No synchronise: the caller's next one covers it.
+struct PackList {
+  CommPack P;
+  PackList() { P.n = 0; }
+  void add(int kind, const void *src, double scale = 1., double hostval = 0.) { const int k = P.n++; P.kind[k] = kind; P.src[k] = src; P.scale[k] = scale; P.hostval[k] = hostval; }
+};
+int comm_reduce_packed(nd_ctx *c, const PackList &L, int off, int n_max, int n_sum) {
+  if (L.P.n != n_max + n_sum || off + L.P.n > 32) return set_err(c, ND_ERR_INVALID_ARG, "comm_reduce_packed: bad sizes");
+  LAUNCH(c, k_comm_pack, 1, 32, 0, L.P, c->d_comm + off);
+  if (n_max > 0) { NCCLCHK(c->nccl_api->AllReduce(c->d_comm + off, c->d_comm + off, (size_t)n_max, ND_NCCL_FLOAT64, ND_NCCL_MAX, c->nccl, c->stream)); c->n_allreduce++; }
+  if (n_sum > 0) { NCCLCHK(c->nccl_api->AllReduce(c->d_comm + off + n_max, c->d_comm + off + n_max, (size_t)n_sum, ND_NCCL_FLOAT64, ND_NCCL_SUM, c->nccl, c->stream)); c->n_allreduce++; }
+  SMALL_D2H(c, c->h_comm + 32 + off, c->d_comm + off, sizeof(double) * L.P.n);
+  return 0;
+}
+
 int sync_flags(nd_ctx *c) {   // D2H of the flag block; returns a pending device-side error code
   SMALL_D2H(c, c->h_flags, c->flags, sizeof(int) * 16);
   CU(cudaStreamSynchronize(c->stream));
@@ -169,6 +185,13 @@ int sync_flags(nd_ctx *c) {   // D2H of the flag block; returns a pending device
 int compute_hhmax(nd_ctx *c) {
   CU(cudaMemsetAsync(c->red, 0, sizeof(unsigned long long) * 16, c->stream));
   LAUNCH(c, k_max_h, std::min(nblocks(c->nown, 256), 1184), 256, 0, c->hh, c->nown, c->red);
+  if (c->has_comm && c->nccl) {   // key -> double, all-reduce and D2H under one synchronise
+    PackList L; L.add(CP_KEY, c->red);
+    if (int e = comm_reduce_packed(c, L, 0, 1, 0)) return e;
+    CU(cudaStreamSynchronize(c->stream));
+    c->hhmax = c->h_comm[32];
+    return 0;
+  }
   SMALL_D2H(c, c->h_red, c->red, sizeof(unsigned long long));
   CU(cudaStreamSynchronize(c->stream));
   double m = c->nown > 0 ? dkey_inv(c->h_red[0]) : 0.;
@@ -414,6 +437,13 @@ int migrate_rows(nd_ctx *c) {
   return 0;
 }
 
+// derivs_host uploads {x, hh, itype, ireal} first and {vel, pmass, rho} behind them: the compute stream joins the second half here,
+// right before its first reader (the ghost rows' velocities, else the sorted records)
+int wait_second_half(nd_ctx *c) {
+  if (c->wait_in1b) { CU(cudaStreamWaitEvent(c->stream, c->ev_in[2], 0)); c->wait_in1b = false; }
+  return 0;
+}
+
 // ---- ghosts (device_ghosts=1): rows [npart, ntotal) from rows [0, npart) ----
 template <int NDIM> int make_ghosts(nd_ctx *c) {
   if (int e = compute_hhmax(c)) return e;
@@ -436,6 +466,7 @@ template <int NDIM> int make_ghosts(nd_ctx *c) {
   // ensure_capacity may have reallocated scanout: redo the scan in that case (cheap)
   if (int e = exclusive_scan(c, c->ghostcount, c->scanout, np)) return e;
   A.offset = c->scanout;
+  if (int e = wait_second_half(c)) return e;
   LAUNCH(c, (k_ghosts<NDIM, true>), nblocks(np, 256), 256, 0, A);
   c->ntotal = np + nghost;
   return 0;
@@ -501,6 +532,7 @@ template <int NDIM> int build_cells(nd_ctx *c) {
   GA.dxcell1 = 1.0 / c->dxcell; GA.hhmax1 = 1.0 / c->hhmax; GA.mixed = c->flags + 6;
   GA.dustfrac = c->dustfrac; GA.sdf = c->o.onef_dust ? c->sdf : nullptr;
   CU(cudaMemsetAsync(c->flags + 6, 0, sizeof(int), c->stream));
+  if (int e = wait_second_half(c)) return e;
   LAUNCH(c, (k_gather_sorted<NDIM>), nblocks(nt, 256), 256, 0, GA);
   return 0;
 }
@@ -508,10 +540,16 @@ template <int NDIM> int build_cells(nd_ctx *c) {
 template <int NDIM> int do_link(nd_ctx *c) {
   if (c->o.device_ghosts) { if (int e = make_ghosts<NDIM>(c)) return e; }
   if (int e = build_cells<NDIM>(c)) return e;
+  const bool packed = c->has_comm && c->nccl;
+  if (packed) {
+    PackList L; L.add(CP_INT_NONZERO, c->flags + 1); L.add(CP_HOST, nullptr, 1., c->slab_too_narrow ? 1. : 0.);
+    if (int e = comm_reduce_packed(c, L, 0, 2, 0)) return e;
+  }
   if (int e = sync_flags(c)) return e;
   c->mixed_types = c->h_flags[6] != 0;
   double ef = (c->h_flags[1] != 0 || (c->has_comm && c->slab_too_narrow)) ? 1. : 0.;
-  if (int e = comm_allreduce(c, &ef, 1, 0)) return e;   // every rank leaves together
+  if (packed) ef = std::max(c->h_comm[32], c->h_comm[33]);
+  else if (int e = comm_allreduce(c, &ef, 1, 0)) return e;   // every rank leaves together
   if (ef != 0.) {
     CU(cudaMemsetAsync(c->flags, 0, sizeof(int) * 16, c->stream));
     if (c->h_flags[1]) return set_err(c, c->h_flags[1], "link: particle outside the boundary / its slab");
@@ -652,10 +690,16 @@ template <int NDIM> int do_iterate_density(nd_ctx *c, int resume) {
     if (int e = exclusive_scan(c, c->redo, c->scanout, c->ntotal)) return e;
     LAUNCH(c, k_compact, nblocks(c->ntotal, 256), 256, 0, c->redo, c->scanout, c->ntotal, c->list);
     SMALL_D2H(c, &c->h_flags[16], c->scanout + c->ntotal, sizeof(int));
+    const bool packed = c->has_comm && c->nccl;
+    if (packed) {   // {unconverged count, relink flag, error flag} summed over the ranks without a host round trip in between
+      PackList L; L.add(CP_INT, c->scanout + c->ntotal); L.add(CP_INT_NONZERO, c->flags); L.add(CP_INT_NONZERO, c->flags + 1);
+      if (int e = comm_reduce_packed(c, L, 0, 0, 3)) return e;
+    }
     if (int e = sync_flags(c)) return e;
     c->ncalc = c->h_flags[16];
     double v[3] = {(double)c->ncalc, (double)(c->h_flags[0] != 0), (double)(c->h_flags[1] != 0)};
-    if (int e = comm_allreduce(c, v, 3, 2)) return e;
+    if (packed) { v[0] = c->h_comm[32]; v[1] = c->h_comm[33]; v[2] = c->h_comm[34]; }
+    else if (int e = comm_allreduce(c, v, 3, 2)) return e;
     c->ncalc_g = (long long)(v[0] + 0.5);
     if (v[2] != 0.) {
       const int code = c->h_flags[1] ? c->h_flags[1] : ND_ERR_COMM;
@@ -790,7 +834,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   CU(cudaMemsetAsync(c->fmean, 0, sizeof(double) * 4, c->stream));
   CU(cudaMemsetAsync(c->flags, 0, sizeof(int) * 16, c->stream));
   RGatherArgs GA;
-  GA.perm = c->perm; GA.ireal = c->ireal; GA.hh = c->hh; GA.pmass = c->pmass; GA.rho = c->rho; GA.pr = c->pr; GA.spsound = c->spsound; GA.uu = c->uu;
+  GA.perm = c->perm; GA.inv = c->inv; GA.ireal = c->ireal; GA.hh = c->hh; GA.pmass = c->pmass; GA.rho = c->rho; GA.pr = c->pr; GA.spsound = c->spsound; GA.uu = c->uu;
   GA.gradh = c->gradh; GA.alpha = c->alpha; GA.psi = c->psi; GA.Bfield = c->Bfield;
   GA.p32 = c->p32; GA.hhmax1 = 1.0 / c->hhmax;
   GA.dustfrac = c->dustfrac; GA.deltav = c->deltav; GA.rhogas = c->rhogas; GA.rhodust = c->rhodust;
@@ -806,10 +850,17 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   LAUNCH(c, k_rates_gather, nblocks(nt, 256), 256, 0, GA);
   RatesOpts O = make_rates_opts(c);
   if (o.imhd != 0) {   // stressmax feeds the pair kernel by value: one 8-byte D2H
-    SMALL_D2H(c, c->h_red, c->red + RED_STRESS, sizeof(unsigned long long));
-    CU(cudaStreamSynchronize(c->stream));
-    O.stressmax = dkey_inv(c->h_red[0]);
-    if (int e = comm_allreduce(c, &O.stressmax, 1, 0)) return e;
+    if (c->has_comm && c->nccl) {
+      PackList L; L.add(CP_KEY, c->red + RED_STRESS);
+      if (int e = comm_reduce_packed(c, L, 0, 1, 0)) return e;
+      CU(cudaStreamSynchronize(c->stream));
+      O.stressmax = c->h_comm[32];
+    } else {
+      SMALL_D2H(c, c->h_red, c->red + RED_STRESS, sizeof(unsigned long long));
+      CU(cudaStreamSynchronize(c->stream));
+      O.stressmax = dkey_inv(c->h_red[0]);
+      if (int e = comm_allreduce(c, &O.stressmax, 1, 0)) return e;
+    }
   }
   RatesIn I; I.bpsi = c->bpsi; I.thermo = c->thermo; I.gal = c->gal; I.srho = c->srho; I.dusta = c->dusta; I.dustb = c->dustb;
   RatesSums S; S.F = c->sF; S.dB = c->sdB; S.C = c->sC; S.P = c->sP; S.V = c->sV; S.D = c->sD;
@@ -838,15 +889,32 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   FA.drhodt_in = c->drhodt; FA.Bevol = c->Bevol; FA.dens = c->dens; FA.hh = c->hh; FA.rho = c->rho; FA.pr = c->pr; FA.vsigmax_key = c->red + RED_VSIG;
   FA.force = c->force; FA.dudt = c->dudt; FA.dendt = c->dendt; FA.dBevoldt = c->dBevoldt; FA.daldt = c->daldt; FA.dpsidt = c->dpsidt; FA.gradpsi = c->gradpsi;
   FA.divB = c->divB; FA.curlB = c->curlB; FA.graddivv = c->graddivv; FA.del2u = c->del2u; FA.drhodt = c->drhodt; FA.dhdt = c->dhdt;
-  FA.R = R; FA.npart = np; FA.ntotal = nt; FA.targets = nullptr; FA.ntargets = 0; FA.drho_from_pairs = (c->drho_pairs && fast) ? 1 : 0; FA.ndim = NDIM;
+  FA.R = R; FA.npart = np; FA.ntotal = nt; FA.inv = c->inv; FA.row0 = 0; FA.row1 = np;
+  FA.vel = c->vel; FA.pmass = c->pmass; FA.spsound = c->spsound; FA.uu = c->uu; FA.alpha = c->alpha; FA.psi = c->psi; FA.Bfield = c->Bfield; FA.itype = c->itype; FA.drho_from_pairs = (c->drho_pairs && fast) ? 1 : 0; FA.ndim = NDIM;
   FA.dusta = o.onef_dust ? c->dusta : nullptr; FA.dustb = c->dustb; FA.fineStart = c->cellStart; FA.cellOf = c->cellOf;
   FA.ddustevoldt = c->ddustevoldt; FA.ddeltavdt = c->ddeltavdt;
+  {
+    const size_t need = (size_t)nblocks(np, 256) * 6 + 6;
+    if (c->finalpartcap < need) {
+      if (c->finalpart) cudaFree(c->finalpart);
+      c->finalpart = nullptr; c->finalpartcap = 0;
+      CU(cudaMalloc(&c->finalpart, sizeof(double) * (need + need / 8)));
+      c->finalpartcap = need + need / 8;
+    }
+    FA.partial = c->finalpart;
+  }
   const int nchunk = (c->rate_chunks > 1 && !c->has_comm && !pi) ? c->rate_chunks : 1;
   c->rate_chunks_used = nchunk;
   if (nchunk == 1) {
     if (int e = pair(nullptr, 0)) return e;
     CU(cudaEventRecord(c->ev[4], c->stream));
-    if (c->has_comm) {   // vsigmax feeds dpsidt in the finalisation loop (:518-520, :902): all ranks need the global maximum
+    if (c->has_comm && c->nccl) {   // the global maximum is consumed on the device (k_rates_final): no host round trip at all
+      PackList L; L.add(CP_KEY, c->red + RED_VSIG);
+      LAUNCH(c, k_comm_pack, 1, 32, 0, L.P, c->d_comm + 8);
+      NCCLCHK(c->nccl_api->AllReduce(c->d_comm + 8, c->d_comm + 8, 1, ND_NCCL_FLOAT64, ND_NCCL_MAX, c->nccl, c->stream));
+      c->n_allreduce++;
+      LAUNCH(c, k_double_to_key, 1, 1, 0, c->d_comm + 8, c->red + RED_VSIG);
+    } else if (c->has_comm) {   // vsigmax feeds dpsidt in the finalisation loop (:518-520, :902): all ranks need the global maximum
       SMALL_D2H(c, c->h_red, c->red + RED_VSIG, sizeof(unsigned long long));
       CU(cudaStreamSynchronize(c->stream));
       double vs = dkey_inv(c->h_red[0]);
@@ -855,7 +923,9 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
       c->h_red[0] = kv.u | 0x8000000000000000ull;   // key of a non-negative double
       CU(cudaMemcpyAsync(c->red + RED_VSIG, c->h_red, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
     }
-    LAUNCH(c, k_rates_final, nblocks(nt, 256), 256, 0, FA);
+    const int fgrid = std::min(nblocks(np, 256), 8 * c->num_sms);   // persistent: 1.87 ms against 2.15 ms with one row a thread at 16.8 M rows
+    LAUNCH(c, k_rates_final, fgrid, 256, 0, FA);
+    LAUNCH(c, k_final_reduce, 1, 1024, 0, c->finalpart, fgrid, R, o.onef_dust ? 1 : 0);
   } else {
     // Row chunks: chunk q gathers and finalises the targets whose ORIGINAL row lies in [q*rows, (q+1)*rows); its output rows are
     // then complete (except dpsidt) and contiguous in the caller's arrays, so on_rates_chunk can start their download while the
@@ -875,8 +945,10 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
       LAUNCH(c, k_compact, nblocks(nt, 256), 256, 0, c->redo, c->scanout, nt, c->rlist);
       const int m = r1 - r0;                         // every row below nown has exactly one slot
       if (int e = pair(c->rlist, m)) return e;
-      FA.targets = c->rlist; FA.ntargets = m;
-      LAUNCH(c, k_rates_final, nblocks(m, 256), 256, 0, FA);
+      FA.row0 = r0; FA.row1 = r1;
+      const int fgrid = std::min(nblocks(m, 256), 8 * c->num_sms);
+      LAUNCH(c, k_rates_final, fgrid, 256, 0, FA);
+      LAUNCH(c, k_final_reduce, 1, 1024, 0, c->finalpart, fgrid, R, o.onef_dust ? 1 : 0);
       if (c->on_rates_chunk) { if (int e = c->on_rates_chunk(q, r0, r1)) return e; }
     }
     CU(cudaEventRecord(c->ev[4], c->stream));
@@ -890,6 +962,14 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   // scalars back to the host (module timestep)
   SMALL_D2H(c, c->h_red, c->red, sizeof(unsigned long long) * 16);
   SMALL_D2H(c, c->h_fmean, c->fmean, sizeof(double) * 4);
+  const bool packed = c->has_comm && c->nccl;
+  if (packed) {   // {error flag, maxima, -minima} and the sums: two all-reduces queued behind the kernels, one synchronise for everything
+    PackList L;
+    L.add(CP_INT, c->flags + 1); L.add(CP_KEY, c->red + RED_VSIG); L.add(CP_KEY, c->red + RED_HCS); L.add(CP_KEY, c->red + RED_FH);
+    L.add(CP_KEY, c->red + RED_DTC, -1.); L.add(CP_KEY, c->red + RED_DTAV, -1.); L.add(CP_KEY, c->red + RED_TS, -1.); L.add(CP_KEY, c->red + RED_DTF, -1.);
+    L.add(CP_DOUBLE, c->fmean); L.add(CP_DOUBLE, c->fmean + 1); L.add(CP_DOUBLE, c->fmean + 2); L.add(CP_INT, c->flags + 4); L.add(CP_U64, c->red + RED_NPAIRS);
+    if (int e3 = comm_reduce_packed(c, L, 0, 8, 5)) return e3;
+  }
   if (int e2 = sync_flags(c)) return e2;
   nd_scalars &s = c->sc;
   s.dtcourant = dkey_inv(c->h_red[RED_DTC]);
@@ -902,8 +982,14 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   if (c->has_comm) {   // two all-reduces: {error flag, maxima, minima} and the sums
     double mx[4] = {ef, s.vsigmax, s.h_on_csts_max, s.fhmax}, mn[4] = {s.dtcourant, s.dtav, s.ts_min, dkey_inv(c->h_red[RED_DTF])};
     double sm[5] = {c->h_fmean[0], c->h_fmean[1], c->h_fmean[2], (double)c->h_flags[4], (double)c->h_red[RED_NPAIRS] /* < 2^53 */};
+    if (packed) {
+      const double *r = c->h_comm + 32;
+      for (int k = 0; k < 4; k++) { mx[k] = r[k]; mn[k] = -r[4 + k]; }
+      for (int k = 0; k < 5; k++) sm[k] = r[8 + k];
+    } else {
     if (int e3 = comm_allreduce_maxmin(c, mx, 4, mn, 4)) return e3;
     if (int e3 = comm_allreduce(c, sm, 5, 2)) return e3;
+    }
     c->h_red[RED_NPAIRS] = (unsigned long long)(sm[4] + 0.5);
     ef = mx[0]; s.vsigmax = mx[1]; s.h_on_csts_max = mx[2]; s.fhmax = mx[3];
     s.dtcourant = mn[0]; s.dtav = mn[1]; s.ts_min = mn[2];

@@ -109,11 +109,24 @@ template <int NDIM, bool WRITE> __global__ void k_ghosts(GhostArgs A) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= A.npart) return;
   double xj[3] = {0, 0, 0}, vj[3];
+#pragma unroll
   for (int d = 0; d < NDIM; d++) xj[d] = A.x[(size_t)j * NDIM + d];
-  for (int d = 0; d < 3; d++) vj[d] = A.vel[(size_t)j * 3 + d];
   double dxbound[3];
+#pragma unroll
   for (int d = 0; d < 3; d++) dxbound[d] = A.radkern * A.hhmax;                                   // :80
+#pragma unroll
   for (int d = 0; d < NDIM; d++) if (A.ibound[d] == 2 || A.ibound[d] == 4 || A.ibound[d] == 6) dxbound[d] = A.radkern * A.hh[j];   // :173
+  // nine particles in ten are farther than the reach from every face: the test of :205 for both faces of every dimension, in registers,
+  // before the general procedure below (whose run-time indexed arrays live in local memory)
+  bool any = false;
+#pragma unroll
+  for (int d = 0; d < NDIM; d++) {
+    if (A.ibound[d] <= 1) continue;
+    const double dhi = A.xmax[d] - xj[d], dlo = xj[d] - A.xmin[d];
+    any = any || ((dhi < dxbound[d]) && (dhi > 0)) || ((dlo < dxbound[d]) && (dlo > 0));
+  }
+  if (!any) { if (!WRITE) A.count[j] = 0; return; }
+  for (int d = 0; d < 3; d++) vj[d] = A.vel[(size_t)j * 3 + d];
   int n = 0;
   const int base = WRITE ? A.npart + A.offset[j] : 0;
   auto make = [&](const double *xp, const double *vp) {                                            // makeghost, :363-431
@@ -250,6 +263,28 @@ __global__ void k_halo_unpack2(HaloPackArgs A) {
   const size_t n = A.n;
   A.hh[r] = A.buf[q]; A.rho[r] = A.buf[n + q]; A.gradh[r] = A.buf[2 * n + q];
 }
+
+// =====================================================================================================
+// native transport (nd_nccl.cuh): the operands of the small collectives are assembled on the device, so ONE stream synchronise serves the
+// local D2H, the collective and the D2H of its result (the callback transport needs the values on the host first: two or three)
+// =====================================================================================================
+enum { CP_KEY = 0, CP_INT = 1, CP_INT_NONZERO = 2, CP_DOUBLE = 3, CP_U64 = 4, CP_HOST = 5 };
+struct CommPack { int n; int kind[16]; const void *src[16]; double scale[16], hostval[16]; };
+__global__ void k_comm_pack(CommPack P, double *dst) {
+  const int k = threadIdx.x;
+  if (k >= P.n) return;
+  double v = 0.;
+  switch (P.kind[k]) {
+    case CP_KEY: { const unsigned long long key = *reinterpret_cast<const unsigned long long *>(P.src[k]); v = key ? dkey_inv(key) : 0.; break; }
+    case CP_INT: v = (double)*reinterpret_cast<const int *>(P.src[k]); break;
+    case CP_INT_NONZERO: v = *reinterpret_cast<const int *>(P.src[k]) != 0 ? 1. : 0.; break;
+    case CP_DOUBLE: v = *reinterpret_cast<const double *>(P.src[k]); break;
+    case CP_U64: v = (double)*reinterpret_cast<const unsigned long long *>(P.src[k]); break;
+    default: v = P.hostval[k];
+  }
+  dst[k] = v * P.scale[k];
+}
+__global__ void k_double_to_key(const double *v, unsigned long long *key) { *key = dkey(*v); }
 
 // =====================================================================================================
 // particle migration between slabs (ndspmhd_b200_step on slab-decomposed contexts).  The reference moves every particle in the predictor
@@ -564,7 +599,7 @@ __global__ void k_take_column(const double *a, int stride, int col, double *out,
 // rates: gather of the sorted inputs, finalisation loop (src/ratesND_mhd.f90:532-965)
 // =====================================================================================================
 struct RGatherArgs {
-  const int *perm, *ireal; const double *hh, *pmass, *rho, *pr, *spsound, *uu, *gradh, *alpha, *psi, *Bfield;
+  const int *perm, *inv, *ireal; const double *hh, *pmass, *rho, *pr, *spsound, *uu, *gradh, *alpha, *psi, *Bfield;
   double4 *posh, *vm, *bpsi, *thermo, *gal; float4 *p32; double hhmax1; double *srho; int npart, ntotal, imhd; unsigned long long *stress_key; int imagforce; double Bconstmax, pext;
   int *err;
   // one-fluid dust (dusta NULL otherwise)
@@ -574,8 +609,9 @@ struct RGatherArgs {
   const double *alphaB_ghost;
 };
 __global__ void k_rates_gather(RGatherArgs A) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  // one thread per sorted slot (measured: one thread per original row with the records scattered through inv[] is 2.2 times slower)
   double stress = 0.;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < A.ntotal) {
     const int r = A.perm[s];
     const int st = (r < A.npart) ? r : A.ireal[r] - 1;
@@ -597,12 +633,18 @@ __global__ void k_rates_gather(RGatherArgs A) {
       const double bx = A.Bfield[(size_t)st * 3], by = A.Bfield[(size_t)st * 3 + 1], bz = A.Bfield[(size_t)st * 3 + 2];
       A.bpsi[s] = make_double4(bx, by, bz, A.psi[st]);
       const double B2i = (bx * bx + by * by) + bz * bz;
-      stress = fmax(fmax(0.5 * B2i - A.pr[st], 0.), A.Bconstmax);                   // :240-241
+      stress = fmax(stress, fmax(fmax(0.5 * B2i - A.pr[st], 0.), A.Bconstmax));     // :240-241
     }
   }
   if (A.imhd != 0) {                                                                // stressmax over 1..ntotal, :231-245
-    stress = warp_max(stress);
-    if ((threadIdx.x & 31) == 0 && stress > 0.) atomic_max_d(A.stress_key, stress);
+    stress = warp_max(stress);                                                      // one atomic per block, not per warp (same address)
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = stress;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < (int)(blockDim.x >> 5); k++) stress = fmax(stress, red[k]);
+      if (stress > 0.) atomic_max_d(A.stress_key, stress);
+    }
   }
 }
 
@@ -612,36 +654,41 @@ struct FinalArgs {
   double *force, *dudt, *dendt, *dBevoldt, *daldt, *dpsidt, *gradpsi, *divB, *curlB, *graddivv, *del2u, *drhodt, *dhdt;
   RatesRed R; int npart, ntotal;
   int drho_from_pairs, ndim;          // fast tuple: drho/dt comes from the pair kernel's sum (S.V.w), dh/dt is made here
-  const int *targets; int ntargets;   // row-chunked finalisation: the chunk's target slots (NULL: every slot)
+  // One thread per ORIGINAL row in [row0,row1) (a row chunk, or every own row): the particle's own state comes from the original-order
+  // arrays and the 13 output arrays are written coalesced; only the five 32-byte sum records of the pair kernel are gathered (whole
+  // sectors) through inv[].
+  const int *inv; int row0, row1; const double *vel, *pmass, *spsound, *uu, *alpha, *psi, *Bfield; const int *itype;
+  double *partial;                    // [gridDim.x][6] block partials of the scalar reductions
   // one-fluid dust (dusta NULL otherwise)
   const double4 *dusta; const double2 *dustb; const int *fineStart, *cellOf; double *ddustevoldt, *ddeltavdt;
 };
 __global__ void k_rates_final(FinalArgs A) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int s = A.targets ? (t < A.ntargets ? A.targets[t] : A.ntotal) : t;
   double fhmax = 0., dtforce = DBL_MAX, fm0 = 0., fm1 = 0., fm2 = 0., tsmin = DBL_MAX;
-  if (s < A.ntotal) {
-    const int i = A.perm[s];
-    if (i < A.npart) {
+  {
+    for (int i = A.row0 + blockIdx.x * blockDim.x + threadIdx.x; i < A.row1; i += gridDim.x * blockDim.x) {
       const RatesOpts &O = A.O;
-      const double4 F = A.S.F[s], dB4 = A.S.dB[s], C = A.S.C[s], P = A.S.P[s], V = A.S.V[s];
-      const double4 p = A.posh[s], v = A.vm[s], th = A.thermo[s], g = A.gal[s];
-      const double rhoi = A.rho[i], rho1i = th.x, hi = A.hh[i], pri = A.pr[i];
+      const int s = A.inv[i];
+      const double4 F = ld4(A.S.F + s), dB4 = ld4(A.S.dB + s), C = ld4(A.S.C + s), P = ld4(A.S.P + s), V = ld4(A.S.V + s);
+      const double rhoi = A.rho[i], hi = A.hh[i], pri = A.pr[i];
+      const double rho1i = 1.0 / rhoi;                                                               // rho1i = 1./rhoi, :325 (thermo.x of the pair kernel)
+      const double4 v = make_double4(A.vel[(size_t)i * 3], A.vel[(size_t)i * 3 + 1], A.vel[(size_t)i * 3 + 2], A.pmass[i]);
+      const double4 th = make_double4(rho1i, 0., A.spsound[i], A.uu[i]);
+      const double4 g = make_double4(0., A.alpha[(size_t)i * 3], A.alpha[(size_t)i * 3 + 1], A.alpha[(size_t)i * 3 + 2]);
       const double vsigmax = dkey_inv(*A.vsigmax_key);
       const double vsig2max = (O.imhd != 0 && O.idivbzero >= 2) ? vsigmax * vsigmax : 0.;           // :518-520
       double fx = F.x, fy = F.y, fz = F.z, dudt = F.w;
       double divB = dB4.w, cbx = C.x, cby = C.y, cbz = C.z;
       double bx = 0, by = 0, bz = 0, psii = 0;
       if (O.imhd != 0) {
-        const double4 b = A.bpsi[s]; bx = b.x; by = b.y; bz = b.z; psii = b.w;
+        bx = A.Bfield[(size_t)i * 3]; by = A.Bfield[(size_t)i * 3 + 1]; bz = A.Bfield[(size_t)i * 3 + 2]; psii = A.psi[i];
         if (O.imhd > 0) { cbx *= rho1i; cby *= rho1i; cbz *= rho1i; }                                // :640
         divB *= rho1i;                                                                               // :643
       }
-      fm0 = v.w * fx; fm1 = v.w * fy; fm2 = v.w * fz;                                                // :678
+      fm0 += v.w * fx; fm1 += v.w * fy; fm2 += v.w * fz;                                             // :678
       const double forcemag = sqrt((fx * fx + fy * fy) + fz * fz);
       const double fonh = forcemag / hi;
-      const int ti = A.typ[s];
-      if (ti != 1) fhmax = fonh;                                                                     // :681
+      const int ti = A.itype[i];
+      if (ti != 1) fhmax = fmax(fhmax, fonh);                                                                     // :681
       double valfven2i = 0.;
       if (O.imhd != 0) valfven2i = ((bx * bx + by * by) + bz * bz) / A.dens[i];                      // :690
       const double vsig = sqrt(th.z * th.z + valfven2i);                                             // :695-696
@@ -661,7 +708,7 @@ __global__ void k_rates_final(FinalArgs A) {
         dbx *= rho1i; dby *= rho1i; dbz *= rho1i;
         if (O.idivbzero >= 2) { const double r2 = rho1i * rho1i; gpx *= r2; gpy *= r2; gpz *= r2; }
       } else { dbx = dby = dbz = 0.; }
-      if (O.iresist > 0 && O.iresist != 2 && O.etamhd > DBL_MIN) dtforce = hi * hi / O.etamhd;       // :808-815
+      if (O.iresist > 0 && O.iresist != 2 && O.etamhd > DBL_MIN) dtforce = fmin(dtforce, hi * hi / O.etamhd);       // :808-815
       double ddv0 = 0., ddv1 = 0., ddv2 = 0., ddust = 0., tstop = DBL_MAX;
       if (A.dusta) {                                                                                 // :548-582 one fluid dust
         const double4 D = A.S.D[s], da = A.dusta[s];
@@ -736,20 +783,47 @@ __global__ void k_rates_final(FinalArgs A) {
       if (A.dusta) {
         A.ddustevoldt[i] = ddust;
         o3 = A.ddeltavdt + (size_t)i * 3; o3[0] = ddv0; o3[1] = ddv1; o3[2] = ddv2;
-        tsmin = tstop;
+        tsmin = fmin(tsmin, tstop);
       }
     }
   }
-  fhmax = warp_max(fhmax); dtforce = warp_min(dtforce);
+  // block partials {fhmax, dtforce, sum m f (3), min tstop} in a fixed order, no atomics: k_final_reduce folds them (a set of atomics per
+  // warp of 32 rows was 2.6 M same-address atomics at 16.8 M particles -- 2.5 of this kernel's 4.3 ms)
+  fhmax = warp_max(fhmax); dtforce = warp_min(dtforce); tsmin = warp_min(tsmin);
   fm0 = warp_sum(fm0); fm1 = warp_sum(fm1); fm2 = warp_sum(fm2);
-  if ((threadIdx.x & 31) == 0) {
-    atomic_max_d(A.R.fhmax_max, fhmax);
-    atomic_min_d(A.R.dtforce_min, dtforce);
-    atomicAdd(A.R.fmean, fm0); atomicAdd(A.R.fmean + 1, fm1); atomicAdd(A.R.fmean + 2, fm2);
+  __shared__ double red[8][6];
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[w][0] = fhmax; red[w][1] = dtforce; red[w][2] = fm0; red[w][3] = fm1; red[w][4] = fm2; red[w][5] = tsmin; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < nw; k++) {
+      fhmax = fmax(fhmax, red[k][0]); dtforce = fmin(dtforce, red[k][1]); fm0 += red[k][2]; fm1 += red[k][3]; fm2 += red[k][4]; tsmin = fmin(tsmin, red[k][5]);
+    }
+    double *o = A.partial + (size_t)blockIdx.x * 6;
+    o[0] = fhmax; o[1] = dtforce; o[2] = fm0; o[3] = fm1; o[4] = fm2; o[5] = tsmin;
   }
-  if (A.dusta) {                                                                                    // dtdrag = min(dtdrag, tstop), :561
-    tsmin = warp_min(tsmin);
-    if ((threadIdx.x & 31) == 0) atomic_min_d(A.R.ts_min, tsmin);
+}
+// one block: the partials of k_rates_final in block order (run-to-run deterministic force sum), then into the reduction keys
+__global__ void k_final_reduce(const double *partial, int nb, RatesRed R, int dust) {
+  double fhmax = 0., dtforce = DBL_MAX, fm0 = 0., fm1 = 0., fm2 = 0., tsmin = DBL_MAX;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+    const double *o = partial + (size_t)b * 6;
+    fhmax = fmax(fhmax, o[0]); dtforce = fmin(dtforce, o[1]); fm0 += o[2]; fm1 += o[3]; fm2 += o[4]; tsmin = fmin(tsmin, o[5]);
+  }
+  fhmax = warp_max(fhmax); dtforce = warp_min(dtforce); tsmin = warp_min(tsmin);
+  fm0 = warp_sum(fm0); fm1 = warp_sum(fm1); fm2 = warp_sum(fm2);
+  __shared__ double red[32][6];
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[w][0] = fhmax; red[w][1] = dtforce; red[w][2] = fm0; red[w][3] = fm1; red[w][4] = fm2; red[w][5] = tsmin; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < nw; k++) {
+      fhmax = fmax(fhmax, red[k][0]); dtforce = fmin(dtforce, red[k][1]); fm0 += red[k][2]; fm1 += red[k][3]; fm2 += red[k][4]; tsmin = fmin(tsmin, red[k][5]);
+    }
+    atomic_max_d(R.fhmax_max, fhmax);
+    atomic_min_d(R.dtforce_min, dtforce);
+    R.fmean[0] += fm0; R.fmean[1] += fm1; R.fmean[2] += fm2;      // the row chunks of one get_rates run one after the other on the stream
+    if (dust) atomic_min_d(R.ts_min, tsmin);
   }
 }
 // Row-chunked rates: dpsidt needs the maximum signal velocity over ALL pairs (:518-520, :902), known only after the last chunk.

@@ -83,6 +83,32 @@ def wrap_shift(x: np.ndarray, xbound: float, xperbound: float) -> np.ndarray:
     return xperbound + (x - xbound)
 
 
+def migration_plan_numpy(x0: np.ndarray, edges: np.ndarray, rank: int, periodic: bool):
+    """numpy restatement of k_migrate_flags + the hole filling of migrate_rows (csrc/nd_host.cuh): which own rows leave to the left and
+    right neighbour after the integrator moved them (x already wrapped into the box, src/boundaryND.f90:65-93), and the moves
+    (src row -> dst row) that fill the holes below m = nown - nleave from the staying rows of the tail, so that rows [0,m) stay and
+    arrivals are appended at m.  Ownership: edges[r] <= x < edges[r+1], the last slab closed at xmax.  A row that is in neither
+    adjacent slab raises (it moved farther than one slab in a step)."""
+    nr = len(edges) - 1
+    left, right = (rank - 1) % nr, (rank + 1) % nr
+
+    def inside(x, r):
+        return (x >= edges[r]) & ((x < edges[r + 1]) | ((r == nr - 1) & (x == edges[r + 1])))
+
+    away = ~inside(x0, rank)
+    to_right = away & inside(x0, right) & (periodic or rank < nr - 1)
+    to_left = away & ~to_right & inside(x0, left) & (periodic or rank > 0)
+    if left == right:                       # ring of two: one peer, everything goes out on the right side
+        to_right, to_left = to_right | to_left, np.zeros_like(to_left)
+    if np.any(away & ~to_right & ~to_left):
+        raise ValueError("a row left its slab by more than the adjacent slab")
+    holes = np.nonzero(away)[0]
+    m = x0.shape[0] - holes.shape[0]
+    tail_stay = m + np.nonzero(~away[m:])[0]
+    moves = np.stack([tail_stay, holes[: tail_stay.shape[0]]], axis=1) if tail_stay.shape[0] else np.zeros((0, 2), np.int64)
+    return np.nonzero(to_left)[0], np.nonzero(to_right)[0], moves, m
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # transport
 # ---------------------------------------------------------------------------------------------------------------------

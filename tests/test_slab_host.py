@@ -165,3 +165,50 @@ def test_slab_halo_model_reproduces_single_domain_neighbour_pairs(world):
     got = np.unique(np.concatenate([np.array(r[0], dtype=np.int64) for r in res]))
     # a slab's local ghost reach uses its own max h (<= global); every rank reports it for the record
     assert np.array_equal(got, want)
+
+
+# ---- row migration between slabs (ndspmhd_b200_step on slab contexts) ---------------------------------------------------------
+def _migrate(rank, world):
+    """A CPU model of migrate_rows: rows drift and wrap, the plan (slab.migration_plan_numpy = the device kernels' rule) says who leaves
+    where and which tail rows fill the holes, payloads travel over the gloo transport; afterwards every id must be owned once, by the
+    rank whose slab holds it, with its payload intact."""
+    rng = np.random.default_rng(7)
+    nglobal = 4000
+    xg = rng.uniform(-0.5, 0.5, nglobal)
+    edges = slab.slab_edges(xg, world, -0.5, 0.5)
+    rows = np.nonzero(slab.owner_of(xg, edges) == rank)[0]
+    x, ids = xg[rows].copy(), rows.astype(np.int64)
+    payload = np.stack([x, ids * 3.25], axis=1)
+    comm = slab.SlabComm(device="cpu")
+    width = float(np.min(np.diff(edges)))
+    moved = 0
+    for step in range(4):
+        drift = np.random.default_rng(100 + step).uniform(-0.4, 0.4, nglobal)[ids] * width     # same draw for an id on every rank
+        x = x + drift
+        x = np.where(x > 0.5, -0.5 + x - 0.5, np.where(x < -0.5, 0.5 - (-0.5 - x), x))           # boundaryND.f90:65-93
+        payload[:, 0] = x
+        li, ri, moves, m = slab.migration_plan_numpy(x, edges, rank, periodic=True)
+        sl = np.ascontiguousarray(np.concatenate([payload[li], ids[li, None].astype(np.float64)], axis=1)).view(np.uint8).reshape(-1)
+        sr = np.ascontiguousarray(np.concatenate([payload[ri], ids[ri, None].astype(np.float64)], axis=1)).view(np.uint8).reshape(-1)
+        nl, nr_ = comm.exchange_counts(sl.size, sr.size)
+        rl, rr = np.zeros(nl, np.uint8), np.zeros(nr_, np.uint8)
+        comm.sendrecv_tensors(torch.from_numpy(sl) if sl.size else None, torch.from_numpy(sr) if sr.size else None,
+                              torch.from_numpy(rl) if nl else None, torch.from_numpy(rr) if nr_ else None)
+        payload[moves[:, 1]] = payload[moves[:, 0]]
+        ids[moves[:, 1]] = ids[moves[:, 0]]
+        arr = np.concatenate([rl.view(np.float64).reshape(-1, 3), rr.view(np.float64).reshape(-1, 3)], axis=0)
+        payload = np.concatenate([payload[:m], arr[:, :2]], axis=0)
+        ids = np.concatenate([ids[:m], arr[:, 2].astype(np.int64)])
+        x = payload[:, 0].copy()
+        moved += li.size + ri.size
+    inside = (x >= edges[rank]) & ((x < edges[rank + 1]) | ((rank == world - 1) & (x == edges[rank + 1])))
+    return {"ids": ids.tolist(), "all_inside": bool(inside.all()), "payload_ok": bool(np.array_equal(payload[:, 1], ids * 3.25)), "moved": int(moved)}
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_migration_plan_over_gloo(world):
+    res = run_ranks(world, _migrate)
+    allids = sorted(i for out in res for i in out["ids"])
+    assert allids == list(range(4000))                      # every particle owned exactly once
+    assert all(out["all_inside"] and out["payload_ok"] for out in res)
+    assert sum(out["moved"] for out in res) > 500           # the case does move rows
