@@ -31,6 +31,7 @@ struct nd_ctx {
   int ndim = 3, device = 0;
   cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;   // compute; copy-in / copy-out of derivs_host
   cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_out[3] = {nullptr, nullptr, nullptr};
+  bool defer_vel = false;   // derivs_host, LIGHT rounds, periodic ghosts only: vel arrives during the density iteration (k_late_vel)
   bool wait_in1b = false;   // derivs_host: vel, pmass, rho are still on their way (ev_in[2]); the link waits for them where it first reads them
   std::string err;
   long long launches = 0;
@@ -294,17 +295,17 @@ int check_upload_args(nd_ctx *c, const nd_arrays *a, int npart, int &ntotal, int
 // group 1: what link + density read; group 2: what cons2prim + rates read in addition
 int upload_group(nd_ctx *c, const nd_arrays *a, size_t n, int group, cudaStream_t st) {
   auto up = [&](void *dst, const void *src, size_t bytes) -> cudaError_t { return src ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) : cudaMemsetAsync(dst, 0, bytes, st); };
-  if (group == 1 || group == 10) {   // 10 = first half of group 1: what hhmax, the ghost count and the cell grid read (40 of the 80 bytes a row)
+  if (group == 1 || group == 10) {   // 10 = first half of group 1: what the link and the LIGHT density rounds read (56 of the 80 bytes a row)
     CU(up(c->x, a->x, sizeof(double) * c->ndim * n));
     CU(up(c->hh, a->hh_in, sizeof(double) * n));
     CU(cudaMemcpyAsync(c->hh0, c->hh, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     CU(up(c->itype, a->itype, sizeof(int) * n));
     CU(up(c->ireal, a->ireal, sizeof(int) * n));
+    CU(up(c->pmass, a->pmass, sizeof(double) * n));
+    CU(up(c->rho, a->rho_in, sizeof(double) * n));   // fixed particles without a parent keep their density (must land before the rounds write rho)
   }
   if (group == 1 || group == 11) {   // 11 = second half: first read when the ghost rows are written / the sorted records are gathered
     CU(up(c->vel, a->vel, sizeof(double) * 3 * n));
-    CU(up(c->pmass, a->pmass, sizeof(double) * n));
-    CU(up(c->rho, a->rho_in, sizeof(double) * n));   // fixed particles without a parent keep their density
     if (c->o.onef_dust) CU(up(c->dustfrac, a->dustfrac_in, sizeof(double) * n));   // read by the density sums (density_sums.f90:280-282)
   }
   if (group == 2) {
@@ -584,17 +585,30 @@ int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int
   CU(cudaStreamWaitEvent(c->stream, c->ev_in[0], 0));
   // slab contexts pack en, Bevol, alpha, psi into the halo records during the link (k_halo_pack1): group 2 must have landed too
   if (c->has_comm) CU(cudaStreamWaitEvent(c->stream, c->ev_in[1], 0));
-  else c->wait_in1b = true;   // hhmax, the ghost count and its scan run while vel, pmass, rho are still on the wire (wait_second_half)
+  else c->wait_in1b = true;   // hhmax, the ghost count and its scan run while vel, rho are still on the wire (wait_second_half)
+  const bool will_light = ND_DENS_LIGHT && fast_tuple(c->o) && (!c->has_comm || c->slab_light) && (mask & ND_DL_RATES);   // the rates of this call make drho/dt
+  {
+    // LIGHT rounds read {x, m, h} only: with periodic ghosts (a ghost's velocity is its parent's) and no fixed particles (they keep the
+    // uploaded rho) the link and the whole density iteration run before vel has landed; k_late_vel then completes the records
+    bool plain_ghosts = true;
+    for (int d = 0; d < c->ndim; d++) if (!(c->o.ibound[d] == 0 || c->o.ibound[d] == 3)) plain_ghosts = false;
+    c->defer_vel = will_light && !c->has_comm && plain_ghosts && c->o.device_ghosts && !c->o.onef_dust && !getenv("NDSPMHD_B200_NO_DEFER");
+  }
   CU(cudaEventRecord(c->ev[0], c->stream));
   int e = DISPATCH_NDIM(c, do_link<1>(c), do_link<2>(c), do_link<3>(c));
-  if (c->wait_in1b) { c->wait_in1b = false; cudaStreamWaitEvent(c->stream, c->ev_in[2], 0); }   // the link left early (error): join anyway
   bool light = false;
   if (!e) {
     CU(cudaEventRecord(c->ev[1], c->stream));
-    c->dens_light = ND_DENS_LIGHT && fast_tuple(c->o) && (!c->has_comm || c->slab_light) && (mask & ND_DL_RATES);   // the rates of this call make drho/dt
+    c->dens_light = will_light;
     light = c->dens_light;
     e = DISPATCH_NDIM(c, do_iterate_density<1>(c, 0), do_iterate_density<2>(c, 0), do_iterate_density<3>(c, 0));
     c->dens_light = false;
+  }
+  if (c->wait_in1b || c->defer_vel) {   // join the second half of the upload (also when the link or the iteration left early)
+    c->wait_in1b = false;
+    cudaStreamWaitEvent(c->stream, c->ev_in[2], 0);
+    if (c->defer_vel && !e) LAUNCH(c, k_late_vel, nblocks(c->ntotal, 256), 256, 0, c->perm, c->ireal, c->vel, c->pmass, c->vm, c->npart, c->ntotal);
+    c->defer_vel = false;
   }
   if (e) { cudaStreamSynchronize(c->stream_h2d); return e; }
   if (idim < c->ntotal) { cudaStreamSynchronize(c->stream_h2d); return set_err(c, ND_ERR_INVALID_ARG, "derivs_host: idim < ntotal after ghost generation"); }

@@ -57,9 +57,14 @@ __device__ __forceinline__ void density_target(const Grid &G, const DensityArgs 
   double xi = 0, yi = 0, zi = 0, vxi = 0, vyi = 0, vzi = 0, mi = 0, hi = 1;
   int cs0 = 0, cs1 = 0, cnt = 0;
   if (active) {
-    double4 p = ld4(G.posh + s), v = ld4(G.vm + s);
-    xi = p.x; yi = p.y; zi = p.z;
-    vxi = v.x; vyi = v.y; vzi = v.z; mi = v.w;
+    if (LIGHT) {                                   // LIGHT rounds read no velocity at all (derivs_host may still be uploading them)
+      const double4 p = ld4(G.posm + s);
+      xi = p.x; yi = p.y; zi = p.z; mi = p.w;
+    } else {
+      const double4 p = ld4(G.posh + s), v = ld4(G.vm + s);
+      xi = p.x; yi = p.y; zi = p.z;
+      vxi = v.x; vyi = v.y; vzi = v.z; mi = v.w;
+    }
     hi = A.hh[orig];                               // current h (1/h == p.w in the first round)
     const int celli = G.cellOf[s];
     cs0 = cell_begin(G, celli); cs1 = cell_begin(G, celli + 1);

@@ -440,6 +440,7 @@ int migrate_rows(nd_ctx *c) {
 // derivs_host uploads {x, hh, itype, ireal} first and {vel, pmass, rho} behind them: the compute stream joins the second half here,
 // right before its first reader (the ghost rows' velocities, else the sorted records)
 int wait_second_half(nd_ctx *c) {
+  if (c->defer_vel) return 0;   // nothing before the end of the density iteration reads them (derivs_host)
   if (c->wait_in1b) { CU(cudaStreamWaitEvent(c->stream, c->ev_in[2], 0)); c->wait_in1b = false; }
   return 0;
 }
@@ -453,7 +454,7 @@ template <int NDIM> int make_ghosts(nd_ctx *c) {
   c->ntotal = np;
   if (!any_ghost_bound(c)) return 0;
   GhostArgs A;
-  A.x = c->x; A.vel = c->vel; A.hh = c->hh; A.itype = c->itype; A.ireal = c->ireal; A.offset = c->scanout; A.count = c->ghostcount;
+  A.x = c->x; A.vel = c->defer_vel ? nullptr : c->vel; A.hh = c->hh; A.itype = c->itype; A.ireal = c->ireal; A.offset = c->scanout; A.count = c->ghostcount;
   A.npart = np; A.cap = c->cap; A.radkern = c->T->radkern; A.hhmax = c->hhmax; A.flags = c->flags;
   for (int d = 0; d < 3; d++) { A.ibound[d] = d < NDIM ? local_ibound(c, d) : 0; A.xmin[d] = c->o.xmin[d]; A.xmax[d] = c->o.xmax[d]; }
   LAUNCH(c, (k_ghosts<NDIM, false>), nblocks(np, 256), 256, 0, A);
@@ -462,7 +463,7 @@ template <int NDIM> int make_ghosts(nd_ctx *c) {
   CU(cudaStreamSynchronize(c->stream));
   const int nghost = c->h_flags[25];
   if (int e = ensure_capacity(c, np + nghost, np)) return e;
-  A.x = c->x; A.vel = c->vel; A.hh = c->hh; A.itype = c->itype; A.ireal = c->ireal; A.offset = c->scanout; A.count = c->ghostcount; A.cap = c->cap;
+  A.x = c->x; A.vel = c->defer_vel ? nullptr : c->vel; A.hh = c->hh; A.itype = c->itype; A.ireal = c->ireal; A.offset = c->scanout; A.count = c->ghostcount; A.cap = c->cap;
   // ensure_capacity may have reallocated scanout: redo the scan in that case (cheap)
   if (int e = exclusive_scan(c, c->ghostcount, c->scanout, np)) return e;
   A.offset = c->scanout;
@@ -526,7 +527,7 @@ template <int NDIM> int build_cells(nd_ctx *c) {
   LAUNCH(c, k_cell_scatter, nblocks(nt, 256), 256, 0, c->cellOfOrig, nt, c->cellStart, c->cellCount, c->permtmp);
   LAUNCH(c, k_cell_order, nblocks((long long)c->ncells * 32, 256), 256, 0, c->cellStart, c->ncells, c->permtmp, c->perm);
   GatherArgs GA;
-  GA.perm = c->perm; GA.cellOfOrig = c->cellOfOrig; GA.itype = c->itype; GA.ireal = c->ireal; GA.x = c->x; GA.vel = c->vel; GA.pmass = c->pmass; GA.hh = c->hh;
+  GA.perm = c->perm; GA.cellOfOrig = c->cellOfOrig; GA.itype = c->itype; GA.ireal = c->ireal; GA.x = c->x; GA.vel = c->defer_vel ? nullptr : c->vel; GA.pmass = c->pmass; GA.hh = c->hh;
   GA.posh = c->posh; GA.vm = c->vm; GA.posm = c->posm; GA.p32 = c->p32; GA.typ = c->typ; GA.cellOf = c->cellOf; GA.inv = c->inv; GA.npart = c->npart; GA.ntotal = nt;
   for (int d = 0; d < 3; d++) GA.xminpart[d] = c->xminpart[d];
   GA.dxcell1 = 1.0 / c->dxcell; GA.hhmax1 = 1.0 / c->hhmax; GA.mixed = c->flags + 6;

@@ -126,7 +126,7 @@ template <int NDIM, bool WRITE> __global__ void k_ghosts(GhostArgs A) {
     any = any || ((dhi < dxbound[d]) && (dhi > 0)) || ((dlo < dxbound[d]) && (dlo > 0));
   }
   if (!any) { if (!WRITE) A.count[j] = 0; return; }
-  for (int d = 0; d < 3; d++) vj[d] = A.vel[(size_t)j * 3 + d];
+  for (int d = 0; d < 3; d++) vj[d] = A.vel ? A.vel[(size_t)j * 3 + d] : 0.;   // vel = NULL: velocities follow later (k_late_vel; periodic ghosts only)
   int n = 0;
   const int base = WRITE ? A.npart + A.offset[j] : 0;
   auto make = [&](const double *xp, const double *vp) {                                            // makeghost, :363-431
@@ -134,7 +134,7 @@ template <int NDIM, bool WRITE> __global__ void k_ghosts(GhostArgs A) {
       const int r = base + n;
       if (r < A.cap) {
         for (int d = 0; d < NDIM; d++) A.x[(size_t)r * NDIM + d] = xp[d];
-        for (int d = 0; d < 3; d++) A.vel[(size_t)r * 3 + d] = vp[d];
+        if (A.vel) for (int d = 0; d < 3; d++) A.vel[(size_t)r * 3 + d] = vp[d];
         A.ireal[r] = j + 1;
         A.itype[r] = A.itype[j];                                                                   // :346
       }
@@ -426,13 +426,25 @@ template <int NDIM> __global__ void k_gather_sorted(GatherArgs A) {
   float q[3] = {0.f, 0.f, 0.f};
   for (int d = 0; d < NDIM; d++) q[d] = (float)((p[d] - A.xminpart[d]) * A.dxcell1);
   A.p32[s] = make_float4(q[0], q[1], q[2], screen_h2(A.hh[st], A.hhmax1));
-  A.vm[s] = make_double4(A.vel[(size_t)r * 3], A.vel[(size_t)r * 3 + 1], A.vel[(size_t)r * 3 + 2], A.pmass[st]);
+  if (A.vel) A.vm[s] = make_double4(A.vel[(size_t)r * 3], A.vel[(size_t)r * 3 + 1], A.vel[(size_t)r * 3 + 2], A.pmass[st]);
   A.posm[s] = make_double4(p[0], p[1], p[2], A.pmass[st]);
   A.typ[s] = A.itype[r];
   if (A.sdf) A.sdf[s] = A.dustfrac[st];
   if (A.itype[r] != A.itype[0]) *A.mixed = 1;
   A.cellOf[s] = A.cellOfOrig[r] / CELL_FX;
   A.inv[r] = s;
+}
+// derivs_host, fast tuple with periodic ghosts only: the LIGHT density rounds never read a velocity, so the link and the density iteration
+// run while vel is still on the wire; this fills what was left out -- the ghost rows' velocities (a periodic ghost carries its parent's,
+// src/ghostND_mhd.f90:363-431) and the sorted {v, m} records -- before cons2prim and the rates
+__global__ void k_late_vel(const int *perm, const int *ireal, double *vel, const double *pmass, double4 *vm, int npart, int ntotal) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ntotal) return;
+  const int r = perm[s];
+  const int st = (r < npart) ? r : ireal[r] - 1;
+  const double vx = vel[(size_t)st * 3], vy = vel[(size_t)st * 3 + 1], vz = vel[(size_t)st * 3 + 2];
+  if (r >= npart) { vel[(size_t)r * 3] = vx; vel[(size_t)r * 3 + 1] = vy; vel[(size_t)r * 3 + 2] = vz; }
+  vm[s] = make_double4(vx, vy, vz, pmass[st]);
 }
 __global__ void k_refresh_h(const int *perm, const int *ireal, const double *hh, double4 *posh, float4 *p32, double hhmax1, int npart, int ntotal) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
