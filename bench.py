@@ -65,7 +65,7 @@ def cfg_of(args):
     return c
 
 
-def workload(args_or_cfg, nx=None, slab=None):
+def workload(args_or_cfg, nx=None, slab=None, weak=False):
     """(options, particles[, info]) of a config at `nx` particles per unit length (default: the config's own size)."""
     from ndspmhd_b200 import setups
 
@@ -82,7 +82,7 @@ def workload(args_or_cfg, nx=None, slab=None):
         kw.update(cube=c["cube"], zfrac=0.125)
     else:
         kw.update(lattice="cp")
-    out = setups.orszag_tang(slab=slab, **kw)
+    out = setups.orszag_tang(slab=slab, weak=weak, **kw)
     out[0].device_ghosts, out[0].want_aux = 1, 0
     return out
 

@@ -122,6 +122,24 @@ module ndspmhd_b200
     integer(c_int) function ndspmhd_b200_download_state(ctx,st,idim) bind(C,name='ndspmhd_b200_download_state')
      import; type(c_ptr), value :: ctx; type(nd_state_out), intent(in) :: st; integer(c_int), value :: idim
     end function
+    ! multi-GPU hosts (one rank per GPU, x-slabs): the native NCCL transport and the row ids that follow a particle between slabs
+    integer(c_int) function ndspmhd_b200_nccl_unique_id(id) bind(C,name='ndspmhd_b200_nccl_unique_id')
+     import; integer(c_signed_char), intent(out) :: id(128)
+    end function
+    integer(c_int) function ndspmhd_b200_set_comm_nccl(ctx,id,rank,nranks,slab_lo,slab_hi,nglobal) &
+                    bind(C,name='ndspmhd_b200_set_comm_nccl')
+     import; type(c_ptr), value :: ctx; integer(c_signed_char), intent(in) :: id(128); integer(c_int), value :: rank,nranks
+     real(c_double), value :: slab_lo,slab_hi; integer(c_long_long), value :: nglobal
+    end function
+    integer(c_int) function ndspmhd_b200_set_row_ids(ctx,ids,n) bind(C,name='ndspmhd_b200_set_row_ids')
+     import; type(c_ptr), value :: ctx; integer(c_long_long), intent(in) :: ids(*); integer(c_int), value :: n
+    end function
+    integer(c_int) function ndspmhd_b200_get_row_ids(ctx,ids,cap) bind(C,name='ndspmhd_b200_get_row_ids')
+     import; type(c_ptr), value :: ctx; integer(c_long_long), intent(out) :: ids(*); integer(c_int), value :: cap
+    end function
+    integer(c_int) function ndspmhd_b200_row_counts(ctx,nown,nsrc,ntotal) bind(C,name='ndspmhd_b200_row_counts')
+     import; type(c_ptr), value :: ctx; integer(c_int), intent(out) :: nown,nsrc,ntotal
+    end function
  end interface
 
  type(c_ptr), save :: b200_ctx = c_null_ptr     ! one context per process (the reference is single-threaded)

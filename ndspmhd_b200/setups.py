@@ -151,11 +151,15 @@ def _alloc(ndim, x, opts, hmax_guess, extra=0):
 # C2 / C3 / C5: Orszag-Tang vortex, 2D or 3D thin slab / cube (src/setup_orszagtang2D_mhd.f90)
 # ---------------------------------------------------------------------------------------------------------
 def orszag_tang(ndim=2, nx=64, lattice="cubic", zfrac=0.125, perturb_amp=0.0, imhd=11, idivbzero=2, iener=2,
-                evolved=True, seed=268, cube=False, slab=None):
+                evolved=True, seed=268, cube=False, slab=None, weak=False):
     """Periodic box [-0.5,0.5]^2 (x [-zfrac/2, zfrac/2] in 3D, or a unit cube with cube=True).
 
     slab=(rank, nranks): build only the rows of one x-slab of the same global particle set (multi-GPU runs); the return
     value is then (options, particles, info) with info = {edges, nglobal, rows (global indices of the local rows)}.
+
+    weak=True (with slab): the box is `nranks` periods long in x -- [-0.5, -0.5 + nranks] -- and every rank makes only its own period (the
+    fields have period 1 in x; lattice points sit at cell centres and the perturbation is < psep/2, so no particle leaves its period):
+    per-GPU work stays fixed as ranks are added.
 
     evolved=True puts non-trivial psi / alpha / energy perturbations on the particles so every term of the
     rates is exercised (the t=0 state has psi=0 and uniform alpha, u).
@@ -174,10 +178,20 @@ def orszag_tang(ndim=2, nx=64, lattice="cubic", zfrac=0.125, perturb_amp=0.0, im
         x, _ = cubic_lattice(xmin, xmax, psep)
     else:
         x, _ = closepacked_lattice(xmin, xmax, psep)
-    x = wrap_periodic(perturb(x, psep, perturb_amp, seed), o)
-    nglobal = x.shape[0]
-    info = None
-    if slab is not None:
+    if weak and slab is not None:
+        rank, nranks = slab
+        x = perturb(x, psep, min(perturb_amp, 0.9), seed + 1000 * rank)       # |dx| < psep/2: stays inside its lattice cell, hence its period
+        x[:, 0] += float(rank)
+        o.xmax[0] = xmax[0] = xmin[0] + float(nranks)
+        nglobal = x.shape[0] * nranks
+        info = {"edges": xmin[0] + np.arange(nranks + 1, dtype=np.float64), "nglobal": nglobal, "rows": np.arange(x.shape[0]) + rank * x.shape[0]}
+        slab_done = True
+    else:
+        x = wrap_periodic(perturb(x, psep, perturb_amp, seed), o)
+        nglobal = x.shape[0]
+        info = None
+        slab_done = False
+    if slab is not None and not slab_done:
         from .slab import owner_of, slab_edges
 
         rank, nranks = slab

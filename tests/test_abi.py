@@ -171,7 +171,7 @@ def test_fortran_module_types_match_the_c_abi():
             v = f["vars"][fa]
             byval = "value" in (v.get("attrspec") or [])
             is_cptr = v.get("typespec") == "type" and "c_ptr" in str(v.get("typename", "")).lower()
-            if "*" in ca:
+            if "*" in ca or "[" in ca:                  # a C array parameter is a pointer
                 assert (not byval) or is_cptr, (f["name"], fa, ca)
             else:
                 assert byval and not is_cptr, (f["name"], fa, ca)
