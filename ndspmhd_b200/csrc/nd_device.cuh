@@ -226,6 +226,7 @@ struct NbrLists {
   int *cnt;        // [targets in the launch]
   int lmax;        // column capacity
   int *overflow;   // set to the largest count seen when a column overflows (host grows lmax and repeats)
+  int split;       // LIST_RATES with drag: cnt = front | back << 16 -- pairs whose types interact from the column's start, gas-dust (drag) pairs from its end
 };
 __device__ __forceinline__ size_t nbr_index(int t, int n, int lmax) { return ((size_t)(t >> 5) * lmax + n) * 32 + (t & 31); }
 
@@ -287,8 +288,9 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
   const int ix = cell % G.nx;
   const int tq = cell / G.nx;
   const int iy = (NDIM >= 2) ? tq % G.ny : 0, iz = (NDIM >= 3) ? tq / G.ny : 0;
-  int cnt = 0, nneigh = 0;
+  int cnt = 0, cntb = 0, nneigh = 0;
   unsigned *col = L.nbr + ((size_t)(t >> 5) * L.lmax) * 32 + (t & 31);
+  const bool split = (MODE == LIST_RATES) && TYPES && L.split;
   const bool hook = (MODE == LIST_RATES) && A.pair_out_i != nullptr;
 
   // Exact inclusion test in the reference's arithmetic (rare path, see below): sets whether the pair counts as a neighbour
@@ -359,6 +361,7 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
         }
       }
     }
+    unsigned mback = 0u;                                          // drag runs: the pairs drag_forces takes (types do not interact)
     if (TYPES) {
       for (unsigned m = mcount; m; m &= m - 1u) {
         const int u = __ffs(m) - 1;
@@ -366,14 +369,22 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
         bool ok;
         if (MODE == LIST_DENS_FIRST) ok = types_interact(ti, tj);   // density_sums.f90:169-174
         else if (MODE == LIST_DENS_PARTIAL) ok = (tj == ti) || (tj == T_BND);   // :517
-        else ok = A.drag || types_interact(ti, tj);                 // ratesND_mhd.f90:436-446
+        else {                                                      // ratesND_mhd.f90:436-446
+          const bool inter = types_interact(ti, tj);
+          ok = A.drag || inter;
+          if (split && !inter) mback |= 1u << u;
+        }
         if (!ok) { mcount &= ~(1u << u); mstore &= ~(1u << u); }
       }
     }
     nneigh += __popc(mcount);                                     // :196-197 / :532
-    for (unsigned m = mstore; m; m &= m - 1u) {
-      if (cnt < L.lmax) col[(size_t)cnt * 32] = (unsigned)(g0 + __ffs(m) - 1);
+    for (unsigned m = mstore & ~mback; m; m &= m - 1u) {
+      if (cnt + cntb < L.lmax) col[(size_t)cnt * 32] = (unsigned)(g0 + __ffs(m) - 1);
       cnt++;
+    }
+    for (unsigned m = mstore & mback; m; m &= m - 1u) {           // from the end of the column downwards
+      if (cnt + cntb < L.lmax) col[(size_t)(L.lmax - 1 - cntb) * 32] = (unsigned)(g0 + __ffs(m) - 1);
+      cntb++;
     }
   };
 
@@ -409,8 +420,8 @@ __global__ void __launch_bounds__(128) build_lists_kernel(Grid G, ListArgs A, Nb
       for (; k < e; k += 32) scan_group(k, min(32, e - k));
     }
   }
-  if (cnt > L.lmax) { atomicMax(L.overflow, cnt); cnt = L.lmax; }
-  L.cnt[t] = cnt;
+  if (cnt + cntb > L.lmax) { atomicMax(L.overflow, cnt + cntb); cnt = min(cnt, L.lmax); cntb = 0; }
+  L.cnt[t] = split ? (cnt | (cntb << 16)) : cnt;
   if (MODE != LIST_RATES) A.numneigh[orig] = nneigh;
 }
 

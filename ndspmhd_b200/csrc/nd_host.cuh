@@ -594,6 +594,7 @@ template <int NDIM, int MODE> int build_lists(nd_ctx *c, const Grid &G, ListArgs
   for (int attempt = 0; attempt < 8; attempt++) {
     if (int e = ensure_lists(c, LA.ntargets)) return e;
     L.nbr = c->nbr; L.cnt = c->lcnt; L.lmax = c->lmax; L.overflow = c->flags + 5;
+    L.split = (MODE == LIST_RATES && LA.drag && c->mixed_types && c->lmax < 65536) ? 1 : 0;   // drag runs: hydro pairs in front, drag pairs at the back
     if (c->mixed_types) LAUNCH(c, (build_lists_kernel<NDIM, MODE, true>), nblocks(LA.ntargets, 128), 128, 0, G, LA, L);
     else LAUNCH(c, (build_lists_kernel<NDIM, MODE, false>), nblocks(LA.ntargets, 128), 128, 0, G, LA, L);
     SMALL_D2H(c, c->h_flags + 20, c->flags + 5, sizeof(int));
@@ -796,7 +797,7 @@ template <int NDIM, bool MHD, bool DRAG, int FAST, bool ONEF> int launch_rates_p
     LA.pair_out_i = pi; LA.pair_out_j = pj; LA.pair_count = pc; LA.pair_cap = cap;
     NbrLists L;
     if (int e = build_lists<NDIM, LIST_RATES>(c, G, LA, L)) return e;
-    LAUNCH(c, k_sum_counts, std::min(nblocks(m, 256), 1184), 256, 0, L.cnt, m, c->red + RED_NPAIRS, c->red + RED_NTRIPS);
+    LAUNCH(c, k_sum_counts, std::min(nblocks(m, 256), 1184), 256, 0, L.cnt, m, L.split, c->red + RED_NPAIRS, c->red + RED_NTRIPS);
     // persistent blocks: one per resident slot (the 64 KB shared-memory table is loaded once per block)
     static int resident = 0, carveout = 100;
     auto kfn = rates_pair_kernel<NDIM, MHD, DRAG, FAST, ONEF>;

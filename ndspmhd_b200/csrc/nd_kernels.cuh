@@ -476,15 +476,16 @@ __global__ void k_minmax_neigh(const int *numneigh, int n, int *out /* [0] min [
 // sum of the list lengths of one build (nd_scalars.npairs_rates)
 // and of the pair-loop trips of the warps that will walk them (a warp owns 32 consecutive targets and loops to its longest list:
 // nd_scalars.ntrips_rates, the work figure of the FP64-pipe roofline)
-__global__ void k_sum_counts(const int *cnt, int n, unsigned long long *out, unsigned long long *out_trips) {
+__global__ void k_sum_counts(const int *cnt, int n, int split, unsigned long long *out, unsigned long long *out_trips) {
   unsigned long long s = 0, tr = 0;
   for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {   // blockDim is a multiple of 32: lanes stay aligned to list columns
     const int i = i0 + threadIdx.x;
     const int v = i < n ? cnt[i] : 0;
-    s += (unsigned long long)v;
-    int m = v;
-    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o));
-    tr += (unsigned long long)m;
+    // split lists (drag runs): front | back << 16, two loops a warp
+    int m = split ? (v & 0xffff) : v, mb = split ? (v >> 16) : 0;
+    s += (unsigned long long)(m + mb);
+    for (int o = 16; o; o >>= 1) { m = max(m, __shfl_xor_sync(FULL, m, o)); mb = max(mb, __shfl_xor_sync(FULL, mb, o)); }
+    tr += (unsigned long long)(m + mb);
   }
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
   if ((threadIdx.x & 31) == 0) { if (s) atomicAdd(out, s); if (tr) atomicAdd(out_trips, tr); }

@@ -166,8 +166,12 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
 
   bool any_coincident = false, vsig_det_bad = false;
   // ---- pair terms over the neighbour list (build_lists_kernel<LIST_RATES> applied src/ratesND_mhd.f90:401-415) ----
-  auto body = [&](int k, const double4 &pj, const double4 &vj, const double4 &tj4, const double4 &gj, const double4 &bj) {
-    const int tj = DRAG ? __ldg(G.typ + k) : 0;   // only the drag dispatch needs the neighbour's type on the fast path
+  // KIND (compile time): 0 = the type rule decides per pair; 1 = a pair of the list's front part (types interact: rates_core);
+  // 2 = a pair of its back part (gas-dust: drag_forces).  The builder splits the lists of drag runs by that rule, so a warp's lanes no
+  // longer take both branches of every trip (gas and dust rows alternate in a cell).
+  auto body = [&](auto kind_c, int k, const double4 &pj, const double4 &vj, const double4 &tj4, const double4 &gj, const double4 &bj) {
+    constexpr int KIND = decltype(kind_c)::value;
+    const int tj = (DRAG && KIND != 1) ? __ldg(G.typ + k) : 0;   // only the drag branch needs the neighbour's type
     const double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
     const double rij2 = dist2_exact(dx, dy, dz);
     const double hj1 = pj.w, hj21 = __dmul_rn(hj1, hj1);
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
     const double pmassj = vj.w;
     const double dvx = vxi - vj.x, dvy = vyi - vj.y, dvz = vzi - vj.z;
     const double h1max = ND_FMAX(hi1, hj1);
-    if (!DRAG || types_interact(ti, tj)) {
+    if (!DRAG || KIND == 1 || (KIND == 0 && types_interact(ti, tj))) {
       // =============================== rates_core ===============================
       // kernel gradient table rows for q2i, q2j: the loads are issued here, the interpolation (their first use) comes after the
       // signal-velocity block so that ~250 independent FP64 instructions cover the lookup latency
@@ -453,7 +457,7 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
           gvx += c * (dvx - dvdotr); gvy += c * (dvy - dvdotr); gvz += c * (dvz - dvdotr);
         }
       }
-    } else if (DRAG) {
+    } else if (DRAG && KIND != 1) {
       // =============================== drag_forces ===============================
       const double rhoj = __ldg(I.srho + k);
       const double dv2 = (dvx * dvx + dvy * dvy) + dvz * dvz;
@@ -479,26 +483,40 @@ __global__ void __launch_bounds__(RATES_BLOCK, ND_RATES_MINB) rates_pair_kernel(
     }
   };
 
-  if (cnt > 0) {
-    const unsigned *col = L.nbr + ((size_t)(tix >> 5) * L.lmax) * 32 + (tix & 31);
+  // drag runs: the builder packs two counts -- low half = front part (pairs whose types interact), high half = back part (gas-dust pairs,
+  // stored from the end of the column downwards)
+  int cnt_drag = 0;
+  if (DRAG && L.split) { cnt_drag = cnt >> 16; cnt &= 0xffff; }
+  {
+    const unsigned *col0 = L.nbr + ((size_t)(tix >> 5) * L.lmax) * 32 + (tix & 31);
     const double4 zero4 = make_double4(0., 0., 0., 0.);
-    if (ONEF) {   // the one-fluid dust instantiations have no registers to spare: direct loads
-      walk_list(col, cnt, [&](int n, int k, int k1, int k2) { body(k, ld4(G.posh + k), ld4(G.vm + k), ld4(I.thermo + k), ld4(I.gal + k), MHD ? ld4(I.bpsi + k) : zero4); });
-    } else {
-      // Register software pipeline: all five records of the next neighbour are in flight while this pair is evaluated.  The list
-      // column is read two entries ahead with plain rotation (k <- k1 <- k2 <- load): one coalesced load per pair and no branch in
-      // the loop besides its own.
-      const int last = cnt - 1;
-      int k = (int)__ldcs(col), k1 = (int)__ldcs(col + (size_t)min(1, last) * 32);
-      double4 pn = ld4(G.posh + k), vn = ld4(G.vm + k), tn = ld4(I.thermo + k), gn = ld4(I.gal + k), bn = MHD ? ld4(I.bpsi + k) : zero4;
+    // walks `count` entries of the column from `col` with stride `step` lines (+1 front part, -1 back part)
+    auto run = [&](auto kind_c, const unsigned *col, int count, long long step) {
+      if (count <= 0) return;
+      if (ONEF) {   // the one-fluid dust instantiations have no registers to spare: direct loads
+        walk_list(col, count, [&](int n, int k, int k1, int k2) { body(kind_c, k, ld4(G.posh + k), ld4(G.vm + k), ld4(I.thermo + k), ld4(I.gal + k), MHD ? ld4(I.bpsi + k) : zero4); });
+      } else {
+        // Register software pipeline: all five records of the next neighbour are in flight while this pair is evaluated.  The list
+        // column is read two entries ahead with plain rotation (k <- k1 <- k2 <- load): one coalesced load per pair and no branch in
+        // the loop besides its own.
+        const int last = count - 1;
+        int k = (int)__ldcs(col), k1 = (int)__ldcs(col + (long long)min(1, last) * 32 * step);
+        double4 pn = ld4(G.posh + k), vn = ld4(G.vm + k), tn = ld4(I.thermo + k), gn = ld4(I.gal + k), bn = MHD ? ld4(I.bpsi + k) : zero4;
 #pragma unroll 1
-      for (int n = 0; n < cnt; n++) {
-        const int k2 = (int)__ldcs(col + (size_t)min(n + 2, last) * 32);
-        const double4 pc = pn, vc = vn, tc = tn, gc = gn, bc = bn;
-        pn = ld4(G.posh + k1); vn = ld4(G.vm + k1); tn = ld4(I.thermo + k1); gn = ld4(I.gal + k1); bn = MHD ? ld4(I.bpsi + k1) : zero4;
-        body(k, pc, vc, tc, gc, bc);
-        k = k1; k1 = k2;
+        for (int n = 0; n < count; n++) {
+          const int k2 = (int)__ldcs(col + (long long)min(n + 2, last) * 32 * step);
+          const double4 pc = pn, vc = vn, tc = tn, gc = gn, bc = bn;
+          pn = ld4(G.posh + k1); vn = ld4(G.vm + k1); tn = ld4(I.thermo + k1); gn = ld4(I.gal + k1); bn = MHD ? ld4(I.bpsi + k1) : zero4;
+          body(kind_c, k, pc, vc, tc, gc, bc);
+          k = k1; k1 = k2;
+        }
       }
+    };
+    if (DRAG && L.split) {
+      run(std::integral_constant<int, 1>{}, col0, cnt, 1);
+      run(std::integral_constant<int, 2>{}, col0 + (size_t)(L.lmax - 1) * 32, cnt_drag, -1);
+    } else {
+      run(std::integral_constant<int, 0>{}, col0, cnt, 1);
     }
   }
 
