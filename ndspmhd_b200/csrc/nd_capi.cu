@@ -630,9 +630,9 @@ int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int
   // The rates run in row chunks (do_get_rates) so that a chunk's rows go down the wire while the next chunk's pair kernel
   // runs; what is left after the last kernel is one chunk, dpsidt and the (zero) ghost rows instead of the whole 168 B/row.
   int nchunk = 1;
-  if (!c->has_comm && (mask & ND_DL_RATES)) {
+  if (mask & ND_DL_RATES) {   // slab contexts too: a rank's own rows go down its own PCIe link while its next chunk runs
     if (const char *ev = getenv("NDSPMHD_B200_RATE_CHUNKS")) nchunk = std::max(1, std::min(64, atoi(ev)));
-    else if (c->npart >= (1 << 20)) nchunk = 4;
+    else if (c->nown >= (1 << 20)) nchunk = 4;
   }
   std::vector<cudaEvent_t> &cev = c->chunk_events;
   while ((int)cev.size() < nchunk) { cudaEvent_t x; CU(cudaEventCreateWithFlags(&x, cudaEventDisableTiming)); cev.push_back(x); }

@@ -611,7 +611,7 @@ template <int NDIM, int MODE> int build_lists(nd_ctx *c, const Grid &G, ListArgs
 // the first-class option tuple (FAST instantiations of the rates pair kernel): no run-time option tests, and the kernel also
 // makes drho/dt (so the density rounds of a fused derivs can run LIGHT)
 static bool fast_tuple(const nd_options &o) {
-  return o.idust != 2 && o.idust != 1 && !o.want_aux && o.iav == 2 && (o.iener == 0 || o.iener == 2) && o.ikernav == 3 && o.iresist == 0 && o.iavlim[0] != 3 &&
+  return (o.idust != 2 || o.imhd == 0) && o.idust != 1 && !o.want_aux && o.iav == 2 && (o.iener == 0 || o.iener == 2) && o.ikernav == 3 && o.iresist == 0 && o.iavlim[0] != 3 &&
          o.iavlim[2] != 2;
 }
 
@@ -877,6 +877,8 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
   auto pair = [&](const int *targets, int ntargets) -> int {
     if (o.idust == 1 && mhd) return launch_rates_pair<NDIM, true, false, 0, true>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
     if (o.idust == 1) return launch_rates_pair<NDIM, false, false, 0, true>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
+    if (!mhd && drag && fast && o.iener != 0) return launch_rates_pair<NDIM, false, true, 2, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);   // two-fluid dust, hydro
+    if (!mhd && drag && fast) return launch_rates_pair<NDIM, false, true, 1, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
     if (mhd && fast && o.iener != 0) return launch_rates_pair<NDIM, true, false, 2, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
     if (mhd && fast) return launch_rates_pair<NDIM, true, false, 1, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
     if (!mhd && fast && o.iener != 0) return launch_rates_pair<NDIM, false, false, 2, false>(c, I, O, S, R, pi, pj, pc, cap, targets, ntargets);
@@ -905,18 +907,17 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
     }
     FA.partial = c->finalpart;
   }
-  const int nchunk = (c->rate_chunks > 1 && !c->has_comm && !pi) ? c->rate_chunks : 1;
+  const int nchunk = (c->rate_chunks > 1 && !pi) ? c->rate_chunks : 1;
   c->rate_chunks_used = nchunk;
-  if (nchunk == 1) {
-    if (int e = pair(nullptr, 0)) return e;
-    CU(cudaEventRecord(c->ev[4], c->stream));
-    if (c->has_comm && c->nccl) {   // the global maximum is consumed on the device (k_rates_final): no host round trip at all
+  // vsigmax feeds dpsidt (:518-520, :902): with slabs all ranks need the global maximum of the pair kernels before it is made
+  auto reduce_vsigmax = [&]() -> int {
+    if (c->has_comm && c->nccl) {   // consumed on the device (k_rates_final / k_rates_dpsidt): no host round trip at all
       PackList L; L.add(CP_KEY, c->red + RED_VSIG);
       LAUNCH(c, k_comm_pack, 1, 32, 0, L.P, c->d_comm + 8);
       NCCLCHK(c->nccl_api->AllReduce(c->d_comm + 8, c->d_comm + 8, 1, ND_NCCL_FLOAT64, ND_NCCL_MAX, c->nccl, c->stream));
       c->n_allreduce++;
       LAUNCH(c, k_double_to_key, 1, 1, 0, c->d_comm + 8, c->red + RED_VSIG);
-    } else if (c->has_comm) {   // vsigmax feeds dpsidt in the finalisation loop (:518-520, :902): all ranks need the global maximum
+    } else if (c->has_comm) {
       SMALL_D2H(c, c->h_red, c->red + RED_VSIG, sizeof(unsigned long long));
       CU(cudaStreamSynchronize(c->stream));
       double vs = dkey_inv(c->h_red[0]);
@@ -925,6 +926,12 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
       c->h_red[0] = kv.u | 0x8000000000000000ull;   // key of a non-negative double
       CU(cudaMemcpyAsync(c->red + RED_VSIG, c->h_red, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
     }
+    return 0;
+  };
+  if (nchunk == 1) {
+    if (int e = pair(nullptr, 0)) return e;
+    CU(cudaEventRecord(c->ev[4], c->stream));
+    if (int e = reduce_vsigmax()) return e;
     const int fgrid = std::min(nblocks(np, 256), 8 * c->num_sms);   // persistent: 1.87 ms against 2.15 ms with one row a thread at 16.8 M rows
     LAUNCH(c, k_rates_final, fgrid, 256, 0, FA);
     LAUNCH(c, k_final_reduce, 1, 1024, 0, c->finalpart, fgrid, R, o.onef_dust ? 1 : 0);
@@ -954,6 +961,7 @@ template <int NDIM> int do_get_rates(nd_ctx *c, int *pi, int *pj, unsigned long 
       if (c->on_rates_chunk) { if (int e = c->on_rates_chunk(q, r0, r1)) return e; }
     }
     CU(cudaEventRecord(c->ev[4], c->stream));
+    if (int e = reduce_vsigmax()) return e;
     LAUNCH(c, k_rates_dpsidt, nblocks(np, 256), 256, 0, c->divB, c->psi, c->hh, c->itype, c->red + RED_VSIG, o.psidecayfact, o.imhd, o.idivbzero, c->dpsidt, np);
   }
   ZeroArgs ZA;

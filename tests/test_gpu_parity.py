@@ -38,6 +38,10 @@ CASES = {
     "dustybox3d": (lambda: setups.dustybox(ndim=3, nx=12), 1),
     "dustybox3d_coincident": (lambda: setups.dustybox(ndim=3, nx=10, coincident=True), 1),
     "dustybox3d_const_ts": (lambda: setups.dustybox(ndim=3, nx=10, idrag_nature=2, Kdrag=0.3), 1),
+    # want_aux=0: the two-fluid hydro tuple on the FAST + DRAG instantiation with LIGHT density rounds and kind-split lists
+    "dustybox3d_noaux": (lambda: setups.dustybox(ndim=3, nx=12), 0),
+    "dustybox3d_coincident_noaux": (lambda: setups.dustybox(ndim=3, nx=10, coincident=True), 0),
+    "dustybox3d_const_ts_noaux": (lambda: setups.dustybox(ndim=3, nx=10, idrag_nature=2, Kdrag=0.3), 0),
     # configs[3] variant: one-fluid dust, dust_derivs + artificial_dissipation_dust
     "onefluid_dust3d": (lambda: setups.dustywave_onefluid(ndim=3, nx=12), 1),
     "onefluid_dust3d_unsmoothed": (lambda: setups.dustywave_onefluid(ndim=3, nx=10, use_smoothed_rhodust=False), 1),
@@ -357,7 +361,7 @@ def test_big_matches_oracle_on_a_sampled_subvolume(big):
     parity.assert_parity(p, p2, s, so, o2, aux=False)
 
 
-@pytest.mark.parametrize("name", ["briowu1d", "sod1d", "ot3d_glass", "ot3d_glass_noaux", "dustybox3d", "onefluid_dust3d"])
+@pytest.mark.parametrize("name", ["briowu1d", "sod1d", "ot3d_glass", "ot3d_glass_noaux", "dustybox3d", "dustybox3d_noaux", "onefluid_dust3d"])
 def test_pipelined_derivs_host_parity(name):
     """ndspmhd_b200_derivs_host (copies overlapped with the kernels) against the oracle, including what only this entry point does: density
     outputs downloaded while cons2prim and the rates run (fixed particles: after cons2prim, which gives them their partner's gradgradh)."""

@@ -69,11 +69,12 @@ def test_c3_list_capacity_retry_at_full_size():
     parity.assert_parity(pg, po, sg, so, o, aux=False)
 
 
-def test_c4_two_fluid_fat_box_1e6_gas_1e6_dust():
-    o, pg, po, sg, so = _both(lambda: setups.dustybox(ndim=3, nx=100, perturb_amp=0.05), aux=1)
+@pytest.mark.parametrize("aux", [1, 0])   # 0: the bench's tuple -- FAST + DRAG instantiation, LIGHT rounds, kind-split lists
+def test_c4_two_fluid_fat_box_1e6_gas_1e6_dust(aux):
+    o, pg, po, sg, so = _both(lambda: setups.dustybox(ndim=3, nx=100, perturb_amp=0.05), aux=aux)
     assert pg.npart == 2_000_000
     assert sg["rate_chunks"] == 4
-    errs = parity.assert_parity(pg, po, sg, so, o, aux=True)
+    errs = parity.assert_parity(pg, po, sg, so, o, aux=bool(aux))
     assert max(errs.values()) <= parity.RTOL
 
 

@@ -30,6 +30,19 @@ def main():
         s = hot.derivs()
         hot.download(pl)
         nown, nsrc, nt = slab.row_counts(hot)
+        # the pipelined host call on the same context, rates in three row chunks (their rows go down while the next chunk runs): must equal
+        # the resident path bit for bit -- every target's sums are its own
+        o2, pl2, _ = setups.orszag_tang(slab=(rank, world), **kw)
+        if name == "ot3d_small_h":
+            pl2.hh[: pl2.npart] *= 0.6
+        os.environ["NDSPMHD_B200_RATE_CHUNKS"] = "3"
+        try:
+            s2 = hot.derivs_host(pl2, abi.DL_DENSITY | abi.DL_PRIM | abi.DL_RATES)
+        finally:
+            os.environ.pop("NDSPMHD_B200_RATE_CHUNKS", None)
+        chunk_ok = all(np.array_equal(np.asarray(pl2.arrays[f][: pl.npart]), np.asarray(pl.arrays[f][: pl.npart]))
+                       for f in ("rho", "hh", "force", "dBevoldt", "dendt", "dpsidt", "divB", "curlB", "daldt", "drhodt", "dhdt", "numneigh")) \
+            and s2["dtcourant"] == s["dtcourant"] and s2["npairs_rates"] == s["npairs_rates"] and s2["rate_chunks"] == 3
         hot.close()
         # single-GPU reference on every rank (same device), compare own rows
         og, pg = setups.orszag_tang(**kw)
@@ -55,11 +68,11 @@ def main():
         sc_ok = all(abs(s[k] - sg[k]) <= 1e-11 * abs(sg[k]) for k in ("dtcourant", "dtforce", "dtav", "vsigmax", "stressmax", "fhmax", "hhmax")) \
             and s["itsdensity"] == sg["itsdensity"] and s["nneigh_min"] == sg["nneigh_min"] and s["nneigh_max"] == sg["nneigh_max"] \
             and s["ncalctotal"] == sg["ncalctotal"] and s["nrelink"] == sg["nrelink"]
-        good = (not bad) and same_nn and sc_ok
+        good = (not bad) and same_nn and sc_ok and chunk_ok
         t = torch.tensor([0.0 if good else 1.0], device="cuda"); dist.all_reduce(t)
         ok = ok and t.item() == 0
         print(f"[rank {rank}] {name}: own {nown} halo {nsrc - nown} ghosts {nt - nsrc} its {s['itsdensity']} relink {s['nrelink']} "
-              f"max err {max(errs.values()):.2e} numneigh_equal {same_nn} scalars_ok {sc_ok} -> {'OK' if good else 'FAIL ' + str(bad)}", flush=True)
+              f"max err {max(errs.values()):.2e} numneigh_equal {same_nn} scalars_ok {sc_ok} chunked_host_call_equal {chunk_ok} -> {'OK' if good else 'FAIL ' + str(bad)}", flush=True)
         if not sc_ok:
             print({k: (s[k], sg[k]) for k in ("dtcourant", "dtforce", "dtav", "vsigmax", "stressmax", "fhmax", "hhmax", "itsdensity", "nneigh_min", "nneigh_max", "ncalctotal", "nrelink")})
     dist.barrier(); dist.destroy_process_group()
