@@ -32,6 +32,7 @@ struct nd_ctx {
   cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;   // compute; copy-in / copy-out of derivs_host
   cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_out[3] = {nullptr, nullptr, nullptr};
   bool defer_vel = false;   // derivs_host, LIGHT rounds, periodic ghosts only: vel arrives during the density iteration (k_late_vel)
+  bool wait_in2 = false;    // derivs_host on a slab context: en, Bevol, alpha, psi (ev_in[1]) are first read by the halo exchange after the density iteration
   bool wait_in1b = false;   // derivs_host: vel, pmass, rho are still on their way (ev_in[2]); the link waits for them where it first reads them
   std::string err;
   long long launches = 0;
@@ -583,8 +584,9 @@ int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int
   c->npart = npart; c->ntotal = ntotal; c->nown = npart;
   c->uploaded = true; c->linked = c->density_done = c->prim_done = c->rates_done = false;
   CU(cudaStreamWaitEvent(c->stream, c->ev_in[0], 0));
-  // slab contexts pack en, Bevol, alpha, psi into the halo records during the link (k_halo_pack1): group 2 must have landed too
-  if (c->has_comm) CU(cudaStreamWaitEvent(c->stream, c->ev_in[1], 0));
+  // slab contexts pack x, vel, pmass, hh, rho into the halo records during the link (k_halo_pack1): the whole first group must have landed;
+  // en, Bevol, alpha, psi travel after the density iteration (halo_exchange_density waits for them)
+  if (c->has_comm) { CU(cudaStreamWaitEvent(c->stream, c->ev_in[2], 0)); c->wait_in2 = true; }
   else c->wait_in1b = true;   // hhmax, the ghost count and its scan run while vel, rho are still on the wire (wait_second_half)
   const bool will_light = ND_DENS_LIGHT && fast_tuple(c->o) && (!c->has_comm || c->slab_light) && (mask & ND_DL_RATES);   // the rates of this call make drho/dt
   {
@@ -604,6 +606,7 @@ int ndspmhd_b200_derivs_host(nd_ctx *c, nd_arrays *a, int npart, int ntotal, int
     e = DISPATCH_NDIM(c, do_iterate_density<1>(c, 0), do_iterate_density<2>(c, 0), do_iterate_density<3>(c, 0));
     c->dens_light = false;
   }
+  if (c->wait_in2) { c->wait_in2 = false; cudaStreamWaitEvent(c->stream, c->ev_in[1], 0); }   // the iteration left early (error): join anyway
   if (c->wait_in1b || c->defer_vel) {   // join the second half of the upload (also when the link or the iteration left early)
     c->wait_in1b = false;
     cudaStreamWaitEvent(c->stream, c->ev_in[2], 0);

@@ -253,7 +253,7 @@ int exchange_counts(nd_ctx *c, const long long sb[2], long long rb[2]) {
 HaloPackArgs halo_args(nd_ctx *c) {
   HaloPackArgs A;
   A.ndim = c->ndim; A.x = c->x; A.vel = c->vel; A.pmass = c->pmass; A.hh = c->hh; A.en = c->en; A.Bevol = c->Bevol; A.alpha = c->alpha; A.psi = c->psi;
-  A.rho = c->rho; A.gradh = c->gradh; A.itype = c->itype; A.shift = 0; A.xbound = A.xperbound = 0.; A.row0 = 0; A.list = nullptr; A.n = 0; A.buf = nullptr;
+  A.rho = c->rho; A.gradh = c->gradh; A.itype = c->itype; A.full = 0; A.shift = 0; A.xbound = A.xperbound = 0.; A.row0 = 0; A.list = nullptr; A.n = 0; A.buf = nullptr;
   return A;
 }
 
@@ -285,7 +285,7 @@ int halo_exchange_inputs(nd_ctx *c) {
     LAUNCH(c, k_halo_compact, nblocks(np, 256), 256, 0, flag, c->scanout, np, c->sendlist[side]);
     c->nsend[side] = n;
   }
-  const long long rec = 8LL * (c->ndim + 14) + 4;
+  const long long rec = 8LL * halo1_nfields(c->ndim) + 4;
   long long sb[2] = {c->nsend[0] * rec, c->nsend[1] * rec}, rb[2] = {0, 0};
   if (int e = exchange_counts(c, sb, rb)) return e;
   if (rb[0] % rec || rb[1] % rec) return set_err(c, ND_ERR_COMM, "halo record size mismatch between ranks");
@@ -317,10 +317,18 @@ int halo_exchange_inputs(nd_ctx *c) {
 }
 
 // ---- halo exchange 2: the owners' converged hh, rho, gradh for the halo rows (the rates test needs h_j: ratesND_mhd.f90:404-415) ----
-int halo_exchange_density(nd_ctx *c) {
-  long long sb[2] = {c->nsend[0] * 24LL, c->nsend[1] * 24LL}, rb[2] = {c->nrecv[0] * 24LL, c->nrecv[1] * 24LL};
+int halo_exchange_density(nd_ctx *c, int full) {
+  const long long recb = 8LL * halo2_nfields(full);
+  long long sb[2] = {c->nsend[0] * recb, c->nsend[1] * recb}, rb[2] = {c->nrecv[0] * recb, c->nrecv[1] * recb};
+  for (int side = 0; side < 2; side++) {   // the full record can be larger than exchange 1's
+    char **sp = (char **)&c->sendbuf[side], **rp = (char **)&c->recvbuf[side];
+    if (int e = grow_buf(c, sp, &c->sendbufcap[side], (size_t)sb[side] + 64)) return e;
+    if (int e = grow_buf(c, rp, &c->recvbufcap[side], (size_t)rb[side] + 64)) return e;
+  }
+  if (full && c->wait_in2) { CU(cudaStreamWaitEvent(c->stream, c->ev_in[1], 0)); c->wait_in2 = false; }   // derivs_host: en, Bevol, alpha, psi have landed
   for (int side = 0; side < 2; side++) {
     HaloPackArgs A = halo_args(c);
+    A.full = full;
     A.list = c->sendlist[side]; A.n = c->nsend[side]; A.buf = (double *)c->sendbuf[side];
     LAUNCH(c, k_halo_pack2, nblocks(A.n, 256), 256, 0, A);
   }
@@ -328,6 +336,7 @@ int halo_exchange_density(nd_ctx *c) {
   int row0 = c->nown;
   for (int side = 0; side < 2; side++) {
     HaloPackArgs A = halo_args(c);
+    A.full = full;
     A.n = c->nrecv[side]; A.buf = (double *)c->recvbuf[side]; A.row0 = row0;
     LAUNCH(c, k_halo_unpack2, nblocks(A.n, 256), 256, 0, A);
     row0 += A.n;
@@ -681,7 +690,7 @@ template <int NDIM> int do_iterate_density(nd_ctx *c, int resume) {
     CU(cudaMemsetAsync(c->redo, 0, sizeof(int) * c->ntotal, c->stream));
     if (first) {                                                                     // :131-132 symmetric `density`
       if (c->itsdensity > 1) {   // the neighbour count of `density` also looks at h_j (:189-190): refresh the sources' 1/h
-        if (c->has_comm) { if (int e = halo_exchange_density(c)) return e; }
+        if (c->has_comm) { if (int e = halo_exchange_density(c, 0)) return e; }
         LAUNCH(c, k_refresh_h, nblocks(c->ntotal, 256), 256, 0, c->perm, c->ireal, c->hh, c->posh, c->p32, 1.0 / c->hhmax, c->npart, c->ntotal);
       }
       if (int e = launch_density_round<NDIM, true>(c, A, c->ntotal)) return e;
@@ -712,7 +721,7 @@ template <int NDIM> int do_iterate_density(nd_ctx *c, int resume) {
   }
   if (c->itsdensity > itsdensitymax && itsdensitymax > 0) return set_err(c, ND_ERR_DENSITY_NOT_CONVERGED, "ERROR: DENSITY NOT CONVERGED");   // :349-351
   // halo rows take the owners' converged values, then :310-344 copies to fixed particles and ghosts
-  if (c->has_comm) { if (int e = halo_exchange_density(c)) return e; }
+  if (c->has_comm) { if (int e = halo_exchange_density(c, 1)) return e; }
   CopyArgs CA;
   CA.rho = c->rho; CA.rhoalt = c->rhoalt; CA.drhodt = c->drhodt; CA.dhdt = c->dhdt; CA.hh = c->hh; CA.gradh = c->gradh; CA.gradhn = c->gradhn;
   CA.gradsoft = c->gradsoft; CA.itype = c->itype; CA.ireal = c->ireal; CA.npart = c->npart; CA.ntotal = c->ntotal; CA.aux = o.want_aux != 0;

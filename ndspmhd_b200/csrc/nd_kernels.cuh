@@ -202,14 +202,18 @@ __global__ void k_halo_compact(const int *flag, const int *scan, int n, int *lis
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n && flag[j]) list[scan[j]] = j;
 }
-// exchange 1 (inputs): [x(ndim) vel(3) pmass hh en Bevol(3) alpha(3) psi rho] as doubles, field-major, then itype as ints
+// exchange 1 (before the link): what the link and the density rounds read of a halo row -- [x(ndim) vel(3) pmass hh rho] as doubles,
+// field-major, then itype as ints.  The evolved variables the rates read (en, Bevol, alpha, psi) travel with exchange 2 after the density
+// iteration, so a pipelined upload (ndspmhd_b200_derivs_host) need not have landed them before the link starts.
 struct HaloPackArgs {
   const int *list; int n, ndim;
   double *x, *vel, *pmass, *hh, *en, *Bevol, *alpha, *psi, *rho, *gradh; int *itype;
   double *buf; int row0;        // pack: buf out; unpack: rows [row0, row0+n) in
   int shift; double xbound, xperbound;   // periodic wrap: x' = xperbound + (x - xbound)
+  int full;                     // exchange 2: 0 = hh, rho, gradh (mid-iteration refresh); 1 = + en, Bevol(3), alpha(3), psi (after the last round)
 };
-__device__ __forceinline__ int halo1_nfields(int ndim) { return ndim + 14; }
+__host__ __device__ inline int halo1_nfields(int ndim) { return ndim + 6; }
+__host__ __device__ inline int halo2_nfields(int full) { return full ? 11 : 3; }
 __global__ void k_halo_pack1(HaloPackArgs A) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= A.n) return;
@@ -224,10 +228,6 @@ __global__ void k_halo_pack1(HaloPackArgs A) {
   for (int d = 0; d < 3; d++) A.buf[(f++) * n + q] = A.vel[(size_t)j * 3 + d];
   A.buf[(f++) * n + q] = A.pmass[j];
   A.buf[(f++) * n + q] = A.hh[j];
-  A.buf[(f++) * n + q] = A.en[j];
-  for (int d = 0; d < 3; d++) A.buf[(f++) * n + q] = A.Bevol[(size_t)j * 3 + d];
-  for (int d = 0; d < 3; d++) A.buf[(f++) * n + q] = A.alpha[(size_t)j * 3 + d];
-  A.buf[(f++) * n + q] = A.psi[j];
   A.buf[(f++) * n + q] = A.rho[j];
   reinterpret_cast<int *>(A.buf + (size_t)f * n)[q] = A.itype[j];
 }
@@ -241,20 +241,23 @@ __global__ void k_halo_unpack1(HaloPackArgs A) {
   for (int d = 0; d < 3; d++) A.vel[(size_t)r * 3 + d] = A.buf[(f++) * n + q];
   A.pmass[r] = A.buf[(f++) * n + q];
   A.hh[r] = A.buf[(f++) * n + q];
-  A.en[r] = A.buf[(f++) * n + q];
-  for (int d = 0; d < 3; d++) A.Bevol[(size_t)r * 3 + d] = A.buf[(f++) * n + q];
-  for (int d = 0; d < 3; d++) A.alpha[(size_t)r * 3 + d] = A.buf[(f++) * n + q];
-  A.psi[r] = A.buf[(f++) * n + q];
   A.rho[r] = A.buf[(f++) * n + q];
   A.itype[r] = reinterpret_cast<const int *>(A.buf + (size_t)f * n)[q];
 }
-// exchange 2 (after the density iteration): hh, rho, gradh
+// exchange 2: the owners' hh, rho, gradh (refresh between `density` rounds); after the last round also en, Bevol, alpha, psi
 __global__ void k_halo_pack2(HaloPackArgs A) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= A.n) return;
   const int j = A.list[q];
   const size_t n = A.n;
   A.buf[q] = A.hh[j]; A.buf[n + q] = A.rho[j]; A.buf[2 * n + q] = A.gradh[j];
+  if (A.full) {
+    int f = 3;
+    A.buf[(f++) * n + q] = A.en[j];
+    for (int d = 0; d < 3; d++) A.buf[(f++) * n + q] = A.Bevol[(size_t)j * 3 + d];
+    for (int d = 0; d < 3; d++) A.buf[(f++) * n + q] = A.alpha[(size_t)j * 3 + d];
+    A.buf[(f++) * n + q] = A.psi[j];
+  }
 }
 __global__ void k_halo_unpack2(HaloPackArgs A) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,6 +265,13 @@ __global__ void k_halo_unpack2(HaloPackArgs A) {
   const int r = A.row0 + q;
   const size_t n = A.n;
   A.hh[r] = A.buf[q]; A.rho[r] = A.buf[n + q]; A.gradh[r] = A.buf[2 * n + q];
+  if (A.full) {
+    int f = 3;
+    A.en[r] = A.buf[(f++) * n + q];
+    for (int d = 0; d < 3; d++) A.Bevol[(size_t)r * 3 + d] = A.buf[(f++) * n + q];
+    for (int d = 0; d < 3; d++) A.alpha[(size_t)r * 3 + d] = A.buf[(f++) * n + q];
+    A.psi[r] = A.buf[(f++) * n + q];
+  }
 }
 
 // =====================================================================================================

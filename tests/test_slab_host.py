@@ -212,3 +212,22 @@ def test_row_migration_plan_over_gloo(world):
     assert allids == list(range(4000))                      # every particle owned exactly once
     assert all(out["all_inside"] and out["payload_ok"] for out in res)
     assert sum(out["moved"] for out in res) > 500           # the case does move rows
+
+
+def test_weak_scaling_setup_makes_one_field_period_per_rank():
+    """setups.orszag_tang(weak=True): every rank makes only its own x-period of the box; together they are a valid periodic particle set --
+    disjoint slabs with faces on the period boundaries, equal masses and h, the fields of period k equal to those of period 0."""
+    world = 3
+    parts = [setups.orszag_tang(ndim=3, nx=12, zfrac=0.25, perturb_amp=0.2, evolved=True, slab=(r, world), weak=True) for r in range(world)]
+    o0, p0, i0 = parts[0]
+    assert i0["nglobal"] == world * p0.npart and o0.xmax[0] - o0.xmin[0] == float(world)
+    single_o, single_p = setups.orszag_tang(ndim=3, nx=12, zfrac=0.25, perturb_amp=0.2, evolved=True)
+    assert np.isclose(p0.pmass[0], single_p.pmass[0], rtol=1e-14) and p0.hh[0] == single_p.hh[0]     # same resolution as the one-period box
+    for r, (o, p, info) in enumerate(parts):
+        x = p.x[: p.npart, 0]
+        assert np.all(x >= info["edges"][r]) and np.all(x < info["edges"][r + 1])
+        assert np.array_equal(info["edges"], o0.xmin[0] + np.arange(world + 1))
+        # the lattice of period r is that of period 0 shifted by r (the perturbation differs: its seed depends on the rank)
+        assert np.allclose(np.sort(np.round((x - r + 0.5) * 12 - 0.5)), np.sort(np.round((parts[0][1].x[: p0.npart, 0] + 0.5) * 12 - 0.5)))
+        # fields have period 1 in x: v_y = sin(2 pi (x - xmin))
+        assert np.allclose(p.vel[: p.npart, 1], np.sin(2.0 * np.pi * (x - o.xmin[0])), atol=1e-12)
