@@ -292,8 +292,9 @@ int ndspmhd_b200_comm_stats(const nd_ctx *c, long long *n_allreduce, long long *
  * slab-decomposed context re-owns the rows whose x left [slab_lo, slab_hi) after the predictor and the periodic wrap
  * (src/stepND_leapfrog_mhd.f90:145, src/boundaryND.f90:65-93): they travel to the adjacent rank with their evolved state and the
  * integrator's `*in` copies, holes are filled from the tail of the own rows and arrivals are appended -- so row numbers change and the
- * ids are how a caller follows a particle.  Moving farther than the adjacent slab in one step is ND_ERR_INVALID_ARG; fixed-particle
- * boundaries are refused on slab contexts (fixed rows are tied to their partners' row numbers).
+ * ids are how a caller follows a particle.  Moving farther than the adjacent slab in one step is ND_ERR_INVALID_ARG, and so is leaving
+ * [xmin, xmax] through an open x boundary (ibound(1) = 0: the end slabs are not open-ended); fixed-particle boundaries are refused on
+ * slab contexts (fixed rows are tied to their partners' row numbers).
  */
 int ndspmhd_b200_set_row_ids(nd_ctx *c, const long long *ids, int n);
 int ndspmhd_b200_get_row_ids(nd_ctx *c, long long *ids, int cap);
