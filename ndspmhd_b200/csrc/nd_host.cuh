@@ -471,10 +471,11 @@ template <int NDIM> int make_ghosts(nd_ctx *c) {
   SMALL_D2H(c, c->h_flags + 25, c->scanout + np, sizeof(int));
   CU(cudaStreamSynchronize(c->stream));
   const int nghost = c->h_flags[25];
+  const int cap_before = c->cap;
   if (int e = ensure_capacity(c, np + nghost, np)) return e;
   A.x = c->x; A.vel = c->defer_vel ? nullptr : c->vel; A.hh = c->hh; A.itype = c->itype; A.ireal = c->ireal; A.offset = c->scanout; A.count = c->ghostcount; A.cap = c->cap;
-  // ensure_capacity may have reallocated scanout: redo the scan in that case (cheap)
-  if (int e = exclusive_scan(c, c->ghostcount, c->scanout, np)) return e;
+  // ensure_capacity reallocates scanout when it grows the arrays: redo the scan in that case only
+  if (c->cap != cap_before) { if (int e = exclusive_scan(c, c->ghostcount, c->scanout, np)) return e; }
   A.offset = c->scanout;
   if (int e = wait_second_half(c)) return e;
   LAUNCH(c, (k_ghosts<NDIM, true>), nblocks(np, 256), 256, 0, A);

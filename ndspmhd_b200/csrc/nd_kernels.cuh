@@ -642,8 +642,7 @@ __global__ void k_rates_gather(RGatherArgs A) {
     if (h <= 0.) atomicCAS(A.err, 0, ND_ERR_H_NONPOSITIVE);                         // :384-387
     A.posh[s].w = 1.0 / h;
     A.p32[s].w = screen_h2(h, A.hhmax1);
-    A.vm[s].w = A.pmass[st];
-    A.srho[s] = rho;
+    A.srho[s] = rho;                                                                // (vm.w = m was set by k_gather_sorted / k_late_vel: masses do not change)
     A.thermo[s] = make_double4(1.0 / rho, fmax(A.pr[st] - A.pext, 0.), A.spsound[st], A.uu[st]);   // rho1i, :325; pri = max(pr - pext, 0), :328
     A.gal[s] = make_double4(A.gradh[st], A.alpha[(size_t)st * 3], A.alpha[(size_t)st * 3 + 1],
                             (A.alphaB_ghost && r >= A.npart) ? A.alphaB_ghost[st] : A.alpha[(size_t)st * 3 + 2]);
