@@ -418,6 +418,7 @@ int ndspmhd_b200_migration_stats(const nd_ctx *c, long long *rows_out, long long
 int ndspmhd_b200_set_comm(nd_ctx *c, const nd_comm *comm) {
   if (!c) return ND_ERR_INVALID_ARG;
   if (c->nccl && c->nccl_api) { c->nccl_api->CommDestroy(c->nccl); c->nccl = nullptr; }   // the callback transport replaces a native one
+  c->edges.clear();   // the slab faces of every rank are gathered again at the next migration (a re-attach is how a caller rebalances)
   if (!comm || comm->nranks <= 1) { c->has_comm = false; return 0; }
   if (!comm->allreduce || !comm->sendrecv_counts || !comm->sendrecv) return set_err(c, ND_ERR_INVALID_ARG, "set_comm: all three callbacks are required");
   if (comm->rank < 0 || comm->rank >= comm->nranks || !(comm->slab_hi > comm->slab_lo) || comm->nglobal < 1) return set_err(c, ND_ERR_INVALID_ARG, "set_comm: bad rank / slab / nglobal");
@@ -440,6 +441,7 @@ int ndspmhd_b200_nccl_unique_id(unsigned char id[128]) {
 
 int ndspmhd_b200_set_comm_nccl(nd_ctx *c, const unsigned char id[128], int rank, int nranks, double slab_lo, double slab_hi, long long nglobal) {
   if (!c || !id) return ND_ERR_INVALID_ARG;
+  c->edges.clear();   // see ndspmhd_b200_set_comm
   if (nranks <= 1) { c->has_comm = false; return 0; }
   if (rank < 0 || rank >= nranks || !(slab_hi > slab_lo) || nglobal < 1) return set_err(c, ND_ERR_INVALID_ARG, "set_comm_nccl: bad rank / slab / nglobal");
   if (nranks > 31) return set_err(c, ND_ERR_INVALID_ARG, "set_comm_nccl: at most 31 ranks");
