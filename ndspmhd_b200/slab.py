@@ -1,16 +1,23 @@
-"""Multi-GPU host side: x-slab decomposition, one rank (process) per GPU, transport over torch.distributed.
+"""Multi-GPU host side: x-slab decomposition, one rank (process) per GPU.
 
 The reference is serial (docs/about.rst:12); its only notion of "image particles" is the periodic ghost of
-src/ghostND_mhd.f90:166-346.  The library (csrc/nd_capi.cu: halo_exchange_inputs / halo_exchange_density) applies the same
-rule at slab faces and owns selection, packing and row layout; this module supplies the transport it calls back into
-(include/ndspmhd_b200.h, `nd_comm`):
+src/ghostND_mhd.f90:166-346.  The library (csrc/nd_host.cuh: halo_exchange_inputs / halo_exchange_density / migrate_rows) applies the
+same rule at slab faces and owns selection, packing, row layout and -- when ndspmhd_b200_step runs on a slab context -- the migration
+of rows whose x left the slab.  Two transports carry its traffic:
 
-    allreduce(v[n], op)            small host-side all-reduces (hhmax, unconverged count, stressmax, vsigmax, dt's)
-    sendrecv_counts(send[2])       byte-count handshake with the two x-neighbours (periodic ring)
-    sendrecv(sendbuf[2], recvbuf[2])   the halo payload, device buffers, NCCL send/recv over NVLink
+  * native (attach_nccl): the library calls NCCL itself on its compute stream (csrc/nd_nccl.cuh); this module only broadcasts the
+    128-byte communicator id.  What bench.py --gpus N uses.
+  * callbacks (SlabComm + attach): the three `nd_comm` callbacks of include/ndspmhd_b200.h over torch.distributed --
 
-`SlabComm` works on CUDA tensors with the NCCL backend and on CPU tensors with gloo (tests/test_slab_host.py runs the
-latter with world_size 2 and 3).
+        allreduce(v[n], op)            small host-side all-reduces (hhmax, unconverged count, stressmax, vsigmax, dt's)
+        sendrecv_counts(send[2])       byte-count handshake with the two x-neighbours (periodic ring)
+        sendrecv(sendbuf[2], recvbuf[2])   the halo / migration payloads, device buffers, NCCL send/recv over NVLink
+
+    on CUDA tensors with the NCCL backend and on CPU tensors with gloo (tests/test_slab_host.py runs the latter with world_size 2
+    and 3): what an MPI host would supply.
+
+slab_edges / owner_of / take_rows partition a global particle set; halo_select_numpy, wrap_shift and migration_plan_numpy restate the
+device kernels' rules in numpy for the CPU tests.
 """
 from __future__ import annotations
 
