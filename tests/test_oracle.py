@@ -454,3 +454,49 @@ def test_ghosts_of_reflecting_walls_are_mirror_images(ndim):
     d_of = np.argmax(moved[one], axis=1)
     vexp[np.arange(vexp.shape[0]), d_of] *= -1.0
     assert np.array_equal(p.vel[n:nt][one], vexp)
+
+
+@pytest.mark.parametrize("name, iener, imhd", [("ot3d", 2, 11), ("ot3d", 0, 11), ("ot3d", 2, 1), ("shock1d", 3, 1), ("dusty3d", 2, 0)])
+def test_cons2prim_and_eos_formulas(name, iener, imhd):
+    """conservative2primitive.f90:190-193, :341-373 and eos.f90:74-100 evaluated independently in numpy on the converged densities:
+    dens = rho; B = Bevol (imhd >= 11) or Bevol*rho (B/rho evolved); u = en (thermal energy), en - v^2/2 - B^2/(2 rho) (total energy),
+    P/((gamma-1) rho) (polytropic, gamma /= 1); P = (gamma-1) u rho or polyk rho^gamma; c_s = sqrt(gamma P/rho); dust particles carry
+    no pressure and no thermal energy."""
+    o, p = CONFIGS[name]() if name != "shock1d" else setups.shock1d(nright=60, iener=iener)   # en = total energy there
+    o.device_ghosts = 1
+    if name != "dusty3d":
+        o.iener = iener
+        if name == "ot3d":
+            o.imhd = imhd
+            if iener == 0:
+                setups.set_gamma(o, 1.0)
+                o.polyk = 0.4
+    en0, Bev0, v0 = p.en.copy(), p.Bevol.copy(), p.vel.copy()
+    s, _ = oracle.derivs(o, p)
+    n = p.npart
+    rho = p.rho[:n]
+    gas = p.itype[:n] != 2
+    assert np.array_equal(p.dens[:n], rho)
+    if o.imhd >= 11:
+        B = Bev0[:n]
+    elif o.imhd > 0:
+        B = Bev0[:n] * rho[:, None]
+    else:
+        B = np.zeros((n, 3))
+    if o.imhd != 0:
+        assert np.max(np.abs(p.Bfield[:n] - B)) <= 1e-15 * max(np.max(np.abs(B)), 1e-300)
+    if o.iener == 3:
+        u = en0[:n] - 0.5 * (v0[:n] ** 2).sum(1) - 0.5 * (B ** 2).sum(1) / rho
+    elif o.iener == 0:
+        P = o.polyk * rho ** o.gamma
+        u = P / ((o.gamma - 1.0) * rho) if abs(o.gamma - 1.0) > 1e-3 else p.uu[:n]
+    else:
+        u = en0[:n]
+    if o.iener != 0:
+        P = (o.gamma - 1.0) * u * rho
+    P = np.where(gas, P, 0.0)
+    tol = 1e-13
+    assert np.max(np.abs(p.uu[:n][gas] - u[gas])) <= tol * np.max(np.abs(u[gas]))
+    assert np.max(np.abs(p.pr[:n] - P)) <= tol * np.max(np.abs(P))
+    cs = np.sqrt(o.gamma * P[gas] / rho[gas])
+    assert np.max(np.abs(p.spsound[:n][gas] - cs)) <= tol * np.max(cs)
